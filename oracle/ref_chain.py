@@ -1,0 +1,405 @@
+"""CPU restatement of the reference's enhance-chain glue (TEST INFRASTRUCTURE ONLY).
+
+Every function follows one body of /root/reference (file:line cited in each docstring) and calls an
+`ops` backend for the OpenCV primitives it uses:
+
+  Cv2Ops   - the REAL OpenCV kernels through cv2 (what the reference links against; 4.13.0 here,
+             the author linked 4.12.0).  Strongest oracle; also the CPU baseline bench.py times.
+  NumpyOps - oracle/restate.py, the CPU-independent numpy restatement of the same arithmetic
+             (what the CUDA kernels are held bit-exact / +-1 LSB against, and what generates
+             tests/golden/).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product path never does: it fails loudly if libvpb200.so is missing.
+
+Scope decisions where the literal reference code is undefined behaviour (SURVEY.md section 8(c),
+Appendix B) -- each is an oracle decision, stated here once:
+  * SelectiveBilateral: only the plain branch (use_multiscale=false, selective=false) is in scope;
+    createDetailMask calls cv::sqrt on a CV_8U Mat (selective_bilateral.cpp:276).
+  * AdaptiveSharpening: only adaptive_sigma=false is in scope; calculateTextureMap has the same
+    defect (adaptive_sharpening.cpp:386).
+  * TemporalConsistency::blendFrames writes Vec3f into a CV_8UC3 Mat (temporal_consistency.cpp:367
+    vs :408); the oracle uses the evidently intended float32 accumulator.  Optical flow / warp /
+    scene-change / reliability masks are out of scope: previous frames enter the blend unwarped
+    with mask == 1.
+Parity status: the reference has no golden vectors and cannot be compiled here, so this glue is
+"parity unpinned" against a reference binary; the arithmetic underneath is pinned against real
+OpenCV (tests/test_oracle_restate.py) and frozen in tests/golden/.
+"""
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import restate as R
+
+F32 = np.float32
+
+PRE_PROCESSING = 0
+POST_PROCESSING = 1
+
+
+# ------------------------------------------------------------------------------------------------
+# Config mirrors (field order == the reference's aggregate structs, callers brace-init positionally)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class BilateralConfig:  # include/selective_bilateral.h:20-40
+    stage: int = PRE_PROCESSING
+    use_gpu: bool = True
+    adaptive_params: bool = True
+    diameter: int = 7
+    sigma_color: float = 30.0
+    sigma_space: float = 30.0
+    selective: bool = True
+    detail_threshold: float = 30.0
+    texture_boost: float = 1.5
+    edge_preserve: float = 2.0
+    use_multiscale: bool = True
+    num_scales: int = 3
+
+
+@dataclass
+class SharpenConfig:  # include/adaptive_sharpening.h:14-24
+    strength: float = 0.8
+    edge_strength: float = 1.2
+    smooth_strength: float = 0.4
+    edge_threshold: float = 30.0
+    sigma: float = 1.5
+    kernel_size: int = 5
+    preserve_tone: bool = True
+    use_gpu: bool = True
+    adaptive_sigma: bool = True
+
+
+@dataclass
+class TemporalConfig:  # include/temporal_consistency.h:18-33 (flow parameters unused: out of scope)
+    buffer_size: int = 3
+    blend_strength: float = 0.6
+    motion_threshold: float = 15.0
+    scene_change_threshold: float = 100.0
+    use_gpu: bool = True
+
+
+# ------------------------------------------------------------------------------------------------
+# primitive backends
+# ------------------------------------------------------------------------------------------------
+class NumpyOps:
+    name = "numpy-restatement"
+
+    def resize_cubic(self, img, dw, dh):
+        return R.resize_cubic(img, dw, dh, "default")
+
+    def bilateral(self, img, d, sc, ss):
+        return R.bilateral_u8c3(img, d, sc, ss)
+
+    def mean_stddev(self, img):
+        m, s, _, _ = R.mean_stddev(img)
+        return m, s
+
+    def gaussian_u8(self, img, k, sigma):
+        return R.gaussian_blur_u8(img, k, sigma)
+
+    def gaussian_f32(self, img, k, sigma):
+        return R.gaussian_blur_f32(img, k, sigma)
+
+    def bgr2gray(self, img):
+        return R.bgr2gray(img)
+
+    def bgr2ycrcb(self, img):
+        return R.bgr2ycrcb(img)
+
+    def ycrcb2bgr(self, img):
+        return R.ycrcb2bgr(img)
+
+    def sobel_abs(self, gray, dx, dy):
+        return R.abs_sat_u8(R.sobel_x(gray) if dx else R.sobel_y(gray))
+
+    def laplacian_abs(self, gray):
+        return R.abs_sat_u8(R.laplacian3(gray))
+
+    def add_weighted(self, a, alpha, b, beta):
+        return R.add_weighted_u8(a, alpha, b, beta)
+
+    def subtract(self, a, b):
+        return R.subtract_sat_u8(a, b)
+
+
+class Cv2Ops:
+    name = "cv2"
+
+    def __init__(self, threads=None):
+        import cv2
+        self.cv2 = cv2
+        cv2.setUseOptimized(True)
+        if threads is not None:
+            cv2.setNumThreads(int(threads))
+
+    def resize_cubic(self, img, dw, dh):
+        return self.cv2.resize(img, (dw, dh), interpolation=self.cv2.INTER_CUBIC)
+
+    def bilateral(self, img, d, sc, ss):
+        return self.cv2.bilateralFilter(img, d, sc, ss)
+
+    def mean_stddev(self, img):
+        m, s = self.cv2.meanStdDev(img)
+        return m.ravel()[:3], s.ravel()[:3]
+
+    def gaussian_u8(self, img, k, sigma):
+        return self.cv2.GaussianBlur(img, (k, k), sigma)
+
+    def gaussian_f32(self, img, k, sigma):
+        return self.cv2.GaussianBlur(img, (k, k), sigma)
+
+    def bgr2gray(self, img):
+        return self.cv2.cvtColor(img, self.cv2.COLOR_BGR2GRAY)
+
+    def bgr2ycrcb(self, img):
+        return self.cv2.cvtColor(img, self.cv2.COLOR_BGR2YCrCb)
+
+    def ycrcb2bgr(self, img):
+        return self.cv2.cvtColor(img, self.cv2.COLOR_YCrCb2BGR)
+
+    def sobel_abs(self, gray, dx, dy):
+        g = self.cv2.Sobel(gray, self.cv2.CV_16S, dx, dy, ksize=3)
+        return self.cv2.convertScaleAbs(g)
+
+    def laplacian_abs(self, gray):
+        return self.cv2.convertScaleAbs(self.cv2.Laplacian(gray, self.cv2.CV_16S, ksize=3))
+
+    def add_weighted(self, a, alpha, b, beta):
+        return self.cv2.addWeighted(a, alpha, b, beta, 0)
+
+    def subtract(self, a, b):
+        return self.cv2.subtract(a, b)
+
+
+# ------------------------------------------------------------------------------------------------
+# SelectiveBilateral (plain branch)
+# ------------------------------------------------------------------------------------------------
+def adaptive_params(ops, img, cfg):
+    """SelectiveBilateral::calculateAdaptiveParams, selective_bilateral.cpp:315-371."""
+    _, std = ops.mean_stddev(img)
+    avg = 0.0
+    for i in range(3):
+        avg += float(std[i])
+    avg /= 3
+    return adaptive_params_from_std(avg, cfg)
+
+
+def adaptive_params_from_std(avg_stddev, cfg):
+    nf = 1.0
+    if avg_stddev < 5.0:
+        nf = 0.7
+    elif avg_stddev > 15.0:
+        nf = 1.5
+    d = max(5, int(cfg.diameter * nf))
+    if d % 2 == 0:
+        d += 1
+    d = min(d, 15)
+    sc = cfg.sigma_color * nf
+    ss = cfg.sigma_space * nf
+    if cfg.stage == POST_PROCESSING:
+        d = max(3, d - 2)
+        sc *= 0.8
+        ss *= 0.8
+    return d, sc, ss
+
+
+def bilateral_plain(ops, img, cfg):
+    """SelectiveBilateral::applyBilateralFilter, selective_bilateral.cpp:84-119 (CPU branch :110)."""
+    d, sc, ss = cfg.diameter, cfg.sigma_color, cfg.sigma_space
+    if cfg.adaptive_params:
+        d, sc, ss = adaptive_params(ops, img, cfg)
+    return ops.bilateral(img, d, sc, ss)
+
+
+# ------------------------------------------------------------------------------------------------
+# AdaptiveSharpening (adaptive_sigma = false)
+# ------------------------------------------------------------------------------------------------
+def edge_strength_u8(ops, img):
+    """adaptive_sharpening.cpp:114-198: gray, Sobel x/y -> convertScaleAbs -> addWeighted(.5,.5),
+    Laplacian -> convertScaleAbs, addWeighted(.6,.4).  Returns the CV_8U `combined_edges`."""
+    gray = ops.bgr2gray(img)
+    ax = ops.sobel_abs(gray, 1, 0)
+    ay = ops.sobel_abs(gray, 0, 1)
+    sobel = ops.add_weighted(ax, 0.5, ay, 0.5)
+    lap = ops.laplacian_abs(gray)
+    return ops.add_weighted(sobel, 0.6, lap, 0.4)
+
+
+def edge_mask(ops, img, cfg):
+    """AdaptiveSharpening::createEdgeMask, adaptive_sharpening.cpp:107-230.  The per-pixel sigmoid
+    loop (:212-219) has a 256-value domain, so it is applied as the exact LUT of restate.sigmoid_lut."""
+    comb = edge_strength_u8(ops, img)
+    lut = R.sigmoid_lut(cfg.edge_threshold)
+    sig = lut[comb]
+    return ops.gaussian_f32(sig, 5, 1.5)  # :222 -- literal Size(5,5), 1.5 (not the config's)
+
+
+def unsharp_mask(ops, img, mask, cfg):
+    """AdaptiveSharpening::applyUnsharpMask, adaptive_sharpening.cpp:232-355 (3-channel branch).
+    All float32, no FMA contraction (the reference is built without -O / -mfma)."""
+    blurred = ops.gaussian_u8(img, cfg.kernel_size, float(F32(cfg.sigma)))
+    um = ops.subtract(img, blurred)  # saturating: negative lobes dropped (:265)
+    e = mask.astype(F32)
+    st, es, ss = F32(cfg.strength), F32(cfg.edge_strength), F32(cfg.smooth_strength)
+    t1 = (e * es).astype(F32)
+    t2 = ((F32(1.0) - e).astype(F32) * ss).astype(F32)
+    strength = (st * (t1 + t2).astype(F32)).astype(F32)
+    prod = (strength[..., None] * um.astype(F32)).astype(F32)
+    sharp = (img.astype(F32) + prod).astype(F32)
+    out = np.clip(np.rint(sharp), 0, 255).astype(np.uint8)
+    if cfg.preserve_tone:  # :326-347
+        yi = ops.bgr2ycrcb(img)
+        yo = ops.bgr2ycrcb(out)
+        yo[..., 1] = yi[..., 1]
+        yo[..., 2] = yi[..., 2]
+        out = ops.ycrcb2bgr(np.ascontiguousarray(yo))
+    return out
+
+
+def sharpen(ops, img, cfg):
+    """AdaptiveSharpening::process with adaptive_sigma=false, adaptive_sharpening.cpp:51-105."""
+    return unsharp_mask(ops, img, edge_mask(ops, img, cfg), cfg)
+
+
+# ------------------------------------------------------------------------------------------------
+# temporal stages
+# ------------------------------------------------------------------------------------------------
+def blend_frames(frames, blend_strength, masks=None):
+    """TemporalConsistency::blendFrames, temporal_consistency.cpp:355-444, with the intended float32
+    accumulator.  frames[0] = current, frames[i] = i-th previous (already aligned); masks default 1.
+    weight = exp(-(float)i/2.0f) * mask * blend_factor in float32 (:376,:405), accumulation in frame
+    order (:411-418), `pixel /= weight` (cv::Vec /= float multiplies by 1.f/weight), convertTo RNE."""
+    h, w = frames[0].shape[:2]
+    acc = np.zeros((h, w, 3), dtype=F32)
+    wsum = np.zeros((h, w), dtype=F32)
+    for i, f in enumerate(frames):
+        fw = F32(math.exp(float(F32(-float(i)) / F32(2.0))))  # std::exp(float) == expf, correctly rounded
+        m = np.ones((h, w), dtype=F32) if masks is None or masks[i] is None else masks[i].astype(F32)
+        bf = F32(1.0) if i == 0 else F32(blend_strength)
+        wt = ((fw * m).astype(F32) * bf).astype(F32)
+        acc = (acc + (wt[..., None] * f.astype(F32)).astype(F32)).astype(F32)
+        wsum = (wsum + wt).astype(F32)
+    inv = (F32(1.0) / wsum).astype(F32)
+    res = (acc * inv[..., None]).astype(F32)
+    res = np.where(wsum[..., None] > 0, res, frames[0].astype(F32))
+    return np.clip(np.rint(res), 0, 255).astype(np.uint8)
+
+
+class TemporalBlendState:
+    """TemporalConsistency::process buffer policy (temporal_consistency.cpp:61-172) with the
+    flow/warp/scene-change front end out of scope: first frame passes through; afterwards the
+    current frame is blended with the up-to (buffer_size-1) most recent *unblended* inputs
+    (m_flow_buffer holds < buffer_size flows, :167-169); the unblended input is what is stored
+    (:158)."""
+
+    def __init__(self, cfg=None):
+        self.cfg = cfg or TemporalConfig()
+        self.frames = []
+
+    def reset(self):
+        self.frames = []
+
+    def process(self, cur):
+        if not self.frames:
+            self.frames.append(cur.copy())
+            return cur.copy()
+        nprev = min(len(self.frames), self.cfg.buffer_size - 1)
+        fr = [cur] + [self.frames[-1 - i] for i in range(nprev)]
+        out = blend_frames(fr, self.cfg.blend_strength) if len(fr) > 1 else cur.copy()
+        self.frames.append(cur.copy())
+        while len(self.frames) > self.cfg.buffer_size:
+            self.frames.pop(0)
+        return out
+
+
+class MainBlendState:
+    """main.cpp:269-292: history of processed (unblended) frames; from the second frame on
+    out = addWeighted(cur, w, prev, 1-w), w = 0.6 (bicubic) / 0.7 (super-res)."""
+
+    def __init__(self, ops, current_weight=0.6):
+        self.ops = ops
+        self.cw = F32(current_weight)
+        self.pw = F32(1.0) - self.cw
+        self.prev = None
+
+    def reset(self):
+        self.prev = None
+
+    def process(self, cur):
+        out = cur.copy() if self.prev is None else self.ops.add_weighted(cur, float(self.cw), self.prev, float(self.pw))
+        self.prev = cur.copy()
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the chain: Upscaler::upscale REAL_ESRGAN branch with the bicubic substitute
+# ------------------------------------------------------------------------------------------------
+TEMPORAL_NONE, TEMPORAL_MAIN_BLEND, TEMPORAL_BLEND_FRAMES = 0, 1, 2
+
+
+@dataclass
+class ChainConfig:
+    dst_w: int = 0
+    dst_h: int = 0
+    use_pre: bool = True
+    use_sharpen: bool = True
+    use_post: bool = True
+    temporal: int = TEMPORAL_MAIN_BLEND
+    # in-scope variants of Upscaler::initializeEnhancements (upscaler.cpp:666-758): same numbers,
+    # with the UB branches (multiscale / selective / adaptive_sigma) switched off.
+    pre: BilateralConfig = field(default_factory=lambda: BilateralConfig(
+        PRE_PROCESSING, True, True, 7, 30.0, 30.0, False, 30.0, 1.5, 2.0, False, 3))
+    sharpen: SharpenConfig = field(default_factory=lambda: SharpenConfig(
+        0.8, 1.2, 0.4, 30.0, 1.5, 5, True, True, False))
+    post: BilateralConfig = field(default_factory=lambda: BilateralConfig(
+        POST_PROCESSING, True, True, 5, 20.0, 20.0, False, 30.0, 1.2, 1.5, False, 2))
+    temporal_cfg: TemporalConfig = field(default_factory=TemporalConfig)
+    main_blend_weight: float = 0.6
+
+
+class Chain:
+    """Upscaler::upscale enhancement chain, upscaler.cpp:772-829 == test_enhancements.cpp:333-377,
+    with step 2 = cv::resize(INTER_CUBIC) (test_enhancements.cpp:346-349)."""
+
+    def __init__(self, ops, cfg):
+        self.ops, self.cfg = ops, cfg
+        if cfg.temporal == TEMPORAL_MAIN_BLEND:
+            self.temporal = MainBlendState(ops, cfg.main_blend_weight)
+        elif cfg.temporal == TEMPORAL_BLEND_FRAMES:
+            self.temporal = TemporalBlendState(cfg.temporal_cfg)
+        else:
+            self.temporal = None
+
+    def reset(self):
+        if self.temporal:
+            self.temporal.reset()
+
+    def spatial(self, frame, stages=None):
+        """Everything before the temporal stage; optionally records the stage outputs."""
+        ops, cfg = self.ops, self.cfg
+        x = bilateral_plain(ops, frame, cfg.pre) if cfg.use_pre else frame
+        if stages is not None:
+            stages["pre"] = x
+        x = ops.resize_cubic(x, cfg.dst_w, cfg.dst_h)
+        if stages is not None:
+            stages["up"] = x
+        if cfg.use_sharpen:
+            x = sharpen(ops, x, cfg.sharpen)
+        if stages is not None:
+            stages["sharp"] = x
+        if cfg.use_post:
+            x = bilateral_plain(ops, x, cfg.post)
+        if stages is not None:
+            stages["post"] = x
+        return x
+
+    def process(self, frame, stages=None):
+        x = self.spatial(frame, stages)
+        return self.temporal.process(x) if self.temporal else x
+
+
+def psnr(a, b):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return float("inf") if mse == 0 else 10.0 * math.log10(255.0 * 255.0 / mse)

@@ -1,0 +1,353 @@
+"""Pure-numpy restatement of the OpenCV arithmetic on the enhance-chain hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product (video_processor_b200/, include/) may import
+this; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+
+The reference (skandvarma/video-processor) has no arithmetic of its own on this path: every
+number comes out of OpenCV (third-party, NOT vendored; the author linked 4.12.0, see
+/root/reference/build/CMakeFiles/video_processor.dir/link.txt).  This file restates the published
+OpenCV 4.x algorithms (modules/imgproc/src/{resize,smooth,color_yuv,deriv,bilateral_filter}.cpp,
+modules/core/src/{arithm,mean}.cpp) so parity does not depend on which SIMD path a given host CPU
+dispatches.  Each function names the reference call site it serves.  tests/test_oracle_*.py pin
+every function here against the real OpenCV kernels through `cv2` 4.13.0 and against the
+committed golden vectors (tests/golden/).
+
+Pinning status: the reference ships no golden vectors / KATs, and its C++
+cannot be compiled here (OpenCV C++ absent), so the *glue* in oracle/ref_chain.py is "parity
+unpinned" against the reference binary; the OpenCV arithmetic restated here IS pinned, against the
+real library.
+"""
+import math
+
+import numpy as np
+
+F32 = np.float32
+
+
+# --------------------------------------------------------------------------------------------
+# borders
+# --------------------------------------------------------------------------------------------
+def reflect101(i, n):
+    """cv::BORDER_REFLECT_101 index map (gfedcb|abcdefgh|gfedcba), valid for any offset."""
+    i = np.asarray(i)
+    if n == 1:
+        return np.zeros_like(i)
+    p = 2 * (n - 1)
+    i = np.mod(i, p)
+    return np.where(i >= n, p - i, i)
+
+
+def pad_reflect101(img, r):
+    h, w = img.shape[:2]
+    ys = reflect101(np.arange(-r, h + r), h)
+    xs = reflect101(np.arange(-r, w + r), w)
+    return img[ys][:, xs]
+
+
+# --------------------------------------------------------------------------------------------
+# cv::resize(INTER_CUBIC) on CV_8UC3  -- reference call sites upscaler.cpp:81,
+# test_enhancements.cpp:348, main.cpp:265
+# --------------------------------------------------------------------------------------------
+def cubic_coeffs(src_len, dst_len):
+    """Per-destination-index source offset and 11-bit fixed-point taps.
+
+    Follows cv::resize's table build (resize.cpp, `interpolateCubic` + the xofs/ialpha loop):
+    scale = 1/(dst/src) in double, f = (float)((d+0.5)*scale-0.5), s=floor(f), A=-0.75 in float32,
+    taps = saturate_cast<short>(c*2048) (round-half-even).  Returns (ofs[int32 dst_len] = s-1,
+    coef[int16 dst_len,4]); tap k reads source index clamp(ofs+k, 0, src_len-1).
+    """
+    inv_scale = float(dst_len) / float(src_len)
+    scale = 1.0 / inv_scale
+    d = np.arange(dst_len, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(F32)
+    s = np.floor(f).astype(np.int32)
+    x = (f - s.astype(F32)).astype(F32)
+    A = F32(-0.75)
+    one = F32(1.0)
+    xp1 = (x + one).astype(F32)
+    omx = (one - x).astype(F32)
+    c0 = ((A * xp1 - F32(5) * A) * xp1 + F32(8) * A) * xp1 - F32(4) * A
+    c1 = ((A + F32(2)) * x - (A + F32(3))) * x * x + one
+    c2 = ((A + F32(2)) * omx - (A + F32(3))) * omx * omx + one
+    c3 = one - c0 - c1 - c2
+    c = np.stack([c0, c1, c2, c3], axis=1).astype(F32)
+    coef = np.rint(c * F32(2048)).astype(np.int16)
+    return (s - 1).astype(np.int32), coef
+
+
+GENERIC_VEC_LANES = 8  # VTraits<v_int16>::vlanes() of the SSE-baseline VResizeCubicVec_32s8u
+
+
+def resize_cubic(src, dst_w, dst_h, path="default"):
+    """Bit-exact model of cv::resize(src8U, dst, Size(dst_w,dst_h), 0, 0, INTER_CUBIC).
+
+    Horizontal pass: int32 with 11-bit short taps (|H| <= 595,680 < 2^24, exact in float32).
+    Vertical pass, b_k = (float)beta_k * 2^-22, S_k = (float)H[ytap_k]:
+      path="default" - what a stock OpenCV build (IPP on, useOptimized) returns for x2 and x4, the
+          only scales on the hot path; verified here against cv2 4.13.0 incl. exact .5 ties and odd
+          row lengths:  t = fma(S0,b0, S1*b1) + fma(S2,b2, S3*b3);  dst = sat_u8(rint(t)) for
+          EVERY element (no separate row tail).
+      path="generic" - OpenCV's own C++ path (cv2.ipp.setUseIPP(False) / setUseOptimized(False)),
+          valid for any scale: vector body (first (width*cn)//8*8 elements of a row)
+          t = S0*b0 + (S1*b1 + (S2*b2 + S3*b3)), every op rounded to float32, no FMA,
+          dst = sat_u8(rint(t)); row tail uses the integer FixedPtCast
+          dst = sat_u8((sum_k H_k*beta_k + 2^21) >> 22).
+    At x2 the two paths agree everywhere except on the generic path's integer row tail at exact ties.
+    """
+    src = np.asarray(src)
+    if src.ndim == 2:
+        src = src[:, :, None]
+    sh, sw, cn = src.shape
+    xofs, alpha = cubic_coeffs(sw, dst_w)
+    yofs, beta = cubic_coeffs(sh, dst_h)
+    H = np.zeros((sh, dst_w, cn), dtype=np.int64)
+    s = src.astype(np.int64)
+    for k in range(4):
+        xi = np.clip(xofs + k, 0, sw - 1)
+        H += s[:, xi, :] * alpha[:, k].astype(np.int64)[None, :, None]
+    H = H.reshape(sh, dst_w * cn)
+    rows = [H[np.clip(yofs + k, 0, sh - 1)] for k in range(4)]  # each (dst_h, dst_w*cn)
+    n = dst_w * cn
+    b = [(beta[:, k].astype(F32) * F32(1.0 / 4194304.0))[:, None] for k in range(4)]
+    S = [rows[k].astype(F32) for k in range(4)]
+    if path == "default":
+        # fma evaluated through float64: the product of two 24-bit significands is exact in
+        # float64 and the following add of a float32 is correctly rounded to float64; the double
+        # rounding float64->float32 cannot differ from a true fma here because |S*b| < 2^9 carries
+        # at most 48 significant bits + alignment < 53 (checked exhaustively in tests on ties).
+        def fma32(a, bb, c):
+            return (a.astype(np.float64) * bb.astype(np.float64) + c.astype(np.float64)).astype(F32)
+        p1 = (S[1] * b[1]).astype(F32)
+        p3 = (S[3] * b[3]).astype(F32)
+        t = (fma32(S[0], b[0], p1) + fma32(S[2], b[2], p3)).astype(F32)
+        out = np.clip(np.rint(t), 0, 255).astype(np.uint8)
+    elif path == "generic":
+        t = ((S[2] * b[2]).astype(F32) + (S[3] * b[3]).astype(F32)).astype(F32)
+        t = ((S[1] * b[1]).astype(F32) + t).astype(F32)
+        t = ((S[0] * b[0]).astype(F32) + t).astype(F32)
+        out = np.clip(np.rint(t), 0, 255).astype(np.uint8)
+        nvec = (n // GENERIC_VEC_LANES) * GENERIC_VEC_LANES
+        if nvec < n:
+            acc = sum(rows[k] * beta[:, k].astype(np.int64)[:, None] for k in range(4))
+            tail = np.clip((acc + (1 << 21)) >> 22, 0, 255).astype(np.uint8)
+            out[:, nvec:] = tail[:, nvec:]
+    else:
+        raise ValueError(path)
+    return out.reshape(dst_h, dst_w, cn)
+
+
+# --------------------------------------------------------------------------------------------
+# cv::GaussianBlur on CV_8U (fixed-point path)  -- upscaler.cpp:78, adaptive_sharpening.cpp:258
+# --------------------------------------------------------------------------------------------
+def gaussian_kernel_f64(ksize, sigma):
+    """cv::getGaussianKernel(ksize, sigma, CV_64F)."""
+    small = {1: [1.0], 3: [0.25, 0.5, 0.25], 5: [0.0625, 0.25, 0.375, 0.25, 0.0625],
+             7: [0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125]}
+    if sigma <= 0 and ksize in small:
+        return np.array(small[ksize], dtype=np.float64)
+    sx = sigma if sigma > 0 else ((ksize - 1) * 0.5 - 1) * 0.3 + 0.8
+    scale2x = -0.5 / (sx * sx)
+    x = np.arange(ksize, dtype=np.float64) - (ksize - 1) * 0.5
+    k = np.exp(scale2x * x * x)
+    return k / k.sum()
+
+
+def gaussian_kernel_q8(ksize, sigma):
+    """Q0.8 kernel used by the 8-bit fixed-point GaussianBlur (getGaussianKernelFixedPoint_ED):
+    side taps outside-in with error diffusion, centre = 256 - 2*sum(sides)."""
+    g = gaussian_kernel_f64(ksize, sigma)
+    n = ksize // 2
+    q = np.zeros(ksize, dtype=np.int64)
+    err = 0.0
+    for i in range(n):
+        v = 256.0 * g[i] + err
+        qi = int(np.rint(v))  # cvRound: half-to-even
+        err = v - qi
+        q[i] = q[ksize - 1 - i] = qi
+    q[n] = 256 - 2 * int(q[:n].sum())
+    return q
+
+
+def gaussian_blur_u8(img, ksize, sigma):
+    """cv::GaussianBlur(img8U, out, Size(k,k), sigma) -- BORDER_REFLECT_101, Q8.8 row pass,
+    Q8.16 column pass, dst = (v + 2^15) >> 16."""
+    img = np.asarray(img)
+    squeeze = img.ndim == 2
+    if squeeze:
+        img = img[:, :, None]
+    q = gaussian_kernel_q8(ksize, sigma)
+    r = ksize // 2
+    p = pad_reflect101(img, r).astype(np.int64)
+    h, w = img.shape[:2]
+    row = sum(p[:, k:k + w] * q[k] for k in range(ksize))
+    col = sum(row[k:k + h] * q[k] for k in range(ksize))
+    out = ((col + (1 << 15)) >> 16).astype(np.uint8)
+    return out[:, :, 0] if squeeze else out
+
+
+def gaussian_blur_f32(img, ksize, sigma):
+    """cv::GaussianBlur on CV_32F (adaptive_sharpening.cpp:222): separable float32, kernel =
+    (float)getGaussianKernel; row pass then column pass, left-to-right accumulation."""
+    k = gaussian_kernel_f64(ksize, sigma).astype(F32)
+    r = ksize // 2
+    p = pad_reflect101(np.asarray(img, dtype=F32), r)
+    h, w = img.shape[:2]
+    row = np.zeros((h + 2 * r, w), dtype=F32)
+    for i in range(ksize):
+        row = (row + p[:, i:i + w] * k[i]).astype(F32)
+    col = np.zeros((h, w), dtype=F32)
+    for i in range(ksize):
+        col = (col + row[i:i + h] * k[i]).astype(F32)
+    return col
+
+
+# --------------------------------------------------------------------------------------------
+# cv::cvtColor 8-bit  -- adaptive_sharpening.cpp:114,329-330,346
+# --------------------------------------------------------------------------------------------
+def bgr2gray(img):
+    b, g, r = (img[..., i].astype(np.int64) for i in range(3))
+    return ((9798 * r + 19235 * g + 3735 * b + (1 << 14)) >> 15).astype(np.uint8)
+
+
+def bgr2ycrcb(img):
+    b, g, r = (img[..., i].astype(np.int64) for i in range(3))
+    y = (4899 * r + 9617 * g + 1868 * b + (1 << 13)) >> 14
+    cr = ((r - y) * 11682 + (128 << 14) + (1 << 13)) >> 14
+    cb = ((b - y) * 9241 + (128 << 14) + (1 << 13)) >> 14
+    return np.stack([y, np.clip(cr, 0, 255), np.clip(cb, 0, 255)], axis=-1).astype(np.uint8)
+
+
+def ycrcb2bgr(img):
+    y, cr, cb = (img[..., i].astype(np.int64) for i in range(3))
+    cr = cr - 128
+    cb = cb - 128
+    b = y + ((cb * 29049 + (1 << 13)) >> 14)
+    g = y + ((cb * -5636 + cr * -11698 + (1 << 13)) >> 14)
+    r = y + ((cr * 22987 + (1 << 13)) >> 14)
+    return np.clip(np.stack([b, g, r], axis=-1), 0, 255).astype(np.uint8)
+
+
+# --------------------------------------------------------------------------------------------
+# derivatives / elementwise  -- adaptive_sharpening.cpp:159-165,192-198,265 ; main.cpp:286-290
+# --------------------------------------------------------------------------------------------
+def _corr3(gray, k):
+    p = pad_reflect101(gray, 1).astype(np.int64)
+    h, w = gray.shape
+    out = np.zeros((h, w), dtype=np.int64)
+    for i in range(3):
+        for j in range(3):
+            if k[i][j]:
+                out += k[i][j] * p[i:i + h, j:j + w]
+    return out
+
+
+def sobel_x(gray):
+    return _corr3(gray, [[-1, 0, 1], [-2, 0, 2], [-1, 0, 1]])
+
+
+def sobel_y(gray):
+    return _corr3(gray, [[-1, -2, -1], [0, 0, 0], [1, 2, 1]])
+
+
+def laplacian3(gray):
+    """cv::Laplacian(gray, CV_16S, 3): aperture 3 kernel [[2,0,2],[0,-8,0],[2,0,2]]."""
+    return _corr3(gray, [[2, 0, 2], [0, -8, 0], [2, 0, 2]])
+
+
+def abs_sat_u8(x):
+    """cv::convertScaleAbs on CV_16S: sat_u8(|x|)."""
+    return np.clip(np.abs(x), 0, 255).astype(np.uint8)
+
+
+def add_weighted_u8(a, alpha, b, beta):
+    """cv::addWeighted(a8U, alpha, b8U, beta, 0): sat_u8(rint(fmaf(a, (float)alpha, b*(float)beta)))
+    (the AVX2 form; for 0.5/0.5 and 0.6/0.4 every formulation agrees)."""
+    fa, fb = F32(alpha), F32(beta)
+    pb = (b.astype(F32) * fb).astype(F32)
+    t = (a.astype(np.float64) * np.float64(fa) + pb.astype(np.float64)).astype(F32)
+    return np.clip(np.rint(t), 0, 255).astype(np.uint8)
+
+
+def subtract_sat_u8(a, b):
+    return np.clip(a.astype(np.int16) - b.astype(np.int16), 0, 255).astype(np.uint8)
+
+
+# --------------------------------------------------------------------------------------------
+# cv::meanStdDev  -- selective_bilateral.cpp:322
+# --------------------------------------------------------------------------------------------
+def mean_stddev(img):
+    """Exact integer sums then double: mean = S/N, std = sqrt(max(SQ/N - mean^2, 0)) per channel."""
+    x = img.reshape(-1, img.shape[-1]).astype(np.int64)
+    n = x.shape[0]
+    s = x.sum(axis=0)
+    sq = (x * x).sum(axis=0)
+    mean = s.astype(np.float64) / n
+    var = np.maximum(sq.astype(np.float64) / n - mean * mean, 0.0)
+    return mean, np.sqrt(var), s, sq
+
+
+# --------------------------------------------------------------------------------------------
+# cv::bilateralFilter CV_8UC3  -- selective_bilateral.cpp:110
+# --------------------------------------------------------------------------------------------
+def bilateral_tables(d, sigma_color, sigma_space):
+    """radius, tap offsets (i-major) and float32 weight tables exactly as bilateralFilter_8u builds
+    them (double exp, stored as float)."""
+    if sigma_color <= 0:
+        sigma_color = 1.0
+    if sigma_space <= 0:
+        sigma_space = 1.0
+    gc = -0.5 / (sigma_color * sigma_color)
+    gs = -0.5 / (sigma_space * sigma_space)
+    radius = d // 2 if d > 0 else int(np.rint(sigma_space * 1.5))
+    radius = max(radius, 1)
+    color_w = np.array([math.exp(i * i * gc) for i in range(256 * 3)], dtype=np.float64).astype(F32)
+    taps, space_w = [], []
+    for i in range(-radius, radius + 1):
+        for j in range(-radius, radius + 1):
+            rr = math.sqrt(float(i) * i + float(j) * j)
+            if rr > radius:
+                continue
+            taps.append((i, j))
+            space_w.append(math.exp(rr * rr * gs))
+    return radius, taps, np.array(space_w, dtype=np.float64).astype(F32), color_w
+
+
+def bilateral_u8c3(img, d, sigma_color, sigma_space, fma=True):
+    """cv::bilateralFilter(img8UC3, out, d, sc, ss) with BORDER_REFLECT_101.
+    w = space_w[k]*color_w[|db|+|dg|+|dr|]; wsum += w; sum_c = fma(p_c, w, sum_c) (the SIMD build)
+    or sum_c += p_c*w (scalar build); dst_c = rint(sum_c * (1/wsum))."""
+    radius, taps, space_w, color_w = bilateral_tables(d, sigma_color, sigma_space)
+    h, w = img.shape[:2]
+    p = pad_reflect101(img, radius)
+    c0 = img.astype(np.int32)
+    wsum = np.zeros((h, w), dtype=F32)
+    acc = np.zeros((h, w, 3), dtype=F32)
+    for (i, j), sw in zip(taps, space_w):
+        q = p[radius + i:radius + i + h, radius + j:radius + j + w]
+        n = np.abs(q.astype(np.int32) - c0).sum(axis=2)
+        wt = (sw * color_w[n]).astype(F32)
+        wsum = (wsum + wt).astype(F32)
+        qf = q.astype(F32)
+        if fma:
+            acc = (qf.astype(np.float64) * wt[..., None].astype(np.float64) + acc.astype(np.float64)).astype(F32)
+        else:
+            acc = (acc + (qf * wt[..., None]).astype(F32)).astype(F32)
+    inv = (F32(1.0) / wsum).astype(F32)
+    return np.clip(np.rint((acc * inv[..., None]).astype(F32)), 0, 255).astype(np.uint8)
+
+
+# --------------------------------------------------------------------------------------------
+# sigmoid LUT of createEdgeMask  -- adaptive_sharpening.cpp:202-219
+# --------------------------------------------------------------------------------------------
+def sigmoid_lut(edge_threshold):
+    """256-entry table: edge_value = ((float)u * (float)(1/255)) * 255.0f  (convertTo(CV_32F,1/255)
+    multiplies in float32, then `* 255.0f`); threshold is a double copy of the float config;
+    sigmoid = (float)(1.0 / (1.0 + exp(-((double)edge_value - thr) * (double)0.1f)))."""
+    thr = float(F32(edge_threshold))
+    lut = np.zeros(256, dtype=F32)
+    s = float(F32(0.1))
+    inv255 = F32(1.0 / 255.0)
+    for u in range(256):
+        ev = F32(F32(F32(u) * inv255) * F32(255.0))
+        lut[u] = F32(1.0 / (1.0 + math.exp(-(float(ev) - thr) * s)))
+    return lut
