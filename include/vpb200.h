@@ -1,0 +1,174 @@
+/* vpb200.h - C ABI of libvpb200.so: the B200 (sm_100a) enhance-chain behind video-processor's
+ * Upscaler / SelectiveBilateral / AdaptiveSharpening / TemporalConsistency / FrameBuffer API.
+ *
+ * The reference (skandvarma/video-processor) is C++ over OpenCV and has no FFI of its own; every
+ * entry point below names the reference interface it replaces (paths relative to the reference
+ * repository).  The C++ classes in include/vp/ (same names, signatures and Config field order as the
+ * reference headers) are thin wrappers over this ABI; INTEGRATION.md shows the binding a maintainer
+ * adds to the reference tree.
+ *
+ * Conventions
+ *   - frames are 8-bit BGR interleaved (CV_8UC3), row-major, `pitch`/`step` in bytes (>= 3*width);
+ *   - every function returns VP_OK (0) or a negative vp_status; nothing throws or aborts;
+ *     vp_last_error() returns a human-readable description of the last failure on that context;
+ *   - a vp_ctx is bound to one CUDA device and is used by one caller thread at a time (the
+ *     reference's "processing thread", src/pipeline.cpp:351-383, src/main.cpp:222-259);
+ *   - device-pointer entry points are asynchronous on `stream` (a cudaStream_t passed as void*,
+ *     NULL = the context's own compute stream); host-pointer entry points are synchronous unless
+ *     named submit/wait;
+ *   - there is NO CPU fallback: without a usable sm_100 device vp_create() fails.
+ */
+#ifndef VPB200_H
+#define VPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPB200_ABI_VERSION 1
+
+typedef enum vp_status {
+    VP_OK = 0,
+    VP_ERR_INVALID_ARG = -1,   /* null pointer, non-positive size, pitch < 3*width ...           */
+    VP_ERR_UNSUPPORTED = -2,   /* configuration outside the built path             */
+    VP_ERR_CUDA = -3,          /* a CUDA runtime call failed; vp_last_error() carries the string   */
+    VP_ERR_NO_DEVICE = -4,     /* no CUDA device / not sm_100                                      */
+    VP_ERR_STATE = -5,         /* call sequence error (e.g. vp_wait without vp_submit)             */
+    VP_ERR_NOMEM = -6
+} vp_status;
+
+/* SelectiveBilateral::Config (include/selective_bilateral.h:20-40), plain branch only:
+ * use_multiscale=false, selective=false (the other branches call cv::sqrt on CV_8U,
+ * src/selective_bilateral.cpp:276 - undefined behaviour). */
+enum { VP_STAGE_PRE = 0, VP_STAGE_POST = 1 };   /* SelectiveBilateral::ProcessingStage */
+typedef struct vp_bilateral_config {
+    int32_t stage;             /* VP_STAGE_PRE / VP_STAGE_POST                                    */
+    int32_t adaptive_params;   /* calculateAdaptiveParams, src/selective_bilateral.cpp:315-371    */
+    int32_t diameter;
+    int32_t reserved_;         /* keeps the doubles 8-byte aligned on every ABI                   */
+    double sigma_color;        /* double in the reference's Config                                */
+    double sigma_space;
+} vp_bilateral_config;
+
+/* AdaptiveSharpening::Config (include/adaptive_sharpening.h:14-24), adaptive_sigma=false branch
+ * (createEdgeMask + applyUnsharpMask, src/adaptive_sharpening.cpp:107-355). */
+typedef struct vp_sharpen_config {
+    float strength;
+    float edge_strength;
+    float smooth_strength;
+    float edge_threshold;
+    float sigma;
+    int32_t kernel_size;       /* odd, 3..7 */
+    int32_t preserve_tone;
+} vp_sharpen_config;
+
+/* Temporal stage.  VP_TEMPORAL_MAIN_BLEND = src/main.cpp:269-292 (addWeighted(cur,w,prev,1-w) on
+ * the history of unblended frames).  VP_TEMPORAL_BLEND_FRAMES = TemporalConsistency::blendFrames
+ * (src/temporal_consistency.cpp:355-444) over the current and up to buffer_size-1 previous
+ * unblended frames, masks == 1, float32 accumulator. */
+enum { VP_TEMPORAL_NONE = 0, VP_TEMPORAL_MAIN_BLEND = 1, VP_TEMPORAL_BLEND_FRAMES = 2 };
+typedef struct vp_temporal_config {
+    int32_t mode;
+    int32_t buffer_size;       /* TemporalConsistency::Config::buffer_size (2 or 3)              */
+    float blend_strength;      /* TemporalConsistency::Config::blend_strength                    */
+    float main_weight;         /* current-frame weight of the main.cpp blend (0.6 / 0.7)         */
+} vp_temporal_config;
+
+/* The chain of Upscaler::upscale (src/upscaler.cpp:772-829) with step 2 = cv::resize(INTER_CUBIC)
+ * (src/test_enhancements.cpp:346-349). */
+typedef struct vp_chain_config {
+    int32_t src_w, src_h;      /* input frame size                                               */
+    int32_t dst_w, dst_h;      /* Upscaler::initialize(target_width, target_height)              */
+    int32_t use_pre;           /* m_bilateral_pre   (src/upscaler.cpp:777-784)                   */
+    int32_t use_sharpen;       /* m_sharpening      (:800-807)                                   */
+    int32_t use_post;          /* m_bilateral_post  (:810-817)                                   */
+    vp_bilateral_config pre;
+    vp_sharpen_config sharpen;
+    vp_bilateral_config post;
+    vp_temporal_config temporal;
+} vp_chain_config;
+
+typedef struct vp_ctx vp_ctx;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int vp_abi_version(void);
+/* number of usable sm_100 devices (Upscaler::isGPUAvailable, src/upscaler.cpp:912-921) */
+int vp_device_count(void);
+/* fills `cfg` with the in-scope form of Upscaler::initializeEnhancements (src/upscaler.cpp:666-758) */
+int vp_default_chain_config(vp_chain_config* cfg, int src_w, int src_h, int dst_w, int dst_h);
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* Upscaler::initialize + initializeEnhancements (src/upscaler.cpp:569-758).  `cfg` may be NULL for
+ * a context used only through the stage-wise entry points. */
+int vp_create(vp_ctx** out, int device, const vp_chain_config* cfg);
+void vp_destroy(vp_ctx* ctx);
+const char* vp_last_error(const vp_ctx* ctx);   /* ctx may be NULL: last vp_create failure */
+/* number of kernels this library launched on the context so far (bench.py's gpu_launches) */
+uint64_t vp_launch_count(const vp_ctx* ctx);
+int vp_synchronize(vp_ctx* ctx);                /* waits for every stream the context owns */
+
+/* ---- the chain: Upscaler::upscale(const cv::Mat&, cv::Mat&) (src/upscaler.cpp:760-861) ------ */
+/* Device frames.  d_dst == NULL runs the frame through everything except the temporal blend and
+ * the output store: the warm-up frame of a multi-GPU segment (multi-GPU). */
+int vp_process_device(vp_ctx* ctx, const uint8_t* d_src, size_t src_pitch,
+                      uint8_t* d_dst, size_t dst_pitch, void* stream);
+/* Host frames, synchronous (pinned staging inside when the buffers are not pinned). */
+int vp_process_host(vp_ctx* ctx, const uint8_t* src, size_t src_step, uint8_t* dst, size_t dst_step);
+/* Host frames, pipelined: up to vp_pipeline_depth() frames in flight; H2D, kernels and D2H run on
+ * three streams so copy overlaps compute (replaces FrameBuffer's deep copy, src/frame_buffer.cpp:
+ * 31-37, and the per-op upload/download of src/processor.cpp:98-124).  vp_wait returns the oldest
+ * submitted frame.  dst == NULL at submit = warm-up frame (no output; vp_wait still pairs with it). */
+int vp_pipeline_depth(const vp_ctx* ctx);
+int vp_submit_host(vp_ctx* ctx, const uint8_t* src, size_t src_step, uint8_t* dst, size_t dst_step);
+int vp_wait(vp_ctx* ctx);
+/* TemporalConsistency::reset (src/temporal_consistency.cpp:52-59); also main.cpp's history clear */
+int vp_reset_temporal(vp_ctx* ctx);
+/* (d, sigma_color, sigma_space) calculateAdaptiveParams selected for the LAST processed frame;
+ * which = VP_STAGE_PRE / VP_STAGE_POST.  Synchronises the context. */
+int vp_get_stage_params(vp_ctx* ctx, int which, int* d, double* sigma_color, double* sigma_space);
+
+/* pinned host memory for FrameBuffer slots / cv::Mat data (FrameBuffer, include/frame_buffer.h) */
+int vp_host_alloc(void** p, size_t bytes);
+int vp_host_free(void* p);
+
+/* ---- stage-wise entry points (device pointers; used by the C++ stage classes and parity tests) */
+/* cv::resize(src, dst, Size(dst_w,dst_h), 0, 0, INTER_CUBIC) - src/upscaler.cpp:81,
+ * src/test_enhancements.cpp:348.  dst_w >= src_w and dst_h >= src_h. */
+int vp_bicubic(vp_ctx* ctx, const uint8_t* d_src, size_t src_pitch, int src_w, int src_h,
+               uint8_t* d_dst, size_t dst_pitch, int dst_w, int dst_h, void* stream);
+/* cv::bilateralFilter(src, dst, d, sigma_color, sigma_space) - src/selective_bilateral.cpp:110 */
+int vp_bilateral(vp_ctx* ctx, const uint8_t* d_src, size_t src_pitch, uint8_t* d_dst, size_t dst_pitch,
+                 int w, int h, int d, double sigma_color, double sigma_space, void* stream);
+/* SelectiveBilateral::process, plain branch (src/selective_bilateral.cpp:57-119): adaptive
+ * parameters from the frame's own mean/std-dev, then the bilateral filter. */
+int vp_selective_bilateral(vp_ctx* ctx, const vp_bilateral_config* cfg, const uint8_t* d_src, size_t src_pitch,
+                           uint8_t* d_dst, size_t dst_pitch, int w, int h, void* stream);
+/* cv::meanStdDev sums (src/selective_bilateral.cpp:321-322): d_sums[0..2] = sum x per channel,
+ * d_sums[3..5] = sum x^2 per channel (uint64, device memory, overwritten). */
+int vp_mean_stddev_sums(vp_ctx* ctx, const uint8_t* d_src, size_t src_pitch, int w, int h,
+                        uint64_t* d_sums, void* stream);
+/* AdaptiveSharpening::createEdgeMask (src/adaptive_sharpening.cpp:107-230): float32 mask, pitch in bytes */
+int vp_edge_mask(vp_ctx* ctx, const vp_sharpen_config* cfg, const uint8_t* d_src, size_t src_pitch,
+                 float* d_mask, size_t mask_pitch, int w, int h, void* stream);
+/* AdaptiveSharpening::applyUnsharpMask (src/adaptive_sharpening.cpp:232-355) with a caller-supplied mask */
+int vp_unsharp(vp_ctx* ctx, const vp_sharpen_config* cfg, const uint8_t* d_src, size_t src_pitch,
+               const float* d_mask, size_t mask_pitch, uint8_t* d_dst, size_t dst_pitch, int w, int h, void* stream);
+/* AdaptiveSharpening::process, adaptive_sigma=false (src/adaptive_sharpening.cpp:51-105) */
+int vp_sharpen(vp_ctx* ctx, const vp_sharpen_config* cfg, const uint8_t* d_src, size_t src_pitch,
+               uint8_t* d_dst, size_t dst_pitch, int w, int h, void* stream);
+/* cv::addWeighted(a, alpha, b, beta, 0, dst) on CV_8UC3 - src/main.cpp:286-290 */
+int vp_add_weighted(vp_ctx* ctx, const uint8_t* d_a, size_t a_pitch, double alpha,
+                    const uint8_t* d_b, size_t b_pitch, double beta,
+                    uint8_t* d_dst, size_t dst_pitch, int w, int h, void* stream);
+/* TemporalConsistency::blendFrames (src/temporal_consistency.cpp:355-444): frames[0] = current,
+ * frames[i] = i-th previous; nframes in 1..3; all frames share `pitch`. */
+int vp_temporal_blend(vp_ctx* ctx, const uint8_t* const* d_frames, int nframes, size_t pitch,
+                      float blend_strength, uint8_t* d_dst, size_t dst_pitch, int w, int h, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPB200_H */

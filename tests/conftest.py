@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+
+
+@pytest.fixture(scope="session")
+def vp():
+    """ctypes binding of libvpb200.so (builds it in-tree first if it is stale or missing)."""
+    from video_processor_b200 import build
+    build.build()
+    from video_processor_b200 import capi
+    return capi

@@ -1,0 +1,139 @@
+"""End-to-end parity of the fused chain (vp_process_device / vp_process_host / submit-wait) against the
+oracle chain, incl. the temporal stage, adaptive-parameter selection and multi-GPU segment equivalence."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import ref_chain as RC
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from tests import gpu_util as G  # noqa: E402
+
+
+def run_chain_device(vp, ocfg, frames, sw, sh, outputs=None):
+    cfg = G.chain_cfg(vp, ocfg, sw, sh)
+    outs = []
+    with vp.Context(cfg) as ctx:
+        for i, f in enumerate(frames):
+            src = G.to_dev(f)
+            want = outputs is None or outputs[i]
+            dst = G.dev_empty(ocfg.dst_h, ocfg.dst_w) if want else None
+            ctx.call("vp_process_device", src.data_ptr(), G.pitch(src), dst.data_ptr() if want else None,
+                     G.pitch(dst) if want else 0, None)
+            ctx.call("vp_synchronize")
+            outs.append(dst.cpu().numpy() if want else None)
+        params = (ctx.stage_params(0), ctx.stage_params(1))
+    return outs, params
+
+
+@pytest.mark.parametrize("kind", ["noise", "scene", "flat"])
+@pytest.mark.parametrize("temporal", [RC.TEMPORAL_NONE, RC.TEMPORAL_MAIN_BLEND, RC.TEMPORAL_BLEND_FRAMES])
+def test_chain_vs_oracle(vp, kind, temporal):
+    sw, sh, n = 160, 96, 4
+    ocfg = RC.ChainConfig(dst_w=2 * sw, dst_h=2 * sh, temporal=temporal)
+    frames = synth.clip(kind, sw, sh, n)
+    oracle = RC.Chain(RC.NumpyOps(), ocfg)
+    refs = [oracle.process(f) for f in frames]
+    outs, params = run_chain_device(vp, ocfg, frames, sw, sh)
+    # adaptive parameter selection agrees with calculateAdaptiveParams
+    assert params[0][0] == RC.adaptive_params(RC.NumpyOps(), frames[-1], ocfg.pre)[0]
+    for o, r in zip(outs, refs):
+        mx, nd = G.diff_stats(o, r)
+        assert RC.psnr(o, r) >= 50.0, (mx, nd)
+        assert mx <= 4, (mx, nd)
+
+
+def test_chain_stage_toggles(vp):
+    sw, sh = 96, 64
+    frames = synth.clip("scene", sw, sh, 3)
+    for use_pre, use_sharpen, use_post in [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (0, 1, 1)]:
+        ocfg = RC.ChainConfig(dst_w=2 * sw, dst_h=2 * sh, use_pre=bool(use_pre), use_sharpen=bool(use_sharpen),
+                              use_post=bool(use_post), temporal=RC.TEMPORAL_MAIN_BLEND)
+        oracle = RC.Chain(RC.NumpyOps(), ocfg)
+        refs = [oracle.process(f) for f in frames]
+        outs, _ = run_chain_device(vp, ocfg, frames, sw, sh)
+        for o, r in zip(outs, refs):
+            mx, nd = G.diff_stats(o, r)
+            assert RC.psnr(o, r) >= 50.0 and mx <= 4, (use_pre, use_sharpen, use_post, mx, nd)
+            if not use_pre and not use_post and not use_sharpen:
+                assert mx == 0   # bicubic + addWeighted only: bit-exact
+
+
+@pytest.mark.parametrize("temporal,warm", [(RC.TEMPORAL_MAIN_BLEND, 1), (RC.TEMPORAL_BLEND_FRAMES, 2)])
+def test_segment_sharding_is_bit_identical(vp, temporal, warm):
+    """file/--fast mode partitioning (DESIGN.md multi-GPU): a segment started with `warm` warm-up frames
+    (d_dst = NULL) reproduces the single-context outputs exactly."""
+    sw, sh, n = 128, 72, 7
+    ocfg = RC.ChainConfig(dst_w=2 * sw, dst_h=2 * sh, temporal=temporal)
+    frames = synth.clip("scene", sw, sh, n)
+    full, _ = run_chain_device(vp, ocfg, frames, sw, sh)
+    start = 4
+    seg_frames = frames[start - warm:]
+    flags = [False] * warm + [True] * (n - start)
+    seg, _ = run_chain_device(vp, ocfg, seg_frames, sw, sh, outputs=flags)
+    for i in range(start, n):
+        assert np.array_equal(full[i], seg[warm + i - start])
+
+
+def test_host_paths_match_device_path(vp):
+    sw, sh, n = 128, 72, 6
+    ocfg = RC.ChainConfig(dst_w=2 * sw, dst_h=2 * sh, temporal=RC.TEMPORAL_BLEND_FRAMES)
+    frames = synth.clip("noise", sw, sh, n)
+    dev, _ = run_chain_device(vp, ocfg, frames, sw, sh)
+    cfg = G.chain_cfg(vp, ocfg, sw, sh)
+    # synchronous host call with pageable numpy buffers
+    with vp.Context(cfg) as ctx:
+        for f, d in zip(frames, dev):
+            out = np.zeros((ocfg.dst_h, ocfg.dst_w, 3), np.uint8)
+            ctx.call("vp_process_host", f.ctypes.data, f.strides[0], out.ctypes.data, out.strides[0])
+            assert np.array_equal(out, d)
+    # pipelined submit/wait with pinned buffers, depth frames in flight
+    with vp.Context(cfg) as ctx:
+        depth = vp.lib.vp_pipeline_depth(ctx.handle)
+        pin_in = [torch.from_numpy(f).pin_memory() for f in frames]
+        pin_out = [torch.zeros((ocfg.dst_h, ocfg.dst_w, 3), dtype=torch.uint8).pin_memory() for _ in frames]
+        inflight = 0
+        for i in range(n):
+            if inflight == depth:
+                ctx.call("vp_wait")
+                inflight -= 1
+            ctx.call("vp_submit_host", pin_in[i].data_ptr(), sw * 3, pin_out[i].data_ptr(), ocfg.dst_w * 3)
+            inflight += 1
+        assert vp.lib.vp_submit_host(ctx.handle, pin_in[0].data_ptr(), sw * 3, pin_out[0].data_ptr(), ocfg.dst_w * 3) in (vp.VP_OK, vp.VP_ERR_STATE)
+        while True:
+            rc = vp.lib.vp_wait(ctx.handle)
+            if rc != vp.VP_OK:
+                assert rc == vp.VP_ERR_STATE
+                break
+        for o, d in zip(pin_out, dev):
+            assert np.array_equal(o.numpy(), d)
+
+
+def test_full_size_c2_against_cv2(vp):
+    """BASELINE config C2 at full size against the real OpenCV kernels (cv2) on one scene frame pair."""
+    sw, sh = 1920, 1080
+    ocfg = RC.ChainConfig(dst_w=3840, dst_h=2160, temporal=RC.TEMPORAL_MAIN_BLEND)
+    frames = synth.clip("scene", sw, sh, 2)
+    oracle = RC.Chain(RC.Cv2Ops(), ocfg)
+    refs = [oracle.process(f) for f in frames]
+    outs, params = run_chain_device(vp, ocfg, frames, sw, sh)
+    assert params[0][0] == 11 and params[1][0] == 5
+    for o, r in zip(outs, refs):
+        mx, nd = G.diff_stats(o, r)
+        assert RC.psnr(o, r) >= 50.0 and mx <= 4, (mx, nd)
+
+
+@pytest.mark.parametrize("cfgname,sw,sh,scale", [("C1", 1280, 720, 2), ("C2", 1920, 1080, 2), ("C5", 960, 540, 4)])
+def test_full_size_bicubic_bit_exact(vp, cfgname, sw, sh, scale):
+    import cv2
+    img = synth.frame("noise", sw, sh, 0)
+    with vp.Context() as ctx:
+        out = G.run_bicubic(vp, ctx, img, sw * scale, sh * scale)
+    assert np.array_equal(out, cv2.resize(img, (sw * scale, sh * scale), interpolation=cv2.INTER_CUBIC))

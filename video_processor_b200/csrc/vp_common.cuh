@@ -1,0 +1,119 @@
+// vp_common.cuh - device helpers shared by the sm_100a kernels of libvpb200.
+// Border maps, TMA (bulk async copy) row staging with an mbarrier, saturating casts.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vp {
+
+// --------------------------------------------------------------------------------------------
+// border maps
+// --------------------------------------------------------------------------------------------
+// cv::BORDER_REFLECT_101 (gfedcb|abcdefgh|gfedcba), valid for any offset.
+__host__ __device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    if ((unsigned)i < (unsigned)n) return i;
+    int p = 2 * (n - 1);
+    i %= p;
+    if (i < 0) i += p;
+    return i >= n ? p - i : i;
+}
+__host__ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__device__ __forceinline__ int sat_u8(int v) { return min(max(v, 0), 255); }
+// cv::saturate_cast<uchar>(float): cvRound (round-half-even) then clamp
+__device__ __forceinline__ int rne_sat_u8(float v) { return sat_u8(__float2int_rn(v)); }
+
+// --------------------------------------------------------------------------------------------
+// mbarrier + bulk async copy (TMA, SASS UBLKCP) : global -> shared rows
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+// 16-byte aligned src, dst; bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Stage image rows [y0,y1) x bytes [bx0,bx1) (bx0 a multiple of 16) into shared memory,
+// row r at s_raw + (r-y0)*s_pitch, byte b at offset b-bx0.  `fast` (base and pitch 16-byte
+// aligned) uses one TMA bulk copy per row issued by warp 0 and completes on `bar` (parity 0);
+// otherwise all threads copy bytes.  Every thread must call it; returns after the data is visible.
+__device__ __forceinline__ void stage_rows(uint8_t* s_raw, int s_pitch, const uint8_t* __restrict__ g, size_t gpitch,
+                                           int row_bytes, int y0, int y1, int bx0, int bx1, bool fast, uint64_t* bar) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int nrows = y1 - y0;
+    if (fast) {
+        // over-fetch to the next 16-byte boundary stays inside the row's pitch span (pitch % 16 == 0)
+        const int nb = ((bx1 + 15) & ~15) - bx0;
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (tid < 32) {
+            if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nb * nrows));
+            __syncwarp();
+            for (int r = tid; r < nrows; r += 32)
+                bulk_g2s(s_raw + r * s_pitch, g + (size_t)(y0 + r) * gpitch + bx0, (uint32_t)nb, bar);
+        }
+        mbar_wait(bar, 0);
+    } else {
+        const int e = min(bx1, row_bytes);
+        const int nb = e - bx0;
+        for (int i = tid; i < nb * nrows; i += nt) {
+            int r = i / nb, b = i - r * nb;
+            s_raw[r * s_pitch + b] = g[(size_t)(y0 + r) * gpitch + bx0 + b];
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ bool aligned16(const void* p, size_t pitch) {
+    return ((((uintptr_t)p) | pitch) & 15) == 0;
+}
+
+// warp + block reduction of 6 uint32 partial sums into uint64 global accumulators
+__device__ __forceinline__ void reduce_sums6(unsigned v[6], unsigned long long* __restrict__ gsums, unsigned long long* s_red) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long w[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        unsigned long long x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        w[k] = x;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) atomicAdd(&s_red[k], w[k]);
+    }
+}
+
+}  // namespace vp

@@ -1,0 +1,778 @@
+// vpb200.cu - context, stage scheduling and the C ABI (include/vpb200.h) of libvpb200.so.
+//
+// The chain is Upscaler::upscale's REAL_ESRGAN branch (reference src/upscaler.cpp:772-829) with the
+// bicubic substitute of src/test_enhancements.cpp:346-349:
+//     [k_stats] -> k_bilateral(PRE) -> k_upsharp(bicubic + AdaptiveSharpening, +stats of its output)
+//               -> k_bilateral(POST, + fused temporal blend and state store)
+// Kernel boundaries sit exactly where the reference needs a whole-frame reduction
+// (calculateAdaptiveParams' cv::meanStdDev, src/selective_bilateral.cpp:321-322); the parameter
+// choice itself happens on the device so no stage waits for the host.
+#include "../../include/vpb200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "vp_bilateral.cuh"
+#include "vp_blend.cuh"
+#include "vp_stats.cuh"
+#include "vp_tables.h"
+#include "vp_upsharp.cuh"
+
+using namespace vp;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct ResizeCache {
+    int sw = 0, sh = 0, dw = 0, dh = 0;
+    int* xofs = nullptr; short4* xcoef = nullptr; int* yofs = nullptr; float4* ycoef = nullptr;
+    int max_rows[2] = {0, 0}, max_cols[2] = {0, 0};   // [0] halo 0, [1] halo US_HALO
+};
+
+struct HostSlot {
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    uint8_t *h_in = nullptr, *h_out = nullptr;        // pinned staging (allocated on first need)
+    cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
+    uint8_t* user_dst = nullptr; size_t user_dst_step = 0;
+    bool staged_out = false;
+};
+
+}  // namespace
+
+struct vp_ctx {
+    int device = 0;
+    cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    bool has_chain = false;
+    vp_chain_config cfg{};
+    std::string err;
+    uint64_t launches = 0;
+    int sm_count = 148;
+
+    // chain buffers
+    uint8_t* d_pre = nullptr; size_t pre_pitch = 0;
+    uint8_t* d_sharp = nullptr; size_t frame_pitch = 0;     // dst-sized intermediates / states
+    uint8_t* d_state[3] = {nullptr, nullptr, nullptr};
+    int nring = 0, head = 0, nvalid = 0;                    // temporal ring
+    unsigned long long* d_sums = nullptr;                   // [0..5] PRE input, [6..11] POST input, [12..17] scratch
+    int* d_sel = nullptr;                                   // [0] PRE class, [1] POST class
+    BilCand* d_cand_pre = nullptr; BilCand* d_cand_post = nullptr; BilCand* d_cand_tmp = nullptr;
+    int cand_pre_rmax = 0, cand_post_rmax = 0;
+    // cached stage-wise tables
+    int tmp_d = -1; double tmp_sc = 0, tmp_ss = 0; int tmp_r = 0;
+    vp_bilateral_config tmp_sel_cfg{}; bool tmp_sel_valid = false; int tmp_sel_rmax = 0;
+    BilCand* d_cand_sel = nullptr;
+    ResizeCache rc_chain, rc_tmp;
+    float* d_siglut = nullptr; float siglut_thr = -1e30f; bool siglut_valid = false;
+    float* d_siglut_tmp = nullptr; float siglut_tmp_thr = 0; bool siglut_tmp_valid = false;
+
+    // host pipeline
+    std::vector<HostSlot> slots;
+    std::deque<int> inflight;
+    int next_slot = 0;
+};
+
+namespace {
+
+int fail(vp_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define VP_CUDA(ctx, call)                                                                          \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail((ctx), VP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int check_frame(vp_ctx* c, const void* p, size_t pitch, int w, int h, const char* what) {
+    if (!p) return fail(c, VP_ERR_INVALID_ARG, std::string(what) + ": null pointer");
+    if (w <= 0 || h <= 0) return fail(c, VP_ERR_INVALID_ARG, std::string(what) + ": empty frame");
+    if (pitch < (size_t)w * 3) return fail(c, VP_ERR_INVALID_ARG, std::string(what) + ": pitch < 3*width");
+    return VP_OK;
+}
+
+// ---- table uploads ------------------------------------------------------------------------------
+void fill_cand(BilCand& bc, const vp_host::BilateralTables& t) {
+    std::memset(&bc, 0, sizeof(bc));
+    bc.radius = t.radius;
+    bc.d = t.d;
+    std::memcpy(bc.space_w, t.space_w.data(), t.space_w.size() * sizeof(float));
+    std::memcpy(bc.color_w, t.color_w.data(), 768 * sizeof(float));
+}
+
+int build_selective_cands(vp_ctx* c, const vp_bilateral_config& cfg, BilCand* d_cand, int* rmax, cudaStream_t st) {
+    std::vector<BilCand> h(3);
+    int rm = 0;
+    for (int cls = 0; cls < 3; ++cls) {
+        int d; double sc, ss;
+        if (cfg.adaptive_params)
+            vp_host::adaptive_params_for_class(cls, cfg.stage == VP_STAGE_POST, cfg.diameter, cfg.sigma_color, cfg.sigma_space, &d, &sc, &ss);
+        else { d = cfg.diameter; sc = cfg.sigma_color; ss = cfg.sigma_space; }
+        vp_host::BilateralTables t = vp_host::bilateral_tables(d, sc, ss);
+        if (t.radius > BIL_RMAX)
+            return fail(c, VP_ERR_UNSUPPORTED, "bilateral radius > 7 (diameter > 15) is not built");
+        fill_cand(h[cls], t);
+        rm = t.radius > rm ? t.radius : rm;
+    }
+    VP_CUDA(c, cudaMemcpyAsync(d_cand, h.data(), 3 * sizeof(BilCand), cudaMemcpyHostToDevice, st));
+    VP_CUDA(c, cudaStreamSynchronize(st));
+    *rmax = rm;
+    return VP_OK;
+}
+
+void free_resize(ResizeCache& rc) {
+    cudaFree(rc.xofs); cudaFree(rc.xcoef); cudaFree(rc.yofs); cudaFree(rc.ycoef);
+    rc = ResizeCache();
+}
+
+int tile_span(const std::vector<int>& ofs, int src_len, int dst_len, int tile, int halo) {
+    int best = 0;
+    for (int t0 = 0; t0 < dst_len; t0 += tile) {
+        const int a = std::max(0, t0 - halo), b = std::min(dst_len - 1, t0 + tile - 1 + halo);
+        const int s0 = clampi(ofs[a], 0, src_len - 1), s1 = clampi(ofs[b] + 3, 0, src_len - 1);
+        best = std::max(best, s1 - s0 + 1);
+    }
+    return best;
+}
+
+int ensure_resize(vp_ctx* c, ResizeCache& rc, int sw, int sh, int dw, int dh, cudaStream_t st) {
+    if (rc.sw == sw && rc.sh == sh && rc.dw == dw && rc.dh == dh && rc.xofs) return VP_OK;
+    VP_CUDA(c, cudaStreamSynchronize(st));
+    free_resize(rc);
+    const vp_host::CubicTable tx = vp_host::cubic_table(sw, dw), ty = vp_host::cubic_table(sh, dh);
+    std::vector<float> yb((size_t)dh * 4);
+    for (size_t i = 0; i < yb.size(); ++i) yb[i] = (float)ty.coef[i] * (1.0f / 4194304.0f);
+    VP_CUDA(c, cudaMalloc(&rc.xofs, (size_t)dw * sizeof(int)));
+    VP_CUDA(c, cudaMalloc(&rc.xcoef, (size_t)dw * sizeof(short4)));
+    VP_CUDA(c, cudaMalloc(&rc.yofs, (size_t)dh * sizeof(int)));
+    VP_CUDA(c, cudaMalloc(&rc.ycoef, (size_t)dh * sizeof(float4)));
+    VP_CUDA(c, cudaMemcpyAsync(rc.xofs, tx.ofs.data(), (size_t)dw * sizeof(int), cudaMemcpyHostToDevice, st));
+    VP_CUDA(c, cudaMemcpyAsync(rc.xcoef, tx.coef.data(), (size_t)dw * sizeof(short4), cudaMemcpyHostToDevice, st));
+    VP_CUDA(c, cudaMemcpyAsync(rc.yofs, ty.ofs.data(), (size_t)dh * sizeof(int), cudaMemcpyHostToDevice, st));
+    VP_CUDA(c, cudaMemcpyAsync(rc.ycoef, yb.data(), (size_t)dh * sizeof(float4), cudaMemcpyHostToDevice, st));
+    VP_CUDA(c, cudaStreamSynchronize(st));
+    for (int k = 0; k < 2; ++k) {
+        const int halo = k ? US_HALO : 0;
+        rc.max_cols[k] = tile_span(tx.ofs, sw, dw, US_TW, halo);
+        rc.max_rows[k] = tile_span(ty.ofs, sh, dh, US_TH, halo);
+    }
+    rc.sw = sw; rc.sh = sh; rc.dw = dw; rc.dh = dh;
+    return VP_OK;
+}
+
+int ensure_siglut(vp_ctx* c, float** d_lut, float* cached_thr, bool* valid, float thr, cudaStream_t st) {
+    if (*valid && *cached_thr == thr) return VP_OK;
+    if (!*d_lut) VP_CUDA(c, cudaMalloc(d_lut, 256 * sizeof(float)));
+    float lut[256];
+    vp_host::sigmoid_lut(thr, lut);
+    VP_CUDA(c, cudaMemcpyAsync(*d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice, st));
+    VP_CUDA(c, cudaStreamSynchronize(st));
+    *cached_thr = thr; *valid = true;
+    return VP_OK;
+}
+
+// ---- launches -----------------------------------------------------------------------------------
+int launch_stats(vp_ctx* c, const uint8_t* src, size_t pitch, int w, int h, unsigned long long* sums, cudaStream_t st) {
+    const long long groups = (long long)(3 * w / 12 + 255) / 256 * h;   // 256-group chunks
+    long long grid = std::min<long long>(std::max<long long>(groups, 1), (long long)c->sm_count * 8);
+    grid = std::max<long long>(grid, (groups + 15999) / 16000);
+    k_stats<<<(unsigned)grid, 256, 0, st>>>(src, pitch, w, h, sums);
+    VP_CUDA(c, cudaGetLastError());
+    c->launches++;
+    return VP_OK;
+}
+
+int launch_bilateral(vp_ctx* c, BilArgs& a, int rmax, cudaStream_t st) {
+    const dim3 grid((a.w + BIL_TW - 1) / BIL_TW, (a.h + BIL_TH - 1) / BIL_TH);
+    k_bilateral<<<grid, BIL_NT, bil_smem_bytes(rmax), st>>>(a);
+    VP_CUDA(c, cudaGetLastError());
+    c->launches++;
+    return VP_OK;
+}
+
+int fill_sharpen_args(vp_ctx* c, UpsharpArgs& a, const vp_sharpen_config& s) {
+    if (s.kernel_size != 3 && s.kernel_size != 5 && s.kernel_size != 7)
+        return fail(c, VP_ERR_UNSUPPORTED, "AdaptiveSharpening kernel_size must be 3, 5 or 7");
+    a.strength = s.strength; a.edge_strength = s.edge_strength; a.smooth_strength = s.smooth_strength;
+    a.preserve_tone = s.preserve_tone;
+    a.gk = s.kernel_size;
+    vp_host::gaussian_kernel_q8(s.kernel_size, (double)s.sigma, a.gq);
+    const std::vector<double> g = vp_host::gaussian_kernel_f64(5, 1.5);   // literal Size(5,5), 1.5 at :222
+    for (int i = 0; i < 5; ++i) a.gf[i] = (float)g[i];
+    return VP_OK;
+}
+
+int launch_upsharp(vp_ctx* c, UpsharpArgs& a, cudaStream_t st) {
+    if (a.do_sharpen && (a.dw < 8 || a.dh < 8))
+        return fail(c, VP_ERR_UNSUPPORTED, "AdaptiveSharpening needs frames of at least 8x8");
+    const int halo = a.do_sharpen ? US_HALO : 0;
+    const UpsharpSmem L = upsharp_layout(halo, a.max_src_rows, a.max_src_cols, a.do_sharpen);
+    if (L.total > 200 * 1024) return fail(c, VP_ERR_UNSUPPORTED, "resize ratio needs more shared memory than a CTA has");
+    const dim3 grid((a.dw + US_TW - 1) / US_TW, (a.dh + US_TH - 1) / US_TH);
+    k_upsharp<<<grid, US_NT, L.total, st>>>(a);
+    VP_CUDA(c, cudaGetLastError());
+    c->launches++;
+    return VP_OK;
+}
+
+int launch_blend(vp_ctx* c, BlendKArgs& a, cudaStream_t st) {
+    const long long work = ((long long)a.row_bytes * a.h + 15) / 16;
+    const unsigned grid = (unsigned)std::min<long long>((work + 255) / 256, (long long)c->sm_count * 16);
+    k_blend<<<std::max(grid, 1u), 256, 0, st>>>(a);
+    VP_CUDA(c, cudaGetLastError());
+    c->launches++;
+    return VP_OK;
+}
+
+void blend_weights(const vp_temporal_config& t, int nprev, BlendArgs& b) {
+    b.mode = t.mode;
+    b.nprev = nprev;
+    if (t.mode == VP_TEMPORAL_MAIN_BLEND) {
+        volatile float cw = t.main_weight;
+        volatile float pw = 1.0f - cw;
+        b.w[0] = cw; b.w[1] = pw; b.w[2] = 0.f; b.inv_wsum = 1.f;
+    } else {
+        // frame_weights[i] = std::exp(-(float)i / 2.0f) (float overload, correctly rounded here through double)
+        volatile float wsum = 0.f;
+        for (int i = 0; i < 3; ++i) {
+            volatile float arg = -(float)i / 2.0f;
+            volatile float fw = (float)std::exp((double)arg);
+            volatile float bf = i == 0 ? 1.0f : t.blend_strength;
+            volatile float m = fw * 1.0f;
+            volatile float wt = m * bf;
+            b.w[i] = wt;
+            if (i <= nprev) wsum = wsum + wt;
+        }
+        volatile float inv = 1.0f / wsum;
+        b.inv_wsum = inv;
+    }
+}
+
+void destroy_slots(vp_ctx* c) {
+    for (HostSlot& s : c->slots) {
+        cudaFree(s.d_in); cudaFree(s.d_out);
+        if (s.h_in) cudaFreeHost(s.h_in);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+        if (s.ev_comp) cudaEventDestroy(s.ev_comp);
+        if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
+    }
+    c->slots.clear();
+}
+
+bool host_ptr_is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+constexpr int PIPE_DEPTH = 3;
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int vp_abi_version(void) { return VPB200_ABI_VERSION; }
+
+int vp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+int vp_default_chain_config(vp_chain_config* cfg, int src_w, int src_h, int dst_w, int dst_h) {
+    if (!cfg) return VP_ERR_INVALID_ARG;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->src_w = src_w; cfg->src_h = src_h; cfg->dst_w = dst_w; cfg->dst_h = dst_h;
+    cfg->use_pre = cfg->use_sharpen = cfg->use_post = 1;
+    cfg->pre = vp_bilateral_config{VP_STAGE_PRE, 1, 7, 0, 30.0, 30.0};          // src/upscaler.cpp:668-682
+    cfg->sharpen = vp_sharpen_config{0.8f, 1.2f, 0.4f, 30.0f, 1.5f, 5, 1};      // :691-702
+    cfg->post = vp_bilateral_config{VP_STAGE_POST, 1, 5, 0, 20.0, 20.0};        // :711-725
+    cfg->temporal = vp_temporal_config{VP_TEMPORAL_BLEND_FRAMES, 3, 0.6f, 0.6f}; // :734-748, main.cpp:282
+    return VP_OK;
+}
+
+const char* vp_last_error(const vp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+uint64_t vp_launch_count(const vp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void vp_destroy(vp_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    destroy_slots(c);
+    cudaFree(c->d_pre); cudaFree(c->d_sharp);
+    for (auto& p : c->d_state) cudaFree(p);
+    cudaFree(c->d_sums); cudaFree(c->d_sel);
+    cudaFree(c->d_cand_pre); cudaFree(c->d_cand_post); cudaFree(c->d_cand_tmp); cudaFree(c->d_cand_sel);
+    free_resize(c->rc_chain); free_resize(c->rc_tmp);
+    cudaFree(c->d_siglut); cudaFree(c->d_siglut_tmp);
+    if (c->s_compute) cudaStreamDestroy(c->s_compute);
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    cudaGetLastError();
+    delete c;
+}
+
+static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
+    VP_CUDA(c, cudaSetDevice(c->device));
+    VP_CUDA(c, cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+    VP_CUDA(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    VP_CUDA(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    VP_CUDA(c, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+    VP_CUDA(c, cudaFuncSetAttribute(k_bilateral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bil_smem_bytes(BIL_RMAX)));
+    VP_CUDA(c, cudaFuncSetAttribute(k_upsharp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VP_CUDA(c, cudaMalloc(&c->d_sums, 18 * sizeof(unsigned long long)));
+    VP_CUDA(c, cudaMemset(c->d_sums, 0, 18 * sizeof(unsigned long long)));
+    VP_CUDA(c, cudaMalloc(&c->d_sel, 4 * sizeof(int)));
+    VP_CUDA(c, cudaMemset(c->d_sel, 0, 4 * sizeof(int)));
+    VP_CUDA(c, cudaMalloc(&c->d_cand_tmp, sizeof(BilCand)));
+    VP_CUDA(c, cudaMalloc(&c->d_cand_sel, 3 * sizeof(BilCand)));
+    if (!cfg) return VP_OK;
+
+    c->cfg = *cfg;
+    const vp_chain_config& g = c->cfg;
+    if (g.src_w <= 0 || g.src_h <= 0 || g.dst_w <= 0 || g.dst_h <= 0)
+        return fail(c, VP_ERR_INVALID_ARG, "vp_create: non-positive frame size");
+    if (g.dst_w < g.src_w || g.dst_h < g.src_h)
+        return fail(c, VP_ERR_UNSUPPORTED, "vp_create: the chain upscales (dst >= src); downscaling is not built");
+    if (g.temporal.mode < 0 || g.temporal.mode > 2) return fail(c, VP_ERR_INVALID_ARG, "vp_create: temporal.mode");
+    if (g.temporal.mode == VP_TEMPORAL_BLEND_FRAMES && (g.temporal.buffer_size < 1 || g.temporal.buffer_size > 3))
+        return fail(c, VP_ERR_UNSUPPORTED, "vp_create: temporal.buffer_size must be 1..3");
+    c->pre_pitch = align_up((size_t)g.src_w * 3, 256);
+    c->frame_pitch = align_up((size_t)g.dst_w * 3, 256);
+    if (g.use_pre) {
+        VP_CUDA(c, cudaMalloc(&c->d_pre, c->pre_pitch * g.src_h));
+        VP_CUDA(c, cudaMalloc(&c->d_cand_pre, 3 * sizeof(BilCand)));
+        int rc = build_selective_cands(c, g.pre, c->d_cand_pre, &c->cand_pre_rmax, c->s_compute);
+        if (rc) return rc;
+    }
+    if (g.use_post) {
+        VP_CUDA(c, cudaMalloc(&c->d_cand_post, 3 * sizeof(BilCand)));
+        int rc = build_selective_cands(c, g.post, c->d_cand_post, &c->cand_post_rmax, c->s_compute);
+        if (rc) return rc;
+    }
+    VP_CUDA(c, cudaMalloc(&c->d_sharp, c->frame_pitch * g.dst_h));
+    c->nring = g.temporal.mode == VP_TEMPORAL_MAIN_BLEND ? 2
+             : g.temporal.mode == VP_TEMPORAL_BLEND_FRAMES ? std::max(1, g.temporal.buffer_size) : 0;
+    for (int i = 0; i < c->nring; ++i) VP_CUDA(c, cudaMalloc(&c->d_state[i], c->frame_pitch * g.dst_h));
+    if (g.dst_w != g.src_w || g.dst_h != g.src_h) {
+        int rc = ensure_resize(c, c->rc_chain, g.src_w, g.src_h, g.dst_w, g.dst_h, c->s_compute);
+        if (rc) return rc;
+    }
+    if (g.use_sharpen) {
+        UpsharpArgs tmp{};
+        int rc = fill_sharpen_args(c, tmp, g.sharpen);
+        if (rc) return rc;
+        rc = ensure_siglut(c, &c->d_siglut, &c->siglut_thr, &c->siglut_valid, g.sharpen.edge_threshold, c->s_compute);
+        if (rc) return rc;
+    }
+    c->has_chain = true;
+    return VP_OK;
+}
+
+int vp_create(vp_ctx** out, int device, const vp_chain_config* cfg) {
+    if (!out) return fail(nullptr, VP_ERR_INVALID_ARG, "vp_create: out is null");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, VP_ERR_NO_DEVICE, "vp_create: no CUDA device (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return fail(nullptr, VP_ERR_INVALID_ARG, "vp_create: device index out of range");
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (major != 10) return fail(nullptr, VP_ERR_NO_DEVICE, "vp_create: device is not sm_100 (kernels are built for sm_100a only)");
+    vp_ctx* c = new (std::nothrow) vp_ctx();
+    if (!c) return fail(nullptr, VP_ERR_NOMEM, "vp_create: out of host memory");
+    c->device = device;
+    const int rc = create_impl(c, cfg);
+    if (rc != VP_OK) {
+        g_create_error = c->err;
+        vp_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return VP_OK;
+}
+
+int vp_synchronize(vp_ctx* c) {
+    if (!c) return VP_ERR_INVALID_ARG;
+    VP_CUDA(c, cudaSetDevice(c->device));
+    VP_CUDA(c, cudaStreamSynchronize(c->s_h2d));
+    VP_CUDA(c, cudaStreamSynchronize(c->s_compute));
+    VP_CUDA(c, cudaStreamSynchronize(c->s_d2h));
+    return VP_OK;
+}
+
+int vp_reset_temporal(vp_ctx* c) {
+    if (!c) return VP_ERR_INVALID_ARG;
+    c->nvalid = 0;
+    c->head = 0;
+    return VP_OK;
+}
+
+// ---- the chain -----------------------------------------------------------------------------------
+int vp_process_device(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t* d_dst, size_t dst_pitch, void* stream) {
+    if (!c) return VP_ERR_INVALID_ARG;
+    if (!c->has_chain) return fail(c, VP_ERR_STATE, "vp_process_device: context was created without a chain config");
+    const vp_chain_config& g = c->cfg;
+    int rc = check_frame(c, d_src, src_pitch, g.src_w, g.src_h, "vp_process_device(src)");
+    if (rc) return rc;
+    if (d_dst && dst_pitch < (size_t)g.dst_w * 3) return fail(c, VP_ERR_INVALID_ARG, "vp_process_device(dst): pitch < 3*width");
+    VP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    const bool temporal = g.temporal.mode != VP_TEMPORAL_NONE && c->nring > 0;
+    if (!d_dst && !temporal) return VP_OK;   // warm-up frame of a chain without temporal state: nothing to do
+
+    const bool need_pre_stats = g.use_pre && g.pre.adaptive_params;
+    const bool need_post_stats = g.use_post && g.post.adaptive_params;
+    if (need_pre_stats || need_post_stats)
+        VP_CUDA(c, cudaMemsetAsync(c->d_sums, 0, 12 * sizeof(unsigned long long), st));
+
+    const uint8_t* cur = d_src; size_t cur_pitch = src_pitch;
+    // 1. SelectiveBilateral PRE (src resolution)
+    if (g.use_pre) {
+        if (need_pre_stats) { rc = launch_stats(c, cur, cur_pitch, g.src_w, g.src_h, c->d_sums, st); if (rc) return rc; }
+        BilArgs a{};
+        a.src = cur; a.spitch = cur_pitch; a.dst = c->d_pre; a.dpitch = c->pre_pitch; a.w = g.src_w; a.h = g.src_h;
+        a.cand = c->d_cand_pre; a.sums = need_pre_stats ? c->d_sums : nullptr; a.npx = (double)g.src_w * g.src_h;
+        a.sel_out = c->d_sel;
+        rc = launch_bilateral(c, a, c->cand_pre_rmax, st); if (rc) return rc;
+        cur = c->d_pre; cur_pitch = c->pre_pitch;
+    }
+    // 2+3. bicubic resize + AdaptiveSharpening (dst resolution)
+    const bool do_resize = (g.dst_w != g.src_w || g.dst_h != g.src_h);
+    const bool last_is_upsharp = !g.use_post && !temporal;
+    if (do_resize || g.use_sharpen) {
+        UpsharpArgs a{};
+        a.src = cur; a.spitch = cur_pitch; a.sw = g.src_w; a.sh = g.src_h;
+        a.dst = last_is_upsharp ? d_dst : c->d_sharp; a.dpitch = last_is_upsharp ? dst_pitch : c->frame_pitch;
+        a.dw = g.dst_w; a.dh = g.dst_h;
+        a.do_resize = do_resize; a.do_sharpen = g.use_sharpen;
+        const int k = g.use_sharpen ? 1 : 0, halo = g.use_sharpen ? US_HALO : 0;
+        if (do_resize) {
+            a.rt = ResizeTables{c->rc_chain.xofs, c->rc_chain.xcoef, c->rc_chain.yofs, c->rc_chain.ycoef};
+            a.max_src_rows = c->rc_chain.max_rows[k]; a.max_src_cols = c->rc_chain.max_cols[k];
+        } else {
+            a.max_src_rows = US_TH + 2 * halo; a.max_src_cols = US_TW + 2 * halo;
+        }
+        if (g.use_sharpen) { rc = fill_sharpen_args(c, a, g.sharpen); if (rc) return rc; a.sig_lut = c->d_siglut; }
+        a.sums = need_post_stats ? c->d_sums + 6 : nullptr;
+        rc = launch_upsharp(c, a, st); if (rc) return rc;
+        cur = a.dst; cur_pitch = a.dpitch;
+    } else if (need_post_stats) {
+        rc = launch_stats(c, cur, cur_pitch, g.dst_w, g.dst_h, c->d_sums + 6, st); if (rc) return rc;
+    }
+    // temporal bookkeeping (host side: which ring slots hold t-1, t-2)
+    BlendArgs bl{};
+    if (temporal) {
+        const int maxprev = g.temporal.mode == VP_TEMPORAL_MAIN_BLEND ? 1 : g.temporal.buffer_size - 1;
+        const int nprev = std::min(c->nvalid, maxprev);
+        blend_weights(g.temporal, nprev, bl);
+        for (int i = 0; i < nprev; ++i) bl.prev[i] = c->d_state[(c->head - 1 - i + 2 * c->nring) % c->nring];
+        bl.ppitch = c->frame_pitch;
+        // with a single ring slot (buffer_size 1) nothing is ever blended and no state is kept
+        bl.state = c->nring > 1 ? c->d_state[c->head] : nullptr;
+        bl.spitch = c->frame_pitch;
+    }
+    // 4+5. SelectiveBilateral POST with the temporal blend in its epilogue
+    if (g.use_post) {
+        BilArgs a{};
+        a.src = cur; a.spitch = cur_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.w = g.dst_w; a.h = g.dst_h;
+        a.cand = c->d_cand_post; a.sums = need_post_stats ? c->d_sums + 6 : nullptr; a.npx = (double)g.dst_w * g.dst_h;
+        a.sel_out = c->d_sel + 1;
+        a.blend = bl;
+        rc = launch_bilateral(c, a, c->cand_post_rmax, st); if (rc) return rc;
+    } else if (temporal) {
+        BlendKArgs a{};
+        a.cur = cur; a.cpitch = cur_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.row_bytes = g.dst_w * 3; a.h = g.dst_h;
+        a.blend = bl;
+        rc = launch_blend(c, a, st); if (rc) return rc;
+    } else if (cur == d_src) {
+        VP_CUDA(c, cudaMemcpy2DAsync(d_dst, dst_pitch, d_src, src_pitch, (size_t)g.src_w * 3, g.src_h, cudaMemcpyDeviceToDevice, st));
+    }
+    if (temporal && c->nring > 1) {
+        c->head = (c->head + 1) % c->nring;
+        c->nvalid = std::min(c->nvalid + 1, c->nring - 1);
+    }
+    return VP_OK;
+}
+
+int vp_get_stage_params(vp_ctx* c, int which, int* d, double* sigma_color, double* sigma_space) {
+    if (!c || which < 0 || which > 1) return VP_ERR_INVALID_ARG;
+    if (!c->has_chain) return fail(c, VP_ERR_STATE, "vp_get_stage_params: no chain");
+    int rc = vp_synchronize(c); if (rc) return rc;
+    int sel[2];
+    VP_CUDA(c, cudaMemcpy(sel, c->d_sel, sizeof(sel), cudaMemcpyDeviceToHost));
+    const vp_bilateral_config& b = which == VP_STAGE_PRE ? c->cfg.pre : c->cfg.post;
+    int dd = b.diameter; double sc = b.sigma_color, ss = b.sigma_space;
+    if (b.adaptive_params)
+        vp_host::adaptive_params_for_class(sel[which], b.stage == VP_STAGE_POST, b.diameter, b.sigma_color, b.sigma_space, &dd, &sc, &ss);
+    if (d) *d = dd;
+    if (sigma_color) *sigma_color = sc;
+    if (sigma_space) *sigma_space = ss;
+    return VP_OK;
+}
+
+// ---- host frames: pinned, pipelined -------------------------------------------------------------------
+int vp_host_alloc(void** p, size_t bytes) {
+    if (!p || !bytes) return VP_ERR_INVALID_ARG;
+    if (cudaHostAlloc(p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); *p = nullptr; return VP_ERR_NOMEM; }
+    return VP_OK;
+}
+int vp_host_free(void* p) {
+    if (!p) return VP_OK;
+    if (cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); return VP_ERR_CUDA; }
+    return VP_OK;
+}
+
+int vp_pipeline_depth(const vp_ctx* c) { return c ? PIPE_DEPTH : 0; }
+
+static int ensure_slots(vp_ctx* c) {
+    if (!c->slots.empty()) return VP_OK;
+    const vp_chain_config& g = c->cfg;
+    c->slots.resize(PIPE_DEPTH);
+    for (HostSlot& s : c->slots) {
+        VP_CUDA(c, cudaMalloc(&s.d_in, c->pre_pitch * g.src_h));
+        VP_CUDA(c, cudaMalloc(&s.d_out, c->frame_pitch * g.dst_h));
+        VP_CUDA(c, cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+        VP_CUDA(c, cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming));
+        VP_CUDA(c, cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming));
+    }
+    return VP_OK;
+}
+
+int vp_submit_host(vp_ctx* c, const uint8_t* src, size_t src_step, uint8_t* dst, size_t dst_step) {
+    if (!c) return VP_ERR_INVALID_ARG;
+    if (!c->has_chain) return fail(c, VP_ERR_STATE, "vp_submit_host: context was created without a chain config");
+    const vp_chain_config& g = c->cfg;
+    int rc = check_frame(c, src, src_step, g.src_w, g.src_h, "vp_submit_host(src)");
+    if (rc) return rc;
+    if (dst && dst_step < (size_t)g.dst_w * 3) return fail(c, VP_ERR_INVALID_ARG, "vp_submit_host(dst): step < 3*width");
+    if ((int)c->inflight.size() >= PIPE_DEPTH) return fail(c, VP_ERR_STATE, "vp_submit_host: pipeline full, call vp_wait first");
+    VP_CUDA(c, cudaSetDevice(c->device));
+    rc = ensure_slots(c); if (rc) return rc;
+    HostSlot& s = c->slots[c->next_slot];
+    const size_t in_row = (size_t)g.src_w * 3, out_row = (size_t)g.dst_w * 3;
+
+    const uint8_t* hsrc = src; size_t hstep = src_step;
+    if (!host_ptr_is_pinned(src)) {   // stage through pinned memory so the copy is a real async DMA
+        if (!s.h_in) VP_CUDA(c, cudaHostAlloc((void**)&s.h_in, in_row * g.src_h, cudaHostAllocDefault));
+        for (int y = 0; y < g.src_h; ++y) std::memcpy(s.h_in + (size_t)y * in_row, src + (size_t)y * src_step, in_row);
+        hsrc = s.h_in; hstep = in_row;
+    }
+    VP_CUDA(c, cudaMemcpy2DAsync(s.d_in, c->pre_pitch, hsrc, hstep, in_row, g.src_h, cudaMemcpyHostToDevice, c->s_h2d));
+    VP_CUDA(c, cudaEventRecord(s.ev_h2d, c->s_h2d));
+    VP_CUDA(c, cudaStreamWaitEvent(c->s_compute, s.ev_h2d, 0));
+    rc = vp_process_device(c, s.d_in, c->pre_pitch, dst ? s.d_out : nullptr, c->frame_pitch, c->s_compute);
+    if (rc) return rc;
+    VP_CUDA(c, cudaEventRecord(s.ev_comp, c->s_compute));
+    s.user_dst = dst; s.user_dst_step = dst_step; s.staged_out = false;
+    if (dst) {
+        VP_CUDA(c, cudaStreamWaitEvent(c->s_d2h, s.ev_comp, 0));
+        uint8_t* hdst = dst; size_t hdstep = dst_step;
+        if (!host_ptr_is_pinned(dst)) {
+            if (!s.h_out) VP_CUDA(c, cudaHostAlloc((void**)&s.h_out, out_row * g.dst_h, cudaHostAllocDefault));
+            hdst = s.h_out; hdstep = out_row; s.staged_out = true;
+        }
+        VP_CUDA(c, cudaMemcpy2DAsync(hdst, hdstep, s.d_out, c->frame_pitch, out_row, g.dst_h, cudaMemcpyDeviceToHost, c->s_d2h));
+        VP_CUDA(c, cudaEventRecord(s.ev_d2h, c->s_d2h));
+    }
+    c->inflight.push_back(c->next_slot);
+    c->next_slot = (c->next_slot + 1) % PIPE_DEPTH;
+    return VP_OK;
+}
+
+int vp_wait(vp_ctx* c) {
+    if (!c) return VP_ERR_INVALID_ARG;
+    if (c->inflight.empty()) return fail(c, VP_ERR_STATE, "vp_wait: nothing submitted");
+    VP_CUDA(c, cudaSetDevice(c->device));
+    HostSlot& s = c->slots[c->inflight.front()];
+    c->inflight.pop_front();
+    VP_CUDA(c, cudaEventSynchronize(s.user_dst ? s.ev_d2h : s.ev_comp));
+    if (s.user_dst && s.staged_out) {
+        const size_t out_row = (size_t)c->cfg.dst_w * 3;
+        for (int y = 0; y < c->cfg.dst_h; ++y)
+            std::memcpy(s.user_dst + (size_t)y * s.user_dst_step, s.h_out + (size_t)y * out_row, out_row);
+    }
+    return VP_OK;
+}
+
+int vp_process_host(vp_ctx* c, const uint8_t* src, size_t src_step, uint8_t* dst, size_t dst_step) {
+    if (!c) return VP_ERR_INVALID_ARG;
+    if (!c->inflight.empty()) return fail(c, VP_ERR_STATE, "vp_process_host: frames still in flight, call vp_wait first");
+    int rc = vp_submit_host(c, src, src_step, dst, dst_step);
+    if (rc) return rc;
+    return vp_wait(c);
+}
+
+// ---- stage-wise entry points -----------------------------------------------------------------------
+int vp_bicubic(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, int src_w, int src_h,
+               uint8_t* d_dst, size_t dst_pitch, int dst_w, int dst_h, void* stream) {
+    if (!c) return VP_ERR_INVALID_ARG;
+    int rc = check_frame(c, d_src, src_pitch, src_w, src_h, "vp_bicubic(src)"); if (rc) return rc;
+    rc = check_frame(c, d_dst, dst_pitch, dst_w, dst_h, "vp_bicubic(dst)"); if (rc) return rc;
+    if (dst_w < src_w || dst_h < src_h) return fail(c, VP_ERR_UNSUPPORTED, "vp_bicubic: downscaling is not built");
+    VP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    ResizeCache& rcache = (c->has_chain && c->rc_chain.sw == src_w && c->rc_chain.sh == src_h &&
+                           c->rc_chain.dw == dst_w && c->rc_chain.dh == dst_h && c->rc_chain.xofs) ? c->rc_chain : c->rc_tmp;
+    rc = ensure_resize(c, rcache, src_w, src_h, dst_w, dst_h, st); if (rc) return rc;
+    UpsharpArgs a{};
+    a.src = d_src; a.spitch = src_pitch; a.sw = src_w; a.sh = src_h;
+    a.dst = d_dst; a.dpitch = dst_pitch; a.dw = dst_w; a.dh = dst_h;
+    a.rt = ResizeTables{rcache.xofs, rcache.xcoef, rcache.yofs, rcache.ycoef};
+    a.do_resize = 1; a.do_sharpen = 0;
+    a.max_src_rows = rcache.max_rows[0]; a.max_src_cols = rcache.max_cols[0];
+    return launch_upsharp(c, a, st);
+}
+
+int vp_bilateral(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t* d_dst, size_t dst_pitch,
+                 int w, int h, int d, double sigma_color, double sigma_space, void* stream) {
+    if (!c) return VP_ERR_INVALID_ARG;
+    int rc = check_frame(c, d_src, src_pitch, w, h, "vp_bilateral(src)"); if (rc) return rc;
+    rc = check_frame(c, d_dst, dst_pitch, w, h, "vp_bilateral(dst)"); if (rc) return rc;
+    VP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    if (!(c->tmp_d == d && c->tmp_sc == sigma_color && c->tmp_ss == sigma_space)) {
+        vp_host::BilateralTables t = vp_host::bilateral_tables(d, sigma_color, sigma_space);
+        if (t.radius > BIL_RMAX) return fail(c, VP_ERR_UNSUPPORTED, "vp_bilateral: radius > 7 (diameter > 15) is not built");
+        BilCand bc; fill_cand(bc, t);
+        VP_CUDA(c, cudaMemcpyAsync(c->d_cand_tmp, &bc, sizeof(bc), cudaMemcpyHostToDevice, st));
+        VP_CUDA(c, cudaStreamSynchronize(st));
+        c->tmp_d = d; c->tmp_sc = sigma_color; c->tmp_ss = sigma_space; c->tmp_r = t.radius;
+    }
+    BilArgs a{};
+    a.src = d_src; a.spitch = src_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.w = w; a.h = h;
+    a.cand = c->d_cand_tmp; a.npx = (double)w * h;
+    return launch_bilateral(c, a, c->tmp_r, st);
+}
+
+int vp_selective_bilateral(vp_ctx* c, const vp_bilateral_config* cfg, const uint8_t* d_src, size_t src_pitch,
+                           uint8_t* d_dst, size_t dst_pitch, int w, int h, void* stream) {
+    if (!c || !cfg) return VP_ERR_INVALID_ARG;
+    int rc = check_frame(c, d_src, src_pitch, w, h, "vp_selective_bilateral(src)"); if (rc) return rc;
+    rc = check_frame(c, d_dst, dst_pitch, w, h, "vp_selective_bilateral(dst)"); if (rc) return rc;
+    VP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    if (!c->tmp_sel_valid || std::memcmp(&c->tmp_sel_cfg, cfg, sizeof(*cfg)) != 0) {
+        VP_CUDA(c, cudaStreamSynchronize(st));
+        c->tmp_sel_valid = false;
+        rc = build_selective_cands(c, *cfg, c->d_cand_sel, &c->tmp_sel_rmax, st); if (rc) return rc;
+        c->tmp_sel_cfg = *cfg; c->tmp_sel_valid = true;
+    }
+    unsigned long long* sums = c->d_sums + 12;
+    if (cfg->adaptive_params) {
+        VP_CUDA(c, cudaMemsetAsync(sums, 0, 6 * sizeof(unsigned long long), st));
+        rc = launch_stats(c, d_src, src_pitch, w, h, sums, st); if (rc) return rc;
+    }
+    BilArgs a{};
+    a.src = d_src; a.spitch = src_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.w = w; a.h = h;
+    a.cand = c->d_cand_sel; a.sums = cfg->adaptive_params ? sums : nullptr; a.npx = (double)w * h;
+    a.sel_out = c->d_sel + 2;
+    return launch_bilateral(c, a, c->tmp_sel_rmax, st);
+}
+
+int vp_mean_stddev_sums(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, int w, int h, uint64_t* d_sums, void* stream) {
+    if (!c || !d_sums) return VP_ERR_INVALID_ARG;
+    int rc = check_frame(c, d_src, src_pitch, w, h, "vp_mean_stddev_sums(src)"); if (rc) return rc;
+    VP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    VP_CUDA(c, cudaMemsetAsync(d_sums, 0, 6 * sizeof(uint64_t), st));
+    return launch_stats(c, d_src, src_pitch, w, h, reinterpret_cast<unsigned long long*>(d_sums), st);
+}
+
+static int sharpen_common(vp_ctx* c, const vp_sharpen_config* cfg, const uint8_t* d_src, size_t src_pitch,
+                          const float* mask_in, size_t mask_in_pitch, float* mask_out, size_t mask_out_pitch,
+                          uint8_t* d_dst, size_t dst_pitch, int w, int h, void* stream, const char* who) {
+    if (!c || !cfg) return VP_ERR_INVALID_ARG;
+    int rc = check_frame(c, d_src, src_pitch, w, h, who); if (rc) return rc;
+    if (d_dst && dst_pitch < (size_t)w * 3) return fail(c, VP_ERR_INVALID_ARG, std::string(who) + ": dst pitch < 3*width");
+    if ((mask_in && mask_in_pitch < (size_t)w * 4) || (mask_out && mask_out_pitch < (size_t)w * 4))
+        return fail(c, VP_ERR_INVALID_ARG, std::string(who) + ": mask pitch < 4*width");
+    VP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    UpsharpArgs a{};
+    rc = fill_sharpen_args(c, a, *cfg); if (rc) return rc;
+    rc = ensure_siglut(c, &c->d_siglut_tmp, &c->siglut_tmp_thr, &c->siglut_tmp_valid, cfg->edge_threshold, st); if (rc) return rc;
+    a.sig_lut = c->d_siglut_tmp;
+    a.src = d_src; a.spitch = src_pitch; a.sw = w; a.sh = h;
+    a.dst = d_dst; a.dpitch = dst_pitch; a.dw = w; a.dh = h;
+    a.do_resize = 0; a.do_sharpen = 1;
+    a.max_src_rows = US_TH + 2 * US_HALO; a.max_src_cols = US_TW + 2 * US_HALO;
+    a.mask_in = mask_in; a.mask_in_pitch = mask_in_pitch; a.mask_out = mask_out; a.mask_out_pitch = mask_out_pitch;
+    return launch_upsharp(c, a, st);
+}
+
+int vp_edge_mask(vp_ctx* c, const vp_sharpen_config* cfg, const uint8_t* d_src, size_t src_pitch,
+                 float* d_mask, size_t mask_pitch, int w, int h, void* stream) {
+    if (!d_mask) return VP_ERR_INVALID_ARG;
+    return sharpen_common(c, cfg, d_src, src_pitch, nullptr, 0, d_mask, mask_pitch, nullptr, 0, w, h, stream, "vp_edge_mask");
+}
+
+int vp_unsharp(vp_ctx* c, const vp_sharpen_config* cfg, const uint8_t* d_src, size_t src_pitch,
+               const float* d_mask, size_t mask_pitch, uint8_t* d_dst, size_t dst_pitch, int w, int h, void* stream) {
+    if (!d_mask || !d_dst) return VP_ERR_INVALID_ARG;
+    return sharpen_common(c, cfg, d_src, src_pitch, d_mask, mask_pitch, nullptr, 0, d_dst, dst_pitch, w, h, stream, "vp_unsharp");
+}
+
+int vp_sharpen(vp_ctx* c, const vp_sharpen_config* cfg, const uint8_t* d_src, size_t src_pitch,
+               uint8_t* d_dst, size_t dst_pitch, int w, int h, void* stream) {
+    if (!d_dst) return VP_ERR_INVALID_ARG;
+    return sharpen_common(c, cfg, d_src, src_pitch, nullptr, 0, nullptr, 0, d_dst, dst_pitch, w, h, stream, "vp_sharpen");
+}
+
+int vp_add_weighted(vp_ctx* c, const uint8_t* d_a, size_t a_pitch, double alpha, const uint8_t* d_b, size_t b_pitch, double beta,
+                    uint8_t* d_dst, size_t dst_pitch, int w, int h, void* stream) {
+    if (!c) return VP_ERR_INVALID_ARG;
+    int rc = check_frame(c, d_a, a_pitch, w, h, "vp_add_weighted(a)"); if (rc) return rc;
+    rc = check_frame(c, d_b, b_pitch, w, h, "vp_add_weighted(b)"); if (rc) return rc;
+    rc = check_frame(c, d_dst, dst_pitch, w, h, "vp_add_weighted(dst)"); if (rc) return rc;
+    VP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    BlendKArgs a{};
+    a.cur = d_a; a.cpitch = a_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.row_bytes = 3 * w; a.h = h;
+    a.blend.mode = VP_TEMPORAL_MAIN_BLEND; a.blend.nprev = 1; a.blend.prev[0] = d_b; a.blend.ppitch = b_pitch;
+    a.blend.w[0] = (float)alpha; a.blend.w[1] = (float)beta;
+    return launch_blend(c, a, st);
+}
+
+int vp_temporal_blend(vp_ctx* c, const uint8_t* const* d_frames, int nframes, size_t pitch, float blend_strength,
+                      uint8_t* d_dst, size_t dst_pitch, int w, int h, void* stream) {
+    if (!c || !d_frames) return VP_ERR_INVALID_ARG;
+    if (nframes < 1 || nframes > 3) return fail(c, VP_ERR_UNSUPPORTED, "vp_temporal_blend: 1..3 frames");
+    int rc = VP_OK;
+    for (int i = 0; i < nframes; ++i) { rc = check_frame(c, d_frames[i], pitch, w, h, "vp_temporal_blend(frame)"); if (rc) return rc; }
+    rc = check_frame(c, d_dst, dst_pitch, w, h, "vp_temporal_blend(dst)"); if (rc) return rc;
+    VP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    BlendKArgs a{};
+    a.cur = d_frames[0]; a.cpitch = pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.row_bytes = 3 * w; a.h = h;
+    vp_temporal_config t{VP_TEMPORAL_BLEND_FRAMES, 3, blend_strength, 0.6f};
+    blend_weights(t, nframes - 1, a.blend);
+    for (int i = 1; i < nframes; ++i) a.blend.prev[i - 1] = d_frames[i];
+    a.blend.ppitch = pitch;
+    if (nframes == 1) a.blend.mode = VP_TEMPORAL_NONE;
+    return launch_blend(c, a, st);
+}
+
+}  // extern "C"
