@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""bench.py - 1080p->4K enhance-chain frames/s on N B200s (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py --gpus 1 --steps K --warmup W                     # this repo's CUDA path
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                               # the reference's OpenCV CPU path
+
+Workload (config.workload): file/--fast mode of the chain
+    SelectiveBilateral(PRE) -> cv::resize(INTER_CUBIC) x2 -> AdaptiveSharpening -> SelectiveBilateral(POST)
+    -> temporal blend,   1920x1080 -> 3840x2160, 8-bit BGR, synthetic `scene` clip.
+A "step" is one contiguous segment of --frames frames per GPU (weak scaling: N GPUs process N segments
+of one clip; rank k>0 first runs the temporal warm-up frames of its segment, inside the timed region).
+`value` = frames of all ranks / max-over-ranks device time (CUDA events), inputs resident in HBM.
+`e2e`   = the same through vp_submit_host/vp_wait with pinned HOST frames (H2D + D2H inside the timed
+region, three streams).  The roofline object describes the kernel that takes the most device time.
+torch is plumbing only (device buffers, stream, events, process group); every kernel is libvpb200's.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (src_w, src_h, dst_w, dst_h, use_pre, use_sharpen, use_post, temporal)
+    "c4": (1920, 1080, 3840, 2160, 1, 1, 1, "frames"),   # C2 chain + temporal (C4 at n_gpus = N)
+    "c2": (1920, 1080, 3840, 2160, 1, 1, 1, "none"),
+    "c3": (3840, 2160, 7680, 4320, 1, 1, 1, "frames"),
+    "c1": (1280, 720, 2560, 1440, 0, 0, 0, "none"),      # bicubic only
+    "c5": (960, 540, 3840, 2160, 0, 0, 0, "none"),       # bicubic x4
+}
+SEED = 20260
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------
+# synthetic clip on the device (same integer hash as oracle/synth.py; tests/test_bench_synth.py pins it)
+# ---------------------------------------------------------------------------------------------------
+def _mix32(h):
+    M = 0xFFFFFFFF
+    h = h & M
+    h = h ^ (h >> 15)
+    h = (h * 0x2C1B3C6D) & M
+    h = h ^ (h >> 12)
+    h = (h * 0x297A2D39) & M
+    h = h ^ (h >> 15)
+    return h
+
+
+def torch_frame(kind, w, h, t, seed, device):
+    import torch
+    x = torch.arange(w, dtype=torch.int64, device=device)[None, :, None]
+    y = torch.arange(h, dtype=torch.int64, device=device)[:, None, None]
+    c = torch.arange(3, dtype=torch.int64, device=device)[None, None, :]
+    M = 0xFFFFFFFF
+    k = ((x * 0x9E3779B1) & M) ^ ((y * 0x85EBCA77) & M) ^ ((c * 0xC2B2AE3D) & M) ^ (((t + seed) * 0x27D4EB2F) & M)
+    n = _mix32(k) & 0xFF
+    if kind == "noise":
+        return n.to(torch.uint8).contiguous()
+    if kind == "flat":
+        return (128 + (n & 3)).to(torch.uint8).contiguous()
+
+    def tri(v, p):
+        return torch.abs((v % (2 * p)) - p) * 255 // p
+    v = tri(x + 2 * t + 13 * c, 96) * 3 // 8 + tri(y + t, 64) * 3 // 8 + 64 * (((x >> 5) ^ (y >> 5) ^ (t >> 4)) & 1) + (n & 15)
+    return v.clamp(0, 255).to(torch.uint8).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [q.strip() for q in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_cfg(capi, wl, temporal):
+    sw, sh, dw, dh, pre, sharpen, post, tdef = WORKLOADS[wl]
+    cfg = capi.default_chain_config(sw, sh, dw, dh)
+    cfg.use_pre, cfg.use_sharpen, cfg.use_post = pre, sharpen, post
+    t = temporal or tdef
+    cfg.temporal.mode = {"none": capi.VP_TEMPORAL_NONE, "main": capi.VP_TEMPORAL_MAIN_BLEND, "frames": capi.VP_TEMPORAL_BLEND_FRAMES}[t]
+    return cfg, t
+
+
+def algorithmic_bytes(wl, temporal, cfg):
+    """in + out (+ state reads + state write when the temporal stage is on), per frame."""
+    sw, sh, dw, dh = WORKLOADS[wl][:4]
+    inb, outb = sw * sh * 3, dw * dh * 3
+    nprev = {"none": 0, "main": 1, "frames": max(cfg.temporal.buffer_size - 1, 0)}[temporal]
+    chain = inb + outb + (nprev * outb + outb if nprev else 0)
+    per_kernel = {
+        "stats": inb,
+        "bilateral_pre": 2 * inb,
+        "upsharp": inb + outb,
+        "bilateral_post": 2 * outb + (nprev * outb + outb if nprev else 0),
+        "blend": outb + outb + (nprev * outb + outb if nprev else 0),
+    }
+    return chain, per_kernel, inb, outb
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_chain_fps(wl, temporal, nframes, kind, threads=None):
+    """The reference's OpenCV CPU path: oracle/ref_chain.py over the real cv2 kernels (the one place
+    bench.py executes oracle/)."""
+    import cv2
+    from oracle import ref_chain as RC, synth
+    sw, sh, dw, dh, pre, sharpen, post, tdef = WORKLOADS[wl]
+    t = temporal or tdef
+    ocfg = RC.ChainConfig(dst_w=dw, dst_h=dh, use_pre=bool(pre), use_sharpen=bool(sharpen), use_post=bool(post),
+                          temporal={"none": RC.TEMPORAL_NONE, "main": RC.TEMPORAL_MAIN_BLEND, "frames": RC.TEMPORAL_BLEND_FRAMES}[t])
+    ops = RC.Cv2Ops(threads=threads or os.cpu_count())
+    chain = RC.Chain(ops, ocfg)
+    frames = synth.clip(kind, sw, sh, nframes, SEED)
+    chain.process(frames[0])   # warm the temporal state and cv2's thread pool (untimed)
+    t0 = time.perf_counter()
+    for f in frames:
+        chain.process(f)
+    dt = time.perf_counter() - t0
+    return nframes / dt, cv2.getNumThreads(), dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import cv2
+    wl = args.workload
+    per_step = args.ref_frames
+    sw, sh, dw, dh = WORKLOADS[wl][:4]
+    from oracle import ref_chain as RC, synth
+    pre, sharpen, post, tdef = WORKLOADS[wl][4:]
+    t = args.temporal or tdef
+    ocfg = RC.ChainConfig(dst_w=dw, dst_h=dh, use_pre=bool(pre), use_sharpen=bool(sharpen), use_post=bool(post),
+                          temporal={"none": RC.TEMPORAL_NONE, "main": RC.TEMPORAL_MAIN_BLEND, "frames": RC.TEMPORAL_BLEND_FRAMES}[t])
+    chain = RC.Chain(RC.Cv2Ops(threads=os.cpu_count()), ocfg)
+    frames = synth.clip(args.kind, sw, sh, per_step, SEED)
+    for _ in range(args.warmup):
+        for f in frames:
+            chain.process(f)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for f in frames:
+            chain.process(f)
+    dt = time.perf_counter() - t0
+    fps = per_step * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "enhance_chain_frames_per_s", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(wl, t), "clip": args.kind, "frames_per_step": per_step,
+                   "note": "reference CPU path = oracle/ref_chain.py over the real OpenCV kernels (cv2 %s); the reference's "
+                           "C++ cannot be compiled here (no OpenCV C++), see DESIGN.md" % cv2.__version__},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cv2.getNumThreads(), "kind": "port",
+                         "sample": f"{per_step} frames x {args.steps} steps of the same workload"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(wl, temporal):
+    sw, sh, dw, dh, pre, sharpen, post, _ = WORKLOADS[wl]
+    stages = (["bilateral_pre"] if pre else []) + ["bicubic"] + (["adaptive_sharpen"] if sharpen else []) + \
+             (["bilateral_post"] if post else []) + ([f"temporal_{temporal}"] if temporal != "none" else [])
+    return f"{wl.upper()}: {sw}x{sh}->{dw}x{dh} BGR8 " + "+".join(stages)
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--temporal", default=None, choices=["none", "main", "frames"])
+    ap.add_argument("--kind", default="scene", choices=["scene", "noise", "flat"])
+    ap.add_argument("--frames", type=int, default=64, help="frames per GPU per step (one segment)")
+    ap.add_argument("--ref-frames", type=int, default=4, help="frames per step of the reference arm")
+    ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch N>1 with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N bench.py --gpus N ...")
+    if args.warmup < 3:
+        print("warning: --warmup < 3 breaks the timing rules", file=sys.stderr)
+
+    import torch
+    import torch.distributed as dist
+    from video_processor_b200 import build as vb
+    if rank == 0:
+        vb.build()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    from video_processor_b200 import capi
+
+    wl = args.workload
+    cfg, temporal = build_cfg(capi, wl, args.temporal)
+    sw, sh, dw, dh = WORKLOADS[wl][:4]
+    chain_bytes, kbytes, inb, outb = algorithmic_bytes(wl, temporal, cfg)
+    F = args.frames
+    warm = {"none": 0, "main": 1, "frames": max(cfg.temporal.buffer_size - 1, 0)}[temporal] if rank > 0 else 0
+
+    # device-resident clip segment of this rank: frames [rank*F - warm, (rank+1)*F)
+    seg = [torch_frame(args.kind, sw, sh, rank * F - warm + i, SEED, dev) for i in range(F + warm)]
+    NOUT = max(2, min(8, (512 << 20) // outb))     # output ring larger than L2 together with the inputs
+    outs = [torch.empty((dh, dw, 3), dtype=torch.uint8, device=dev) for _ in range(NOUT)]
+    ctx = capi.Context(cfg, device=local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    h = ctx.handle
+    process = capi.lib.vp_process_device
+
+    def step():
+        capi.lib.vp_reset_temporal(h)
+        for i in range(warm):
+            rc = process(h, seg[i].data_ptr(), sw * 3, None, 0, stream)
+            if rc:
+                capi.check(rc, h)
+        for i in range(F):
+            rc = process(h, seg[warm + i].data_ptr(), sw * 3, outs[i % NOUT].data_ptr(), dw * 3, stream)
+            if rc:
+                capi.check(rc, h)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launches - l0
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tl = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
+    ms_max = float(tms.item())
+    fps = world * F * args.steps / (ms_max / 1e3)
+
+    # ---- per-kernel device times (second pass, events around every launch) -> roofline ---------------
+    roof = None
+    kernels = {}
+    if rank == 0:
+        capi.lib.vp_profile_enable(h, 1)
+        step()
+        torch.cuda.synchronize()
+        prof = ctx.profile_read()
+        capi.lib.vp_profile_enable(h, 0)
+        peak, peak_src = peaks()
+        tot = sum(v[0] for v in prof.values()) or 1.0
+        for k, (tms_k, n) in prof.items():
+            if n:
+                us = tms_k / n * 1e3
+                kernels[k] = {"launches_per_step": n, "avg_us": round(us, 2), "share": round(tms_k / tot, 4),
+                              "alg_bytes": kbytes.get(k), "achieved_gbs": round(kbytes[k] / (us * 1e-6) / 1e9, 1) if k in kbytes else None}
+        dom = max(kernels, key=lambda k: kernels[k]["share"])
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(wl, {}).get(dom)
+        except Exception:
+            pass
+        ach = kernels[dom]["achieved_gbs"]
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                "traffic": traffic, "peak_source": peak_src, "avg_us": kernels[dom]["avg_us"], "share_of_step": kernels[dom]["share"],
+                "chain": {"alg_bytes_per_frame": chain_bytes, "achieved": round(chain_bytes * fps / world / 1e9, 1),
+                          "frac": round(chain_bytes * fps / world / 1e9 / peak, 4)},
+                "kernels": kernels}
+
+    # ---- e2e: pinned host frames through vp_submit_host / vp_wait -----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        nin = min(F + warm, 16)
+        hin = [seg[i].cpu().pin_memory() for i in range(nin)]
+        depth = capi.lib.vp_pipeline_depth(h)
+        hout = [torch.empty((dh, dw, 3), dtype=torch.uint8).pin_memory() for _ in range(depth + 1)]
+        submit, wait = capi.lib.vp_submit_host, capi.lib.vp_wait
+
+        def e2e_step():
+            capi.lib.vp_reset_temporal(h)
+            inflight = 0
+            for i in range(warm + F):
+                if inflight == depth:
+                    capi.check(wait(h), h)
+                    inflight -= 1
+                dst = hout[i % (depth + 1)].data_ptr() if i >= warm else None
+                capi.check(submit(h, hin[i % nin].data_ptr(), sw * 3, dst, dw * 3), h)
+                inflight += 1
+            while inflight:
+                capi.check(wait(h), h)
+                inflight -= 1
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        nsteps = max(1, min(args.steps, 3))
+        for _ in range(nsteps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tdt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * F * nsteps / float(tdt.item()), "unit": "frames/s",
+               "h2d_bytes_per_step": (F + warm) * inb, "d2h_bytes_per_step": F * outb,
+               "timing": "host wall clock around submit/wait of whole steps, synchronised both sides, max over ranks",
+               "api": "vp_submit_host/vp_wait (pinned host frames, 3 streams, depth %d)" % depth}
+
+    cpu = None
+    if rank == 0 and world == 1 and args.cpu_frames > 0:
+        v, cores, dt = cpu_chain_fps(wl, temporal, args.cpu_frames, args.kind)
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_frames} frames of the same workload ({dt:.1f} s), oracle chain over cv2 kernels"}
+
+    if rank == 0:
+        line = {
+            "metric": "enhance_chain_frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload_name(wl, temporal), "clip": args.kind, "frames_per_step_per_gpu": F,
+                       "temporal_warmup_frames_rank_gt0": {"none": 0, "main": 1, "frames": max(cfg.temporal.buffer_size - 1, 0)}[temporal],
+                       "sharding": "contiguous frame segments, no collective",
+                       "l2": f"inputs ({F}x{inb >> 20} MiB) and output ring ({NOUT}x{outb >> 20} MiB) exceed the 126 MB L2",
+                       "roofline_pass": "per-kernel CUDA events in a separate untimed-for-value pass of one step"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(tl.item()), "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -109,6 +109,12 @@ const char* vp_last_error(const vp_ctx* ctx);   /* ctx may be NULL: last vp_crea
 /* number of kernels this library launched on the context so far (bench.py's gpu_launches) */
 uint64_t vp_launch_count(const vp_ctx* ctx);
 int vp_synchronize(vp_ctx* ctx);                /* waits for every stream the context owns */
+/* Per-kernel device timing for the roofline report: while enabled every kernel launch is bracketed by
+ * CUDA events on its stream.  vp_profile_read sums them per kernel kind (0 stats, 1 bilateral PRE,
+ * 2 bicubic+sharpen, 3 bilateral POST (+blend), 4 blend, 5 stage-wise bilateral) and clears the log. */
+#define VP_PROFILE_KINDS 6
+int vp_profile_enable(vp_ctx* ctx, int on);
+int vp_profile_read(vp_ctx* ctx, double* total_ms, uint64_t* launches, int nkinds);
 
 /* ---- the chain: Upscaler::upscale(const cv::Mat&, cv::Mat&) (src/upscaler.cpp:760-861) ------ */
 /* Device frames.  d_dst == NULL runs the frame through everything except the temporal blend and

@@ -53,6 +53,8 @@ PROTOTYPES = {
     "vp_last_error": (C.c_char_p, [_vp]),
     "vp_launch_count": (C.c_uint64, [_vp]),
     "vp_synchronize": (C.c_int, [_vp]),
+    "vp_profile_enable": (C.c_int, [_vp, C.c_int]),
+    "vp_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
     "vp_process_device": (C.c_int, [_vp, _u8p, _sz, _u8p, _sz, C.c_void_p]),
     "vp_process_host": (C.c_int, [_vp, _u8p, _sz, _u8p, _sz]),
     "vp_pipeline_depth": (C.c_int, [_vp]),
@@ -143,6 +145,13 @@ class Context:
     @property
     def launches(self):
         return int(lib.vp_launch_count(self.handle))
+
+    def profile_read(self):
+        ms = (C.c_double * 6)()
+        n = (C.c_uint64 * 6)()
+        self.call("vp_profile_read", ms, n, 6)
+        names = ["stats", "bilateral_pre", "upsharp", "bilateral_post", "blend", "bilateral_other"]
+        return {k: (ms[i], int(n[i])) for i, k in enumerate(names)}
 
     def stage_params(self, which):
         d, sc, ss = C.c_int(), C.c_double(), C.c_double()

@@ -108,11 +108,11 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
         sx0 = clampi(a.rt.xofs[dxa], 0, a.sw - 1); sx1 = clampi(a.rt.xofs[dxb] + 3, 0, a.sw - 1);
         sy0 = clampi(a.rt.yofs[dya], 0, a.sh - 1); sy1 = clampi(a.rt.yofs[dyb] + 3, 0, a.sh - 1);
         for (int i = tid; i < EW; i += US_NT) {
-            const int dx = reflect101(x0 - halo + i, a.dw);
+            const int dx = clampi(reflect101(x0 - halo + i, a.dw), dxa, dxb);   // clamp: unused columns of partial tiles
             s_xo[i] = a.rt.xofs[dx]; s_xc[i] = a.rt.xcoef[dx];
         }
         for (int i = tid; i < EH; i += US_NT) {
-            const int dy = reflect101(y0 - halo + i, a.dh);
+            const int dy = clampi(reflect101(y0 - halo + i, a.dh), dya, dyb);
             s_yo[i] = a.rt.yofs[dy]; s_yc[i] = a.rt.ycoef[dy];
         }
     } else {
@@ -179,12 +179,19 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
     const int vw = min(US_TW, a.dw - x0), vh = min(US_TH, a.dh - y0);   // valid part of the tile
 
     if (!a.do_sharpen) {
+        unsigned acc6[6] = {0, 0, 0, 0, 0, 0};
         for (int i = tid; i < US_TH * US_TW; i += US_NT) {
             const int y = i / US_TW, x = i - y * US_TW;
             const uint32_t px = s_up[y * EW + x];
             uint8_t* o = s_out + y * (US_TW * 3) + x * 3;
-            o[0] = px & 0xff; o[1] = (px >> 8) & 0xff; o[2] = (px >> 16) & 0xff;
+            const unsigned v0 = px & 0xff, v1 = (px >> 8) & 0xff, v2 = (px >> 16) & 0xff;
+            o[0] = v0; o[1] = v1; o[2] = v2;
+            if (x < vw && y < vh) {
+                acc6[0] += v0; acc6[1] += v1; acc6[2] += v2;
+                acc6[3] += v0 * v0; acc6[4] += v1 * v1; acc6[5] += v2 * v2;
+            }
         }
+        if (a.sums) reduce_sums6(acc6, a.sums, s_red);
     } else {
         const bool own_mask = (a.mask_in == nullptr);
         constexpr int CW = US_TW + 4, CH = US_TH + 4;

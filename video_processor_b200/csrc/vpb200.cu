@@ -73,6 +73,12 @@ struct vp_ctx {
     float* d_siglut = nullptr; float siglut_thr = -1e30f; bool siglut_valid = false;
     float* d_siglut_tmp = nullptr; float siglut_tmp_thr = 0; bool siglut_tmp_valid = false;
 
+    // optional per-kernel timing (bench.py's roofline leg)
+    bool prof_on = false;
+    struct ProfRec { int kind; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+
     // host pipeline
     std::vector<HostSlot> slots;
     std::deque<int> inflight;
@@ -85,6 +91,24 @@ int fail(vp_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg; else g_create_error = msg;
     return code;
 }
+
+enum { K_STATS = 0, K_BIL_PRE = 1, K_UPSHARP = 2, K_BIL_POST = 3, K_BLEND = 4, K_BIL_OTHER = 5, K_NKINDS = 6 };
+
+struct ProfScope {   // brackets one launch with CUDA events on its stream when profiling is on
+    vp_ctx* c; int kind; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    static cudaEvent_t get(vp_ctx* c) {
+        cudaEvent_t e = nullptr;
+        if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    }
+    ProfScope(vp_ctx* c_, int k, cudaStream_t s) : c(c_), kind(k), st(s) {
+        if (c->prof_on) { e0 = get(c); e1 = get(c); cudaEventRecord(e0, st); }
+    }
+    ~ProfScope() {
+        if (e0) { cudaEventRecord(e1, st); c->prof_recs.push_back({kind, e0, e1}); }
+    }
+};
 
 #define VP_CUDA(ctx, call)                                                                          \
     do {                                                                                            \
@@ -184,6 +208,7 @@ int ensure_siglut(vp_ctx* c, float** d_lut, float* cached_thr, bool* valid, floa
 
 // ---- launches -----------------------------------------------------------------------------------
 int launch_stats(vp_ctx* c, const uint8_t* src, size_t pitch, int w, int h, unsigned long long* sums, cudaStream_t st) {
+    ProfScope ps(c, K_STATS, st);
     const long long groups = (long long)(3 * w / 12 + 255) / 256 * h;   // 256-group chunks
     long long grid = std::min<long long>(std::max<long long>(groups, 1), (long long)c->sm_count * 8);
     grid = std::max<long long>(grid, (groups + 15999) / 16000);
@@ -193,7 +218,8 @@ int launch_stats(vp_ctx* c, const uint8_t* src, size_t pitch, int w, int h, unsi
     return VP_OK;
 }
 
-int launch_bilateral(vp_ctx* c, BilArgs& a, int rmax, cudaStream_t st) {
+int launch_bilateral(vp_ctx* c, BilArgs& a, int rmax, cudaStream_t st, int kind = K_BIL_OTHER) {
+    ProfScope ps(c, kind, st);
     const dim3 grid((a.w + BIL_TW - 1) / BIL_TW, (a.h + BIL_TH - 1) / BIL_TH);
     k_bilateral<<<grid, BIL_NT, bil_smem_bytes(rmax), st>>>(a);
     VP_CUDA(c, cudaGetLastError());
@@ -220,6 +246,7 @@ int launch_upsharp(vp_ctx* c, UpsharpArgs& a, cudaStream_t st) {
     const UpsharpSmem L = upsharp_layout(halo, a.max_src_rows, a.max_src_cols, a.do_sharpen);
     if (L.total > 200 * 1024) return fail(c, VP_ERR_UNSUPPORTED, "resize ratio needs more shared memory than a CTA has");
     const dim3 grid((a.dw + US_TW - 1) / US_TW, (a.dh + US_TH - 1) / US_TH);
+    ProfScope ps(c, K_UPSHARP, st);
     k_upsharp<<<grid, US_NT, L.total, st>>>(a);
     VP_CUDA(c, cudaGetLastError());
     c->launches++;
@@ -229,6 +256,7 @@ int launch_upsharp(vp_ctx* c, UpsharpArgs& a, cudaStream_t st) {
 int launch_blend(vp_ctx* c, BlendKArgs& a, cudaStream_t st) {
     const long long work = ((long long)a.row_bytes * a.h + 15) / 16;
     const unsigned grid = (unsigned)std::min<long long>((work + 255) / 256, (long long)c->sm_count * 16);
+    ProfScope ps(c, K_BLEND, st);
     k_blend<<<std::max(grid, 1u), 256, 0, st>>>(a);
     VP_CUDA(c, cudaGetLastError());
     c->launches++;
@@ -319,6 +347,8 @@ void vp_destroy(vp_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     destroy_slots(c);
+    for (auto& r : c->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (auto& e : c->prof_pool) cudaEventDestroy(e);
     cudaFree(c->d_pre); cudaFree(c->d_sharp);
     for (auto& p : c->d_state) cudaFree(p);
     cudaFree(c->d_sums); cudaFree(c->d_sel);
@@ -414,6 +444,27 @@ int vp_create(vp_ctx** out, int device, const vp_chain_config* cfg) {
     return VP_OK;
 }
 
+int vp_profile_enable(vp_ctx* c, int on) {
+    if (!c) return VP_ERR_INVALID_ARG;
+    c->prof_on = on != 0;
+    return VP_OK;
+}
+
+int vp_profile_read(vp_ctx* c, double* total_ms, uint64_t* launches, int nkinds) {
+    if (!c || !total_ms || !launches || nkinds < 1) return VP_ERR_INVALID_ARG;
+    VP_CUDA(c, cudaSetDevice(c->device));
+    for (int k = 0; k < nkinds; ++k) { total_ms[k] = 0.0; launches[k] = 0; }
+    for (auto& r : c->prof_recs) {
+        VP_CUDA(c, cudaEventSynchronize(r.e1));
+        float ms = 0.f;
+        VP_CUDA(c, cudaEventElapsedTime(&ms, r.e0, r.e1));
+        if (r.kind < nkinds) { total_ms[r.kind] += ms; launches[r.kind]++; }
+        c->prof_pool.push_back(r.e0); c->prof_pool.push_back(r.e1);
+    }
+    c->prof_recs.clear();
+    return VP_OK;
+}
+
 int vp_synchronize(vp_ctx* c) {
     if (!c) return VP_ERR_INVALID_ARG;
     VP_CUDA(c, cudaSetDevice(c->device));
@@ -456,7 +507,7 @@ int vp_process_device(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t
         a.src = cur; a.spitch = cur_pitch; a.dst = c->d_pre; a.dpitch = c->pre_pitch; a.w = g.src_w; a.h = g.src_h;
         a.cand = c->d_cand_pre; a.sums = need_pre_stats ? c->d_sums : nullptr; a.npx = (double)g.src_w * g.src_h;
         a.sel_out = c->d_sel;
-        rc = launch_bilateral(c, a, c->cand_pre_rmax, st); if (rc) return rc;
+        rc = launch_bilateral(c, a, c->cand_pre_rmax, st, K_BIL_PRE); if (rc) return rc;
         cur = c->d_pre; cur_pitch = c->pre_pitch;
     }
     // 2+3. bicubic resize + AdaptiveSharpening (dst resolution)
@@ -501,7 +552,7 @@ int vp_process_device(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t
         a.cand = c->d_cand_post; a.sums = need_post_stats ? c->d_sums + 6 : nullptr; a.npx = (double)g.dst_w * g.dst_h;
         a.sel_out = c->d_sel + 1;
         a.blend = bl;
-        rc = launch_bilateral(c, a, c->cand_post_rmax, st); if (rc) return rc;
+        rc = launch_bilateral(c, a, c->cand_post_rmax, st, K_BIL_POST); if (rc) return rc;
     } else if (temporal) {
         BlendKArgs a{};
         a.cur = cur; a.cpitch = cur_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.row_bytes = g.dst_w * 3; a.h = g.dst_h;
