@@ -276,7 +276,12 @@ def main():
     NOUT = max(2, min(8, (512 << 20) // outb))     # output ring larger than L2 together with the inputs
     outs = [torch.empty((dh, dw, 3), dtype=torch.uint8, device=dev) for _ in range(NOUT)]
     ctx = capi.Context(cfg, device=local_rank)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a non-default torch stream: the chain's kernels are launched on it (vp_process_device's stream
+    # argument) and torch.cuda.Event brackets them on the same stream
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     h = ctx.handle
     process = capi.lib.vp_process_device
 

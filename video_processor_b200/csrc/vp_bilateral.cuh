@@ -10,7 +10,10 @@
 // Layout: a CTA owns a TW x TH output tile.  The halo tile is staged from HBM by TMA bulk row copies
 // into raw bytes, expanded once to packed BGR0 words with the border map resolved, and each thread
 // then filters a strip of PX horizontally adjacent pixels so a staged neighbour is reused by up to
-// PX outputs from registers (VABSDIFF4 + IDP.4A for the L1 colour distance).
+// PX outputs from registers (VABSDIFF4 + IDP.4A for the L1 colour distance).  The tap rows run in a
+// rolled loop whose body is specialised on the row's half-width (a handful of variants per radius),
+// which keeps the unrolled code inside the instruction cache; u8->f32 uses the exact PRMT "magic
+// number" form (0x4B0000xx - 2^23) instead of I2F so the conversion pipe is not the limiter.
 #pragma once
 #include "vp_common.cuh"
 #include "vp_stats.cuh"
@@ -22,6 +25,7 @@ constexpr int BIL_TW = 64, BIL_TH = 16, BIL_PX = 4, BIL_NT = 256, BIL_RMAX = 7;
 struct BilCand {                   // one (d, sigma) parameter set, device memory
     int radius;
     int d;
+    int xmax[2 * BIL_RMAX + 1];    // half-width of tap row i (index i + r): floor(sqrt(r^2 - i^2))
     float space_w[(2 * BIL_RMAX + 1) * (2 * BIL_RMAX + 1)];  // [(i+r)*(2r+1) + (j+r)]
     float color_w[768];
 };
@@ -41,23 +45,36 @@ struct BilArgs {
     const uint8_t* src; size_t spitch;
     uint8_t* dst; size_t dpitch;   // dst may be null when only `blend.state` is wanted
     int w, h;
-    const BilCand* cand;           // 3 candidates indexed by noise class (or 1 when sums == null)
-    const unsigned long long* sums;
-    double npx;
-    int* sel_out;                  // class actually used (debug / vp_get_stage_params), may be null
+    const BilCand* cand;           // candidates indexed by noise class (or 1 when sel == null)
+    const int* sel;                // noise class chosen by the stats producer's last CTA (may be null)
     BlendArgs blend;
 };
 
-__device__ __forceinline__ int blend_byte(const BlendArgs& b, int cur, int p0, int p1) {
-    if (b.mode == 1) {             // cv::addWeighted AVX2 form: fma(cur, alpha, prev*beta)
-        return rne_sat_u8(__fmaf_rn((float)cur, b.w[0], __fmul_rn((float)p0, b.w[1])));
-    }
-    float acc = __fmul_rn(b.w[0], (float)cur);
-    acc = __fadd_rn(acc, __fmul_rn(b.w[1], (float)p0));
-    if (b.nprev > 1) acc = __fadd_rn(acc, __fmul_rn(b.w[2], (float)p1));
-    return rne_sat_u8(__fmul_rn(acc, b.inv_wsum));
+// exact u8 -> f32: bytes [b,0,0,0x4B] are the float 2^23 + b
+__device__ __forceinline__ float u8f(uint32_t word, int byte) {
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440 + byte)) - 8388608.0f;
+}
+// cv::saturate_cast<uchar>(float): one cvt (round-to-nearest-even, clamped to [0,255])
+__device__ __forceinline__ uint32_t f2u8(float v) {
+    uint32_t r;
+    asm("cvt.rni.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
 }
 
+__device__ __forceinline__ uint32_t blend_byte(const BlendArgs& b, float cur, float p0, float p1) {
+    if (b.mode == 1)               // cv::addWeighted AVX2 form: fma(cur, alpha, prev*beta)
+        return f2u8(__fmaf_rn(cur, b.w[0], __fmul_rn(p0, b.w[1])));
+    float acc = __fmul_rn(b.w[0], cur);
+    acc = __fadd_rn(acc, __fmul_rn(b.w[1], p0));
+    if (b.nprev > 1) acc = __fadd_rn(acc, __fmul_rn(b.w[2], p1));
+    return f2u8(__fmul_rn(acc, b.inv_wsum));
+}
+__device__ __forceinline__ uint32_t blend_word(const BlendArgs& b, uint32_t cur, uint32_t p0, uint32_t p1) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r |= blend_byte(b, u8f(cur, k), u8f(p0, k), u8f(p1, k)) << (8 * k);
+    return r;
+}
 
 // 12 packed bytes (4 BGR pixels) <-> memory; word accesses when the address is 4-byte aligned
 __device__ __forceinline__ void store12(uint8_t* p, const uint32_t v[3], int npx) {
@@ -65,36 +82,78 @@ __device__ __forceinline__ void store12(uint8_t* p, const uint32_t v[3], int npx
         uint32_t* q = reinterpret_cast<uint32_t*>(p);
         q[0] = v[0]; q[1] = v[1]; q[2] = v[2];
     } else {
-        for (int k = 0; k < 3 * npx; ++k) p[k] = (uint8_t)(v[k >> 2] >> (8 * (k & 3)));
+#pragma unroll
+        for (int k = 0; k < 12; ++k)
+            if (k < 3 * npx) p[k] = (uint8_t)(v[k >> 2] >> (8 * (k & 3)));
     }
 }
 __device__ __forceinline__ void load12(const uint8_t* p, uint32_t v[3], int npx) {
     if (npx == 4 && (((uintptr_t)p) & 3) == 0) {
         const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
-        v[0] = q[0]; v[1] = q[1]; v[2] = q[2];
+        v[0] = __ldg(q); v[1] = __ldg(q + 1); v[2] = __ldg(q + 2);
     } else {
         v[0] = v[1] = v[2] = 0;
-        for (int k = 0; k < 3 * npx; ++k) v[k >> 2] |= (uint32_t)p[k] << (8 * (k & 3));
-    }
-}
-__device__ __forceinline__ void blend12(const BlendArgs& b, const uint32_t cur[3], const uint32_t p0[3],
-                                        const uint32_t p1[3], uint32_t o[3]) {
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        uint32_t r = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            r |= (uint32_t)blend_byte(b, (cur[q] >> (8 * k)) & 0xff, (p0[q] >> (8 * k)) & 0xff, (p1[q] >> (8 * k)) & 0xff) << (8 * k);
-        o[q] = r;
+        for (int k = 0; k < 12; ++k)
+            if (k < 3 * npx) v[k >> 2] |= (uint32_t)p[k] << (8 * (k & 3));
     }
 }
 
+template <int R> struct BilGeom {
+    static constexpr int TP = (BIL_TW + 2 * R + 3) & ~3;      // tile pitch in pixels (16-byte rows)
+    static constexpr int NSEG = (BIL_PX + 2 * R + 3) & ~3;    // staged neighbours per row, whole uint4s
+    static constexpr int D = 2 * R + 1;
+};
+
+// one tap row of half-width XM: taps dx = -XM..XM against the PX outputs of the strip
+template <int R, int XM>
+__device__ __forceinline__ void bil_row(const uint32_t (&seg)[BilGeom<R>::NSEG], const float* __restrict__ sw_row,
+                                        const float* __restrict__ s_cw, const uint32_t (&ctr)[BIL_PX],
+                                        float (&sb)[BIL_PX], float (&sg)[BIL_PX], float (&sr)[BIL_PX], float (&ws)[BIL_PX]) {
+    constexpr int N = BIL_PX + 2 * XM;                        // neighbours this row touches
+    float fb[N], fg[N], fr[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const uint32_t p = seg[i + R - XM];
+        fb[i] = u8f(p, 0); fg[i] = u8f(p, 1); fr[i] = u8f(p, 2);
+    }
+#pragma unroll
+    for (int dx = -XM; dx <= XM; ++dx) {
+        const float sw = sw_row[dx + R];
+#pragma unroll
+        for (int j = 0; j < BIL_PX; ++j) {
+            const int i = j + dx + XM;
+            const unsigned n = __dp4a(__vabsdiffu4(seg[i + R - XM], ctr[j]), 0x01010101u, 0u);
+            const float wgt = __fmul_rn(sw, s_cw[n]);
+            ws[j] = __fadd_rn(ws[j], wgt);
+            sb[j] = __fmaf_rn(fb[i], wgt, sb[j]);
+            sg[j] = __fmaf_rn(fg[i], wgt, sg[j]);
+            sr[j] = __fmaf_rn(fr[i], wgt, sr[j]);
+        }
+    }
+}
+
+template <int R, int XM>
+struct BilRowSwitch {
+    __device__ __forceinline__ static void run(int xm, const uint32_t (&seg)[BilGeom<R>::NSEG], const float* sw_row, const float* s_cw,
+                                               const uint32_t (&ctr)[BIL_PX], float (&sb)[BIL_PX], float (&sg)[BIL_PX],
+                                               float (&sr)[BIL_PX], float (&ws)[BIL_PX]) {
+        if (xm == XM) bil_row<R, XM>(seg, sw_row, s_cw, ctr, sb, sg, sr, ws);
+        else BilRowSwitch<R, XM - 1>::run(xm, seg, sw_row, s_cw, ctr, sb, sg, sr, ws);
+    }
+};
+template <int R>
+struct BilRowSwitch<R, -1> {
+    __device__ __forceinline__ static void run(int, const uint32_t (&)[BilGeom<R>::NSEG], const float*, const float*,
+                                               const uint32_t (&)[BIL_PX], float (&)[BIL_PX], float (&)[BIL_PX],
+                                               float (&)[BIL_PX], float (&)[BIL_PX]) {}
+};
+
 template <int R>
 __device__ __forceinline__ void bil_strip(const uint32_t* __restrict__ s_tile, const float* __restrict__ s_sw,
-                                          const float* __restrict__ s_cw, int lx, int ly, uint32_t out[BIL_PX]) {
-    constexpr int TP = (BIL_TW + 2 * R + 3) & ~3;          // tile pitch in pixels (16-byte rows)
-    constexpr int NSEG = (BIL_PX + 2 * R + 3) & ~3;        // staged neighbours per row, whole uint4s
-    constexpr int D = 2 * R + 1;
+                                       const float* __restrict__ s_cw, const int* __restrict__ s_xm,
+                                       int lx, int ly, uint32_t out[BIL_PX]) {
+    constexpr int TP = BilGeom<R>::TP, NSEG = BilGeom<R>::NSEG, D = BilGeom<R>::D;
     uint32_t ctr[BIL_PX];
     float sb[BIL_PX], sg[BIL_PX], sr[BIL_PX], ws[BIL_PX];
 #pragma unroll
@@ -102,73 +161,39 @@ __device__ __forceinline__ void bil_strip(const uint32_t* __restrict__ s_tile, c
         ctr[j] = s_tile[(ly + R) * TP + lx + R + j];
         sb[j] = sg[j] = sr[j] = ws[j] = 0.f;
     }
-#pragma unroll
-    for (int dy = -R; dy <= R; ++dy) {
-        const uint4* rowp = reinterpret_cast<const uint4*>(s_tile + (ly + R + dy) * TP + lx);
+#pragma unroll 1
+    for (int row = 0; row < D; ++row) {
+        const uint4* rowp = reinterpret_cast<const uint4*>(s_tile + (ly + row) * TP + lx);
         uint32_t seg[NSEG];
 #pragma unroll
         for (int q = 0; q < NSEG / 4; ++q) {
             const uint4 v = rowp[q];
             seg[4 * q] = v.x; seg[4 * q + 1] = v.y; seg[4 * q + 2] = v.z; seg[4 * q + 3] = v.w;
         }
-        float fb[NSEG], fg[NSEG], fr[NSEG];
-#pragma unroll
-        for (int i = 0; i < BIL_PX + 2 * R; ++i) {
-            fb[i] = (float)(seg[i] & 0xffu);
-            fg[i] = (float)((seg[i] >> 8) & 0xffu);
-            fr[i] = (float)((seg[i] >> 16) & 0xffu);
-        }
-#pragma unroll
-        for (int dx = -R; dx <= R; ++dx) {
-            if (dx * dx + dy * dy <= R * R) {
-                const float sw = s_sw[(dy + R) * D + (dx + R)];
-#pragma unroll
-                for (int j = 0; j < BIL_PX; ++j) {
-                    const int i = j + dx + R;
-                    const unsigned n = __dp4a(__vabsdiffu4(seg[i], ctr[j]), 0x01010101u, 0u);
-                    const float wgt = __fmul_rn(sw, s_cw[n]);
-                    ws[j] = __fadd_rn(ws[j], wgt);
-                    sb[j] = __fmaf_rn(fb[i], wgt, sb[j]);
-                    sg[j] = __fmaf_rn(fg[i], wgt, sg[j]);
-                    sr[j] = __fmaf_rn(fr[i], wgt, sr[j]);
-                }
-            }
-        }
+        BilRowSwitch<R, R>::run(s_xm[row], seg, s_sw + row * D, s_cw, ctr, sb, sg, sr, ws);
     }
 #pragma unroll
     for (int j = 0; j < BIL_PX; ++j) {
         const float inv = __frcp_rn(ws[j]);
-        const int b = rne_sat_u8(__fmul_rn(sb[j], inv));
-        const int g = rne_sat_u8(__fmul_rn(sg[j], inv));
-        const int r = rne_sat_u8(__fmul_rn(sr[j], inv));
-        out[j] = (uint32_t)b | ((uint32_t)g << 8) | ((uint32_t)r << 16);
+        out[j] = f2u8(__fmul_rn(sb[j], inv)) | (f2u8(__fmul_rn(sg[j], inv)) << 8) | (f2u8(__fmul_rn(sr[j], inv)) << 16);
     }
 }
 
-// shared memory: [ tile words | space_w | color_w | raw bytes | mbarrier ]
+// shared memory: [ tile words | space_w | color_w | xmax | raw bytes | mbarrier ]
 __host__ __device__ inline int bil_tile_pitch(int r) { return (BIL_TW + 2 * r + 3) & ~3; }
 __host__ __device__ inline int bil_raw_pitch(int r) { return (((BIL_TW + 2 * r) * 3 + 15 + 15) & ~15) + 16; }
+__host__ __device__ inline int bil_sw_words(int r) { return ((2 * r + 1) * (2 * r + 1) + 3) & ~3; }
 __host__ inline size_t bil_smem_bytes(int r) {
     size_t tile = (size_t)bil_tile_pitch(r) * (BIL_TH + 2 * r) * 4;
-    size_t sw = (size_t)(2 * r + 1) * (2 * r + 1) * 4;
-    sw = (sw + 15) & ~(size_t)15;
-    size_t cw = 768 * 4;
     size_t raw = (size_t)bil_raw_pitch(r) * (BIL_TH + 2 * r);
-    return tile + sw + cw + raw + 16;
+    return tile + bil_sw_words(r) * 4 + 768 * 4 + 16 * 4 + raw + 16;
 }
 
-__global__ void __launch_bounds__(BIL_NT) k_bilateral(const BilArgs a) {
+__global__ void __launch_bounds__(BIL_NT, 3) k_bilateral(const BilArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ int s_sel;
     const int tid = threadIdx.x;
-    if (tid == 0) {
-        int sel = 0;
-        if (a.sums) sel = noise_class_from_sums(a.sums, a.npx);
-        s_sel = sel;
-        if (a.sel_out && blockIdx.x == 0 && blockIdx.y == 0) *a.sel_out = sel;
-    }
-    __syncthreads();
-    const BilCand* __restrict__ cand = a.cand + s_sel;
+    const int sel = a.sel ? *a.sel : 0;
+    const BilCand* __restrict__ cand = a.cand + sel;
     const int R = cand->radius;
     const int D = 2 * R + 1;
     const int TP = bil_tile_pitch(R);
@@ -177,8 +202,9 @@ __global__ void __launch_bounds__(BIL_NT) k_bilateral(const BilArgs a) {
 
     uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem);
     float* s_sw = reinterpret_cast<float*>(smem + (size_t)TP * TROWS * 4);
-    float* s_cw = s_sw + ((D * D + 3) & ~3);
-    uint8_t* s_raw = reinterpret_cast<uint8_t*>(s_cw + 768);
+    float* s_cw = s_sw + bil_sw_words(R);
+    int* s_xm = reinterpret_cast<int*>(s_cw + 768);
+    uint8_t* s_raw = reinterpret_cast<uint8_t*>(s_xm + 16);
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_raw + (size_t)RP * TROWS);
 
     const int x0 = blockIdx.x * BIL_TW, y0 = blockIdx.y * BIL_TH;
@@ -190,19 +216,32 @@ __global__ void __launch_bounds__(BIL_NT) k_bilateral(const BilArgs a) {
 
     for (int i = tid; i < D * D; i += BIL_NT) s_sw[i] = cand->space_w[i];
     for (int i = tid; i < 768; i += BIL_NT) s_cw[i] = cand->color_w[i];
+    if (tid < D) s_xm[tid] = cand->xmax[tid];
     stage_rows(s_raw, RP, a.src, a.spitch, 3 * a.w, vy0, vy1, bx0, bx1, fast, bar);
 
-    // expand raw bytes -> BGR0 words with BORDER_REFLECT_101 resolved
-    const int TWH = BIL_TW + 2 * R;
-    for (int i = tid; i < TWH * TROWS; i += BIL_NT) {
-        const int ty = i / TWH, tx = i - ty * TWH;
-        const int sx = reflect101(x0 - R + tx, a.w), sy = reflect101(y0 - R + ty, a.h);
-        uint32_t v = 0;
-        if (sx >= vx0 && sx < vx1 && sy >= vy0 && sy < vy1) {   // always true for w,h > R
-            const uint8_t* p = s_raw + (sy - vy0) * RP + (sx * 3 - bx0);
-            v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+    // expand raw bytes -> BGR0 words with BORDER_REFLECT_101 resolved; warp per row, lanes along x
+    {
+        const int TWH = BIL_TW + 2 * R;
+        const bool simple = (a.w > R) && (a.h > R);      // one mirror step suffices
+        const int lane = tid & 31, wrp = tid >> 5;
+        for (int ty = wrp; ty < TROWS; ty += BIL_NT / 32) {
+            int sy = y0 - R + ty;
+            if (simple) { sy = sy < 0 ? -sy : sy; sy = sy >= a.h ? 2 * a.h - 2 - sy : sy; }
+            else sy = reflect101(sy, a.h);
+            const bool rowok = sy >= vy0 && sy < vy1;
+            const uint8_t* rrow = s_raw + (sy - vy0) * RP - bx0;
+            for (int tx = lane; tx < TWH; tx += 32) {
+                int sx = x0 - R + tx;
+                if (simple) { sx = sx < 0 ? -sx : sx; sx = sx >= a.w ? 2 * a.w - 2 - sx : sx; }
+                else sx = reflect101(sx, a.w);
+                uint32_t v = 0;
+                if (rowok && sx >= vx0 && sx < vx1) {        // false only for unused positions of edge tiles
+                    const uint8_t* p = rrow + sx * 3;
+                    v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+                }
+                s_tile[ty * TP + tx] = v;
+            }
         }
-        s_tile[ty * TP + tx] = v;
     }
     __syncthreads();
 
@@ -211,13 +250,13 @@ __global__ void __launch_bounds__(BIL_NT) k_bilateral(const BilArgs a) {
     if (gy >= a.h || gx >= a.w) return;
     uint32_t out[BIL_PX];
     switch (R) {
-        case 1: bil_strip<1>(s_tile, s_sw, s_cw, lx, ly, out); break;
-        case 2: bil_strip<2>(s_tile, s_sw, s_cw, lx, ly, out); break;
-        case 3: bil_strip<3>(s_tile, s_sw, s_cw, lx, ly, out); break;
-        case 4: bil_strip<4>(s_tile, s_sw, s_cw, lx, ly, out); break;
-        case 5: bil_strip<5>(s_tile, s_sw, s_cw, lx, ly, out); break;
-        case 6: bil_strip<6>(s_tile, s_sw, s_cw, lx, ly, out); break;
-        default: bil_strip<7>(s_tile, s_sw, s_cw, lx, ly, out); break;
+        case 1: bil_strip<1>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
+        case 2: bil_strip<2>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
+        case 3: bil_strip<3>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
+        case 4: bil_strip<4>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
+        case 5: bil_strip<5>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
+        case 6: bil_strip<6>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
+        default: bil_strip<7>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
     }
 
     // epilogue: optional temporal blend, state store, output store (12 contiguous bytes per strip)
@@ -236,7 +275,8 @@ __global__ void __launch_bounds__(BIL_NT) k_bilateral(const BilArgs a) {
         load12(b.prev[0] + (size_t)gy * b.ppitch + boff, p0, npx);
         if (b.nprev > 1) load12(b.prev[1] + (size_t)gy * b.ppitch + boff, p1, npx);
         else { p1[0] = p0[0]; p1[1] = p0[1]; p1[2] = p0[2]; }
-        blend12(b, cur, p0, p1, o);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) o[q] = blend_word(b, cur[q], p0[q], p1[q]);
         store12(dp, o, npx);
     } else {
         store12(dp, cur, npx);

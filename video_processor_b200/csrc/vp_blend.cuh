@@ -37,16 +37,9 @@ __global__ void __launch_bounds__(256) k_blend(const BlendKArgs a) {
         if (doblend) {
             const uint4 p0 = *reinterpret_cast<const uint4*>(b.prev[0] + (size_t)y * b.ppitch + off);
             const uint4 p1 = b.nprev > 1 ? *reinterpret_cast<const uint4*>(b.prev[1] + (size_t)y * b.ppitch + off) : p0;
-            const uint32_t cw[4] = {c.x, c.y, c.z, c.w}, pa[4] = {p0.x, p0.y, p0.z, p0.w}, pb[4] = {p1.x, p1.y, p1.z, p1.w};
             uint32_t r[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t v = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    v |= (uint32_t)blend_byte(b, (cw[q] >> (8 * k)) & 0xff, (pa[q] >> (8 * k)) & 0xff, (pb[q] >> (8 * k)) & 0xff) << (8 * k);
-                r[q] = v;
-            }
+            r[0] = blend_word(b, c.x, p0.x, p1.x); r[1] = blend_word(b, c.y, p0.y, p1.y);
+            r[2] = blend_word(b, c.z, p0.z, p1.z); r[3] = blend_word(b, c.w, p0.w, p1.w);
             o = make_uint4(r[0], r[1], r[2], r[3]);
         }
         *reinterpret_cast<uint4*>(a.dst + (size_t)y * a.dpitch + off) = o;
@@ -64,7 +57,7 @@ __global__ void __launch_bounds__(256) k_blend(const BlendKArgs a) {
         if (doblend) {
             const int p0 = b.prev[0][(size_t)y * b.ppitch + off];
             const int p1 = b.nprev > 1 ? b.prev[1][(size_t)y * b.ppitch + off] : p0;
-            o = blend_byte(b, c, p0, p1);
+            o = (int)blend_byte(b, (float)c, (float)p0, (float)p1);
         }
         a.dst[(size_t)y * a.dpitch + off] = (uint8_t)o;
     }

@@ -99,8 +99,8 @@ __device__ __forceinline__ bool aligned16(const void* p, size_t pitch) {
     return ((((uintptr_t)p) | pitch) & 15) == 0;
 }
 
-// warp + block reduction of 6 uint32 partial sums into uint64 global accumulators
-__device__ __forceinline__ void reduce_sums6(unsigned v[6], unsigned long long* __restrict__ gsums, unsigned long long* s_red) {
+// warp reduction of 6 uint32 partial sums into the CTA's shared uint64 accumulators
+__device__ __forceinline__ void reduce_sums6(const unsigned v[6], unsigned long long* s_red) {
     const int lane = threadIdx.x & 31;
     unsigned long long w[6];
 #pragma unroll

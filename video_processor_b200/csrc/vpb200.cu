@@ -33,7 +33,7 @@ thread_local std::string g_create_error;
 
 struct ResizeCache {
     int sw = 0, sh = 0, dw = 0, dh = 0;
-    int* xofs = nullptr; short4* xcoef = nullptr; int* yofs = nullptr; float4* ycoef = nullptr;
+    int* xofs = nullptr; int4* xcoef = nullptr; int* yofs = nullptr; float4* ycoef = nullptr;
     int max_rows[2] = {0, 0}, max_cols[2] = {0, 0};   // [0] halo 0, [1] halo US_HALO
 };
 
@@ -62,7 +62,8 @@ struct vp_ctx {
     uint8_t* d_state[3] = {nullptr, nullptr, nullptr};
     int nring = 0, head = 0, nvalid = 0;                    // temporal ring
     unsigned long long* d_sums = nullptr;                   // [0..5] PRE input, [6..11] POST input, [12..17] scratch
-    int* d_sel = nullptr;                                   // [0] PRE class, [1] POST class
+    int* d_sel = nullptr;                                   // [0] PRE class, [1] POST class, [2] stage-wise
+    unsigned* d_counter = nullptr;                          // CTA ticket counters of the three sel producers
     BilCand* d_cand_pre = nullptr; BilCand* d_cand_post = nullptr; BilCand* d_cand_tmp = nullptr;
     int cand_pre_rmax = 0, cand_post_rmax = 0;
     // cached stage-wise tables
@@ -131,6 +132,11 @@ void fill_cand(BilCand& bc, const vp_host::BilateralTables& t) {
     std::memset(&bc, 0, sizeof(bc));
     bc.radius = t.radius;
     bc.d = t.d;
+    for (int i = -t.radius; i <= t.radius; ++i) {
+        int xm = 0;
+        while ((xm + 1) * (xm + 1) + i * i <= t.radius * t.radius) ++xm;
+        bc.xmax[i + t.radius] = xm;
+    }
     std::memcpy(bc.space_w, t.space_w.data(), t.space_w.size() * sizeof(float));
     std::memcpy(bc.color_w, t.color_w.data(), 768 * sizeof(float));
 }
@@ -160,12 +166,11 @@ void free_resize(ResizeCache& rc) {
     rc = ResizeCache();
 }
 
-int tile_span(const std::vector<int>& ofs, int src_len, int dst_len, int tile, int halo) {
+int tile_span(const std::vector<int>& ofs, int dst_len, int tile, int halo) {
     int best = 0;
     for (int t0 = 0; t0 < dst_len; t0 += tile) {
         const int a = std::max(0, t0 - halo), b = std::min(dst_len - 1, t0 + tile - 1 + halo);
-        const int s0 = clampi(ofs[a], 0, src_len - 1), s1 = clampi(ofs[b] + 3, 0, src_len - 1);
-        best = std::max(best, s1 - s0 + 1);
+        best = std::max(best, ofs[b] + 3 - ofs[a] + 1);   // unclamped window (border columns are materialised)
     }
     return best;
 }
@@ -178,18 +183,20 @@ int ensure_resize(vp_ctx* c, ResizeCache& rc, int sw, int sh, int dw, int dh, cu
     std::vector<float> yb((size_t)dh * 4);
     for (size_t i = 0; i < yb.size(); ++i) yb[i] = (float)ty.coef[i] * (1.0f / 4194304.0f);
     VP_CUDA(c, cudaMalloc(&rc.xofs, (size_t)dw * sizeof(int)));
-    VP_CUDA(c, cudaMalloc(&rc.xcoef, (size_t)dw * sizeof(short4)));
+    VP_CUDA(c, cudaMalloc(&rc.xcoef, (size_t)dw * sizeof(int4)));
+    std::vector<int> xc((size_t)dw * 4);
+    for (size_t i = 0; i < xc.size(); ++i) xc[i] = tx.coef[i];
     VP_CUDA(c, cudaMalloc(&rc.yofs, (size_t)dh * sizeof(int)));
     VP_CUDA(c, cudaMalloc(&rc.ycoef, (size_t)dh * sizeof(float4)));
     VP_CUDA(c, cudaMemcpyAsync(rc.xofs, tx.ofs.data(), (size_t)dw * sizeof(int), cudaMemcpyHostToDevice, st));
-    VP_CUDA(c, cudaMemcpyAsync(rc.xcoef, tx.coef.data(), (size_t)dw * sizeof(short4), cudaMemcpyHostToDevice, st));
+    VP_CUDA(c, cudaMemcpyAsync(rc.xcoef, xc.data(), (size_t)dw * sizeof(int4), cudaMemcpyHostToDevice, st));
     VP_CUDA(c, cudaMemcpyAsync(rc.yofs, ty.ofs.data(), (size_t)dh * sizeof(int), cudaMemcpyHostToDevice, st));
     VP_CUDA(c, cudaMemcpyAsync(rc.ycoef, yb.data(), (size_t)dh * sizeof(float4), cudaMemcpyHostToDevice, st));
     VP_CUDA(c, cudaStreamSynchronize(st));
     for (int k = 0; k < 2; ++k) {
         const int halo = k ? US_HALO : 0;
-        rc.max_cols[k] = tile_span(tx.ofs, sw, dw, US_TW, halo);
-        rc.max_rows[k] = tile_span(ty.ofs, sh, dh, US_TH, halo);
+        rc.max_cols[k] = tile_span(tx.ofs, dw, US_TW, halo);
+        rc.max_rows[k] = tile_span(ty.ofs, dh, US_TH, halo);
     }
     rc.sw = sw; rc.sh = sh; rc.dw = dw; rc.dh = dh;
     return VP_OK;
@@ -207,12 +214,14 @@ int ensure_siglut(vp_ctx* c, float** d_lut, float* cached_thr, bool* valid, floa
 }
 
 // ---- launches -----------------------------------------------------------------------------------
-int launch_stats(vp_ctx* c, const uint8_t* src, size_t pitch, int w, int h, unsigned long long* sums, cudaStream_t st) {
+int launch_stats(vp_ctx* c, const uint8_t* src, size_t pitch, int w, int h, unsigned long long* sums, const SelOut& fin, cudaStream_t st) {
     ProfScope ps(c, K_STATS, st);
-    const long long groups = (long long)(3 * w / 12 + 255) / 256 * h;   // 256-group chunks
-    long long grid = std::min<long long>(std::max<long long>(groups, 1), (long long)c->sm_count * 8);
-    grid = std::max<long long>(grid, (groups + 15999) / 16000);
-    k_stats<<<(unsigned)grid, 256, 0, st>>>(src, pitch, w, h, sums);
+    // every thread folds at most ~4000 16-pixel groups (uint32 partial sums): size the grid for that
+    const long long groups48 = ((long long)3 * w * h + 47) / 48;
+    long long grid = std::min<long long>((groups48 + 255) / 256, (long long)c->sm_count * 4);
+    grid = std::max<long long>(grid, (groups48 + 256LL * 2000 - 1) / (256LL * 2000));
+    grid = std::max<long long>(grid, 1);
+    k_stats<<<(unsigned)grid, 256, 0, st>>>(src, pitch, w, h, sums, fin);
     VP_CUDA(c, cudaGetLastError());
     c->launches++;
     return VP_OK;
@@ -239,15 +248,23 @@ int fill_sharpen_args(vp_ctx* c, UpsharpArgs& a, const vp_sharpen_config& s) {
     return VP_OK;
 }
 
-int launch_upsharp(vp_ctx* c, UpsharpArgs& a, cudaStream_t st) {
-    if (a.do_sharpen && (a.dw < 8 || a.dh < 8))
+int launch_upsharp(vp_ctx* c, UpsharpArgs& a, bool do_resize, bool do_sharpen, cudaStream_t st) {
+    if (do_sharpen && (a.dw < 8 || a.dh < 8))
         return fail(c, VP_ERR_UNSUPPORTED, "AdaptiveSharpening needs frames of at least 8x8");
-    const int halo = a.do_sharpen ? US_HALO : 0;
-    const UpsharpSmem L = upsharp_layout(halo, a.max_src_rows, a.max_src_cols, a.do_sharpen);
+    const UpsharpSmem L = upsharp_layout(do_resize, do_sharpen, a.max_src_rows, a.max_src_cols);
     if (L.total > 200 * 1024) return fail(c, VP_ERR_UNSUPPORTED, "resize ratio needs more shared memory than a CTA has");
     const dim3 grid((a.dw + US_TW - 1) / US_TW, (a.dh + US_TH - 1) / US_TH);
     ProfScope ps(c, K_UPSHARP, st);
-    k_upsharp<<<grid, US_NT, L.total, st>>>(a);
+    if (!do_sharpen) k_upsharp<true, false, 5><<<grid, US_NT, L.total, st>>>(a);
+    else if (do_resize) {
+        if (a.gk == 3) k_upsharp<true, true, 3><<<grid, US_NT, L.total, st>>>(a);
+        else if (a.gk == 5) k_upsharp<true, true, 5><<<grid, US_NT, L.total, st>>>(a);
+        else k_upsharp<true, true, 7><<<grid, US_NT, L.total, st>>>(a);
+    } else {
+        if (a.gk == 3) k_upsharp<false, true, 3><<<grid, US_NT, L.total, st>>>(a);
+        else if (a.gk == 5) k_upsharp<false, true, 5><<<grid, US_NT, L.total, st>>>(a);
+        else k_upsharp<false, true, 7><<<grid, US_NT, L.total, st>>>(a);
+    }
     VP_CUDA(c, cudaGetLastError());
     c->launches++;
     return VP_OK;
@@ -351,7 +368,7 @@ void vp_destroy(vp_ctx* c) {
     for (auto& e : c->prof_pool) cudaEventDestroy(e);
     cudaFree(c->d_pre); cudaFree(c->d_sharp);
     for (auto& p : c->d_state) cudaFree(p);
-    cudaFree(c->d_sums); cudaFree(c->d_sel);
+    cudaFree(c->d_sums); cudaFree(c->d_sel); cudaFree(c->d_counter);
     cudaFree(c->d_cand_pre); cudaFree(c->d_cand_post); cudaFree(c->d_cand_tmp); cudaFree(c->d_cand_sel);
     free_resize(c->rc_chain); free_resize(c->rc_tmp);
     cudaFree(c->d_siglut); cudaFree(c->d_siglut_tmp);
@@ -369,11 +386,19 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
     VP_CUDA(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
     VP_CUDA(c, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
     VP_CUDA(c, cudaFuncSetAttribute(k_bilateral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bil_smem_bytes(BIL_RMAX)));
-    VP_CUDA(c, cudaFuncSetAttribute(k_upsharp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<false, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<false, true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaMalloc(&c->d_sums, 18 * sizeof(unsigned long long)));
     VP_CUDA(c, cudaMemset(c->d_sums, 0, 18 * sizeof(unsigned long long)));
     VP_CUDA(c, cudaMalloc(&c->d_sel, 4 * sizeof(int)));
     VP_CUDA(c, cudaMemset(c->d_sel, 0, 4 * sizeof(int)));
+    VP_CUDA(c, cudaMalloc(&c->d_counter, 4 * sizeof(unsigned)));
+    VP_CUDA(c, cudaMemset(c->d_counter, 0, 4 * sizeof(unsigned)));
     VP_CUDA(c, cudaMalloc(&c->d_cand_tmp, sizeof(BilCand)));
     VP_CUDA(c, cudaMalloc(&c->d_cand_sel, 3 * sizeof(BilCand)));
     if (!cfg) return VP_OK;
@@ -502,11 +527,13 @@ int vp_process_device(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t
     const uint8_t* cur = d_src; size_t cur_pitch = src_pitch;
     // 1. SelectiveBilateral PRE (src resolution)
     if (g.use_pre) {
-        if (need_pre_stats) { rc = launch_stats(c, cur, cur_pitch, g.src_w, g.src_h, c->d_sums, st); if (rc) return rc; }
+        if (need_pre_stats) {
+            rc = launch_stats(c, cur, cur_pitch, g.src_w, g.src_h, c->d_sums, SelOut{c->d_counter, c->d_sel, (double)g.src_w * g.src_h}, st);
+            if (rc) return rc;
+        }
         BilArgs a{};
         a.src = cur; a.spitch = cur_pitch; a.dst = c->d_pre; a.dpitch = c->pre_pitch; a.w = g.src_w; a.h = g.src_h;
-        a.cand = c->d_cand_pre; a.sums = need_pre_stats ? c->d_sums : nullptr; a.npx = (double)g.src_w * g.src_h;
-        a.sel_out = c->d_sel;
+        a.cand = c->d_cand_pre; a.sel = need_pre_stats ? c->d_sel : nullptr;
         rc = launch_bilateral(c, a, c->cand_pre_rmax, st, K_BIL_PRE); if (rc) return rc;
         cur = c->d_pre; cur_pitch = c->pre_pitch;
     }
@@ -518,7 +545,6 @@ int vp_process_device(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t
         a.src = cur; a.spitch = cur_pitch; a.sw = g.src_w; a.sh = g.src_h;
         a.dst = last_is_upsharp ? d_dst : c->d_sharp; a.dpitch = last_is_upsharp ? dst_pitch : c->frame_pitch;
         a.dw = g.dst_w; a.dh = g.dst_h;
-        a.do_resize = do_resize; a.do_sharpen = g.use_sharpen;
         const int k = g.use_sharpen ? 1 : 0, halo = g.use_sharpen ? US_HALO : 0;
         if (do_resize) {
             a.rt = ResizeTables{c->rc_chain.xofs, c->rc_chain.xcoef, c->rc_chain.yofs, c->rc_chain.ycoef};
@@ -528,10 +554,12 @@ int vp_process_device(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t
         }
         if (g.use_sharpen) { rc = fill_sharpen_args(c, a, g.sharpen); if (rc) return rc; a.sig_lut = c->d_siglut; }
         a.sums = need_post_stats ? c->d_sums + 6 : nullptr;
-        rc = launch_upsharp(c, a, st); if (rc) return rc;
+        if (need_post_stats) a.fin = SelOut{c->d_counter + 1, c->d_sel + 1, (double)g.dst_w * g.dst_h};
+        rc = launch_upsharp(c, a, do_resize, g.use_sharpen != 0, st); if (rc) return rc;
         cur = a.dst; cur_pitch = a.dpitch;
     } else if (need_post_stats) {
-        rc = launch_stats(c, cur, cur_pitch, g.dst_w, g.dst_h, c->d_sums + 6, st); if (rc) return rc;
+        rc = launch_stats(c, cur, cur_pitch, g.dst_w, g.dst_h, c->d_sums + 6, SelOut{c->d_counter + 1, c->d_sel + 1, (double)g.dst_w * g.dst_h}, st);
+        if (rc) return rc;
     }
     // temporal bookkeeping (host side: which ring slots hold t-1, t-2)
     BlendArgs bl{};
@@ -549,8 +577,7 @@ int vp_process_device(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t
     if (g.use_post) {
         BilArgs a{};
         a.src = cur; a.spitch = cur_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.w = g.dst_w; a.h = g.dst_h;
-        a.cand = c->d_cand_post; a.sums = need_post_stats ? c->d_sums + 6 : nullptr; a.npx = (double)g.dst_w * g.dst_h;
-        a.sel_out = c->d_sel + 1;
+        a.cand = c->d_cand_post; a.sel = need_post_stats ? c->d_sel + 1 : nullptr;
         a.blend = bl;
         rc = launch_bilateral(c, a, c->cand_post_rmax, st, K_BIL_POST); if (rc) return rc;
     } else if (temporal) {
@@ -692,9 +719,8 @@ int vp_bicubic(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, int src_w, int
     a.src = d_src; a.spitch = src_pitch; a.sw = src_w; a.sh = src_h;
     a.dst = d_dst; a.dpitch = dst_pitch; a.dw = dst_w; a.dh = dst_h;
     a.rt = ResizeTables{rcache.xofs, rcache.xcoef, rcache.yofs, rcache.ycoef};
-    a.do_resize = 1; a.do_sharpen = 0;
     a.max_src_rows = rcache.max_rows[0]; a.max_src_cols = rcache.max_cols[0];
-    return launch_upsharp(c, a, st);
+    return launch_upsharp(c, a, true, false, st);
 }
 
 int vp_bilateral(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t* d_dst, size_t dst_pitch,
@@ -714,7 +740,7 @@ int vp_bilateral(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t* d_d
     }
     BilArgs a{};
     a.src = d_src; a.spitch = src_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.w = w; a.h = h;
-    a.cand = c->d_cand_tmp; a.npx = (double)w * h;
+    a.cand = c->d_cand_tmp;
     return launch_bilateral(c, a, c->tmp_r, st);
 }
 
@@ -734,12 +760,11 @@ int vp_selective_bilateral(vp_ctx* c, const vp_bilateral_config* cfg, const uint
     unsigned long long* sums = c->d_sums + 12;
     if (cfg->adaptive_params) {
         VP_CUDA(c, cudaMemsetAsync(sums, 0, 6 * sizeof(unsigned long long), st));
-        rc = launch_stats(c, d_src, src_pitch, w, h, sums, st); if (rc) return rc;
+        rc = launch_stats(c, d_src, src_pitch, w, h, sums, SelOut{c->d_counter + 2, c->d_sel + 2, (double)w * h}, st); if (rc) return rc;
     }
     BilArgs a{};
     a.src = d_src; a.spitch = src_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.w = w; a.h = h;
-    a.cand = c->d_cand_sel; a.sums = cfg->adaptive_params ? sums : nullptr; a.npx = (double)w * h;
-    a.sel_out = c->d_sel + 2;
+    a.cand = c->d_cand_sel; a.sel = cfg->adaptive_params ? c->d_sel + 2 : nullptr;
     return launch_bilateral(c, a, c->tmp_sel_rmax, st);
 }
 
@@ -749,7 +774,7 @@ int vp_mean_stddev_sums(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, int w
     VP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
     VP_CUDA(c, cudaMemsetAsync(d_sums, 0, 6 * sizeof(uint64_t), st));
-    return launch_stats(c, d_src, src_pitch, w, h, reinterpret_cast<unsigned long long*>(d_sums), st);
+    return launch_stats(c, d_src, src_pitch, w, h, reinterpret_cast<unsigned long long*>(d_sums), SelOut{nullptr, nullptr, 0.0}, st);
 }
 
 static int sharpen_common(vp_ctx* c, const vp_sharpen_config* cfg, const uint8_t* d_src, size_t src_pitch,
@@ -768,10 +793,9 @@ static int sharpen_common(vp_ctx* c, const vp_sharpen_config* cfg, const uint8_t
     a.sig_lut = c->d_siglut_tmp;
     a.src = d_src; a.spitch = src_pitch; a.sw = w; a.sh = h;
     a.dst = d_dst; a.dpitch = dst_pitch; a.dw = w; a.dh = h;
-    a.do_resize = 0; a.do_sharpen = 1;
     a.max_src_rows = US_TH + 2 * US_HALO; a.max_src_cols = US_TW + 2 * US_HALO;
     a.mask_in = mask_in; a.mask_in_pitch = mask_in_pitch; a.mask_out = mask_out; a.mask_out_pitch = mask_out_pitch;
-    return launch_upsharp(c, a, st);
+    return launch_upsharp(c, a, false, true, st);
 }
 
 int vp_edge_mask(vp_ctx* c, const vp_sharpen_config* cfg, const uint8_t* d_src, size_t src_pitch,
