@@ -47,6 +47,8 @@ struct BilArgs {
     int w, h;
     const BilCand* cand;           // candidates indexed by noise class (or 1 when sel == null)
     const int* sel;                // noise class chosen by the stats producer's last CTA (may be null)
+    int radius[3];                 // radius of each candidate (host copy, saves a dependent global load)
+    int ns;                        // strips per thread: the CTA tile is BIL_TW x (BIL_TH * ns)
     BlendArgs blend;
 };
 
@@ -123,7 +125,7 @@ __device__ __forceinline__ void bil_row(const uint32_t (&seg)[BilGeom<R>::NSEG],
 #pragma unroll
         for (int j = 0; j < BIL_PX; ++j) {
             const int i = j + dx + XM;
-            const unsigned n = __dp4a(__vabsdiffu4(seg[i + R - XM], ctr[j]), 0x01010101u, 0u);
+            const unsigned n = __vsadu4(seg[i + R - XM], ctr[j]);   // VABSDIFF4.ACC: |db|+|dg|+|dr|
             const float wgt = __fmul_rn(sw, s_cw[n]);
             ws[j] = __fadd_rn(ws[j], wgt);
             sb[j] = __fmaf_rn(fb[i], wgt, sb[j]);
@@ -179,38 +181,40 @@ __device__ __forceinline__ void bil_strip(const uint32_t* __restrict__ s_tile, c
     }
 }
 
-// shared memory: [ tile words | space_w | color_w | xmax | raw bytes | mbarrier ]
+// dynamic shared memory: [ tile words | space_w | xmax | raw bytes | mbarrier ]; the colour LUT is static
+// shared memory so its base folds into the LDS immediate
 __host__ __device__ inline int bil_tile_pitch(int r) { return (BIL_TW + 2 * r + 3) & ~3; }
 __host__ __device__ inline int bil_raw_pitch(int r) { return (((BIL_TW + 2 * r) * 3 + 15 + 15) & ~15) + 16; }
 __host__ __device__ inline int bil_sw_words(int r) { return ((2 * r + 1) * (2 * r + 1) + 3) & ~3; }
-__host__ inline size_t bil_smem_bytes(int r) {
-    size_t tile = (size_t)bil_tile_pitch(r) * (BIL_TH + 2 * r) * 4;
-    size_t raw = (size_t)bil_raw_pitch(r) * (BIL_TH + 2 * r);
-    return tile + bil_sw_words(r) * 4 + 768 * 4 + 16 * 4 + raw + 16;
+__host__ inline size_t bil_smem_bytes(int r, int ns) {
+    size_t tile = (size_t)bil_tile_pitch(r) * (BIL_TH * ns + 2 * r) * 4;
+    size_t raw = (size_t)bil_raw_pitch(r) * (BIL_TH * ns + 2 * r);
+    return tile + bil_sw_words(r) * 4 + 16 * 4 + raw + 16;
 }
 
 __global__ void __launch_bounds__(BIL_NT, 3) k_bilateral(const BilArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ float s_cw[768];
     const int tid = threadIdx.x;
     const int sel = a.sel ? *a.sel : 0;
     const BilCand* __restrict__ cand = a.cand + sel;
-    const int R = cand->radius;
+    const int R = a.radius[sel];
     const int D = 2 * R + 1;
     const int TP = bil_tile_pitch(R);
-    const int TROWS = BIL_TH + 2 * R;
+    const int TH = BIL_TH * a.ns;
+    const int TROWS = TH + 2 * R;
     const int RP = bil_raw_pitch(R);
 
     uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem);
     float* s_sw = reinterpret_cast<float*>(smem + (size_t)TP * TROWS * 4);
-    float* s_cw = s_sw + bil_sw_words(R);
-    int* s_xm = reinterpret_cast<int*>(s_cw + 768);
+    int* s_xm = reinterpret_cast<int*>(s_sw + bil_sw_words(R));
     uint8_t* s_raw = reinterpret_cast<uint8_t*>(s_xm + 16);
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_raw + (size_t)RP * TROWS);
 
-    const int x0 = blockIdx.x * BIL_TW, y0 = blockIdx.y * BIL_TH;
+    const int x0 = blockIdx.x * BIL_TW, y0 = blockIdx.y * TH;
     // valid source window (image coordinates) the halo tile touches
     const int vx0 = max(x0 - R, 0), vx1 = min(x0 + BIL_TW + R, a.w);
-    const int vy0 = max(y0 - R, 0), vy1 = min(y0 + BIL_TH + R, a.h);
+    const int vy0 = max(y0 - R, 0), vy1 = min(y0 + TH + R, a.h);
     const int bx0 = (vx0 * 3) & ~15, bx1 = vx1 * 3;
     const bool fast = aligned16(a.src, a.spitch);
 
@@ -245,41 +249,49 @@ __global__ void __launch_bounds__(BIL_NT, 3) k_bilateral(const BilArgs a) {
     }
     __syncthreads();
 
-    const int lx = (tid & 15) * BIL_PX, ly = tid >> 4;
-    const int gx = x0 + lx, gy = y0 + ly;
-    if (gy >= a.h || gx >= a.w) return;
-    uint32_t out[BIL_PX];
-    switch (R) {
-        case 1: bil_strip<1>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
-        case 2: bil_strip<2>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
-        case 3: bil_strip<3>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
-        case 4: bil_strip<4>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
-        case 5: bil_strip<5>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
-        case 6: bil_strip<6>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
-        default: bil_strip<7>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
-    }
-
-    // epilogue: optional temporal blend, state store, output store (12 contiguous bytes per strip)
-    const int npx = min(BIL_PX, a.w - gx);
     const BlendArgs& b = a.blend;
-    uint32_t cur[3];   // 12 packed bytes B G R B | G R B G | R B G R
-    cur[0] = (out[0] & 0xffffffu) | (out[1] << 24);
-    cur[1] = ((out[1] >> 8) & 0xffffu) | (out[2] << 16);
-    cur[2] = ((out[2] >> 16) & 0xffu) | (out[3] << 8);
+    const bool doblend = a.dst && b.mode != 0 && b.nprev > 0;
+    const int lx = (tid & 15) * BIL_PX;
+    const int gx = x0 + lx;
+    if (gx >= a.w) return;
+    const int npx = min(BIL_PX, a.w - gx);
     const size_t boff = (size_t)gx * 3;
-    if (b.state) store12(b.state + (size_t)gy * b.spitch + boff, cur, npx);
-    if (!a.dst) return;
-    uint8_t* dp = a.dst + (size_t)gy * a.dpitch + boff;
-    if (b.mode != 0 && b.nprev > 0) {
-        uint32_t p0[3], p1[3], o[3];
-        load12(b.prev[0] + (size_t)gy * b.ppitch + boff, p0, npx);
-        if (b.nprev > 1) load12(b.prev[1] + (size_t)gy * b.ppitch + boff, p1, npx);
-        else { p1[0] = p0[0]; p1[1] = p0[1]; p1[2] = p0[2]; }
+    for (int s = 0; s < a.ns; ++s) {
+        const int ly = (tid >> 4) + s * BIL_TH;
+        const int gy = y0 + ly;
+        if (gy >= a.h) break;
+        // previous frames of the temporal blend: issue the loads before the tap loop hides their latency
+        uint32_t p0[3] = {0, 0, 0}, p1[3] = {0, 0, 0};
+        if (doblend) {
+            load12(b.prev[0] + (size_t)gy * b.ppitch + boff, p0, npx);
+            if (b.nprev > 1) load12(b.prev[1] + (size_t)gy * b.ppitch + boff, p1, npx);
+        }
+        uint32_t out[BIL_PX];
+        switch (R) {
+            case 1: bil_strip<1>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
+            case 2: bil_strip<2>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
+            case 3: bil_strip<3>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
+            case 4: bil_strip<4>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
+            case 5: bil_strip<5>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
+            case 6: bil_strip<6>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
+            default: bil_strip<7>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
+        }
+        // epilogue: optional temporal blend, state store, output store (12 contiguous bytes per strip)
+        uint32_t cur[3];   // 12 packed bytes B G R B | G R B G | R B G R
+        cur[0] = (out[0] & 0xffffffu) | (out[1] << 24);
+        cur[1] = ((out[1] >> 8) & 0xffffu) | (out[2] << 16);
+        cur[2] = ((out[2] >> 16) & 0xffu) | (out[3] << 8);
+        if (b.state) store12(b.state + (size_t)gy * b.spitch + boff, cur, npx);
+        if (!a.dst) continue;
+        uint8_t* dp = a.dst + (size_t)gy * a.dpitch + boff;
+        if (doblend) {
+            uint32_t o[3];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) o[q] = blend_word(b, cur[q], p0[q], p1[q]);
-        store12(dp, o, npx);
-    } else {
-        store12(dp, cur, npx);
+            for (int q = 0; q < 3; ++q) o[q] = blend_word(b, cur[q], p0[q], b.nprev > 1 ? p1[q] : p0[q]);
+            store12(dp, o, npx);
+        } else {
+            store12(dp, cur, npx);
+        }
     }
 }
 

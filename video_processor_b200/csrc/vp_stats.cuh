@@ -35,9 +35,11 @@ struct SelOut {
 __device__ __forceinline__ void flush_and_finalize(unsigned long long* s_red, unsigned long long* __restrict__ sums,
                                                    const SelOut f, unsigned nblocks) {
     __shared__ bool s_last;
-    if (threadIdx.x < 6 && s_red[threadIdx.x]) atomicAdd(&sums[threadIdx.x], s_red[threadIdx.x]);
+    if (threadIdx.x < 6) {
+        if (s_red[threadIdx.x]) atomicAdd(&sums[threadIdx.x], s_red[threadIdx.x]);
+        if (f.counter) __threadfence();      // only the threads that published need the fence
+    }
     if (!f.counter) return;
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned ticket = atomicAdd(f.counter, 1u);

@@ -65,10 +65,10 @@ struct vp_ctx {
     int* d_sel = nullptr;                                   // [0] PRE class, [1] POST class, [2] stage-wise
     unsigned* d_counter = nullptr;                          // CTA ticket counters of the three sel producers
     BilCand* d_cand_pre = nullptr; BilCand* d_cand_post = nullptr; BilCand* d_cand_tmp = nullptr;
-    int cand_pre_rmax = 0, cand_post_rmax = 0;
+    int cand_pre_rad[3] = {0, 0, 0}, cand_post_rad[3] = {0, 0, 0};
     // cached stage-wise tables
     int tmp_d = -1; double tmp_sc = 0, tmp_ss = 0; int tmp_r = 0;
-    vp_bilateral_config tmp_sel_cfg{}; bool tmp_sel_valid = false; int tmp_sel_rmax = 0;
+    vp_bilateral_config tmp_sel_cfg{}; bool tmp_sel_valid = false; int tmp_sel_rad[3] = {0, 0, 0};
     BilCand* d_cand_sel = nullptr;
     ResizeCache rc_chain, rc_tmp;
     float* d_siglut = nullptr; float siglut_thr = -1e30f; bool siglut_valid = false;
@@ -141,7 +141,7 @@ void fill_cand(BilCand& bc, const vp_host::BilateralTables& t) {
     std::memcpy(bc.color_w, t.color_w.data(), 768 * sizeof(float));
 }
 
-int build_selective_cands(vp_ctx* c, const vp_bilateral_config& cfg, BilCand* d_cand, int* rmax, cudaStream_t st) {
+int build_selective_cands(vp_ctx* c, const vp_bilateral_config& cfg, BilCand* d_cand, int radius[3], cudaStream_t st) {
     std::vector<BilCand> h(3);
     int rm = 0;
     for (int cls = 0; cls < 3; ++cls) {
@@ -153,11 +153,12 @@ int build_selective_cands(vp_ctx* c, const vp_bilateral_config& cfg, BilCand* d_
         if (t.radius > BIL_RMAX)
             return fail(c, VP_ERR_UNSUPPORTED, "bilateral radius > 7 (diameter > 15) is not built");
         fill_cand(h[cls], t);
+        radius[cls] = t.radius;
         rm = t.radius > rm ? t.radius : rm;
     }
+    (void)rm;
     VP_CUDA(c, cudaMemcpyAsync(d_cand, h.data(), 3 * sizeof(BilCand), cudaMemcpyHostToDevice, st));
     VP_CUDA(c, cudaStreamSynchronize(st));
-    *rmax = rm;
     return VP_OK;
 }
 
@@ -227,10 +228,13 @@ int launch_stats(vp_ctx* c, const uint8_t* src, size_t pitch, int w, int h, unsi
     return VP_OK;
 }
 
-int launch_bilateral(vp_ctx* c, BilArgs& a, int rmax, cudaStream_t st, int kind = K_BIL_OTHER) {
+int launch_bilateral(vp_ctx* c, BilArgs& a, const int radius[3], cudaStream_t st, int kind = K_BIL_OTHER) {
     ProfScope ps(c, kind, st);
-    const dim3 grid((a.w + BIL_TW - 1) / BIL_TW, (a.h + BIL_TH - 1) / BIL_TH);
-    k_bilateral<<<grid, BIL_NT, bil_smem_bytes(rmax), st>>>(a);
+    int rmax = 0;
+    for (int i = 0; i < 3; ++i) { a.radius[i] = radius[i]; rmax = std::max(rmax, radius[i]); }
+    a.ns = rmax <= 3 ? 2 : 1;     // small windows: taller tiles amortise the per-CTA table/halo cost
+    const dim3 grid((a.w + BIL_TW - 1) / BIL_TW, (a.h + BIL_TH * a.ns - 1) / (BIL_TH * a.ns));
+    k_bilateral<<<grid, BIL_NT, bil_smem_bytes(rmax, a.ns), st>>>(a);
     VP_CUDA(c, cudaGetLastError());
     c->launches++;
     return VP_OK;
@@ -385,7 +389,7 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
     VP_CUDA(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     VP_CUDA(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
     VP_CUDA(c, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
-    VP_CUDA(c, cudaFuncSetAttribute(k_bilateral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bil_smem_bytes(BIL_RMAX)));
+    VP_CUDA(c, cudaFuncSetAttribute(k_bilateral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(bil_smem_bytes(BIL_RMAX, 1), bil_smem_bytes(3, 2))));
     VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -417,12 +421,12 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
     if (g.use_pre) {
         VP_CUDA(c, cudaMalloc(&c->d_pre, c->pre_pitch * g.src_h));
         VP_CUDA(c, cudaMalloc(&c->d_cand_pre, 3 * sizeof(BilCand)));
-        int rc = build_selective_cands(c, g.pre, c->d_cand_pre, &c->cand_pre_rmax, c->s_compute);
+        int rc = build_selective_cands(c, g.pre, c->d_cand_pre, c->cand_pre_rad, c->s_compute);
         if (rc) return rc;
     }
     if (g.use_post) {
         VP_CUDA(c, cudaMalloc(&c->d_cand_post, 3 * sizeof(BilCand)));
-        int rc = build_selective_cands(c, g.post, c->d_cand_post, &c->cand_post_rmax, c->s_compute);
+        int rc = build_selective_cands(c, g.post, c->d_cand_post, c->cand_post_rad, c->s_compute);
         if (rc) return rc;
     }
     VP_CUDA(c, cudaMalloc(&c->d_sharp, c->frame_pitch * g.dst_h));
@@ -534,7 +538,7 @@ int vp_process_device(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t
         BilArgs a{};
         a.src = cur; a.spitch = cur_pitch; a.dst = c->d_pre; a.dpitch = c->pre_pitch; a.w = g.src_w; a.h = g.src_h;
         a.cand = c->d_cand_pre; a.sel = need_pre_stats ? c->d_sel : nullptr;
-        rc = launch_bilateral(c, a, c->cand_pre_rmax, st, K_BIL_PRE); if (rc) return rc;
+        rc = launch_bilateral(c, a, c->cand_pre_rad, st, K_BIL_PRE); if (rc) return rc;
         cur = c->d_pre; cur_pitch = c->pre_pitch;
     }
     // 2+3. bicubic resize + AdaptiveSharpening (dst resolution)
@@ -579,7 +583,7 @@ int vp_process_device(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t
         a.src = cur; a.spitch = cur_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.w = g.dst_w; a.h = g.dst_h;
         a.cand = c->d_cand_post; a.sel = need_post_stats ? c->d_sel + 1 : nullptr;
         a.blend = bl;
-        rc = launch_bilateral(c, a, c->cand_post_rmax, st, K_BIL_POST); if (rc) return rc;
+        rc = launch_bilateral(c, a, c->cand_post_rad, st, K_BIL_POST); if (rc) return rc;
     } else if (temporal) {
         BlendKArgs a{};
         a.cur = cur; a.cpitch = cur_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.row_bytes = g.dst_w * 3; a.h = g.dst_h;
@@ -741,7 +745,8 @@ int vp_bilateral(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t* d_d
     BilArgs a{};
     a.src = d_src; a.spitch = src_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.w = w; a.h = h;
     a.cand = c->d_cand_tmp;
-    return launch_bilateral(c, a, c->tmp_r, st);
+    const int rad[3] = {c->tmp_r, c->tmp_r, c->tmp_r};
+    return launch_bilateral(c, a, rad, st);
 }
 
 int vp_selective_bilateral(vp_ctx* c, const vp_bilateral_config* cfg, const uint8_t* d_src, size_t src_pitch,
@@ -754,7 +759,7 @@ int vp_selective_bilateral(vp_ctx* c, const vp_bilateral_config* cfg, const uint
     if (!c->tmp_sel_valid || std::memcmp(&c->tmp_sel_cfg, cfg, sizeof(*cfg)) != 0) {
         VP_CUDA(c, cudaStreamSynchronize(st));
         c->tmp_sel_valid = false;
-        rc = build_selective_cands(c, *cfg, c->d_cand_sel, &c->tmp_sel_rmax, st); if (rc) return rc;
+        rc = build_selective_cands(c, *cfg, c->d_cand_sel, c->tmp_sel_rad, st); if (rc) return rc;
         c->tmp_sel_cfg = *cfg; c->tmp_sel_valid = true;
     }
     unsigned long long* sums = c->d_sums + 12;
@@ -765,7 +770,7 @@ int vp_selective_bilateral(vp_ctx* c, const vp_bilateral_config* cfg, const uint
     BilArgs a{};
     a.src = d_src; a.spitch = src_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.w = w; a.h = h;
     a.cand = c->d_cand_sel; a.sel = cfg->adaptive_params ? c->d_sel + 2 : nullptr;
-    return launch_bilateral(c, a, c->tmp_sel_rmax, st);
+    return launch_bilateral(c, a, c->tmp_sel_rad, st);
 }
 
 int vp_mean_stddev_sums(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, int w, int h, uint64_t* d_sums, void* stream) {
