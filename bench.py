@@ -269,7 +269,10 @@ def main():
     sw, sh, dw, dh = WORKLOADS[wl][:4]
     chain_bytes, kbytes, inb, outb = algorithmic_bytes(wl, temporal, cfg)
     F = args.frames
-    warm = {"none": 0, "main": 1, "frames": max(cfg.temporal.buffer_size - 1, 0)}[temporal] if rank > 0 else 0
+    from video_processor_b200 import sharding
+    # weak scaling: the clip has world*F frames, rank k owns [k*F, (k+1)*F) and first feeds the warm-up frames
+    first, warm, seg_start, seg_stop = sharding.plan(world * F, world, rank, temporal, cfg.temporal.buffer_size)
+    assert (seg_start, seg_stop) == (rank * F, (rank + 1) * F)
 
     # device-resident clip segment of this rank: frames [rank*F - warm, (rank+1)*F)
     seg = [torch_frame(args.kind, sw, sh, rank * F - warm + i, SEED, dev) for i in range(F + warm)]

@@ -1,0 +1,47 @@
+// temporal_consistency.h - TemporalConsistency with the reference's interface
+// (reference include/temporal_consistency.h:16-141).
+//
+// Built: the frame-buffer policy of process() (src/temporal_consistency.cpp:61-172) and blendFrames
+// (:355-444, with the float32 accumulator the code evidently intends; the literal code writes Vec3f
+// into a CV_8UC3 Mat, :367 vs :408).  The optical-flow / warp / scene-change front end is outside the
+// hot path: previous frames enter the blend unwarped with reliability 1, the
+// flow fields of Config are carried but unused.
+#pragma once
+#include <memory>
+#include <mutex>
+#include "vp/mat.h"
+
+class TemporalConsistency {
+public:
+    struct Config {                       // field order is ABI
+        int buffer_size = 3;
+        float blend_strength = 0.6f;
+        float motion_threshold = 15.0f;
+        float scene_change_threshold = 100.0f;
+        bool use_gpu = true;
+        double pyr_scale = 0.5;
+        int levels = 3;
+        int winsize = 15;
+        int iterations = 3;
+        int poly_n = 5;
+        double poly_sigma = 1.2;
+        int flags = 0;
+    };
+
+    TemporalConsistency();
+    explicit TemporalConsistency(const Config& config);
+    ~TemporalConsistency();
+
+    bool initialize();
+    bool process(const cv::Mat& input, cv::Mat& output);
+    void reset();
+    void setConfig(const Config& config);
+    Config getConfig() const;
+
+private:
+    struct Impl;
+    Config m_config;
+    bool m_initialized = false;
+    std::mutex m_buffer_mutex;            // the reference guards its deques the same way (:77)
+    std::unique_ptr<Impl> m_impl;
+};

@@ -1,0 +1,203 @@
+"""CPU-only checks of the host side: the C ABI library loads and exports every symbol the header
+declares, the host-built tables equal the oracle's restatement of OpenCV's formulas bit for bit, the
+C++ API refuses cleanly without a GPU, and the frame-segment sharding (incl. a world_size-2 gloo run)
+reproduces the single-process result."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import ref_chain as RC
+from oracle import restate as R
+from oracle import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+# ---- C ABI ----------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol(vp):
+    hdr = open(os.path.join(ROOT, "include", "vpb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(vp_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"vp_ctx"}
+    assert declared == set(vp.PROTOTYPES), declared ^ set(vp.PROTOTYPES)
+    for name in declared:
+        assert hasattr(vp.lib, name)
+    assert vp.lib.vp_abi_version() == 1
+
+
+def test_struct_layout_matches_header(vp):
+    import ctypes as C
+    # doubles 8-aligned behind the reserved word; the chain config is a plain concatenation
+    assert C.sizeof(vp.BilateralConfig) == 32 and vp.BilateralConfig.sigma_color.offset == 16
+    assert C.sizeof(vp.SharpenConfig) == 28 and C.sizeof(vp.TemporalConfig) == 16
+    assert vp.ChainConfig.pre.offset == 32 and vp.ChainConfig.post.offset == 96
+    cfg = vp.default_chain_config(1920, 1080, 3840, 2160)
+    assert (cfg.pre.diameter, cfg.pre.sigma_color, cfg.post.diameter, cfg.post.sigma_space) == (7, 30.0, 5, 20.0)
+    assert (cfg.sharpen.kernel_size, cfg.temporal.mode, cfg.temporal.buffer_size) == (5, vp.VP_TEMPORAL_BLEND_FRAMES, 3)
+    assert abs(cfg.sharpen.strength - 0.8) < 1e-7 and abs(cfg.temporal.blend_strength - 0.6) < 1e-7
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device behaviour")
+def test_no_cpu_fallback(vp):
+    assert vp.lib.vp_device_count() == 0
+    with pytest.raises(vp.VpError) as e:
+        vp.Context(vp.default_chain_config(64, 64, 128, 128))
+    assert e.value.code == vp.VP_ERR_NO_DEVICE
+    assert vp.lib.vp_process_device(None, None, 0, None, 0, None) == vp.VP_ERR_INVALID_ARG
+
+
+# ---- host tables ----------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def dump(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("bin") / "tables_dump")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I", os.path.join(ROOT, "video_processor_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "cpp", "tables_dump.cpp"), "-o", exe], check=True)
+    return lambda *a: json.loads(subprocess.run([exe, *map(str, a)], check=True, capture_output=True, text=True).stdout)
+
+
+def _f32(bits):
+    return np.array(bits, dtype=np.uint32).view(np.float32)
+
+
+@pytest.mark.parametrize("s,d", [(1920, 3840), (1080, 2160), (960, 3840), (540, 2160), (131, 262), (67, 268), (100, 300), (77, 100)])
+def test_cubic_tables(dump, s, d):
+    t = dump("cubic", s, d)
+    ofs, coef = R.cubic_coeffs(s, d)
+    assert t["ofs"] == ofs.tolist() and t["coef"] == coef.reshape(-1).tolist()
+
+
+@pytest.mark.parametrize("k,sigma", [(5, 1.5), (3, 0.5), (7, 2.5), (3, 0.8), (5, 1.0)])
+def test_gaussian_tables(dump, k, sigma):
+    t = dump("gauss", k, sigma)
+    assert t["q"] == R.gaussian_kernel_q8(k, sigma).tolist()
+    assert np.array_equal(_f32(t["f32"]), R.gaussian_kernel_f64(k, sigma).astype(np.float32))
+
+
+@pytest.mark.parametrize("d,sc,ss", [(5, 24.0, 24.0), (11, 45.0, 45.0), (3, 16.8, 16.8), (15, 45.0, 45.0), (4, 10.0, 50.0)])
+def test_bilateral_tables(dump, d, sc, ss):
+    t = dump("bilateral", d, sc, ss)
+    radius, taps, space_w, color_w = R.bilateral_tables(d, sc, ss)
+    assert t["radius"] == radius
+    assert np.array_equal(_f32(t["color"]), color_w)
+    D = 2 * radius + 1
+    dense = _f32(t["space"]).reshape(D, D)
+    ref = np.zeros((D, D), np.float32)
+    for (i, j), w in zip(taps, space_w):
+        ref[i + radius, j + radius] = w
+    assert np.array_equal(dense, ref)
+
+
+def test_sigmoid_table(dump):
+    assert np.array_equal(_f32(dump("sigmoid", 30.0)["lut"]), R.sigmoid_lut(30.0))
+    assert np.array_equal(_f32(dump("sigmoid", 12.5)["lut"]), R.sigmoid_lut(12.5))
+
+
+@pytest.mark.parametrize("stage,d,s", [(0, 7, 30.0), (1, 5, 20.0), (1, 7, 30.0), (0, 9, 12.0)])
+def test_adaptive_param_classes(dump, stage, d, s):
+    cfg = RC.BilateralConfig(stage, True, True, d, s, s, False, 30.0, 1.5, 2.0, False, 3)
+    for cls, std in ((0, 2.0), (1, 10.0), (2, 40.0)):
+        t = dump("adaptive", cls, stage, d, s, s)
+        assert (t["d"], t["sc"], t["ss"]) == RC.adaptive_params_from_std(std, cfg)
+
+
+# ---- C++ API without a GPU --------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def api_driver(vp, tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("bin") / "api_driver")
+    libdir = os.path.join(ROOT, "video_processor_b200")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-DVP_FORCE_MAT_SHIM", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "api_driver.cpp"), "-o", exe, "-L", libdir, "-lvpb200",
+                    f"-Wl,-rpath,{libdir}", "-lpthread"], check=True)
+    return exe
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device behaviour")
+def test_cpp_api_refuses_without_gpu(api_driver):
+    r = subprocess.run([api_driver, "nogpu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "no CPU" in r.stderr
+
+
+# ---- sharding --------------------------------------------------------------------------------------
+def test_segments_cover_clip():
+    from video_processor_b200 import sharding as S
+    for n in (1, 7, 64, 300):
+        for world in (1, 2, 4, 8):
+            segs = [S.segment(n, world, r) for r in range(world)]
+            assert segs[0][0] == 0 and segs[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(segs, segs[1:]))
+    assert S.plan(300, 8, 0, "frames", 3) == (0, 0, 0, 37)
+    assert S.plan(300, 8, 3, "frames", 3) == (110, 2, 112, 150)
+    assert S.plan(300, 8, 3, "main") == (111, 1, 112, 150)
+    assert S.plan(4, 4, 1, "frames", 3) == (0, 1, 1, 2)      # warm-up clipped at the start of the clip
+
+
+_WORKER = r"""
+import os, sys, pickle
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from oracle import ref_chain as RC, synth
+from video_processor_b200 import sharding as S
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, world = dist.get_rank(), dist.get_world_size()
+n, sw, sh = 7, 40, 24
+mode = {"frames": RC.TEMPORAL_BLEND_FRAMES, "main": RC.TEMPORAL_MAIN_BLEND}[sys.argv[4]]
+cfg = RC.ChainConfig(dst_w=2 * sw, dst_h=2 * sh, temporal=mode)
+first, warm, start, stop = S.plan(n, world, rank, sys.argv[4], cfg.temporal_cfg.buffer_size)
+chain = RC.Chain(RC.NumpyOps(), cfg)
+outs = {}
+for t in range(first, stop):
+    o = chain.process(synth.frame("scene", sw, sh, t))
+    if t >= start:
+        outs[t] = o
+gathered = [None, None]
+dist.all_gather_object(gathered, outs)
+if rank == 0:
+    full = RC.Chain(RC.NumpyOps(), cfg)
+    merged = {}
+    for g in gathered:
+        merged.update(g)
+    assert sorted(merged) == list(range(n))
+    for t in range(n):
+        assert np.array_equal(full.process(synth.frame("scene", sw, sh, t)), merged[t]), t
+    print("SHARD_OK")
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+@pytest.mark.parametrize("mode", ["frames", "main"])
+def test_gloo_two_rank_segments_match_single_process(tmp_path, mode):
+    """world_size 2 on CPU (gloo): each rank runs the ORACLE chain over its segment + warm-up frames;
+    the gathered outputs equal the single-process run bit for bit (no collective on the data path)."""
+    pytest.importorskip("torch")
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29500 + (os.getpid() % 500) + (0 if mode == "frames" else 501))
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), mode], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "SHARD_OK" in outs[0]
+
+
+def test_bench_synthetic_clip_matches_oracle_synth():
+    torch = pytest.importorskip("torch")
+    import bench
+    for kind in ("noise", "scene", "flat"):
+        a = bench.torch_frame(kind, 96, 40, 3, bench.SEED, torch.device("cpu")).numpy()
+        assert np.array_equal(a, synth.frame(kind, 96, 40, 3, bench.SEED))

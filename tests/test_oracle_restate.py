@@ -1,0 +1,132 @@
+"""Pins oracle/restate.py (the numpy restatement) against the REAL OpenCV kernels through cv2, and
+against the committed golden vectors.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_chain as RC
+from oracle import restate as R
+from oracle import synth
+
+cv2 = pytest.importorskip("cv2")
+cv2.setUseOptimized(True)
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "golden_small.npz")
+
+
+@pytest.mark.parametrize("kind", ["noise", "scene", "flat"])
+@pytest.mark.parametrize("scale", [2, 4])
+@pytest.mark.parametrize("size", [(131, 67), (64, 48), (17, 9)])
+def test_resize_cubic_bit_exact(kind, scale, size):
+    w, h = size
+    img = synth.frame(kind, w, h, 2)
+    ref = cv2.resize(img, (w * scale, h * scale), interpolation=cv2.INTER_CUBIC)
+    assert np.array_equal(R.resize_cubic(img, w * scale, h * scale), ref)
+
+
+def test_resize_cubic_taps():
+    _, c2 = R.cubic_coeffs(100, 200)
+    assert c2[1].tolist() == [-216, 1800, 536, -72] and c2[2].tolist() == [-72, 536, 1800, -216]
+    _, c4 = R.cubic_coeffs(100, 400)
+    assert sorted(map(tuple, c4[4:8].tolist())) == sorted([(-135, 873, 1535, -225), (-21, 235, 1981, -147),
+                                                           (-147, 1981, 235, -21), (-225, 1535, 873, -135)])
+    assert (c4.sum(axis=1) == 2048).all()
+
+
+@pytest.mark.parametrize("k,sigma,q", [(3, 0.5, [27, 202, 27]), (5, 1.5, [31, 60, 74, 60, 31]), (5, 1.0, [14, 62, 104, 62, 14]),
+                                       (5, 0.8, [6, 58, 128, 58, 6]), (5, 2.5, [43, 55, 60, 55, 43]), (3, 0, [64, 128, 64])])
+def test_gaussian_q8_kernels(k, sigma, q):
+    assert R.gaussian_kernel_q8(k, sigma).tolist() == q
+
+
+@pytest.mark.parametrize("k,sigma", [(3, 0.5), (5, 1.5), (7, 2.5), (3, 0.8)])
+def test_gaussian_u8_bit_exact(k, sigma):
+    img = synth.frame("noise", 97, 53, 1)
+    assert np.array_equal(R.gaussian_blur_u8(img, k, sigma), cv2.GaussianBlur(img, (k, k), sigma))
+
+
+def test_color_conversions_bit_exact():
+    img = synth.frame("noise", 211, 97, 3)
+    assert np.array_equal(R.bgr2gray(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+    ycc = cv2.cvtColor(img, cv2.COLOR_BGR2YCrCb)
+    assert np.array_equal(R.bgr2ycrcb(img), ycc)
+    assert np.array_equal(R.ycrcb2bgr(ycc), cv2.cvtColor(ycc, cv2.COLOR_YCrCb2BGR))
+    assert np.array_equal(R.ycrcb2bgr(img), cv2.cvtColor(img, cv2.COLOR_YCrCb2BGR))   # arbitrary triples
+
+
+def test_derivatives_bit_exact():
+    g = synth.frame("noise", 120, 77, 4)[..., 0].copy()
+    assert np.array_equal(R.abs_sat_u8(R.sobel_x(g)), cv2.convertScaleAbs(cv2.Sobel(g, cv2.CV_16S, 1, 0, ksize=3)))
+    assert np.array_equal(R.abs_sat_u8(R.sobel_y(g)), cv2.convertScaleAbs(cv2.Sobel(g, cv2.CV_16S, 0, 1, ksize=3)))
+    assert np.array_equal(R.abs_sat_u8(R.laplacian3(g)), cv2.convertScaleAbs(cv2.Laplacian(g, cv2.CV_16S, ksize=3)))
+
+
+@pytest.mark.parametrize("alpha,beta", [(0.6, 0.4), (0.5, 0.5), (0.7, 0.3)])
+def test_add_weighted_all_pairs(alpha, beta):
+    a = np.repeat(np.arange(256, dtype=np.uint8), 256).reshape(256, 256)
+    b = np.tile(np.arange(256, dtype=np.uint8), 256).reshape(256, 256)
+    assert np.array_equal(R.add_weighted_u8(a, alpha, b, beta), cv2.addWeighted(a, alpha, b, beta, 0))
+
+
+def test_edge_combination_integer_form():
+    """The kernel evaluates RNE(fma(e1, 0.6f, lap*0.4f)) as (6*e1 + 4*lap + 5)//10 and
+    RNE(fma(ax,.5,ay*.5)) as (s + ((s>>1)&1))>>1: exhaustive over all 65,536 pairs."""
+    a = np.repeat(np.arange(256, dtype=np.int64), 256)
+    b = np.tile(np.arange(256, dtype=np.int64), 256)
+    f1 = R.add_weighted_u8(a.astype(np.uint8), 0.6, b.astype(np.uint8), 0.4).astype(np.int64)
+    assert np.array_equal(f1, ((6 * a + 4 * b + 5) * 6554) >> 16)
+    assert np.array_equal(f1, (6 * a + 4 * b + 5) // 10)
+    f2 = R.add_weighted_u8(a.astype(np.uint8), 0.5, b.astype(np.uint8), 0.5).astype(np.int64)
+    s = a + b
+    assert np.array_equal(f2, (s + ((s >> 1) & 1)) >> 1)
+
+
+def test_mean_stddev_matches_cv2():
+    img = synth.frame("scene", 160, 90, 0)
+    m, s, _, _ = R.mean_stddev(img)
+    mc, sc = cv2.meanStdDev(img)
+    assert np.allclose(m, mc.ravel(), rtol=0, atol=1e-9) and np.allclose(s, sc.ravel(), rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("d,sc,ss", [(5, 24, 24), (11, 45, 45), (3, 16, 16)])
+def test_bilateral_within_1lsb_of_cv2(d, sc, ss):
+    img = synth.frame("scene", 120, 70, 1)
+    diff = np.abs(R.bilateral_u8c3(img, d, sc, ss).astype(int) - cv2.bilateralFilter(img, d, sc, ss).astype(int))
+    assert diff.max() <= 1 and (diff > 0).sum() <= img.size // 1000
+
+
+def test_sigmoid_lut_known_values():
+    lut = R.sigmoid_lut(30.0)
+    for u, v in [(0, 0.047425870), (15, 0.18242553), (30, 0.50000006), (45, 0.81757450), (60, 0.95257413), (255, 1.0)]:
+        assert abs(float(lut[u]) - v) < 5e-8
+
+
+@pytest.mark.parametrize("kind", ["noise", "scene"])
+def test_chain_numpy_vs_cv2_backend(kind):
+    """The whole oracle chain over the numpy restatement vs over the real cv2 kernels."""
+    sw, sh = 96, 64
+    cfg = RC.ChainConfig(dst_w=2 * sw, dst_h=2 * sh, temporal=RC.TEMPORAL_BLEND_FRAMES)
+    a, b = RC.Chain(RC.NumpyOps(), cfg), RC.Chain(RC.Cv2Ops(), cfg)
+    for f in synth.clip(kind, sw, sh, 3):
+        x, y = a.process(f), b.process(f)
+        assert RC.psnr(x, y) >= 60.0 and np.abs(x.astype(int) - y.astype(int)).max() <= 4
+
+
+def test_golden_vectors():
+    """Frozen outputs of the oracle (tests/golden/make_golden.py): guards the oracle itself against drift."""
+    g = np.load(GOLD)
+    img = synth.frame("scene", 48, 32, 5)
+    assert np.array_equal(g["scene_48x32_t5"], img)
+    assert np.array_equal(g["bicubic_x2"], R.resize_cubic(img, 96, 64))
+    assert np.array_equal(g["bicubic_x4"], R.resize_cubic(img, 192, 128))
+    assert np.array_equal(g["bilateral_d5"], R.bilateral_u8c3(img, 5, 24.0, 24.0))
+    scfg = RC.SharpenConfig(adaptive_sigma=False)
+    assert np.allclose(g["edge_mask"], RC.edge_mask(RC.NumpyOps(), img, scfg), rtol=0, atol=1e-7)
+    assert np.array_equal(g["sharpen"], RC.sharpen(RC.NumpyOps(), img, scfg))
+    cfg = RC.ChainConfig(dst_w=96, dst_h=64, temporal=RC.TEMPORAL_BLEND_FRAMES)
+    ch = RC.Chain(RC.NumpyOps(), cfg)
+    for t in range(3):
+        assert np.array_equal(g[f"chain_t{t}"], ch.process(synth.frame("scene", 48, 32, t)))
+    # the same vectors out of the real OpenCV kernels
+    assert np.array_equal(g["bicubic_x2"], cv2.resize(img, (96, 64), interpolation=cv2.INTER_CUBIC))
+    assert np.array_equal(g["bicubic_x4"], cv2.resize(img, (192, 128), interpolation=cv2.INTER_CUBIC))
