@@ -58,7 +58,7 @@ bool SelectiveBilateral::process(const cv::Mat& input, cv::Mat& output) {
     c.sigma_color = m_config.sigma_color;
     c.sigma_space = m_config.sigma_space;
     bool ok = vp_host_api::is_bgr8(input) && r.upload(input, input.cols, input.rows, 3);
-    ok = ok && vp_selective_bilateral(r.ctx(), &c, r.d_in(), r.in_pitch(), r.d_out(), r.out_pitch(), input.cols, input.rows, nullptr) == VP_OK;
+    ok = ok && vp_selective_bilateral(r.ctx(), &c, r.d_in(), r.in_pitch(), r.d_out(), r.out_pitch(), input.cols, input.rows, r.stream()) == VP_OK;
     ok = ok && r.download(output, input.cols, input.rows, CV_8UC3, 3);
     if (!ok) {
         std::cerr << "Error in selective bilateral filtering: " << r.error() << std::endl;
@@ -108,7 +108,7 @@ bool AdaptiveSharpening::process(const cv::Mat& input, cv::Mat& output) {
     vp_sharpen_config c{m_config.strength, m_config.edge_strength, m_config.smooth_strength, m_config.edge_threshold,
                         m_config.sigma, m_config.kernel_size, m_config.preserve_tone ? 1 : 0};
     bool ok = vp_host_api::is_bgr8(input) && r.upload(input, input.cols, input.rows, 3);
-    ok = ok && vp_sharpen(r.ctx(), &c, r.d_in(), r.in_pitch(), r.d_out(), r.out_pitch(), input.cols, input.rows, nullptr) == VP_OK;
+    ok = ok && vp_sharpen(r.ctx(), &c, r.d_in(), r.in_pitch(), r.d_out(), r.out_pitch(), input.cols, input.rows, r.stream()) == VP_OK;
     ok = ok && r.download(output, input.cols, input.rows, CV_8UC3, 3);
     if (!ok) {
         std::cerr << "Error in adaptive sharpening: " << r.error() << std::endl;
@@ -175,14 +175,15 @@ bool TemporalConsistency::process(const cv::Mat& input, cv::Mat& output) {
     const uint8_t* ptrs[3] = {r.d_in(), nullptr, nullptr};
     for (int i = 0; i < nprev; ++i) ptrs[1 + i] = s.frames[s.frames.size() - 1 - i];
     bool ok = vp_temporal_blend(r.ctx(), ptrs, 1 + nprev, s.pitch, m_config.blend_strength, r.d_out(), r.out_pitch(),
-                                input.cols, input.rows, nullptr) == VP_OK;
+                                input.cols, input.rows, r.stream()) == VP_OK;
     ok = ok && r.download(output, input.cols, input.rows, CV_8UC3, 3);
     // keep the unblended input (src/temporal_consistency.cpp:158-159), trim to buffer_size (:162-169)
     uint8_t* keep = nullptr;
     if ((int)s.frames.size() >= buffer) { keep = s.frames.front(); s.frames.pop_front(); }
     if (!keep && cudaMalloc(&keep, s.pitch * input.rows) != cudaSuccess) { cudaGetLastError(); keep = nullptr; }
     if (keep) {
-        cudaMemcpy2D(keep, s.pitch, r.d_in(), s.pitch, (size_t)input.cols * 3, input.rows, cudaMemcpyDeviceToDevice);
+        cudaMemcpy2DAsync(keep, s.pitch, r.d_in(), s.pitch, (size_t)input.cols * 3, input.rows, cudaMemcpyDeviceToDevice, (cudaStream_t)r.stream());
+        cudaStreamSynchronize((cudaStream_t)r.stream());
         s.frames.push_back(keep);
     }
     if (!ok) {

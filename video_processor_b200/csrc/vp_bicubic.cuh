@@ -1,0 +1,142 @@
+// vp_bicubic.cuh - lean cv::resize(INTER_CUBIC) for CV_8UC3 (reference call sites src/upscaler.cpp:81,
+// src/test_enhancements.cpp:348, src/main.cpp:265): the bicubic-only path (BASELINE configs C1, C5 and
+// Upscaler::BICUBIC).  Bit-exact to OpenCV (oracle/restate.py:resize_cubic): int32 horizontal pass with
+// 11-bit taps, float32 vertical pass t = fma(S0,b0,S1*b1) + fma(S2,b2,S3*b3), RNE + saturate.
+//
+// One thread owns one destination column of a 128 x 32 tile and walks down its rows:
+//   * the source window is staged by TMA bulk row copies and expanded once to BGR0 words in UNclamped
+//     coordinates (replicate border materialised), so the inner loops have no clamps;
+//   * the column's four tap offsets and taps are per-thread constants; a sliding window of four
+//     horizontally filtered rows (3 channels) lives in registers and advances only when the vertical
+//     tap origin changes (warp-uniform), so every H value is computed exactly once per tile column;
+//   * four adjacent lanes repack their 4 x 3 output bytes into three aligned 32-bit words with one
+//     shuffle and a funnel shift: no shared-memory staging of the output, 96 contiguous bytes per warp row.
+// Any upscale ratio works (tables come from the host exactly as cv::resize builds them).
+#pragma once
+#include "vp_bilateral.cuh"   // f2u8
+#include "vp_common.cuh"
+#include "vp_upsharp.cuh"     // ResizeTables
+
+namespace vp {
+
+constexpr int BC_TW = 128, BC_TH = 32, BC_NT = 128;
+
+struct BicubicArgs {
+    const uint8_t* src; size_t spitch; int sw, sh;
+    uint8_t* dst; size_t dpitch; int dw, dh;
+    ResizeTables rt;
+    int max_src_rows, max_src_cols;     // unclamped per-tile source window bounds
+};
+
+struct BicubicSmem { int raw, raw_pitch, src, src_pitch, tabs, total; };
+
+__host__ __device__ inline BicubicSmem bicubic_layout(int max_src_rows, int max_src_cols) {
+    BicubicSmem L{};
+    int o = 0;
+    L.raw_pitch = ((max_src_cols * 3 + 15 + 15) & ~15) + 16;
+    L.raw = o; o += L.raw_pitch * max_src_rows;
+    L.src_pitch = max_src_cols | 1;
+    L.src = o; o += (L.src_pitch * max_src_rows * 4 + 15) & ~15;
+    L.tabs = o; o += BC_TH * 16 + BC_TH * 4 + 16;      // ycoef float4[TH], yofs int[TH], mbarrier
+    L.total = o;
+    return L;
+}
+
+__global__ void __launch_bounds__(BC_NT) k_bicubic(const BicubicArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x;
+    const BicubicSmem L = bicubic_layout(a.max_src_rows, a.max_src_cols);
+    uint8_t* s_raw = smem + L.raw;
+    uint32_t* s_src = reinterpret_cast<uint32_t*>(smem + L.src);
+    float4* s_yc = reinterpret_cast<float4*>(smem + L.tabs);
+    int* s_yo = reinterpret_cast<int*>(smem + L.tabs + BC_TH * 16);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.tabs + BC_TH * 16 + BC_TH * 4);
+
+    const int x0 = blockIdx.x * BC_TW, y0 = blockIdx.y * BC_TH;
+    const int dxb = min(a.dw - 1, x0 + BC_TW - 1), dyb = min(a.dh - 1, y0 + BC_TH - 1);
+    const int ux0 = a.rt.xofs[x0], ux1 = a.rt.xofs[dxb] + 3;      // unclamped source window (inclusive)
+    const int uy0 = a.rt.yofs[y0], uy1 = a.rt.yofs[dyb] + 3;
+    if (tid < BC_TH) {
+        const int dy = min(y0 + tid, dyb);
+        s_yo[tid] = a.rt.yofs[dy] - uy0;
+        s_yc[tid] = a.rt.ycoef[dy];
+    }
+    // this thread's column: tap origin (relative to the window) and taps
+    const int dx = min(x0 + tid, dxb);
+    const int cx = a.rt.xofs[dx] - ux0;
+    const int4 kx = a.rt.xcoef[dx];
+
+    const int sx0 = clampi(ux0, 0, a.sw - 1), sx1 = clampi(ux1, 0, a.sw - 1);
+    const int sy0 = clampi(uy0, 0, a.sh - 1), sy1 = clampi(uy1, 0, a.sh - 1);
+    const int bx0 = (sx0 * 3) & ~15, bx1 = (sx1 + 1) * 3;
+    const int RP = L.raw_pitch, SP = L.src_pitch;
+    stage_rows(s_raw, RP, a.src, a.spitch, 3 * a.sw, sy0, sy1 + 1, bx0, bx1, aligned16(a.src, a.spitch), bar);
+
+    const int ncols = ux1 - ux0 + 1, nrows = uy1 - uy0 + 1;
+    {   // raw bytes -> BGR0 words, replicate border materialised; warp per row, lanes along x
+        const int lane = tid & 31, wrp = tid >> 5;
+        for (int rr = wrp; rr < nrows; rr += BC_NT / 32) {
+            const uint8_t* rrow = s_raw + (clampi(uy0 + rr, 0, a.sh - 1) - sy0) * RP - bx0;
+            for (int cc = lane; cc < ncols; cc += 32) {
+                const uint8_t* p = rrow + 3 * clampi(ux0 + cc, 0, a.sw - 1);
+                s_src[rr * SP + cc] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+            }
+        }
+    }
+    __syncthreads();
+
+    // horizontal pass of one source row for this column: exact int32, returned as float32 (|H| < 2^22)
+    auto hrow = [&](int rr, float (&h)[3]) {
+        const uint32_t* p = s_src + rr * SP + cx;
+        const uint32_t p0 = p[0], p1 = p[1], p2 = p[2], p3 = p[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const int sel = 0x4440 + ch;
+            const int v = (int)__byte_perm(p0, 0, sel) * kx.x + (int)__byte_perm(p1, 0, sel) * kx.y +
+                          (int)__byte_perm(p2, 0, sel) * kx.z + (int)__byte_perm(p3, 0, sel) * kx.w;
+            h[ch] = __int_as_float(v + 0x4B400000) - 12582912.0f;
+        }
+    };
+
+    const int vh = dyb - y0 + 1;
+    const int gx = x0 + tid;
+    const bool col_ok = gx < a.dw;
+    const int lane = tid & 31, q = lane & 3;
+    // word path: the whole quad of columns is inside the image and the row addresses are 4-byte aligned
+    const bool quad_ok = ((gx | 3) < a.dw) && ((((uintptr_t)a.dst) | a.dpitch) & 3) == 0;
+    float w0[3], w1[3], w2[3], w3[3];
+    int yo = s_yo[0];
+    hrow(yo, w0); hrow(yo + 1, w1); hrow(yo + 2, w2); hrow(yo + 3, w3);
+    for (int y = 0; y < vh; ++y) {
+        const int yn = s_yo[y];           // uniform across the CTA: no divergence below
+        const int d = yn - yo;
+        if (d == 1) {                     // the only non-zero step an upscale produces
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) { w0[ch] = w1[ch]; w1[ch] = w2[ch]; w2[ch] = w3[ch]; }
+            hrow(yn + 3, w3);
+        } else if (d != 0) {
+            hrow(yn, w0); hrow(yn + 1, w1); hrow(yn + 2, w2); hrow(yn + 3, w3);
+        }
+        yo = yn;
+        const float4 b = s_yc[y];
+        uint32_t v[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+            v[ch] = f2u8(__fadd_rn(__fmaf_rn(w0[ch], b.x, __fmul_rn(w1[ch], b.y)),
+                                   __fmaf_rn(w2[ch], b.z, __fmul_rn(w3[ch], b.w))));
+        const uint32_t px = v[0] | (v[1] << 8) | (v[2] << 16);
+        const uint32_t nxt = __shfl_down_sync(0xffffffffu, px, 1);
+        uint8_t* row = a.dst + (size_t)(y0 + y) * a.dpitch;
+        if (quad_ok) {
+            if (q != 3) {
+                const uint32_t lo = px | (nxt << 24), hi = nxt >> 8;
+                *reinterpret_cast<uint32_t*>(row + (size_t)(gx - q) * 3 + 4 * q) = __funnelshift_r(lo, hi, 8 * q);
+            }
+        } else if (col_ok) {
+            uint8_t* o = row + (size_t)gx * 3;
+            o[0] = (uint8_t)v[0]; o[1] = (uint8_t)v[1]; o[2] = (uint8_t)v[2];
+        }
+    }
+}
+
+}  // namespace vp

@@ -19,6 +19,7 @@
 #include <string>
 #include <vector>
 
+#include "vp_bicubic.cuh"
 #include "vp_bilateral.cuh"
 #include "vp_blend.cuh"
 #include "vp_stats.cuh"
@@ -34,7 +35,8 @@ thread_local std::string g_create_error;
 struct ResizeCache {
     int sw = 0, sh = 0, dw = 0, dh = 0;
     int* xofs = nullptr; int4* xcoef = nullptr; int* yofs = nullptr; float4* ycoef = nullptr;
-    int max_rows[2] = {0, 0}, max_cols[2] = {0, 0};   // [0] halo 0, [1] halo US_HALO
+    int max_rows[2] = {0, 0}, max_cols[2] = {0, 0};   // [0] halo 0, [1] halo US_HALO (k_upsharp tiles)
+    int bc_rows = 0, bc_cols = 0;                     // k_bicubic tiles
 };
 
 struct HostSlot {
@@ -199,6 +201,8 @@ int ensure_resize(vp_ctx* c, ResizeCache& rc, int sw, int sh, int dw, int dh, cu
         rc.max_cols[k] = tile_span(tx.ofs, dw, US_TW, halo);
         rc.max_rows[k] = tile_span(ty.ofs, dh, US_TH, halo);
     }
+    rc.bc_cols = tile_span(tx.ofs, dw, BC_TW, 0);
+    rc.bc_rows = tile_span(ty.ofs, dh, BC_TH, 0);
     rc.sw = sw; rc.sh = sh; rc.dw = dw; rc.dh = dh;
     return VP_OK;
 }
@@ -269,6 +273,22 @@ int launch_upsharp(vp_ctx* c, UpsharpArgs& a, bool do_resize, bool do_sharpen, c
         else if (a.gk == 5) k_upsharp<false, true, 5><<<grid, US_NT, L.total, st>>>(a);
         else k_upsharp<false, true, 7><<<grid, US_NT, L.total, st>>>(a);
     }
+    VP_CUDA(c, cudaGetLastError());
+    c->launches++;
+    return VP_OK;
+}
+
+int launch_bicubic(vp_ctx* c, const uint8_t* src, size_t spitch, int sw, int sh, uint8_t* dst, size_t dpitch, int dw, int dh,
+                   const ResizeCache& rcache, cudaStream_t st) {
+    BicubicArgs a{};
+    a.src = src; a.spitch = spitch; a.sw = sw; a.sh = sh; a.dst = dst; a.dpitch = dpitch; a.dw = dw; a.dh = dh;
+    a.rt = ResizeTables{rcache.xofs, rcache.xcoef, rcache.yofs, rcache.ycoef};
+    a.max_src_rows = rcache.bc_rows; a.max_src_cols = rcache.bc_cols;
+    const BicubicSmem L = bicubic_layout(a.max_src_rows, a.max_src_cols);
+    if (L.total > 200 * 1024) return fail(c, VP_ERR_UNSUPPORTED, "resize ratio needs more shared memory than a CTA has");
+    const dim3 grid((dw + BC_TW - 1) / BC_TW, (dh + BC_TH - 1) / BC_TH);
+    ProfScope ps(c, K_UPSHARP, st);
+    k_bicubic<<<grid, BC_NT, L.total, st>>>(a);
     VP_CUDA(c, cudaGetLastError());
     c->launches++;
     return VP_OK;
@@ -390,6 +410,7 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
     VP_CUDA(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
     VP_CUDA(c, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
     VP_CUDA(c, cudaFuncSetAttribute(k_bilateral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(bil_smem_bytes(BIL_RMAX, 1), bil_smem_bytes(3, 2))));
+    VP_CUDA(c, cudaFuncSetAttribute(k_bicubic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -544,7 +565,13 @@ int vp_process_device(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t
     // 2+3. bicubic resize + AdaptiveSharpening (dst resolution)
     const bool do_resize = (g.dst_w != g.src_w || g.dst_h != g.src_h);
     const bool last_is_upsharp = !g.use_post && !temporal;
-    if (do_resize || g.use_sharpen) {
+    if (do_resize && !g.use_sharpen && !need_post_stats) {
+        uint8_t* out = last_is_upsharp ? d_dst : c->d_sharp;
+        const size_t opitch = last_is_upsharp ? dst_pitch : c->frame_pitch;
+        rc = launch_bicubic(c, cur, cur_pitch, g.src_w, g.src_h, out, opitch, g.dst_w, g.dst_h, c->rc_chain, st);
+        if (rc) return rc;
+        cur = out; cur_pitch = opitch;
+    } else if (do_resize || g.use_sharpen) {
         UpsharpArgs a{};
         a.src = cur; a.spitch = cur_pitch; a.sw = g.src_w; a.sh = g.src_h;
         a.dst = last_is_upsharp ? d_dst : c->d_sharp; a.dpitch = last_is_upsharp ? dst_pitch : c->frame_pitch;
@@ -719,12 +746,7 @@ int vp_bicubic(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, int src_w, int
     ResizeCache& rcache = (c->has_chain && c->rc_chain.sw == src_w && c->rc_chain.sh == src_h &&
                            c->rc_chain.dw == dst_w && c->rc_chain.dh == dst_h && c->rc_chain.xofs) ? c->rc_chain : c->rc_tmp;
     rc = ensure_resize(c, rcache, src_w, src_h, dst_w, dst_h, st); if (rc) return rc;
-    UpsharpArgs a{};
-    a.src = d_src; a.spitch = src_pitch; a.sw = src_w; a.sh = src_h;
-    a.dst = d_dst; a.dpitch = dst_pitch; a.dw = dst_w; a.dh = dst_h;
-    a.rt = ResizeTables{rcache.xofs, rcache.xcoef, rcache.yofs, rcache.ycoef};
-    a.max_src_rows = rcache.max_rows[0]; a.max_src_cols = rcache.max_cols[0];
-    return launch_upsharp(c, a, true, false, st);
+    return launch_bicubic(c, d_src, src_pitch, src_w, src_h, d_dst, dst_pitch, dst_w, dst_h, rcache, st);
 }
 
 int vp_bilateral(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t* d_dst, size_t dst_pitch,
