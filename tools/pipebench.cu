@@ -39,6 +39,11 @@ template<int OP> __global__ void k(float* out, long long* cyc, const float* lut_
       if (OP == 17) { f[i] = __fmaf_rn(f[i], c1, c2); u[i] = __vabsdiffu4(u[i], uc); }        // FFMA + VABSDIFF4
       if (OP == 18) { asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(p[(i+1)%NCH]), "l"(p[(i+2)%NCH])); u[i] = __byte_perm(u[i], uc, 0x7440); }
       if (OP == 19) f[i] = __fmaf_rn(f[i], 1.0001f, 0.5f);                  // FFMA imm
+      if (OP == 20) { unsigned long long wb = pack2(c1, c1); asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p[i]) : "l"(p[(i+1)%NCH]), "l"(wb)); }   // acc += data * w(bcast)
+      if (OP == 21) { unsigned long long wb = pack2(f[i], f[i]); asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p[i]) : "l"(p[(i+1)%NCH]), "l"(wb)); f[i] = __fmul_rn(f[i], c1); }  // FMUL + FFMA2 bcast
+      if (OP == 22) { f[i] = __fmaf_rn(f[(i+1)%NCH], c1, f[i]); }            // FFMA acc form
+      if (OP == 23) { unsigned long long wb = pack2(c1, c1); asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(wb)); }   // FADD2 bcast
+      if (OP == 24) { unsigned long long wb = pack2(c1, c1); asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(wb)); }   // FMUL2 bcast
     }
   }
   long long t1 = clock64();
@@ -63,6 +68,8 @@ int main() {
   run<7>("LEA/IMAD x4+c", 1, out, cyc, lut); run<12>("IMAD", 1, out, cyc, lut); run<13>("IADD+SHF+LOP", 3, out, cyc, lut);
   run<8>("LDS random + FADD", 2, out, cyc, lut); run<9>("LDS linear + FADD", 2, out, cyc, lut);
   run<10>("F2I.U8 + IADD", 2, out, cyc, lut); run<11>("I2F + FADD (+LOP)", 2, out, cyc, lut);
+  run<20>("FFMA2 acc+=d*w.bcast", 1, out, cyc, lut); run<21>("FMUL + FFMA2 bcast", 2, out, cyc, lut); run<22>("FFMA acc+=d*w", 1, out, cyc, lut);
+  run<23>("FADD2 bcast", 1, out, cyc, lut); run<24>("FMUL2 bcast", 1, out, cyc, lut);
   run<15>("FFMA + PRMT", 2, out, cyc, lut); run<16>("FFMA + IDP4A", 2, out, cyc, lut); run<17>("FFMA + VABSDIFF4", 2, out, cyc, lut); run<18>("FFMA2 + PRMT", 2, out, cyc, lut);
   return 0;
 }

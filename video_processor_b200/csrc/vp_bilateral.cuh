@@ -8,7 +8,7 @@
 //   w = space_w[tap] * color_w[|db|+|dg|+|dr|]  (float32 product), wsum += w, sum_c = fma(p_c, w, sum_c);
 //   dst_c = RNE(sum_c * (1.f / wsum)).
 // Layout: a CTA owns a TW x TH output tile.  The halo tile is staged from HBM by TMA bulk row copies
-// into raw bytes, expanded once to packed BGR0 words with the border map resolved, and each thread
+// into raw bytes, expanded once to packed BGR1 words with the border map resolved, and each thread
 // then filters a strip of PX horizontally adjacent pixels so a staged neighbour is reused by up to
 // PX outputs from registers (VABSDIFF4 + IDP.4A for the L1 colour distance).  The tap rows run in a
 // rolled loop whose body is specialised on the row's half-width (a handful of variants per radius),
@@ -107,17 +107,35 @@ template <int R> struct BilGeom {
     static constexpr int D = 2 * R + 1;
 };
 
-// one tap row of half-width XM: taps dx = -XM..XM against the PX outputs of the strip
+// packed f32x2 helpers (sm_100 FFMA2 / FADD2): two float lanes per 64-bit register pair, one issue slot
+__device__ __forceinline__ unsigned long long pack2(uint32_t lo, uint32_t hi) {
+    unsigned long long r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(lo), "r"(hi)); return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+    unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+
+// one tap row of half-width XM: taps dx = -XM..XM against the PX outputs of the strip.
+// Accumulators are (sum_b, sum_g) and (sum_r, wsum) pairs: the tile's 4th byte is 1, so the pixel's
+// (r, 1.0) pair turns wsum += w into the second half of one FFMA2 (fma(1, w, wsum) == wsum + w).
 template <int R, int XM>
 __device__ __forceinline__ void bil_row(const uint32_t (&seg)[BilGeom<R>::NSEG], const float* __restrict__ sw_row,
                                         const float* __restrict__ s_cw, const uint32_t (&ctr)[BIL_PX],
-                                        float (&sb)[BIL_PX], float (&sg)[BIL_PX], float (&sr)[BIL_PX], float (&ws)[BIL_PX]) {
+                                        unsigned long long (&abg)[BIL_PX], unsigned long long (&arw)[BIL_PX]) {
     constexpr int N = BIL_PX + 2 * XM;                        // neighbours this row touches
-    float fb[N], fg[N], fr[N];
+    unsigned long long pbg[N], pra[N];
+    const unsigned long long bias = pack2(0xCB000000u, 0xCB000000u);   // (-2^23, -2^23)
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const uint32_t p = seg[i + R - XM];
-        fb[i] = u8f(p, 0); fg[i] = u8f(p, 1); fr[i] = u8f(p, 2);
+        pbg[i] = fadd2(pack2(__byte_perm(p, 0x4B000000u, 0x7440), __byte_perm(p, 0x4B000000u, 0x7441)), bias);
+        pra[i] = fadd2(pack2(__byte_perm(p, 0x4B000000u, 0x7442), __byte_perm(p, 0x4B000000u, 0x7443)), bias);
     }
 #pragma unroll
     for (int dx = -XM; dx <= XM; ++dx) {
@@ -125,12 +143,11 @@ __device__ __forceinline__ void bil_row(const uint32_t (&seg)[BilGeom<R>::NSEG],
 #pragma unroll
         for (int j = 0; j < BIL_PX; ++j) {
             const int i = j + dx + XM;
-            const unsigned n = __vsadu4(seg[i + R - XM], ctr[j]);   // VABSDIFF4.ACC: |db|+|dg|+|dr|
-            const float wgt = __fmul_rn(sw, s_cw[n]);
-            ws[j] = __fadd_rn(ws[j], wgt);
-            sb[j] = __fmaf_rn(fb[i], wgt, sb[j]);
-            sg[j] = __fmaf_rn(fg[i], wgt, sg[j]);
-            sr[j] = __fmaf_rn(fr[i], wgt, sr[j]);
+            const unsigned n = __vsadu4(seg[i + R - XM], ctr[j]);   // VABSDIFF4.ACC: |db|+|dg|+|dr| (+|1-1|)
+            const uint32_t wgt = __float_as_uint(__fmul_rn(sw, s_cw[n]));
+            const unsigned long long w2 = pack2(wgt, wgt);
+            abg[j] = ffma2(pbg[i], w2, abg[j]);
+            arw[j] = ffma2(pra[i], w2, arw[j]);
         }
     }
 }
@@ -138,17 +155,17 @@ __device__ __forceinline__ void bil_row(const uint32_t (&seg)[BilGeom<R>::NSEG],
 template <int R, int XM>
 struct BilRowSwitch {
     __device__ __forceinline__ static void run(int xm, const uint32_t (&seg)[BilGeom<R>::NSEG], const float* sw_row, const float* s_cw,
-                                               const uint32_t (&ctr)[BIL_PX], float (&sb)[BIL_PX], float (&sg)[BIL_PX],
-                                               float (&sr)[BIL_PX], float (&ws)[BIL_PX]) {
-        if (xm == XM) bil_row<R, XM>(seg, sw_row, s_cw, ctr, sb, sg, sr, ws);
-        else BilRowSwitch<R, XM - 1>::run(xm, seg, sw_row, s_cw, ctr, sb, sg, sr, ws);
+                                               const uint32_t (&ctr)[BIL_PX], unsigned long long (&abg)[BIL_PX],
+                                               unsigned long long (&arw)[BIL_PX]) {
+        if (xm == XM) bil_row<R, XM>(seg, sw_row, s_cw, ctr, abg, arw);
+        else BilRowSwitch<R, XM - 1>::run(xm, seg, sw_row, s_cw, ctr, abg, arw);
     }
 };
 template <int R>
 struct BilRowSwitch<R, -1> {
     __device__ __forceinline__ static void run(int, const uint32_t (&)[BilGeom<R>::NSEG], const float*, const float*,
-                                               const uint32_t (&)[BIL_PX], float (&)[BIL_PX], float (&)[BIL_PX],
-                                               float (&)[BIL_PX], float (&)[BIL_PX]) {}
+                                               const uint32_t (&)[BIL_PX], unsigned long long (&)[BIL_PX],
+                                               unsigned long long (&)[BIL_PX]) {}
 };
 
 template <int R>
@@ -157,11 +174,11 @@ __device__ __forceinline__ void bil_strip(const uint32_t* __restrict__ s_tile, c
                                        int lx, int ly, uint32_t out[BIL_PX]) {
     constexpr int TP = BilGeom<R>::TP, NSEG = BilGeom<R>::NSEG, D = BilGeom<R>::D;
     uint32_t ctr[BIL_PX];
-    float sb[BIL_PX], sg[BIL_PX], sr[BIL_PX], ws[BIL_PX];
+    unsigned long long abg[BIL_PX], arw[BIL_PX];
 #pragma unroll
     for (int j = 0; j < BIL_PX; ++j) {
         ctr[j] = s_tile[(ly + R) * TP + lx + R + j];
-        sb[j] = sg[j] = sr[j] = ws[j] = 0.f;
+        abg[j] = arw[j] = 0ull;
     }
 #pragma unroll 1
     for (int row = 0; row < D; ++row) {
@@ -172,12 +189,15 @@ __device__ __forceinline__ void bil_strip(const uint32_t* __restrict__ s_tile, c
             const uint4 v = rowp[q];
             seg[4 * q] = v.x; seg[4 * q + 1] = v.y; seg[4 * q + 2] = v.z; seg[4 * q + 3] = v.w;
         }
-        BilRowSwitch<R, R>::run(s_xm[row], seg, s_sw + row * D, s_cw, ctr, sb, sg, sr, ws);
+        BilRowSwitch<R, R>::run(s_xm[row], seg, s_sw + row * D, s_cw, ctr, abg, arw);
     }
 #pragma unroll
     for (int j = 0; j < BIL_PX; ++j) {
-        const float inv = __frcp_rn(ws[j]);
-        out[j] = f2u8(__fmul_rn(sb[j], inv)) | (f2u8(__fmul_rn(sg[j], inv)) << 8) | (f2u8(__fmul_rn(sr[j], inv)) << 16);
+        float sb, sg, sr, ws;
+        unpack2(abg[j], sb, sg);
+        unpack2(arw[j], sr, ws);
+        const float inv = __frcp_rn(ws);
+        out[j] = f2u8(__fmul_rn(sb, inv)) | (f2u8(__fmul_rn(sg, inv)) << 8) | (f2u8(__fmul_rn(sr, inv)) << 16);
     }
 }
 
@@ -238,10 +258,10 @@ __global__ void __launch_bounds__(BIL_NT, 3) k_bilateral(const BilArgs a) {
                 int sx = x0 - R + tx;
                 if (simple) { sx = sx < 0 ? -sx : sx; sx = sx >= a.w ? 2 * a.w - 2 - sx : sx; }
                 else sx = reflect101(sx, a.w);
-                uint32_t v = 0;
+                uint32_t v = 0x01000000u;                    // 4th byte 1: the (r, 1.0) pair accumulates wsum
                 if (rowok && sx >= vx0 && sx < vx1) {        // false only for unused positions of edge tiles
                     const uint8_t* p = rrow + sx * 3;
-                    v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+                    v |= (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
                 }
                 s_tile[ty * TP + tx] = v;
             }
