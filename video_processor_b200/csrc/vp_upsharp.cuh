@@ -73,9 +73,16 @@ __host__ __device__ inline UpsharpSmem upsharp_layout(bool resize, bool sharpen,
     const int EW = US_TW + 2 * halo, EH = US_TH + 2 * halo;
     int o = 0;
     L.raw_pitch = ((max_src_cols * 3 + 15 + 15) & ~15) + 16;
-    L.raw = o; o += L.raw_pitch * max_src_rows;
+    // region U: raw source bytes + BGR0 source words (dead after P1 / the expand), later the sigmoid
+    // image (68 x 36 f32, P3-P4) and finally the staged output tile (US_TH x US_TW*3 bytes, P5-P6)
     L.src_pitch = max_src_cols + 1;
-    L.src = o; o += resize ? ((L.src_pitch * max_src_rows * 4 + 15) & ~15) : 0;
+    const int rawb = L.raw_pitch * max_src_rows;
+    const int srcb = resize ? ((L.src_pitch * max_src_rows * 4 + 15) & ~15) : 0;
+    const int sig = sharpen ? (US_TW + 4) * (US_TH + 4) * 4 : 0;
+    const int outb = US_TH * US_TW * 3;
+    const int sigout = ((sig > outb ? sig : outb) + 15) & ~15;
+    L.raw = o; L.src = o + rawb; L.sig = o;
+    o += (rawb + srcb > sigout ? rawb + srcb : sigout);
     // region A: H-pass rows (float x 3 per ext column) during P1/P2, then the row-pass planes of P4
     const int hs = resize ? max_src_rows * EW * 3 * 4 : 0;
     const int rowbg = (US_TH + 6) * US_TW * 4, rowr = (US_TH + 6) * US_TW * 2, rowf = (US_TH + 4) * US_TW * 4;
@@ -84,10 +91,6 @@ __host__ __device__ inline UpsharpSmem upsharp_layout(bool resize, bool sharpen,
     o += ((hs > p4 ? hs : p4) + 15) & ~15;
     L.up = o; o += EW * EH * 4;
     L.gray = o; o += sharpen ? ((US_GP * EH + 15) & ~15) : 0;
-    // sig (68 x 36 f32) later reused for the staged output tile (US_TH x US_TW*3 bytes)
-    const int sig = sharpen ? (US_TW + 4) * (US_TH + 4) * 4 : 0;
-    const int outb = US_TH * US_TW * 3;
-    L.sig = o; o += ((sig > outb ? sig : outb) + 15) & ~15;
     // tables: ycoef float4[EH] | xcoef int4[EW] | mbarrier(16) | xofs int[EW] | yofs int[EH] | lut float[256]
     L.tabs = o; o += EH * 16 + EW * 16 + 16 + EW * 4 + EH * 4 + 256 * 4 + 32;
     L.total = o;
@@ -390,8 +393,8 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
                     const int um = max(u[ch] - bl[ch], 0);
-                    const float umf = __int_as_float(um + 0x4B000000) - 8388608.0f;
-                    o[ch] = (int)f2u8(__fadd_rn(u8f(px, ch), __fmul_rn(st, umf)));
+                    // I2F here on purpose: the conversion pipe is idle in this kernel, the issue slots are not
+                    o[ch] = (int)f2u8(__fadd_rn((float)u[ch], __fmul_rn(st, (float)um)));
                 }
                 if (a.preserve_tone) {
                     const int yi = (4899 * u[2] + 9617 * u[1] + 1868 * u[0] + (1 << 13)) >> 14;
