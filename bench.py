@@ -94,7 +94,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -130,6 +130,22 @@ class ClockSampler:
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def traffic_for(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the newest ncu --set full
+    capture summarised in profiles/traffic.json (tools/ncu_summary.py), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        entries = t[sorted(t)[-1]]
+        bil = sorted((k for k in entries if "k_bilateral" in k), key=lambda k: int(k.split("@grid")[1]))
+        pick = {"stats": [k for k in entries if "k_stats" in k],
+                "upsharp": [k for k in entries if "k_upsharp" in k or "k_bicubic" in k],
+                "bilateral_pre": bil[:1], "bilateral_post": bil[-1:]}.get(kernel, [])
+        return entries[pick[0]] if pick else None
+    except Exception:
+        return None
 
 
 def build_cfg(capi, wl, temporal):
@@ -233,7 +249,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--temporal", default=None, choices=["none", "main", "frames"])
     ap.add_argument("--kind", default="scene", choices=["scene", "noise", "flat"])
-    ap.add_argument("--frames", type=int, default=64, help="frames per GPU per step (one segment)")
+    ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step (one segment)")
     ap.add_argument("--ref-frames", type=int, default=4, help="frames per step of the reference arm")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -347,12 +363,7 @@ def main():
                 kernels[k] = {"launches_per_step": n, "avg_us": round(us, 2), "share": round(tms_k / tot, 4),
                               "alg_bytes": kbytes.get(k), "achieved_gbs": round(kbytes[k] / (us * 1e-6) / 1e9, 1) if k in kbytes else None}
         dom = max(kernels, key=lambda k: kernels[k]["share"])
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(wl, {}).get(dom)
-        except Exception:
-            pass
+        traffic = traffic_for(dom)
         ach = kernels[dom]["achieved_gbs"]
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
                 "traffic": traffic, "peak_source": peak_src, "avg_us": kernels[dom]["avg_us"], "share_of_step": kernels[dom]["share"],
@@ -394,8 +405,11 @@ def main():
         tdt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+        twarm = torch.tensor([warm], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(twarm, op=dist.ReduceOp.SUM)
         e2e = {"value": world * F * nsteps / float(tdt.item()), "unit": "frames/s",
-               "h2d_bytes_per_step": (F + warm) * inb, "d2h_bytes_per_step": F * outb,
+               "h2d_bytes_per_step": (world * F + int(twarm.item())) * inb, "d2h_bytes_per_step": world * F * outb,
                "timing": "host wall clock around submit/wait of whole steps, synchronised both sides, max over ranks",
                "api": "vp_submit_host/vp_wait (pinned host frames, 3 streams, depth %d)" % depth}
 
