@@ -253,6 +253,8 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=4, help="frames per step of the reference arm")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--latency-frames", type=int, default=None,
+                    help="single-frame latency sample (p50/p99); default 1000 for workload c5, else 0")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -413,6 +415,37 @@ def main():
                "timing": "host wall clock around submit/wait of whole steps, synchronised both sides, max over ranks",
                "api": "vp_submit_host/vp_wait (pinned host frames, 3 streams, depth %d)" % depth}
 
+    # ---- single-frame latency (BASELINE config C5): one frame in flight, synchronise after each ---------
+    latency = None
+    nlat = args.latency_frames if args.latency_frames is not None else (1000 if wl == "c5" else 0)
+    if rank == 0 and nlat > 0:
+        def pct(v, q):
+            v = sorted(v)
+            return v[min(len(v) - 1, int(q * len(v)))]
+        capi.lib.vp_reset_temporal(h)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nlat)]
+        wall = []
+        for i in range(nlat):
+            t0 = time.perf_counter()
+            evs[i][0].record()
+            capi.check(process(h, seg[i % len(seg)].data_ptr(), sw * 3, outs[i % NOUT].data_ptr(), dw * 3, stream), h)
+            evs[i][1].record()
+            evs[i][1].synchronize()
+            wall.append((time.perf_counter() - t0) * 1e6)
+        dev_us = [a.elapsed_time(b) * 1e3 for a, b in evs]
+        hin1 = seg[0].cpu().pin_memory()
+        hout1 = torch.empty((dh, dw, 3), dtype=torch.uint8).pin_memory()
+        host = []
+        for i in range(min(nlat, 300)):
+            t0 = time.perf_counter()
+            capi.check(capi.lib.vp_process_host(h, hin1.data_ptr(), sw * 3, hout1.data_ptr(), dw * 3), h)
+            host.append((time.perf_counter() - t0) * 1e6)
+        latency = {"frames": nlat, "unit": "us",
+                   "device": {"p50": round(pct(dev_us, .5), 2), "p99": round(pct(dev_us, .99), 2)},
+                   "launch_to_done_wall": {"p50": round(pct(wall, .5), 2), "p99": round(pct(wall, .99), 2)},
+                   "host_frame_sync_api": {"p50": round(pct(host, .5), 2), "p99": round(pct(host, .99), 2),
+                                           "note": "vp_process_host: pinned H2D + kernels + pinned D2H, one frame in flight"}}
+
     cpu = None
     if rank == 0 and world == 1 and args.cpu_frames > 0:
         v, cores, dt = cpu_chain_fps(wl, temporal, args.cpu_frames, args.kind)
@@ -429,7 +462,7 @@ def main():
                        "sharding": "contiguous frame segments, no collective",
                        "l2": f"inputs ({F}x{inb >> 20} MiB) and output ring ({NOUT}x{outb >> 20} MiB) exceed the 126 MB L2",
                        "roofline_pass": "per-kernel CUDA events in a separate untimed-for-value pass of one step"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(tl.item()), "roofline": roof, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(tl.item()), "roofline": roof, "cpu_baseline": cpu, "latency": latency,
         }
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -212,7 +212,7 @@ __host__ inline size_t bil_smem_bytes(int r, int ns) {
     return tile + bil_sw_words(r) * 4 + 16 * 4 + raw + 16;
 }
 
-__global__ void __launch_bounds__(BIL_NT, 3) k_bilateral(const BilArgs a) {
+__global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ float s_cw[768];
     const int tid = threadIdx.x;
