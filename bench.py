@@ -253,6 +253,8 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=4, help="frames per step of the reference arm")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--lanes", type=int, default=0, help="stream lanes of the batch API (0 = library default)")
+    ap.add_argument("--per-frame", action="store_true", help="one vp_process_device call per frame on one stream (no batch API)")
     ap.add_argument("--latency-frames", type=int, default=None,
                     help="single-frame latency sample (p50/p99); default 1000 for workload c5, else 0")
     args = ap.parse_args()
@@ -306,16 +308,27 @@ def main():
     h = ctx.handle
     process = capi.lib.vp_process_device
 
-    def step():
+    # file/--fast mode: the whole segment is handed over in one call (vp_process_batch_device), frames
+    # alternate between two internal streams; the context's compute stream is made to follow torch's
+    # stream so the CUDA events below bracket the work
+    src_ptrs = (C.c_void_p * (warm + F))(*[t.data_ptr() for t in seg])
+    dst_ptrs = (C.c_void_p * (warm + F))(*([None] * warm + [outs[i % NOUT].data_ptr() for i in range(F)]))
+    batch = capi.lib.vp_process_batch_device
+    if args.lanes:
+        capi.check(capi.lib.vp_set_batch_lanes(h, args.lanes), h)
+
+    def step_per_frame():
         capi.lib.vp_reset_temporal(h)
         for i in range(warm):
-            rc = process(h, seg[i].data_ptr(), sw * 3, None, 0, stream)
-            if rc:
-                capi.check(rc, h)
+            capi.check(process(h, seg[i].data_ptr(), sw * 3, None, 0, stream), h)
         for i in range(F):
-            rc = process(h, seg[warm + i].data_ptr(), sw * 3, outs[i % NOUT].data_ptr(), dw * 3, stream)
-            if rc:
-                capi.check(rc, h)
+            capi.check(process(h, seg[warm + i].data_ptr(), sw * 3, outs[i % NOUT].data_ptr(), dw * 3, stream), h)
+
+    def step():
+        if args.per_frame:
+            return step_per_frame()
+        capi.lib.vp_reset_temporal(h)
+        capi.check(batch(h, warm + F, src_ptrs, sw * 3, dst_ptrs, dw * 3, stream), h)
 
     def barrier():
         torch.cuda.synchronize()
@@ -331,6 +344,8 @@ def main():
         sampler.start()
     l0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # both APIs take torch's stream (the batch call forks its second lane from it and joins it again),
+    # so these CUDA events bracket all the device work of the timed steps
     e0.record()
     for _ in range(args.steps):
         step()
@@ -353,7 +368,7 @@ def main():
     kernels = {}
     if rank == 0:
         capi.lib.vp_profile_enable(h, 1)
-        step()
+        step_per_frame()
         torch.cuda.synchronize()
         prof = ctx.profile_read()
         capi.lib.vp_profile_enable(h, 0)
@@ -461,7 +476,8 @@ def main():
                        "temporal_warmup_frames_rank_gt0": {"none": 0, "main": 1, "frames": max(cfg.temporal.buffer_size - 1, 0)}[temporal],
                        "sharding": "contiguous frame segments, no collective",
                        "l2": f"inputs ({F}x{inb >> 20} MiB) and output ring ({NOUT}x{outb >> 20} MiB) exceed the 126 MB L2",
-                       "roofline_pass": "per-kernel CUDA events in a separate untimed-for-value pass of one step"},
+                       "roofline_pass": "per-kernel CUDA events in a separate pass of one step, one stream, one frame at a time",
+                       "api": "vp_process_device per frame" if args.per_frame else "vp_process_batch_device (two stream lanes)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(tl.item()), "roofline": roof, "cpu_baseline": cpu, "latency": latency,
         }
         print(json.dumps(line), flush=True)

@@ -121,6 +121,16 @@ int vp_profile_read(vp_ctx* ctx, double* total_ms, uint64_t* launches, int nkind
  * the output store: the warm-up frame of a multi-GPU segment (multi-GPU). */
 int vp_process_device(vp_ctx* ctx, const uint8_t* d_src, size_t src_pitch,
                       uint8_t* d_dst, size_t dst_pitch, void* stream);
+/* file / --fast mode: n device frames known ahead (src/main.cpp:627-629 `simulate_realtime=false`).
+ * Consecutive frames alternate between two internal streams with their own intermediates, so one
+ * frame's reduction / prologue latency overlaps the other's kernels; the temporal stage still sees frames
+ * in order (an event orders frame i's blend after frame i-1's).  Asynchronous on `stream`: the second
+ * lane forks from it and joins it again, so work queued on `stream` before / after the call is ordered
+ * before / after the whole batch.  d_dst[i] == NULL marks a warm-up frame; d_dst[i] and d_dst[i+1]
+ * must not alias. */
+int vp_set_batch_lanes(vp_ctx* ctx, int lanes);     /* 1..4 stream lanes for the batch call (default 3; 4 for bicubic-only) */
+int vp_process_batch_device(vp_ctx* ctx, int n, const uint8_t* const* d_src, size_t src_pitch,
+                            uint8_t* const* d_dst, size_t dst_pitch, void* stream);
 /* Host frames, synchronous (pinned staging inside when the buffers are not pinned). */
 int vp_process_host(vp_ctx* ctx, const uint8_t* src, size_t src_step, uint8_t* dst, size_t dst_step);
 /* Host frames, pipelined: up to vp_pipeline_depth() frames in flight; H2D, kernels and D2H run on

@@ -82,6 +82,29 @@ def test_segment_sharding_is_bit_identical(vp, temporal, warm):
         assert np.array_equal(full[i], seg[warm + i - start])
 
 
+@pytest.mark.parametrize("temporal", [RC.TEMPORAL_NONE, RC.TEMPORAL_MAIN_BLEND, RC.TEMPORAL_BLEND_FRAMES])
+def test_batch_api_is_bit_identical_to_per_frame(vp, temporal):
+    """vp_process_batch_device (two stream lanes, events for the temporal dependency) == one
+    vp_process_device call per frame, including warm-up frames (d_dst = NULL) and repeated batches."""
+    sw, sh, n = 128, 72, 9
+    ocfg = RC.ChainConfig(dst_w=2 * sw, dst_h=2 * sh, temporal=temporal)
+    frames = synth.clip("scene", sw, sh, n)
+    flags = [False, False] + [True] * (n - 2)
+    ref, _ = run_chain_device(vp, ocfg, frames, sw, sh, outputs=flags)
+    cfg = G.chain_cfg(vp, ocfg, sw, sh)
+    with vp.Context(cfg) as ctx:
+        srcs = [G.to_dev(f) for f in frames]
+        dsts = [G.dev_empty(ocfg.dst_h, ocfg.dst_w) if fl else None for fl in flags]
+        for lo, hi in ((0, 5), (5, n)):       # two consecutive batches continue the same temporal state
+            sp = (C.c_void_p * (hi - lo))(*[t.data_ptr() for t in srcs[lo:hi]])
+            dp = (C.c_void_p * (hi - lo))(*[d.data_ptr() if d is not None else None for d in dsts[lo:hi]])
+            ctx.call("vp_process_batch_device", hi - lo, sp, sw * 3, dp, ocfg.dst_w * 3, None)
+        ctx.call("vp_synchronize")
+        for i in range(n):
+            if flags[i]:
+                assert np.array_equal(dsts[i].cpu().numpy(), ref[i]), i
+
+
 def test_host_paths_match_device_path(vp):
     sw, sh, n = 128, 72, 6
     ocfg = RC.ChainConfig(dst_w=2 * sw, dst_h=2 * sh, temporal=RC.TEMPORAL_BLEND_FRAMES)

@@ -4,9 +4,8 @@
 // 11-bit taps, float32 vertical pass t = fma(S0,b0,S1*b1) + fma(S2,b2,S3*b3), RNE + saturate.
 //
 // One thread owns one destination column of a 128 x 32 tile and walks down its rows:
-//   * the source window is staged by TMA bulk row copies and expanded once to BGR0 words in UNclamped
-//     coordinates (replicate border materialised), so the inner loops have no clamps;
-//   * the column's four tap offsets and taps are per-thread constants; a sliding window of four
+//   * the source window is staged by TMA bulk row copies as raw interleaved bytes and read in place;
+//   * the column's four (border-clamped) tap offsets and taps are per-thread constants; a sliding window of four
 //     horizontally filtered rows (3 channels) lives in registers and advances only when the vertical
 //     tap origin changes (warp-uniform), so every H value is computed exactly once per tile column;
 //   * four adjacent lanes repack their 4 x 3 output bytes into three aligned 32-bit words with one
@@ -35,8 +34,7 @@ __host__ __device__ inline BicubicSmem bicubic_layout(int max_src_rows, int max_
     int o = 0;
     L.raw_pitch = ((max_src_cols * 3 + 15 + 15) & ~15) + 16;
     L.raw = o; o += L.raw_pitch * max_src_rows;
-    L.src_pitch = max_src_cols | 1;
-    L.src = o; o += (L.src_pitch * max_src_rows * 4 + 15) & ~15;
+    L.src_pitch = 0; L.src = o;
     L.tabs = o; o += BC_TH * 16 + BC_TH * 4 + 16;      // ycoef float4[TH], yofs int[TH], mbarrier
     L.total = o;
     return L;
@@ -47,7 +45,6 @@ __global__ void __launch_bounds__(BC_NT) k_bicubic(const BicubicArgs a) {
     const int tid = threadIdx.x;
     const BicubicSmem L = bicubic_layout(a.max_src_rows, a.max_src_cols);
     uint8_t* s_raw = smem + L.raw;
-    uint32_t* s_src = reinterpret_cast<uint32_t*>(smem + L.src);
     float4* s_yc = reinterpret_cast<float4*>(smem + L.tabs);
     int* s_yo = reinterpret_cast<int*>(smem + L.tabs + BC_TH * 16);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.tabs + BC_TH * 16 + BC_TH * 4);
@@ -69,31 +66,22 @@ __global__ void __launch_bounds__(BC_NT) k_bicubic(const BicubicArgs a) {
     const int sx0 = clampi(ux0, 0, a.sw - 1), sx1 = clampi(ux1, 0, a.sw - 1);
     const int sy0 = clampi(uy0, 0, a.sh - 1), sy1 = clampi(uy1, 0, a.sh - 1);
     const int bx0 = (sx0 * 3) & ~15, bx1 = (sx1 + 1) * 3;
-    const int RP = L.raw_pitch, SP = L.src_pitch;
+    const int RP = L.raw_pitch;
     stage_rows(s_raw, RP, a.src, a.spitch, 3 * a.sw, sy0, sy1 + 1, bx0, bx1, aligned16(a.src, a.spitch), bar);
 
-    const int ncols = ux1 - ux0 + 1, nrows = uy1 - uy0 + 1;
-    {   // raw bytes -> BGR0 words, replicate border materialised; warp per row, lanes along x
-        const int lane = tid & 31, wrp = tid >> 5;
-        for (int rr = wrp; rr < nrows; rr += BC_NT / 32) {
-            const uint8_t* rrow = s_raw + (clampi(uy0 + rr, 0, a.sh - 1) - sy0) * RP - bx0;
-            for (int cc = lane; cc < ncols; cc += 32) {
-                const uint8_t* p = rrow + 3 * clampi(ux0 + cc, 0, a.sw - 1);
-                s_src[rr * SP + cc] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
-            }
-        }
-    }
-    __syncthreads();
+    // The four taps of this column as byte offsets into a staged row, replicate border applied once;
+    // a source row index is clamped when it is used (only the image's first/last rows ever clamp).
+    const int o0 = 3 * clampi(ux0 + cx, 0, a.sw - 1) - bx0, o1 = 3 * clampi(ux0 + cx + 1, 0, a.sw - 1) - bx0;
+    const int o2 = 3 * clampi(ux0 + cx + 2, 0, a.sw - 1) - bx0, o3 = 3 * clampi(ux0 + cx + 3, 0, a.sw - 1) - bx0;
+    const int ylo = sy0 - uy0, yhi = sy1 - uy0;       // window rows [ylo, yhi] exist in the staged tile
 
     // horizontal pass of one source row for this column: exact int32, returned as float32 (|H| < 2^22)
     auto hrow = [&](int rr, float (&h)[3]) {
-        const uint32_t* p = s_src + rr * SP + cx;
-        const uint32_t p0 = p[0], p1 = p[1], p2 = p[2], p3 = p[3];
+        const uint8_t* row = s_raw + (min(max(rr, ylo), yhi) - ylo) * RP;
+        const uint8_t *p0 = row + o0, *p1 = row + o1, *p2 = row + o2, *p3 = row + o3;
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-            const int sel = 0x4440 + ch;
-            const int v = (int)__byte_perm(p0, 0, sel) * kx.x + (int)__byte_perm(p1, 0, sel) * kx.y +
-                          (int)__byte_perm(p2, 0, sel) * kx.z + (int)__byte_perm(p3, 0, sel) * kx.w;
+            const int v = (int)p0[ch] * kx.x + (int)p1[ch] * kx.y + (int)p2[ch] * kx.z + (int)p3[ch] * kx.w;
             h[ch] = __int_as_float(v + 0x4B400000) - 12582912.0f;
         }
     };

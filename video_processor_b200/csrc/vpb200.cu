@@ -49,8 +49,22 @@ struct HostSlot {
 
 }  // namespace
 
+struct Lane {                       // per-frame intermediates; two lanes let consecutive frames overlap
+    cudaStream_t st = nullptr;      // lane 1's own stream (lane 0 runs on the caller's / the compute stream)
+    uint8_t* d_pre = nullptr;       // PRE-filtered frame, src resolution
+    uint8_t* d_sharp = nullptr;     // bicubic+sharpen output, dst resolution
+    unsigned long long* d_sums = nullptr;   // [0..5] PRE input, [6..11] POST input, [12..17] stage-wise scratch
+    int* d_sel = nullptr;           // [0] PRE class, [1] POST class, [2] stage-wise
+    unsigned* d_counter = nullptr;  // CTA ticket counters of the three sel producers
+    cudaEvent_t ev_done = nullptr;
+};
+
 struct vp_ctx {
     int device = 0;
+    Lane lanes[4];
+    int nlanes = 2;                 // lanes vp_process_batch_device cycles through (vp_set_batch_lanes)
+    cudaEvent_t ev_batch = nullptr;
+    int last_lane = 0;
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     bool has_chain = false;
     vp_chain_config cfg{};
@@ -59,13 +73,10 @@ struct vp_ctx {
     int sm_count = 148;
 
     // chain buffers
-    uint8_t* d_pre = nullptr; size_t pre_pitch = 0;
-    uint8_t* d_sharp = nullptr; size_t frame_pitch = 0;     // dst-sized intermediates / states
+    size_t pre_pitch = 0;
+    size_t frame_pitch = 0;                                 // pitch of dst-sized intermediates / states
     uint8_t* d_state[3] = {nullptr, nullptr, nullptr};
     int nring = 0, head = 0, nvalid = 0;                    // temporal ring
-    unsigned long long* d_sums = nullptr;                   // [0..5] PRE input, [6..11] POST input, [12..17] scratch
-    int* d_sel = nullptr;                                   // [0] PRE class, [1] POST class, [2] stage-wise
-    unsigned* d_counter = nullptr;                          // CTA ticket counters of the three sel producers
     BilCand* d_cand_pre = nullptr; BilCand* d_cand_post = nullptr; BilCand* d_cand_tmp = nullptr;
     int cand_pre_rad[3] = {0, 0, 0}, cand_post_rad[3] = {0, 0, 0};
     // cached stage-wise tables
@@ -390,9 +401,13 @@ void vp_destroy(vp_ctx* c) {
     destroy_slots(c);
     for (auto& r : c->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto& e : c->prof_pool) cudaEventDestroy(e);
-    cudaFree(c->d_pre); cudaFree(c->d_sharp);
+    for (Lane& L : c->lanes) {
+        cudaFree(L.d_pre); cudaFree(L.d_sharp); cudaFree(L.d_sums); cudaFree(L.d_sel); cudaFree(L.d_counter);
+        if (L.ev_done) cudaEventDestroy(L.ev_done);
+        if (L.st) cudaStreamDestroy(L.st);
+    }
+    if (c->ev_batch) cudaEventDestroy(c->ev_batch);
     for (auto& p : c->d_state) cudaFree(p);
-    cudaFree(c->d_sums); cudaFree(c->d_sel); cudaFree(c->d_counter);
     cudaFree(c->d_cand_pre); cudaFree(c->d_cand_post); cudaFree(c->d_cand_tmp); cudaFree(c->d_cand_sel);
     free_resize(c->rc_chain); free_resize(c->rc_tmp);
     cudaFree(c->d_siglut); cudaFree(c->d_siglut_tmp);
@@ -418,12 +433,12 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
     VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<false, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<false, true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    VP_CUDA(c, cudaMalloc(&c->d_sums, 18 * sizeof(unsigned long long)));
-    VP_CUDA(c, cudaMemset(c->d_sums, 0, 18 * sizeof(unsigned long long)));
-    VP_CUDA(c, cudaMalloc(&c->d_sel, 4 * sizeof(int)));
-    VP_CUDA(c, cudaMemset(c->d_sel, 0, 4 * sizeof(int)));
-    VP_CUDA(c, cudaMalloc(&c->d_counter, 4 * sizeof(unsigned)));
-    VP_CUDA(c, cudaMemset(c->d_counter, 0, 4 * sizeof(unsigned)));
+    VP_CUDA(c, cudaMalloc(&c->lanes[0].d_sums, 18 * sizeof(unsigned long long)));
+    VP_CUDA(c, cudaMemset(c->lanes[0].d_sums, 0, 18 * sizeof(unsigned long long)));
+    VP_CUDA(c, cudaMalloc(&c->lanes[0].d_sel, 4 * sizeof(int)));
+    VP_CUDA(c, cudaMemset(c->lanes[0].d_sel, 0, 4 * sizeof(int)));
+    VP_CUDA(c, cudaMalloc(&c->lanes[0].d_counter, 4 * sizeof(unsigned)));
+    VP_CUDA(c, cudaMemset(c->lanes[0].d_counter, 0, 4 * sizeof(unsigned)));
     VP_CUDA(c, cudaMalloc(&c->d_cand_tmp, sizeof(BilCand)));
     VP_CUDA(c, cudaMalloc(&c->d_cand_sel, 3 * sizeof(BilCand)));
     if (!cfg) return VP_OK;
@@ -440,7 +455,7 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
     c->pre_pitch = align_up((size_t)g.src_w * 3, 256);
     c->frame_pitch = align_up((size_t)g.dst_w * 3, 256);
     if (g.use_pre) {
-        VP_CUDA(c, cudaMalloc(&c->d_pre, c->pre_pitch * g.src_h));
+        VP_CUDA(c, cudaMalloc(&c->lanes[0].d_pre, c->pre_pitch * g.src_h));
         VP_CUDA(c, cudaMalloc(&c->d_cand_pre, 3 * sizeof(BilCand)));
         int rc = build_selective_cands(c, g.pre, c->d_cand_pre, c->cand_pre_rad, c->s_compute);
         if (rc) return rc;
@@ -450,7 +465,7 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
         int rc = build_selective_cands(c, g.post, c->d_cand_post, c->cand_post_rad, c->s_compute);
         if (rc) return rc;
     }
-    VP_CUDA(c, cudaMalloc(&c->d_sharp, c->frame_pitch * g.dst_h));
+    VP_CUDA(c, cudaMalloc(&c->lanes[0].d_sharp, c->frame_pitch * g.dst_h));
     c->nring = g.temporal.mode == VP_TEMPORAL_MAIN_BLEND ? 2
              : g.temporal.mode == VP_TEMPORAL_BLEND_FRAMES ? std::max(1, g.temporal.buffer_size) : 0;
     for (int i = 0; i < c->nring; ++i) VP_CUDA(c, cudaMalloc(&c->d_state[i], c->frame_pitch * g.dst_h));
@@ -465,6 +480,7 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
         rc = ensure_siglut(c, &c->d_siglut, &c->siglut_thr, &c->siglut_valid, g.sharpen.edge_threshold, c->s_compute);
         if (rc) return rc;
     }
+    c->nlanes = (!g.use_pre && !g.use_sharpen && !g.use_post) ? 4 : 3;
     c->has_chain = true;
     return VP_OK;
 }
@@ -519,6 +535,8 @@ int vp_synchronize(vp_ctx* c) {
     if (!c) return VP_ERR_INVALID_ARG;
     VP_CUDA(c, cudaSetDevice(c->device));
     VP_CUDA(c, cudaStreamSynchronize(c->s_h2d));
+    for (int l = 1; l < 4; ++l)
+        if (c->lanes[l].st) VP_CUDA(c, cudaStreamSynchronize(c->lanes[l].st));
     VP_CUDA(c, cudaStreamSynchronize(c->s_compute));
     VP_CUDA(c, cudaStreamSynchronize(c->s_d2h));
     return VP_OK;
@@ -532,41 +550,45 @@ int vp_reset_temporal(vp_ctx* c) {
 }
 
 // ---- the chain -----------------------------------------------------------------------------------
-int vp_process_device(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t* d_dst, size_t dst_pitch, void* stream) {
+// One frame through the chain on stream `st`, using lane `ln`'s intermediates.  `temporal_dep` (may be null)
+// is waited on right before the kernel that reads the temporal state (the previous frame's last kernel when
+// consecutive frames run on different streams).
+static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t temporal_dep, const uint8_t* d_src, size_t src_pitch,
+                         uint8_t* d_dst, size_t dst_pitch) {
     if (!c) return VP_ERR_INVALID_ARG;
     if (!c->has_chain) return fail(c, VP_ERR_STATE, "vp_process_device: context was created without a chain config");
     const vp_chain_config& g = c->cfg;
     int rc = check_frame(c, d_src, src_pitch, g.src_w, g.src_h, "vp_process_device(src)");
     if (rc) return rc;
     if (d_dst && dst_pitch < (size_t)g.dst_w * 3) return fail(c, VP_ERR_INVALID_ARG, "vp_process_device(dst): pitch < 3*width");
-    VP_CUDA(c, cudaSetDevice(c->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    Lane& L = c->lanes[ln];
+    c->last_lane = ln;
     const bool temporal = g.temporal.mode != VP_TEMPORAL_NONE && c->nring > 0;
     if (!d_dst && !temporal) return VP_OK;   // warm-up frame of a chain without temporal state: nothing to do
 
     const bool need_pre_stats = g.use_pre && g.pre.adaptive_params;
     const bool need_post_stats = g.use_post && g.post.adaptive_params;
     if (need_pre_stats || need_post_stats)
-        VP_CUDA(c, cudaMemsetAsync(c->d_sums, 0, 12 * sizeof(unsigned long long), st));
+        VP_CUDA(c, cudaMemsetAsync(L.d_sums, 0, 12 * sizeof(unsigned long long), st));
 
     const uint8_t* cur = d_src; size_t cur_pitch = src_pitch;
     // 1. SelectiveBilateral PRE (src resolution)
     if (g.use_pre) {
         if (need_pre_stats) {
-            rc = launch_stats(c, cur, cur_pitch, g.src_w, g.src_h, c->d_sums, SelOut{c->d_counter, c->d_sel, (double)g.src_w * g.src_h}, st);
+            rc = launch_stats(c, cur, cur_pitch, g.src_w, g.src_h, L.d_sums, SelOut{L.d_counter, L.d_sel, (double)g.src_w * g.src_h}, st);
             if (rc) return rc;
         }
         BilArgs a{};
-        a.src = cur; a.spitch = cur_pitch; a.dst = c->d_pre; a.dpitch = c->pre_pitch; a.w = g.src_w; a.h = g.src_h;
-        a.cand = c->d_cand_pre; a.sel = need_pre_stats ? c->d_sel : nullptr;
+        a.src = cur; a.spitch = cur_pitch; a.dst = L.d_pre; a.dpitch = c->pre_pitch; a.w = g.src_w; a.h = g.src_h;
+        a.cand = c->d_cand_pre; a.sel = need_pre_stats ? L.d_sel : nullptr;
         rc = launch_bilateral(c, a, c->cand_pre_rad, st, K_BIL_PRE); if (rc) return rc;
-        cur = c->d_pre; cur_pitch = c->pre_pitch;
+        cur = L.d_pre; cur_pitch = c->pre_pitch;
     }
     // 2+3. bicubic resize + AdaptiveSharpening (dst resolution)
     const bool do_resize = (g.dst_w != g.src_w || g.dst_h != g.src_h);
     const bool last_is_upsharp = !g.use_post && !temporal;
     if (do_resize && !g.use_sharpen && !need_post_stats) {
-        uint8_t* out = last_is_upsharp ? d_dst : c->d_sharp;
+        uint8_t* out = last_is_upsharp ? d_dst : L.d_sharp;
         const size_t opitch = last_is_upsharp ? dst_pitch : c->frame_pitch;
         rc = launch_bicubic(c, cur, cur_pitch, g.src_w, g.src_h, out, opitch, g.dst_w, g.dst_h, c->rc_chain, st);
         if (rc) return rc;
@@ -574,7 +596,7 @@ int vp_process_device(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t
     } else if (do_resize || g.use_sharpen) {
         UpsharpArgs a{};
         a.src = cur; a.spitch = cur_pitch; a.sw = g.src_w; a.sh = g.src_h;
-        a.dst = last_is_upsharp ? d_dst : c->d_sharp; a.dpitch = last_is_upsharp ? dst_pitch : c->frame_pitch;
+        a.dst = last_is_upsharp ? d_dst : L.d_sharp; a.dpitch = last_is_upsharp ? dst_pitch : c->frame_pitch;
         a.dw = g.dst_w; a.dh = g.dst_h;
         const int k = g.use_sharpen ? 1 : 0, halo = g.use_sharpen ? US_HALO : 0;
         if (do_resize) {
@@ -584,12 +606,12 @@ int vp_process_device(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t
             a.max_src_rows = US_TH + 2 * halo; a.max_src_cols = US_TW + 2 * halo;
         }
         if (g.use_sharpen) { rc = fill_sharpen_args(c, a, g.sharpen); if (rc) return rc; a.sig_lut = c->d_siglut; }
-        a.sums = need_post_stats ? c->d_sums + 6 : nullptr;
-        if (need_post_stats) a.fin = SelOut{c->d_counter + 1, c->d_sel + 1, (double)g.dst_w * g.dst_h};
+        a.sums = need_post_stats ? L.d_sums + 6 : nullptr;
+        if (need_post_stats) a.fin = SelOut{L.d_counter + 1, L.d_sel + 1, (double)g.dst_w * g.dst_h};
         rc = launch_upsharp(c, a, do_resize, g.use_sharpen != 0, st); if (rc) return rc;
         cur = a.dst; cur_pitch = a.dpitch;
     } else if (need_post_stats) {
-        rc = launch_stats(c, cur, cur_pitch, g.dst_w, g.dst_h, c->d_sums + 6, SelOut{c->d_counter + 1, c->d_sel + 1, (double)g.dst_w * g.dst_h}, st);
+        rc = launch_stats(c, cur, cur_pitch, g.dst_w, g.dst_h, L.d_sums + 6, SelOut{L.d_counter + 1, L.d_sel + 1, (double)g.dst_w * g.dst_h}, st);
         if (rc) return rc;
     }
     // temporal bookkeeping (host side: which ring slots hold t-1, t-2)
@@ -604,11 +626,12 @@ int vp_process_device(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t
         bl.state = c->nring > 1 ? c->d_state[c->head] : nullptr;
         bl.spitch = c->frame_pitch;
     }
+    if (temporal && temporal_dep) VP_CUDA(c, cudaStreamWaitEvent(st, temporal_dep, 0));
     // 4+5. SelectiveBilateral POST with the temporal blend in its epilogue
     if (g.use_post) {
         BilArgs a{};
         a.src = cur; a.spitch = cur_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.w = g.dst_w; a.h = g.dst_h;
-        a.cand = c->d_cand_post; a.sel = need_post_stats ? c->d_sel + 1 : nullptr;
+        a.cand = c->d_cand_post; a.sel = need_post_stats ? L.d_sel + 1 : nullptr;
         a.blend = bl;
         rc = launch_bilateral(c, a, c->cand_post_rad, st, K_BIL_POST); if (rc) return rc;
     } else if (temporal) {
@@ -626,12 +649,73 @@ int vp_process_device(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t
     return VP_OK;
 }
 
+int vp_process_device(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t* d_dst, size_t dst_pitch, void* stream) {
+    if (!c) return VP_ERR_INVALID_ARG;
+    VP_CUDA(c, cudaSetDevice(c->device));
+    return process_frame(c, 0, stream ? (cudaStream_t)stream : c->s_compute, nullptr, d_src, src_pitch, d_dst, dst_pitch);
+}
+
+static int ensure_lane(vp_ctx* c, int ln) {
+    Lane& L = c->lanes[ln];
+    if (L.st) return VP_OK;
+    const vp_chain_config& g = c->cfg;
+    VP_CUDA(c, cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+    if (g.use_pre) VP_CUDA(c, cudaMalloc(&L.d_pre, c->pre_pitch * g.src_h));
+    VP_CUDA(c, cudaMalloc(&L.d_sharp, c->frame_pitch * g.dst_h));
+    VP_CUDA(c, cudaMalloc(&L.d_sums, 18 * sizeof(unsigned long long)));
+    VP_CUDA(c, cudaMalloc(&L.d_sel, 4 * sizeof(int)));
+    VP_CUDA(c, cudaMemset(L.d_sel, 0, 4 * sizeof(int)));
+    VP_CUDA(c, cudaMalloc(&L.d_counter, 4 * sizeof(unsigned)));
+    VP_CUDA(c, cudaMemset(L.d_counter, 0, 4 * sizeof(unsigned)));
+    for (Lane& X : c->lanes)
+        if (!X.ev_done) VP_CUDA(c, cudaEventCreateWithFlags(&X.ev_done, cudaEventDisableTiming));
+    if (!c->ev_batch) VP_CUDA(c, cudaEventCreateWithFlags(&c->ev_batch, cudaEventDisableTiming));
+    return VP_OK;
+}
+
+int vp_set_batch_lanes(vp_ctx* c, int lanes) {
+    if (!c || lanes < 1 || lanes > 4) return VP_ERR_INVALID_ARG;
+    c->nlanes = lanes;
+    return VP_OK;
+}
+
+int vp_process_batch_device(vp_ctx* c, int n, const uint8_t* const* d_src, size_t src_pitch, uint8_t* const* d_dst, size_t dst_pitch,
+                            void* stream) {
+    if (!c || n < 0 || (n && (!d_src || !d_dst))) return VP_ERR_INVALID_ARG;
+    if (!c->has_chain) return fail(c, VP_ERR_STATE, "vp_process_batch_device: context was created without a chain config");
+    if (n == 0) return VP_OK;
+    VP_CUDA(c, cudaSetDevice(c->device));
+    int rc = VP_OK;
+    const int NL = std::min(c->nlanes, n);
+    for (int l = 1; l < NL; ++l) { rc = ensure_lane(c, l); if (rc) return rc; }
+    if (NL == 1 && !c->lanes[0].ev_done) VP_CUDA(c, cudaEventCreateWithFlags(&c->lanes[0].ev_done, cudaEventDisableTiming));
+    cudaStream_t st0 = stream ? (cudaStream_t)stream : c->s_compute;
+    // lane 1 forks from, and later joins, the caller's stream: everything is ordered after what is already
+    // queued there, and events the caller records on it bracket the whole batch
+    if (NL > 1) {
+        if (!c->ev_batch) VP_CUDA(c, cudaEventCreateWithFlags(&c->ev_batch, cudaEventDisableTiming));
+        VP_CUDA(c, cudaEventRecord(c->ev_batch, st0));
+        for (int l = 1; l < NL; ++l) VP_CUDA(c, cudaStreamWaitEvent(c->lanes[l].st, c->ev_batch, 0));
+    }
+    cudaEvent_t prev_done = nullptr;
+    for (int i = 0; i < n; ++i) {
+        const int ln = i % NL;
+        cudaStream_t st = ln == 0 ? st0 : c->lanes[ln].st;
+        rc = process_frame(c, ln, st, prev_done, d_src[i], src_pitch, d_dst[i], dst_pitch);
+        if (rc) return rc;
+        VP_CUDA(c, cudaEventRecord(c->lanes[ln].ev_done, st));
+        prev_done = c->lanes[ln].ev_done;
+    }
+    for (int l = 1; l < NL; ++l) VP_CUDA(c, cudaStreamWaitEvent(st0, c->lanes[l].ev_done, 0));   // join
+    return VP_OK;
+}
+
 int vp_get_stage_params(vp_ctx* c, int which, int* d, double* sigma_color, double* sigma_space) {
     if (!c || which < 0 || which > 1) return VP_ERR_INVALID_ARG;
     if (!c->has_chain) return fail(c, VP_ERR_STATE, "vp_get_stage_params: no chain");
     int rc = vp_synchronize(c); if (rc) return rc;
     int sel[2];
-    VP_CUDA(c, cudaMemcpy(sel, c->d_sel, sizeof(sel), cudaMemcpyDeviceToHost));
+    VP_CUDA(c, cudaMemcpy(sel, c->lanes[c->last_lane].d_sel, sizeof(sel), cudaMemcpyDeviceToHost));
     const vp_bilateral_config& b = which == VP_STAGE_PRE ? c->cfg.pre : c->cfg.post;
     int dd = b.diameter; double sc = b.sigma_color, ss = b.sigma_space;
     if (b.adaptive_params)
@@ -784,14 +868,14 @@ int vp_selective_bilateral(vp_ctx* c, const vp_bilateral_config* cfg, const uint
         rc = build_selective_cands(c, *cfg, c->d_cand_sel, c->tmp_sel_rad, st); if (rc) return rc;
         c->tmp_sel_cfg = *cfg; c->tmp_sel_valid = true;
     }
-    unsigned long long* sums = c->d_sums + 12;
+    unsigned long long* sums = c->lanes[0].d_sums + 12;
     if (cfg->adaptive_params) {
         VP_CUDA(c, cudaMemsetAsync(sums, 0, 6 * sizeof(unsigned long long), st));
-        rc = launch_stats(c, d_src, src_pitch, w, h, sums, SelOut{c->d_counter + 2, c->d_sel + 2, (double)w * h}, st); if (rc) return rc;
+        rc = launch_stats(c, d_src, src_pitch, w, h, sums, SelOut{c->lanes[0].d_counter + 2, c->lanes[0].d_sel + 2, (double)w * h}, st); if (rc) return rc;
     }
     BilArgs a{};
     a.src = d_src; a.spitch = src_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.w = w; a.h = h;
-    a.cand = c->d_cand_sel; a.sel = cfg->adaptive_params ? c->d_sel + 2 : nullptr;
+    a.cand = c->d_cand_sel; a.sel = cfg->adaptive_params ? c->lanes[0].d_sel + 2 : nullptr;
     return launch_bilateral(c, a, c->tmp_sel_rad, st);
 }
 
