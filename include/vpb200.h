@@ -85,6 +85,10 @@ typedef struct vp_chain_config {
     int32_t use_pre;           /* m_bilateral_pre   (src/upscaler.cpp:777-784)                   */
     int32_t use_sharpen;       /* m_sharpening      (:800-807)                                   */
     int32_t use_post;          /* m_bilateral_post  (:810-817)                                   */
+    int32_t bicubic_enhance;   /* 1: the spatial part is CPUImpl's BICUBIC wrapper instead - GaussianBlur 3x3
+                                  sigma 0.5 -> cv::resize(INTER_CUBIC) -> enhanceBicubicResult (bilateral 5/30/30,
+                                  Canny 50/150, dilate 2x2, 5-point sharpen, select), src/upscaler.cpp:75-148;
+                                  use_pre / use_sharpen / use_post are ignored                       */
     vp_bilateral_config pre;
     vp_sharpen_config sharpen;
     vp_bilateral_config post;

@@ -123,6 +123,12 @@ class NumpyOps:
     def subtract(self, a, b):
         return R.subtract_sat_u8(a, b)
 
+    def canny(self, gray, low, high):
+        return R.canny_u8(gray, low, high)
+
+    def dilate_2x2(self, edges):
+        return R.dilate_2x2(edges)
+
 
 class Cv2Ops:
     name = "cv2"
@@ -171,6 +177,12 @@ class Cv2Ops:
 
     def subtract(self, a, b):
         return self.cv2.subtract(a, b)
+
+    def canny(self, gray, low, high):
+        return self.cv2.Canny(gray, low, high)
+
+    def dilate_2x2(self, edges):
+        return self.cv2.dilate(edges, self.cv2.getStructuringElement(self.cv2.MORPH_RECT, (2, 2)))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -261,6 +273,33 @@ def unsharp_mask(ops, img, mask, cfg):
 def sharpen(ops, img, cfg):
     """AdaptiveSharpening::process with adaptive_sigma=false, adaptive_sharpening.cpp:51-105."""
     return unsharp_mask(ops, img, edge_mask(ops, img, cfg), cfg)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPUImpl BICUBIC wrapper (what Upscaler(BICUBIC) runs on the reference's CPU path)
+# ------------------------------------------------------------------------------------------------
+def enhance_bicubic_result(ops, image):
+    """CPUImpl::enhanceBicubicResult, upscaler.cpp:98-148: bilateral(5,30,30) everywhere, 5-point sharpen
+    on the dilated Canny(50,150) edges (interior pixels only, :118-133), per-pixel select (:138-147)."""
+    blurred = ops.bilateral(image, 5, 30.0, 30.0)
+    gray = ops.bgr2gray(image)
+    edges = ops.canny(gray, 50, 150)
+    mask = ops.dilate_2x2(edges) > 0          # convertTo(CV_8U, 1/255): 255 -> 1, then `> 0`
+    im = image.astype(np.int32)
+    sharp = image.copy()
+    val = 5 * im[1:-1, 1:-1] - im[:-2, 1:-1] - im[2:, 1:-1] - im[1:-1, :-2] - im[1:-1, 2:]
+    inner = np.clip(val, 0, 255).astype(np.uint8)
+    sel = mask[1:-1, 1:-1]
+    sharp[1:-1, 1:-1][sel] = inner[sel]
+    return np.where(mask[..., None], sharp, blurred)
+
+
+def cpuimpl_bicubic(ops, img, dst_w, dst_h):
+    """CPUImpl::upscale for Upscaler::BICUBIC, upscaler.cpp:75-84: GaussianBlur 3x3 sigma 0.5 ->
+    cv::resize(INTER_CUBIC) -> enhanceBicubicResult."""
+    pre = ops.gaussian_u8(img, 3, 0.5)
+    up = ops.resize_cubic(pre, dst_w, dst_h)
+    return enhance_bicubic_result(ops, up)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -357,6 +396,9 @@ class ChainConfig:
         POST_PROCESSING, True, True, 5, 20.0, 20.0, False, 30.0, 1.2, 1.5, False, 2))
     temporal_cfg: TemporalConfig = field(default_factory=TemporalConfig)
     main_blend_weight: float = 0.6
+    # True: the spatial part is CPUImpl's BICUBIC wrapper (upscaler.cpp:75-148) instead of the
+    # enhancement chain; main.cpp then applies its 0.6/0.4 smoothing (temporal = TEMPORAL_MAIN_BLEND)
+    bicubic_enhance: bool = False
 
 
 class Chain:
@@ -379,6 +421,8 @@ class Chain:
     def spatial(self, frame, stages=None):
         """Everything before the temporal stage; optionally records the stage outputs."""
         ops, cfg = self.ops, self.cfg
+        if cfg.bicubic_enhance:
+            return cpuimpl_bicubic(ops, frame, cfg.dst_w, cfg.dst_h)
         x = bilateral_plain(ops, frame, cfg.pre) if cfg.use_pre else frame
         if stages is not None:
             stages["pre"] = x

@@ -351,3 +351,69 @@ def sigmoid_lut(edge_threshold):
         ev = F32(F32(F32(u) * inv255) * F32(255.0))
         lut[u] = F32(1.0 / (1.0 + math.exp(-(float(ev) - thr) * s)))
     return lut
+
+
+# --------------------------------------------------------------------------------------------
+# cv::Canny(gray8U, edges, low, high)  (aperture 3, L1 gradient)  -- upscaler.cpp:108
+# cv::dilate(edges, mask, getStructuringElement(MORPH_RECT, Size(2,2)))  -- upscaler.cpp:112
+# --------------------------------------------------------------------------------------------
+CANNY_TG22 = 13573  # (int)(0.4142135623730950488016887242097 * (1 << 15) + 0.5)
+
+
+def canny_nms_map(gray, low, high):
+    """Sobel (BORDER_REPLICATE) -> |dx|+|dy| -> non-maximum suppression exactly as cv::Canny's integer
+    tangent test.  Returns 0 (no edge), 1 (weak: low < m <= high) or 2 (strong: m > high) per pixel."""
+    g = gray.astype(np.int64)
+    p = np.pad(g, 1, mode="edge")
+    h, w = g.shape
+    dx = (p[0:h, 2:w + 2] + 2 * p[1:h + 1, 2:w + 2] + p[2:h + 2, 2:w + 2]) - (p[0:h, 0:w] + 2 * p[1:h + 1, 0:w] + p[2:h + 2, 0:w])
+    dy = (p[2:h + 2, 0:w] + 2 * p[2:h + 2, 1:w + 1] + p[2:h + 2, 2:w + 2]) - (p[0:h, 0:w] + 2 * p[0:h, 1:w + 1] + p[0:h, 2:w + 2])
+    m = np.abs(dx) + np.abs(dy)
+    mp = np.pad(m, 1, mode="constant")           # magnitude is 0 outside the image
+
+    def nb(oy, ox):
+        return mp[1 + oy:1 + oy + h, 1 + ox:1 + ox + w]
+    x = np.abs(dx)
+    y = np.abs(dy) << 15
+    tg22x = x * CANNY_TG22
+    tg67x = tg22x + (x << 16)
+    horiz = y < tg22x
+    vert = (~horiz) & (y > tg67x)
+    diag = (~horiz) & (~vert)
+    s_pos = (dx ^ dy) >= 0
+    lm_h = (m > nb(0, -1)) & (m >= nb(0, 1))
+    lm_v = (m > nb(-1, 0)) & (m >= nb(1, 0))
+    lm_d = (m > np.where(s_pos, nb(-1, -1), nb(-1, 1))) & (m > np.where(s_pos, nb(1, 1), nb(1, -1)))
+    lm = (m > low) & ((horiz & lm_h) | (vert & lm_v) | (diag & lm_d))
+    return np.where(lm, np.where(m > high, 2, 1), 0).astype(np.uint8)
+
+
+def canny_hysteresis(nms):
+    """Weak pixels 8-connected to a strong pixel become edges: fixed point of a 3x3 dilation masked by
+    the candidate set (the order cv::Canny's stack visits pixels in does not change the result)."""
+    cand = nms > 0
+    edge = nms == 2
+    while True:
+        p = np.pad(edge, 1, mode="constant")
+        h, w = edge.shape
+        grown = np.zeros_like(edge)
+        for oy in range(3):
+            for ox in range(3):
+                grown |= p[oy:oy + h, ox:ox + w]
+        grown &= cand
+        if np.array_equal(grown, edge):
+            return edge
+        edge = grown
+
+
+def canny_u8(gray, low, high):
+    return (canny_hysteresis(canny_nms_map(gray, low, high)) * 255).astype(np.uint8)
+
+
+def dilate_2x2(edges):
+    """cv::dilate with a 2x2 rectangle, default anchor (1,1): max over (y-1..y, x-1..x); outside ignored."""
+    e = edges > 0
+    p = np.pad(e, ((1, 0), (1, 0)), mode="constant")
+    h, w = e.shape
+    out = p[0:h, 0:w] | p[0:h, 1:w + 1] | p[1:h + 1, 0:w] | p[1:h + 1, 1:w + 1]
+    return (out * 255).astype(np.uint8)

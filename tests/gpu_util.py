@@ -66,6 +66,7 @@ def chain_cfg(vp, o, sw, sh):
     c = vp.ChainConfig()
     c.src_w, c.src_h, c.dst_w, c.dst_h = sw, sh, o.dst_w, o.dst_h
     c.use_pre, c.use_sharpen, c.use_post = int(o.use_pre), int(o.use_sharpen), int(o.use_post)
+    c.bicubic_enhance = int(getattr(o, "bicubic_enhance", False))
     c.pre = bilateral_cfg(vp, o.pre)
     c.sharpen = sharpen_cfg(vp, o.sharpen)
     c.post = bilateral_cfg(vp, o.post)

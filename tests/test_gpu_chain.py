@@ -105,6 +105,36 @@ def test_batch_api_is_bit_identical_to_per_frame(vp, temporal):
                 assert np.array_equal(dsts[i].cpu().numpy(), ref[i]), i
 
 
+@pytest.mark.parametrize("kind", ["scene", "noise", "flat"])
+@pytest.mark.parametrize("size,scale", [((160, 96), 2), ((131, 67), 2), ((96, 54), 4)])
+def test_bicubic_wrapper_chain(vp, kind, size, scale):
+    """CPUImpl's BICUBIC wrapper (GaussianBlur 3x3 -> INTER_CUBIC -> enhanceBicubicResult with Canny) followed by
+    main.cpp's 0.6/0.4 smoothing.  Blur, resize, gray, Canny, dilate and the 5-point sharpen are integer and
+    bit-exact; only the bilateral-filtered (non-edge) pixels may differ, by at most 1 LSB."""
+    sw, sh = size
+    ocfg = RC.ChainConfig(dst_w=scale * sw, dst_h=scale * sh, temporal=RC.TEMPORAL_MAIN_BLEND, bicubic_enhance=True)
+    frames = synth.clip(kind, sw, sh, 3)
+    oracle = RC.Chain(RC.NumpyOps(), ocfg)
+    refs = [oracle.process(f) for f in frames]
+    outs, _ = run_chain_device(vp, ocfg, frames, sw, sh)
+    for o, r in zip(outs, refs):
+        mx, nd = G.diff_stats(o, r)
+        assert mx <= 1 and nd <= o.size // 500, (mx, nd)
+
+
+def test_bicubic_wrapper_full_size_against_cv2(vp):
+    """BASELINE config C1 (1280x720 -> 2560x1440) through the wrapper, against the real OpenCV kernels."""
+    sw, sh = 1280, 720
+    ocfg = RC.ChainConfig(dst_w=2 * sw, dst_h=2 * sh, temporal=RC.TEMPORAL_MAIN_BLEND, bicubic_enhance=True)
+    frames = synth.clip("scene", sw, sh, 2)
+    oracle = RC.Chain(RC.Cv2Ops(), ocfg)
+    refs = [oracle.process(f) for f in frames]
+    outs, _ = run_chain_device(vp, ocfg, frames, sw, sh)
+    for o, r in zip(outs, refs):
+        mx, nd = G.diff_stats(o, r)
+        assert mx <= 1 and nd <= o.size // 500, (mx, nd)
+
+
 def test_host_paths_match_device_path(vp):
     sw, sh, n = 128, 72, 6
     ocfg = RC.ChainConfig(dst_w=2 * sw, dst_h=2 * sh, temporal=RC.TEMPORAL_BLEND_FRAMES)

@@ -81,6 +81,20 @@ def test_edge_combination_integer_form():
     assert np.array_equal(f2, (s + ((s >> 1) & 1)) >> 1)
 
 
+@pytest.mark.parametrize("kind", ["scene", "noise", "flat"])
+def test_canny_and_dilate_bit_exact(kind):
+    g = cv2.cvtColor(synth.frame(kind, 257, 131, 3), cv2.COLOR_BGR2GRAY)
+    e = cv2.Canny(g, 50, 150)
+    assert np.array_equal(R.canny_u8(g, 50, 150), e)
+    assert np.array_equal(R.dilate_2x2(e), cv2.dilate(e, cv2.getStructuringElement(cv2.MORPH_RECT, (2, 2))))
+
+
+@pytest.mark.parametrize("kind", ["scene", "noise"])
+def test_cpuimpl_bicubic_wrapper_numpy_vs_cv2(kind):
+    img = synth.frame(kind, 120, 68, 1)
+    assert np.array_equal(RC.cpuimpl_bicubic(RC.NumpyOps(), img, 240, 136), RC.cpuimpl_bicubic(RC.Cv2Ops(), img, 240, 136))
+
+
 def test_mean_stddev_matches_cv2():
     img = synth.frame("scene", 160, 90, 0)
     m, s, _, _ = R.mean_stddev(img)

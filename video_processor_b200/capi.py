@@ -34,7 +34,7 @@ class TemporalConfig(C.Structure):
 
 class ChainConfig(C.Structure):
     _fields_ = [("src_w", C.c_int32), ("src_h", C.c_int32), ("dst_w", C.c_int32), ("dst_h", C.c_int32),
-                ("use_pre", C.c_int32), ("use_sharpen", C.c_int32), ("use_post", C.c_int32),
+                ("use_pre", C.c_int32), ("use_sharpen", C.c_int32), ("use_post", C.c_int32), ("bicubic_enhance", C.c_int32),
                 ("pre", BilateralConfig), ("sharpen", SharpenConfig), ("post", BilateralConfig),
                 ("temporal", TemporalConfig)]
 

@@ -49,6 +49,9 @@ struct BilArgs {
     const int* sel;                // noise class chosen by the stats producer's last CTA (may be null)
     int radius[3];                 // radius of each candidate (host copy, saves a dependent global load)
     int ns;                        // strips per thread: the CTA tile is BIL_TW x (BIL_TH * ns)
+    // CPUImpl::enhanceBicubicResult (src/upscaler.cpp:112-147): where the 2x2-dilated Canny edge map is set
+    // the output is the 5-point sharpened source pixel (interior pixels) instead of the filtered one
+    const uint8_t* emap; size_t epitch;
     BlendArgs blend;
 };
 
@@ -295,6 +298,39 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
             case 5: bil_strip<5>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
             case 6: bil_strip<6>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
             default: bil_strip<7>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
+        }
+        if (a.emap) {
+            constexpr int dummy = 0; (void)dummy;
+            const int TPr = bil_tile_pitch(R);
+#pragma unroll
+            for (int j = 0; j < BIL_PX; ++j) {
+                const int x = gx + j;
+                if (x >= a.w) break;
+                // dilate 2x2, anchor (1,1): max over (y-1..y, x-1..x), outside ignored
+                bool edge = a.emap[(size_t)gy * a.epitch + x] == 2;
+                if (x > 0) edge = edge || a.emap[(size_t)gy * a.epitch + x - 1] == 2;
+                if (gy > 0) {
+                    edge = edge || a.emap[(size_t)(gy - 1) * a.epitch + x] == 2;
+                    if (x > 0) edge = edge || a.emap[(size_t)(gy - 1) * a.epitch + x - 1] == 2;
+                }
+                if (edge) {
+                    const uint32_t* t = s_tile + (ly + R) * TPr + lx + R + j;
+                    uint32_t v = t[0] & 0xffffffu;
+                    if (x >= 1 && x < a.w - 1 && gy >= 1 && gy < a.h - 1) {
+                        const uint32_t up = t[-TPr], dn = t[TPr], lf = t[-1], rt = t[1];
+                        uint32_t r = 0;
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            const int sh = 8 * ch;
+                            const int val = 5 * (int)((v >> sh) & 0xff) - (int)((up >> sh) & 0xff) - (int)((dn >> sh) & 0xff) -
+                                            (int)((lf >> sh) & 0xff) - (int)((rt >> sh) & 0xff);
+                            r |= (uint32_t)sat_u8(val) << sh;
+                        }
+                        v = r;
+                    }
+                    out[j] = v;
+                }
+            }
         }
         // epilogue: optional temporal blend, state store, output store (12 contiguous bytes per strip)
         uint32_t cur[3];   // 12 packed bytes B G R B | G R B G | R B G R

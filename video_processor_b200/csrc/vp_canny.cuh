@@ -1,0 +1,204 @@
+// vp_canny.cuh - the pieces of CPUImpl's BICUBIC wrapper (reference src/upscaler.cpp:75-148) that are not
+// already kernels of the enhancement chain:
+//   k_gauss3      cv::GaussianBlur(input, Size(3,3), 0.5) on CV_8UC3         upscaler.cpp:78
+//   k_canny_nms   cv::cvtColor(BGR2GRAY) + cv::Canny's Sobel / |dx|+|dy| / non-maximum suppression   :107-108
+//   k_canny_hyst  cv::Canny's hysteresis (weak pixels 8-connected to a strong one)                      :108
+// The dilate(2x2) + 5-point sharpen + per-pixel select (:112-147) live in k_bilateral's epilogue.
+// Arithmetic is integer throughout and follows oracle/restate.py (gaussian_blur_u8, bgr2gray,
+// canny_nms_map, canny_hysteresis), which tests/test_oracle_restate.py pins against cv2: bit-exact.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "vp_common.cuh"
+
+namespace vp {
+
+// ---------------------------------------------------------------------------------------------------
+// 3x3 8-bit Gaussian, Q8 taps (q0,q1,q0), BORDER_REFLECT_101; exact: (sum q_i q_j p + 2^15) >> 16
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gauss3(const uint8_t* __restrict__ src, size_t spitch, uint8_t* __restrict__ dst, size_t dpitch,
+                                                int w, int h, int q0, int q1) {
+    const int row_px = w;
+    const long long total = (long long)row_px * h;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / row_px), x = (int)(i - (long long)y * row_px);
+        const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+        const uint8_t* r0 = src + (size_t)reflect101(y - 1, h) * spitch;
+        const uint8_t* r1 = src + (size_t)y * spitch;
+        const uint8_t* r2 = src + (size_t)reflect101(y + 1, h) * spitch;
+        uint8_t* o = dst + (size_t)y * dpitch + (size_t)x * 3;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const int a0 = q0 * (r0[xm * 3 + ch] + r0[xp * 3 + ch]) + q1 * r0[x * 3 + ch];
+            const int a1 = q0 * (r1[xm * 3 + ch] + r1[xp * 3 + ch]) + q1 * r1[x * 3 + ch];
+            const int a2 = q0 * (r2[xm * 3 + ch] + r2[xp * 3 + ch]) + q1 * r2[x * 3 + ch];
+            o[ch] = (uint8_t)((q0 * (a0 + a2) + q1 * a1 + (1 << 15)) >> 16);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// gray + Sobel + magnitude + non-maximum suppression -> map: 0 none, 1 weak (low < m <= high), 2 strong
+// ---------------------------------------------------------------------------------------------------
+constexpr int CN_TW = 64, CN_TH = 32, CN_NT = 256;
+constexpr int CN_GW = CN_TW + 4, CN_GH = CN_TH + 4;      // gray tile, halo 2
+constexpr int CN_MW = CN_TW + 2, CN_MH = CN_TH + 2;      // magnitude tile, halo 1
+
+struct CannyArgs {
+    const uint8_t* img; size_t ipitch; int w, h;         // BGR8 image the edges are taken from
+    uint8_t* map; size_t mpitch;                          // w x h bytes
+    int low, high;
+};
+
+__global__ void __launch_bounds__(CN_NT) k_canny_nms(const CannyArgs a) {
+    __shared__ uint8_t s_gray[CN_GH][CN_GW + 4];
+    __shared__ int s_grad[CN_MH][CN_MW];                  // (dx & 0xffff) | (dy << 16)
+    __shared__ uint16_t s_mag[CN_MH][CN_MW + 2];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * CN_TW, y0 = blockIdx.y * CN_TH;
+    // gray with BORDER_REPLICATE (what cv::Canny's Sobel uses): clamp the coordinates
+    for (int i = tid; i < CN_GW * CN_GH; i += CN_NT) {
+        const int gy = i / CN_GW, gx = i - gy * CN_GW;
+        const int x = clampi(x0 - 2 + gx, 0, a.w - 1), y = clampi(y0 - 2 + gy, 0, a.h - 1);
+        const uint8_t* p = a.img + (size_t)y * a.ipitch + (size_t)x * 3;
+        s_gray[gy][gx] = (uint8_t)((9798 * p[2] + 19235 * p[1] + 3735 * p[0] + (1 << 14)) >> 15);
+    }
+    __syncthreads();
+    for (int i = tid; i < CN_MW * CN_MH; i += CN_NT) {
+        const int my = i / CN_MW, mx = i - my * CN_MW;
+        const int x = x0 - 1 + mx, y = y0 - 1 + my;
+        int dx = 0, dy = 0, mag = 0;
+        if (x >= 0 && x < a.w && y >= 0 && y < a.h) {       // the magnitude is 0 outside the image
+            const int g00 = s_gray[my][mx], g01 = s_gray[my][mx + 1], g02 = s_gray[my][mx + 2];
+            const int g10 = s_gray[my + 1][mx], g12 = s_gray[my + 1][mx + 2];
+            const int g20 = s_gray[my + 2][mx], g21 = s_gray[my + 2][mx + 1], g22 = s_gray[my + 2][mx + 2];
+            dx = (g02 + 2 * g12 + g22) - (g00 + 2 * g10 + g20);
+            dy = (g20 + 2 * g21 + g22) - (g00 + 2 * g01 + g02);
+            mag = abs(dx) + abs(dy);
+        }
+        s_grad[my][mx] = (dx & 0xffff) | (dy << 16);
+        s_mag[my][mx] = (uint16_t)mag;
+    }
+    __syncthreads();
+    for (int i = tid; i < CN_TW * CN_TH; i += CN_NT) {
+        const int ty = i / CN_TW, tx = i - ty * CN_TW;
+        const int x = x0 + tx, y = y0 + ty;
+        if (x >= a.w || y >= a.h) continue;
+        const int my = ty + 1, mx = tx + 1;
+        const int m = s_mag[my][mx];
+        uint8_t out = 0;
+        if (m > a.low) {
+            const int g = s_grad[my][mx];
+            const int dx = (int)(short)(g & 0xffff), dy = g >> 16;
+            const int ax = abs(dx), ay = abs(dy) << 15;       // |dy| <= 1020: fits
+            const int tg22x = ax * 13573;
+            bool lm;
+            if (ay < tg22x) {
+                lm = m > s_mag[my][mx - 1] && m >= s_mag[my][mx + 1];
+            } else {
+                const int tg67x = tg22x + (ax << 16);
+                if (ay > tg67x) {
+                    lm = m > s_mag[my - 1][mx] && m >= s_mag[my + 1][mx];
+                } else {
+                    const int s = ((dx ^ dy) < 0) ? -1 : 1;
+                    lm = m > s_mag[my - 1][mx - s] && m > s_mag[my + 1][mx + s];
+                }
+            }
+            if (lm) out = m > a.high ? 2 : 1;
+        }
+        a.map[(size_t)y * a.mpitch + x] = out;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// hysteresis: one cooperative launch; per tile a breadth-first frontier in shared memory, tiles whose
+// neighbourhood changed are revisited after a grid-wide barrier until nothing changes anywhere
+// ---------------------------------------------------------------------------------------------------
+constexpr int HY_T = 64, HY_NT = 256, HY_P = HY_T + 2;
+
+struct HystArgs {
+    uint8_t* map; size_t mpitch; int w, h;
+    int tiles_x, tiles_y;
+    unsigned char* dirty;          // 2 * ntiles flags (ping-pong); dirty[0..ntiles) preset to 1 by the host memset
+    unsigned* again;               // 2 counters (ping-pong), zeroed by the host memset
+};
+
+__global__ void __launch_bounds__(HY_NT) k_canny_hyst(const HystArgs a) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int s_map[HY_P * HY_P];
+    __shared__ unsigned short s_q[2][HY_P * HY_P];
+    __shared__ int s_n[2];
+    __shared__ int s_changed;
+    const int tid = threadIdx.x;
+    const int ntiles = a.tiles_x * a.tiles_y;
+    for (int iter = 0;; ++iter) {
+        unsigned char* dcur = a.dirty + (iter & 1) * ntiles;
+        unsigned char* dnext = a.dirty + ((iter + 1) & 1) * ntiles;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            if (!*(volatile unsigned char*)&dcur[t]) continue;
+            const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+            const int x0 = tx * HY_T - 1, y0 = ty * HY_T - 1;     // origin of the halo tile
+            if (tid == 0) { s_n[0] = 0; s_n[1] = 0; s_changed = 0; }
+            __syncthreads();
+            for (int i = tid; i < HY_P * HY_P; i += HY_NT) {
+                const int py = i / HY_P, px = i - py * HY_P;
+                const int x = x0 + px, y = y0 + py;
+                int v = 0;
+                if (x >= 0 && x < a.w && y >= 0 && y < a.h) v = __ldcg(a.map + (size_t)y * a.mpitch + x);   // L2: other CTAs write it
+                s_map[i] = v;
+                if (v == 2) s_q[0][atomicAdd(&s_n[0], 1)] = (unsigned short)i;
+            }
+            __syncthreads();
+            int cur = 0;
+            while (true) {
+                const int n = s_n[cur];
+                if (n == 0) break;
+                for (int k = tid; k < n; k += HY_NT) {
+                    const int i = s_q[cur][k];
+                    const int py = i / HY_P, px = i - py * HY_P;
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int qy = py + dy, qx = px + dx;
+                            // only interior pixels are owned (and written back) by this tile
+                            if ((dx | dy) != 0 && qy >= 1 && qy <= HY_T && qx >= 1 && qx <= HY_T) {
+                                const int j = qy * HY_P + qx;
+                                if (s_map[j] == 1 && atomicCAS(&s_map[j], 1, 2) == 1) {
+                                    s_q[cur ^ 1][atomicAdd(&s_n[cur ^ 1], 1)] = (unsigned short)j;
+                                    s_changed = 1;
+                                }
+                            }
+                        }
+                }
+                __syncthreads();
+                if (tid == 0) s_n[cur] = 0;
+                cur ^= 1;
+                __syncthreads();
+            }
+            if (s_changed) {
+                for (int i = tid; i < HY_T * HY_T; i += HY_NT) {
+                    const int py = i / HY_T + 1, px = (i & (HY_T - 1)) + 1;
+                    const int x = x0 + px, y = y0 + py;
+                    if (x < a.w && y < a.h && s_map[py * HY_P + px] == 2) a.map[(size_t)y * a.mpitch + x] = 2;
+                }
+                if (tid < 9) {                                  // neighbours must look again
+                    const int ny = ty + tid / 3 - 1, nx = tx + tid % 3 - 1;
+                    if (tid != 4 && ny >= 0 && ny < a.tiles_y && nx >= 0 && nx < a.tiles_x) dnext[ny * a.tiles_x + nx] = 1;
+                }
+                if (tid == 0) atomicAdd(&a.again[iter & 1], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) dcur[t] = 0;
+        }
+        __threadfence();
+        grid.sync();
+        const unsigned more = *(volatile unsigned*)&a.again[iter & 1];
+        if (blockIdx.x == 0 && tid == 0) a.again[(iter + 1) & 1] = 0;   // next iteration's counter
+        if (!more) break;
+        grid.sync();                                           // everyone has read `again[iter&1]` before it is reused
+    }
+}
+
+}  // namespace vp

@@ -22,6 +22,7 @@
 #include "vp_bicubic.cuh"
 #include "vp_bilateral.cuh"
 #include "vp_blend.cuh"
+#include "vp_canny.cuh"
 #include "vp_stats.cuh"
 #include "vp_tables.h"
 #include "vp_upsharp.cuh"
@@ -57,6 +58,8 @@ struct Lane {                       // per-frame intermediates; two lanes let co
     int* d_sel = nullptr;           // [0] PRE class, [1] POST class, [2] stage-wise
     unsigned* d_counter = nullptr;  // CTA ticket counters of the three sel producers
     cudaEvent_t ev_done = nullptr;
+    uint8_t* d_map = nullptr;       // Canny map (bicubic_enhance chains): 0 none, 1 weak, 2 edge
+    unsigned char* d_dirty = nullptr;   // hysteresis tile flags (2 x ntiles) followed by the 2 `again` counters
 };
 
 struct vp_ctx {
@@ -65,6 +68,8 @@ struct vp_ctx {
     int nlanes = 2;                 // lanes vp_process_batch_device cycles through (vp_set_batch_lanes)
     cudaEvent_t ev_batch = nullptr;
     int last_lane = 0;
+    size_t map_pitch = 0; int hy_tiles_x = 0, hy_tiles_y = 0, hy_grid = 0; size_t dirty_bytes = 0;
+    BilCand* d_cand_be = nullptr; int cand_be_rad[3] = {0, 0, 0};
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     bool has_chain = false;
     vp_chain_config cfg{};
@@ -132,6 +137,7 @@ struct ProfScope {   // brackets one launch with CUDA events on its stream when 
     } while (0)
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
 
 int check_frame(vp_ctx* c, const void* p, size_t pitch, int w, int h, const char* what) {
     if (!p) return fail(c, VP_ERR_INVALID_ARG, std::string(what) + ": null pointer");
@@ -357,6 +363,15 @@ bool host_ptr_is_pinned(const void* p) {
     return at.type == cudaMemoryTypeHost;
 }
 
+int alloc_enhance_buffers(vp_ctx* c, Lane& L) {
+    const vp_chain_config& g = c->cfg;
+    if (!g.bicubic_enhance || L.d_map) return VP_OK;
+    if (!L.d_pre) VP_CUDA(c, cudaMalloc(&L.d_pre, c->pre_pitch * g.src_h));
+    VP_CUDA(c, cudaMalloc(&L.d_map, c->map_pitch * g.dst_h));
+    VP_CUDA(c, cudaMalloc(&L.d_dirty, c->dirty_bytes));
+    return VP_OK;
+}
+
 constexpr int PIPE_DEPTH = 3;
 
 }  // namespace
@@ -403,11 +418,13 @@ void vp_destroy(vp_ctx* c) {
     for (auto& e : c->prof_pool) cudaEventDestroy(e);
     for (Lane& L : c->lanes) {
         cudaFree(L.d_pre); cudaFree(L.d_sharp); cudaFree(L.d_sums); cudaFree(L.d_sel); cudaFree(L.d_counter);
+        cudaFree(L.d_map); cudaFree(L.d_dirty);
         if (L.ev_done) cudaEventDestroy(L.ev_done);
         if (L.st) cudaStreamDestroy(L.st);
     }
     if (c->ev_batch) cudaEventDestroy(c->ev_batch);
     for (auto& p : c->d_state) cudaFree(p);
+    cudaFree(c->d_cand_be);
     cudaFree(c->d_cand_pre); cudaFree(c->d_cand_post); cudaFree(c->d_cand_tmp); cudaFree(c->d_cand_sel);
     free_resize(c->rc_chain); free_resize(c->rc_tmp);
     cudaFree(c->d_siglut); cudaFree(c->d_siglut_tmp);
@@ -454,13 +471,13 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
         return fail(c, VP_ERR_UNSUPPORTED, "vp_create: temporal.buffer_size must be 1..3");
     c->pre_pitch = align_up((size_t)g.src_w * 3, 256);
     c->frame_pitch = align_up((size_t)g.dst_w * 3, 256);
-    if (g.use_pre) {
+    if (g.use_pre && !g.bicubic_enhance) {
         VP_CUDA(c, cudaMalloc(&c->lanes[0].d_pre, c->pre_pitch * g.src_h));
         VP_CUDA(c, cudaMalloc(&c->d_cand_pre, 3 * sizeof(BilCand)));
         int rc = build_selective_cands(c, g.pre, c->d_cand_pre, c->cand_pre_rad, c->s_compute);
         if (rc) return rc;
     }
-    if (g.use_post) {
+    if (g.use_post && !g.bicubic_enhance) {
         VP_CUDA(c, cudaMalloc(&c->d_cand_post, 3 * sizeof(BilCand)));
         int rc = build_selective_cands(c, g.post, c->d_cand_post, c->cand_post_rad, c->s_compute);
         if (rc) return rc;
@@ -473,14 +490,27 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
         int rc = ensure_resize(c, c->rc_chain, g.src_w, g.src_h, g.dst_w, g.dst_h, c->s_compute);
         if (rc) return rc;
     }
-    if (g.use_sharpen) {
+    if (g.bicubic_enhance) {
+        c->map_pitch = align_up((size_t)g.dst_w, 256);
+        c->hy_tiles_x = (g.dst_w + HY_T - 1) / HY_T; c->hy_tiles_y = (g.dst_h + HY_T - 1) / HY_T;
+        c->dirty_bytes = align_up((size_t)2 * c->hy_tiles_x * c->hy_tiles_y, 16) + 16;
+        int per_sm = 0;
+        VP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canny_hyst, HY_NT, 0));
+        c->hy_grid = std::max(1, std::min(per_sm * c->sm_count, c->hy_tiles_x * c->hy_tiles_y));
+        VP_CUDA(c, cudaMalloc(&c->d_cand_be, 3 * sizeof(BilCand)));
+        vp_bilateral_config fixed{VP_STAGE_PRE, 0, 5, 0, 30.0, 30.0};      // cv::bilateralFilter(image, blurred, 5, 30, 30)
+        int rc = build_selective_cands(c, fixed, c->d_cand_be, c->cand_be_rad, c->s_compute);
+        if (rc) return rc;
+        rc = alloc_enhance_buffers(c, c->lanes[0]); if (rc) return rc;
+    }
+    if (g.use_sharpen && !g.bicubic_enhance) {
         UpsharpArgs tmp{};
         int rc = fill_sharpen_args(c, tmp, g.sharpen);
         if (rc) return rc;
         rc = ensure_siglut(c, &c->d_siglut, &c->siglut_thr, &c->siglut_valid, g.sharpen.edge_threshold, c->s_compute);
         if (rc) return rc;
     }
-    c->nlanes = (!g.use_pre && !g.use_sharpen && !g.use_post) ? 4 : 3;
+    c->nlanes = (!g.bicubic_enhance && !g.use_pre && !g.use_sharpen && !g.use_post) ? 4 : 3;
     c->has_chain = true;
     return VP_OK;
 }
@@ -550,6 +580,78 @@ int vp_reset_temporal(vp_ctx* c) {
 }
 
 // ---- the chain -----------------------------------------------------------------------------------
+// temporal bookkeeping shared by both chain forms: which ring slots hold t-1, t-2 and where t is kept
+static void temporal_args(vp_ctx* c, bool temporal, BlendArgs& bl) {
+    const vp_chain_config& g = c->cfg;
+    if (!temporal) return;
+    const int maxprev = g.temporal.mode == VP_TEMPORAL_MAIN_BLEND ? 1 : g.temporal.buffer_size - 1;
+    const int nprev = std::min(c->nvalid, maxprev);
+    blend_weights(g.temporal, nprev, bl);
+    for (int i = 0; i < nprev; ++i) bl.prev[i] = c->d_state[(c->head - 1 - i + 2 * c->nring) % c->nring];
+    bl.ppitch = c->frame_pitch;
+    // with a single ring slot (buffer_size 1) nothing is ever blended and no state is kept
+    bl.state = c->nring > 1 ? c->d_state[c->head] : nullptr;
+    bl.spitch = c->frame_pitch;
+}
+static void temporal_advance(vp_ctx* c, bool temporal) {
+    if (temporal && c->nring > 1) {
+        c->head = (c->head + 1) % c->nring;
+        c->nvalid = std::min(c->nvalid + 1, c->nring - 1);
+    }
+}
+
+// CPUImpl's BICUBIC wrapper (src/upscaler.cpp:75-148) + the temporal stage:
+//   k_gauss3 -> k_bicubic -> k_canny_nms -> k_canny_hyst (cooperative) -> k_bilateral(5,30,30) with the
+//   edge-select epilogue and the fused temporal blend
+static int process_frame_enhance(vp_ctx* c, Lane& L, cudaStream_t st, cudaEvent_t temporal_dep, bool temporal,
+                                 const uint8_t* d_src, size_t src_pitch, uint8_t* d_dst, size_t dst_pitch) {
+    const vp_chain_config& g = c->cfg;
+    int q3[7];
+    vp_host::gaussian_kernel_q8(3, 0.5, q3);
+    {
+        ProfScope ps(c, K_STATS, st);
+        const long long px = (long long)g.src_w * g.src_h;
+        const unsigned grid = (unsigned)std::min<long long>((px + 255) / 256, (long long)c->sm_count * 16);
+        k_gauss3<<<grid, 256, 0, st>>>(d_src, src_pitch, L.d_pre, c->pre_pitch, g.src_w, g.src_h, q3[0], q3[1]);
+        VP_CUDA(c, cudaGetLastError());
+        c->launches++;
+    }
+    int rc;
+    if (g.dst_w != g.src_w || g.dst_h != g.src_h) {
+        rc = launch_bicubic(c, L.d_pre, c->pre_pitch, g.src_w, g.src_h, L.d_sharp, c->frame_pitch, g.dst_w, g.dst_h, c->rc_chain, st);
+        if (rc) return rc;
+    } else {
+        VP_CUDA(c, cudaMemcpy2DAsync(L.d_sharp, c->frame_pitch, L.d_pre, c->pre_pitch, (size_t)g.src_w * 3, g.src_h, cudaMemcpyDeviceToDevice, st));
+    }
+    {
+        ProfScope ps(c, K_BLEND, st);
+        CannyArgs a{L.d_sharp, c->frame_pitch, g.dst_w, g.dst_h, L.d_map, c->map_pitch, 50, 150};
+        const dim3 grid((g.dst_w + CN_TW - 1) / CN_TW, (g.dst_h + CN_TH - 1) / CN_TH);
+        k_canny_nms<<<grid, CN_NT, 0, st>>>(a);
+        VP_CUDA(c, cudaGetLastError());
+        c->launches++;
+        const int ntiles = c->hy_tiles_x * c->hy_tiles_y;
+        VP_CUDA(c, cudaMemsetAsync(L.d_dirty, 1, ntiles, st));
+        VP_CUDA(c, cudaMemsetAsync(L.d_dirty + ntiles, 0, c->dirty_bytes - ntiles, st));
+        HystArgs hy{L.d_map, c->map_pitch, g.dst_w, g.dst_h, c->hy_tiles_x, c->hy_tiles_y, L.d_dirty,
+                    reinterpret_cast<unsigned*>(L.d_dirty + c->dirty_bytes - 16)};
+        void* params[] = {&hy};
+        VP_CUDA(c, cudaLaunchCooperativeKernel((void*)k_canny_hyst, dim3(c->hy_grid), dim3(HY_NT), params, 0, st));
+        c->launches++;
+    }
+    BlendArgs bl{};
+    temporal_args(c, temporal, bl);
+    if (temporal && temporal_dep) VP_CUDA(c, cudaStreamWaitEvent(st, temporal_dep, 0));
+    BilArgs a{};
+    a.src = L.d_sharp; a.spitch = c->frame_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.w = g.dst_w; a.h = g.dst_h;
+    a.cand = c->d_cand_be; a.sel = nullptr;
+    a.emap = L.d_map; a.epitch = c->map_pitch;
+    a.blend = bl;
+    rc = launch_bilateral(c, a, c->cand_be_rad, st, K_BIL_POST); if (rc) return rc;
+    temporal_advance(c, temporal);
+    return VP_OK;
+}
+
 // One frame through the chain on stream `st`, using lane `ln`'s intermediates.  `temporal_dep` (may be null)
 // is waited on right before the kernel that reads the temporal state (the previous frame's last kernel when
 // consecutive frames run on different streams).
@@ -566,6 +668,7 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
     const bool temporal = g.temporal.mode != VP_TEMPORAL_NONE && c->nring > 0;
     if (!d_dst && !temporal) return VP_OK;   // warm-up frame of a chain without temporal state: nothing to do
 
+    if (g.bicubic_enhance) return process_frame_enhance(c, L, st, temporal_dep, temporal, d_src, src_pitch, d_dst, dst_pitch);
     const bool need_pre_stats = g.use_pre && g.pre.adaptive_params;
     const bool need_post_stats = g.use_post && g.post.adaptive_params;
     if (need_pre_stats || need_post_stats)
@@ -614,18 +717,8 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
         rc = launch_stats(c, cur, cur_pitch, g.dst_w, g.dst_h, L.d_sums + 6, SelOut{L.d_counter + 1, L.d_sel + 1, (double)g.dst_w * g.dst_h}, st);
         if (rc) return rc;
     }
-    // temporal bookkeeping (host side: which ring slots hold t-1, t-2)
     BlendArgs bl{};
-    if (temporal) {
-        const int maxprev = g.temporal.mode == VP_TEMPORAL_MAIN_BLEND ? 1 : g.temporal.buffer_size - 1;
-        const int nprev = std::min(c->nvalid, maxprev);
-        blend_weights(g.temporal, nprev, bl);
-        for (int i = 0; i < nprev; ++i) bl.prev[i] = c->d_state[(c->head - 1 - i + 2 * c->nring) % c->nring];
-        bl.ppitch = c->frame_pitch;
-        // with a single ring slot (buffer_size 1) nothing is ever blended and no state is kept
-        bl.state = c->nring > 1 ? c->d_state[c->head] : nullptr;
-        bl.spitch = c->frame_pitch;
-    }
+    temporal_args(c, temporal, bl);
     if (temporal && temporal_dep) VP_CUDA(c, cudaStreamWaitEvent(st, temporal_dep, 0));
     // 4+5. SelectiveBilateral POST with the temporal blend in its epilogue
     if (g.use_post) {
@@ -642,10 +735,7 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
     } else if (cur == d_src) {
         VP_CUDA(c, cudaMemcpy2DAsync(d_dst, dst_pitch, d_src, src_pitch, (size_t)g.src_w * 3, g.src_h, cudaMemcpyDeviceToDevice, st));
     }
-    if (temporal && c->nring > 1) {
-        c->head = (c->head + 1) % c->nring;
-        c->nvalid = std::min(c->nvalid + 1, c->nring - 1);
-    }
+    temporal_advance(c, temporal);
     return VP_OK;
 }
 
@@ -655,18 +745,20 @@ int vp_process_device(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t
     return process_frame(c, 0, stream ? (cudaStream_t)stream : c->s_compute, nullptr, d_src, src_pitch, d_dst, dst_pitch);
 }
 
+
 static int ensure_lane(vp_ctx* c, int ln) {
     Lane& L = c->lanes[ln];
     if (L.st) return VP_OK;
     const vp_chain_config& g = c->cfg;
     VP_CUDA(c, cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
-    if (g.use_pre) VP_CUDA(c, cudaMalloc(&L.d_pre, c->pre_pitch * g.src_h));
+    if (g.use_pre && !g.bicubic_enhance) VP_CUDA(c, cudaMalloc(&L.d_pre, c->pre_pitch * g.src_h));
     VP_CUDA(c, cudaMalloc(&L.d_sharp, c->frame_pitch * g.dst_h));
     VP_CUDA(c, cudaMalloc(&L.d_sums, 18 * sizeof(unsigned long long)));
     VP_CUDA(c, cudaMalloc(&L.d_sel, 4 * sizeof(int)));
     VP_CUDA(c, cudaMemset(L.d_sel, 0, 4 * sizeof(int)));
     VP_CUDA(c, cudaMalloc(&L.d_counter, 4 * sizeof(unsigned)));
     VP_CUDA(c, cudaMemset(L.d_counter, 0, 4 * sizeof(unsigned)));
+    { int rc = alloc_enhance_buffers(c, L); if (rc) return rc; }
     for (Lane& X : c->lanes)
         if (!X.ev_done) VP_CUDA(c, cudaEventCreateWithFlags(&X.ev_done, cudaEventDisableTiming));
     if (!c->ev_batch) VP_CUDA(c, cudaEventCreateWithFlags(&c->ev_batch, cudaEventDisableTiming));
