@@ -33,9 +33,13 @@ WORKLOADS = {
     "c4": (1920, 1080, 3840, 2160, 1, 1, 1, "frames"),   # C2 chain + temporal (C4 at n_gpus = N)
     "c2": (1920, 1080, 3840, 2160, 1, 1, 1, "none"),
     "c3": (3840, 2160, 7680, 4320, 1, 1, 1, "frames"),
-    "c1": (1280, 720, 2560, 1440, 0, 0, 0, "none"),      # bicubic only
-    "c5": (960, 540, 3840, 2160, 0, 0, 0, "none"),       # bicubic x4
+    "c1": (1280, 720, 2560, 1440, 0, 0, 0, "none"),      # bare cv::resize(INTER_CUBIC) x2
+    "c5": (960, 540, 3840, 2160, 0, 0, 0, "none"),       # bare cv::resize(INTER_CUBIC) x4
+    # C1 as `video_processor <file> --fast` literally runs it: Upscaler(BICUBIC) = CPUImpl's wrapper
+    # (pre-blur, bicubic, enhanceBicubicResult) + main.cpp's 0.6/0.4 smoothing
+    "c1w": (1280, 720, 2560, 1440, 0, 0, 0, "main"),
 }
+ENHANCE = {"c1w"}
 SEED = 20260
 
 
@@ -152,6 +156,7 @@ def build_cfg(capi, wl, temporal):
     sw, sh, dw, dh, pre, sharpen, post, tdef = WORKLOADS[wl]
     cfg = capi.default_chain_config(sw, sh, dw, dh)
     cfg.use_pre, cfg.use_sharpen, cfg.use_post = pre, sharpen, post
+    cfg.bicubic_enhance = 1 if wl in ENHANCE else 0
     t = temporal or tdef
     cfg.temporal.mode = {"none": capi.VP_TEMPORAL_NONE, "main": capi.VP_TEMPORAL_MAIN_BLEND, "frames": capi.VP_TEMPORAL_BLEND_FRAMES}[t]
     return cfg, t
@@ -163,6 +168,9 @@ def algorithmic_bytes(wl, temporal, cfg):
     inb, outb = sw * sh * 3, dw * dh * 3
     nprev = {"none": 0, "main": 1, "frames": max(cfg.temporal.buffer_size - 1, 0)}[temporal]
     chain = inb + outb + (nprev * outb + outb if nprev else 0)
+    if wl in ENHANCE:   # profile kinds are reused: stats = gauss3, upsharp = bicubic, blend = canny (nms + hysteresis)
+        return chain, {"stats": 2 * inb, "upsharp": inb + outb, "blend": outb + 2 * (outb // 3),
+                       "bilateral_post": 2 * outb + outb // 3 + (nprev * outb + outb if nprev else 0)}, inb, outb
     per_kernel = {
         "stats": inb,
         "bilateral_pre": 2 * inb,
@@ -182,7 +190,8 @@ def cpu_chain_fps(wl, temporal, nframes, kind, threads=None):
     sw, sh, dw, dh, pre, sharpen, post, tdef = WORKLOADS[wl]
     t = temporal or tdef
     ocfg = RC.ChainConfig(dst_w=dw, dst_h=dh, use_pre=bool(pre), use_sharpen=bool(sharpen), use_post=bool(post),
-                          temporal={"none": RC.TEMPORAL_NONE, "main": RC.TEMPORAL_MAIN_BLEND, "frames": RC.TEMPORAL_BLEND_FRAMES}[t])
+                          temporal={"none": RC.TEMPORAL_NONE, "main": RC.TEMPORAL_MAIN_BLEND, "frames": RC.TEMPORAL_BLEND_FRAMES}[t],
+                          bicubic_enhance=wl in ENHANCE)
     ops = RC.Cv2Ops(threads=threads or os.cpu_count())
     chain = RC.Chain(ops, ocfg)
     frames = synth.clip(kind, sw, sh, nframes, SEED)
@@ -205,7 +214,8 @@ def run_reference(args, rank):
     pre, sharpen, post, tdef = WORKLOADS[wl][4:]
     t = args.temporal or tdef
     ocfg = RC.ChainConfig(dst_w=dw, dst_h=dh, use_pre=bool(pre), use_sharpen=bool(sharpen), use_post=bool(post),
-                          temporal={"none": RC.TEMPORAL_NONE, "main": RC.TEMPORAL_MAIN_BLEND, "frames": RC.TEMPORAL_BLEND_FRAMES}[t])
+                          temporal={"none": RC.TEMPORAL_NONE, "main": RC.TEMPORAL_MAIN_BLEND, "frames": RC.TEMPORAL_BLEND_FRAMES}[t],
+                          bicubic_enhance=wl in ENHANCE)
     chain = RC.Chain(RC.Cv2Ops(threads=os.cpu_count()), ocfg)
     frames = synth.clip(args.kind, sw, sh, per_step, SEED)
     for _ in range(args.warmup):
@@ -234,6 +244,9 @@ def run_reference(args, rank):
 
 def workload_name(wl, temporal):
     sw, sh, dw, dh, pre, sharpen, post, _ = WORKLOADS[wl]
+    if wl in ENHANCE:
+        stages = ["gauss3x3", "bicubic", "enhanceBicubicResult(bilateral5+canny+sharpen)"] + ([f"temporal_{temporal}"] if temporal != "none" else [])
+        return f"{wl.upper()}: {sw}x{sh}->{dw}x{dh} BGR8 Upscaler(BICUBIC) " + "+".join(stages)
     stages = (["bilateral_pre"] if pre else []) + ["bicubic"] + (["adaptive_sharpen"] if sharpen else []) + \
              (["bilateral_post"] if post else []) + ([f"temporal_{temporal}"] if temporal != "none" else [])
     return f"{wl.upper()}: {sw}x{sh}->{dw}x{dh} BGR8 " + "+".join(stages)

@@ -5,7 +5,8 @@
 //   REAL_ESRGAN : SelectiveBilateral(PRE) -> cv::resize(INTER_CUBIC) -> AdaptiveSharpening ->
 //                 SelectiveBilateral(POST) -> TemporalConsistency blend   (src/upscaler.cpp:772-829,
 //                 the resize standing in for the ONNX model exactly as src/test_enhancements.cpp:346-349)
-//   BICUBIC     : cv::resize(INTER_CUBIC), bit-exact (src/upscaler.cpp:81)
+//   BICUBIC     : CPUImpl's wrapper - GaussianBlur 3x3 -> cv::resize(INTER_CUBIC) -> enhanceBicubicResult
+//                 (src/upscaler.cpp:75-148); a bare bit-exact resize is vp::resizeCubic (vp/imgproc.h)
 // NEAREST / BILINEAR / LANCZOS / SUPER_RES are not on the hot path this library accelerates:
 // initialize() reports that and returns false.  There is no CPU fallback: use_gpu=true without a
 // B200 makes initialize() fail, and isUsingGPU() stays truthful.

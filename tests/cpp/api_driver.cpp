@@ -18,6 +18,7 @@
 #include "temporal_consistency.h"
 #include "upscaler.h"
 #include "video_enhancer.h"
+#include "vp/imgproc.h"
 
 static int fail(const char* what) { std::fprintf(stderr, "api_driver: FAILED: %s\n", what); return 1; }
 
@@ -81,6 +82,12 @@ int main(int argc, char** argv) {
         capture.join();
         cv::Mat empty, out;
         if (up.upscale(empty, out)) return fail("empty input accepted");
+    } else if (mode == "resize") {
+        for (int i = 0; i < n; ++i) {
+            cv::Mat out;
+            if (!vp::resizeCubic(frames[i], out, cv::Size(tw, th))) return fail("resizeCubic");
+            outs.push_back(out.clone());
+        }
     } else if (mode == "pipelined") {
         Upscaler up(Upscaler::REAL_ESRGAN, true);
         if (!up.initialize(tw, th)) return fail("Upscaler::initialize");
@@ -110,12 +117,11 @@ int main(int argc, char** argv) {
         SelectiveBilateral post(SelectiveBilateral::Config{SelectiveBilateral::POST_PROCESSING, true, true, 5, 20.0, 20.0, false, 30.0, 1.2, 1.5, false, 2});
         AdaptiveSharpening sharp(AdaptiveSharpening::Config{0.8f, 1.2f, 0.4f, 30.0f, 1.5f, 5, true, true, false});
         TemporalConsistency temporal(TemporalConsistency::Config{3, 0.6f, 15.0f, 100.0f, true, 0.5, 3, 15, 3, 5, 1.2, 0});
-        Upscaler resize(Upscaler::BICUBIC, true);
-        if (!pre.initialize() || !post.initialize() || !sharp.initialize() || !temporal.initialize() || !resize.initialize(tw, th))
+        if (!pre.initialize() || !post.initialize() || !sharp.initialize() || !temporal.initialize())
             return fail("stage initialize");
         for (int i = 0; i < n; ++i) {
             cv::Mat a, b, c, d, e;
-            if (!pre.process(frames[i], a) || !resize.upscale(a, b) || !sharp.process(b, c) || !post.process(c, d) || !temporal.process(d, e))
+            if (!pre.process(frames[i], a) || !vp::resizeCubic(a, b, cv::Size(tw, th)) || !sharp.process(b, c) || !post.process(c, d) || !temporal.process(d, e))
                 return fail("stage process");
             outs.push_back(e.clone());
         }

@@ -51,12 +51,22 @@ def test_upscaler_chain_modes(driver, tmp_path, mode):
         assert close(o, oracle.process(f))
 
 
-def test_upscaler_bicubic_bit_exact(driver, tmp_path):
+def test_resize_cubic_bit_exact(driver, tmp_path):
     import cv2
     frames = synth.clip("noise", SW, SH, 3)
-    outs = run(driver, tmp_path, "bicubic", frames, 4 * SW, 4 * SH)
+    outs = run(driver, tmp_path, "resize", frames, 4 * SW, 4 * SH)
     for o, f in zip(outs, frames):
         assert np.array_equal(o, cv2.resize(f, (4 * SW, 4 * SH), interpolation=cv2.INTER_CUBIC))
+
+
+def test_upscaler_bicubic_is_the_reference_wrapper(driver, tmp_path):
+    """Upscaler(BICUBIC) == CPUImpl::upscale: pre-blur, INTER_CUBIC, enhanceBicubicResult (src/upscaler.cpp:75-148)."""
+    frames = synth.clip("scene", SW, SH, 3)
+    outs = run(driver, tmp_path, "bicubic", frames, 2 * SW, 2 * SH)
+    for o, f in zip(outs, frames):
+        r = RC.cpuimpl_bicubic(RC.Cv2Ops(), f, 2 * SW, 2 * SH)
+        d = np.abs(o.astype(int) - r.astype(int))
+        assert d.max() <= 1 and (d > 0).sum() <= o.size // 500
 
 
 def test_upscaler_toggles(driver, tmp_path):

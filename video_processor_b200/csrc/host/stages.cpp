@@ -9,6 +9,7 @@
 #include "host_common.h"
 #include "selective_bilateral.h"
 #include "temporal_consistency.h"
+#include "vp/imgproc.h"
 
 using vp_host_api::StageRunner;
 
@@ -192,3 +193,22 @@ bool TemporalConsistency::process(const cv::Mat& input, cv::Mat& output) {
     }
     return ok;
 }
+
+// ------------------------------------------------------------------------------------------------
+// vp::resizeCubic - stand-in for cv::resize(..., INTER_CUBIC) in OpenCV-less builds
+// ------------------------------------------------------------------------------------------------
+namespace vp {
+bool resizeCubic(const cv::Mat& src, cv::Mat& dst, cv::Size dsize) {
+    static thread_local StageRunner runner;       // one context per calling thread
+    if (src.empty() || !vp_host_api::is_bgr8(src) || dsize.width < src.cols || dsize.height < src.rows) return false;
+    std::string err;
+    if (!runner.ready() && !runner.create(0, &err)) {
+        std::cerr << "vp::resizeCubic: no B200 context (" << err << ")" << std::endl;
+        return false;
+    }
+    bool ok = runner.upload(src, dsize.width, dsize.height, 3);
+    ok = ok && vp_bicubic(runner.ctx(), runner.d_in(), runner.in_pitch(), src.cols, src.rows, runner.d_out(), runner.out_pitch(),
+                          dsize.width, dsize.height, runner.stream()) == VP_OK;
+    return ok && runner.download(dst, dsize.width, dsize.height, CV_8UC3, 3);
+}
+}  // namespace vp

@@ -97,7 +97,10 @@ bool Upscaler::ensureChain(int src_w, int src_h) {
     vp_chain_config c{};
     vp_default_chain_config(&c, src_w, src_h, m_target_width, m_target_height);
     if (m_algorithm == BICUBIC) {
+        // CPUImpl::upscale for BICUBIC (src/upscaler.cpp:75-84): pre-blur, cv::resize(INTER_CUBIC),
+        // enhanceBicubicResult; the temporal smoothing of main.cpp:269-292 stays with the caller
         c.use_pre = c.use_sharpen = c.use_post = 0;
+        c.bicubic_enhance = 1;
         c.temporal.mode = VP_TEMPORAL_NONE;
     } else {
         const SelectiveBilateral::Config pre = m_bilateral_pre->getConfig(), post = m_bilateral_post->getConfig();
