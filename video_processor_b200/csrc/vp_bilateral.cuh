@@ -300,20 +300,24 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
             default: bil_strip<7>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
         }
         if (a.emap) {
-            constexpr int dummy = 0; (void)dummy;
-            const int TPr = bil_tile_pitch(R);
+            // 2x2 dilate (anchor (1,1)): pixel x is an edge if map[y-1..y][x-1..x] holds a 2.  The strip's four
+            // map bytes of a row arrive as one aligned word (gx % 4 == 0, pitch % 4 == 0) plus the byte left of it.
+            uint32_t m = 0;
 #pragma unroll
-            for (int j = 0; j < BIL_PX; ++j) {
-                const int x = gx + j;
-                if (x >= a.w) break;
-                // dilate 2x2, anchor (1,1): max over (y-1..y, x-1..x), outside ignored
-                bool edge = a.emap[(size_t)gy * a.epitch + x] == 2;
-                if (x > 0) edge = edge || a.emap[(size_t)gy * a.epitch + x - 1] == 2;
-                if (gy > 0) {
-                    edge = edge || a.emap[(size_t)(gy - 1) * a.epitch + x] == 2;
-                    if (x > 0) edge = edge || a.emap[(size_t)(gy - 1) * a.epitch + x - 1] == 2;
-                }
-                if (edge) {
+            for (int r = 0; r < 2; ++r) {
+                const int y = gy - r;
+                if (y < 0) continue;
+                const uint8_t* row = a.emap + (size_t)y * a.epitch + gx;
+                const uint32_t e = __vcmpeq4(__ldg(reinterpret_cast<const uint32_t*>(row)), 0x02020202u);   // 0xff per edge byte
+                const uint32_t left = (gx > 0 && __ldg(row - 1) == 2) ? 0xffu : 0u;
+                m |= e | (e << 8) | left;
+            }
+            if (m) {
+                const int TPr = bil_tile_pitch(R);
+#pragma unroll
+                for (int j = 0; j < BIL_PX; ++j) {
+                    const int x = gx + j;
+                    if (!((m >> (8 * j)) & 0xff) || x >= a.w) continue;
                     const uint32_t* t = s_tile + (ly + R) * TPr + lx + R + j;
                     uint32_t v = t[0] & 0xffffffu;
                     if (x >= 1 && x < a.w - 1 && gy >= 1 && gy < a.h - 1) {

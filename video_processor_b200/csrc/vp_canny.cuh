@@ -56,57 +56,68 @@ __global__ void __launch_bounds__(CN_NT) k_canny_nms(const CannyArgs a) {
     __shared__ uint16_t s_mag[CN_MH][CN_MW + 2];
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * CN_TW, y0 = blockIdx.y * CN_TH;
+    // 256 threads = 64 columns x 4 row phases: every loop below walks rows with a fixed column, no div/mod
+    const int cx = tid & 63, cr = tid >> 6;
     // gray with BORDER_REPLICATE (what cv::Canny's Sobel uses): clamp the coordinates
-    for (int i = tid; i < CN_GW * CN_GH; i += CN_NT) {
-        const int gy = i / CN_GW, gx = i - gy * CN_GW;
-        const int x = clampi(x0 - 2 + gx, 0, a.w - 1), y = clampi(y0 - 2 + gy, 0, a.h - 1);
-        const uint8_t* p = a.img + (size_t)y * a.ipitch + (size_t)x * 3;
-        s_gray[gy][gx] = (uint8_t)((9798 * p[2] + 19235 * p[1] + 3735 * p[0] + (1 << 14)) >> 15);
-    }
-    __syncthreads();
-    for (int i = tid; i < CN_MW * CN_MH; i += CN_NT) {
-        const int my = i / CN_MW, mx = i - my * CN_MW;
-        const int x = x0 - 1 + mx, y = y0 - 1 + my;
-        int dx = 0, dy = 0, mag = 0;
-        if (x >= 0 && x < a.w && y >= 0 && y < a.h) {       // the magnitude is 0 outside the image
-            const int g00 = s_gray[my][mx], g01 = s_gray[my][mx + 1], g02 = s_gray[my][mx + 2];
-            const int g10 = s_gray[my + 1][mx], g12 = s_gray[my + 1][mx + 2];
-            const int g20 = s_gray[my + 2][mx], g21 = s_gray[my + 2][mx + 1], g22 = s_gray[my + 2][mx + 2];
-            dx = (g02 + 2 * g12 + g22) - (g00 + 2 * g10 + g20);
-            dy = (g20 + 2 * g21 + g22) - (g00 + 2 * g01 + g02);
-            mag = abs(dx) + abs(dy);
+    for (int gx = cx; gx < CN_GW; gx += 64) {
+        const int x = clampi(x0 - 2 + gx, 0, a.w - 1);
+        for (int gy = cr; gy < CN_GH; gy += 4) {
+            const int y = clampi(y0 - 2 + gy, 0, a.h - 1);
+            const uint8_t* p = a.img + (size_t)y * a.ipitch + (size_t)x * 3;
+            s_gray[gy][gx] = (uint8_t)((9798 * p[2] + 19235 * p[1] + 3735 * p[0] + (1 << 14)) >> 15);
         }
-        s_grad[my][mx] = (dx & 0xffff) | (dy << 16);
-        s_mag[my][mx] = (uint16_t)mag;
     }
     __syncthreads();
-    for (int i = tid; i < CN_TW * CN_TH; i += CN_NT) {
-        const int ty = i / CN_TW, tx = i - ty * CN_TW;
-        const int x = x0 + tx, y = y0 + ty;
-        if (x >= a.w || y >= a.h) continue;
-        const int my = ty + 1, mx = tx + 1;
-        const int m = s_mag[my][mx];
-        uint8_t out = 0;
-        if (m > a.low) {
-            const int g = s_grad[my][mx];
-            const int dx = (int)(short)(g & 0xffff), dy = g >> 16;
-            const int ax = abs(dx), ay = abs(dy) << 15;       // |dy| <= 1020: fits
-            const int tg22x = ax * 13573;
-            bool lm;
-            if (ay < tg22x) {
-                lm = m > s_mag[my][mx - 1] && m >= s_mag[my][mx + 1];
-            } else {
-                const int tg67x = tg22x + (ax << 16);
-                if (ay > tg67x) {
-                    lm = m > s_mag[my - 1][mx] && m >= s_mag[my + 1][mx];
-                } else {
-                    const int s = ((dx ^ dy) < 0) ? -1 : 1;
-                    lm = m > s_mag[my - 1][mx - s] && m > s_mag[my + 1][mx + s];
-                }
+    for (int mx = cx; mx < CN_MW; mx += 64) {
+        const int x = x0 - 1 + mx;
+        const bool xin = x >= 0 && x < a.w;
+        for (int my = cr; my < CN_MH; my += 4) {
+            const int y = y0 - 1 + my;
+            int dx = 0, dy = 0, mag = 0;
+            if (xin && y >= 0 && y < a.h) {                     // the magnitude is 0 outside the image
+                const int g00 = s_gray[my][mx], g01 = s_gray[my][mx + 1], g02 = s_gray[my][mx + 2];
+                const int g10 = s_gray[my + 1][mx], g12 = s_gray[my + 1][mx + 2];
+                const int g20 = s_gray[my + 2][mx], g21 = s_gray[my + 2][mx + 1], g22 = s_gray[my + 2][mx + 2];
+                dx = (g02 + 2 * g12 + g22) - (g00 + 2 * g10 + g20);
+                dy = (g20 + 2 * g21 + g22) - (g00 + 2 * g01 + g02);
+                mag = abs(dx) + abs(dy);
             }
-            if (lm) out = m > a.high ? 2 : 1;
+            s_grad[my][mx] = (dx & 0xffff) | (dy << 16);
+            s_mag[my][mx] = (uint16_t)mag;
         }
-        a.map[(size_t)y * a.mpitch + x] = out;
+    }
+    __syncthreads();
+    {
+        const int tx = cx, x = x0 + tx, mx = tx + 1;
+        if (x < a.w) {
+            for (int ty = cr; ty < CN_TH; ty += 4) {
+                const int y = y0 + ty;
+                if (y >= a.h) break;
+                const int my = ty + 1;
+                const int m = s_mag[my][mx];
+                uint8_t out = 0;
+                if (m > a.low) {
+                    const int g = s_grad[my][mx];
+                    const int dx = (int)(short)(g & 0xffff), dy = g >> 16;
+                    const int ax = abs(dx), ay = abs(dy) << 15;       // |dy| <= 1020: fits
+                    const int tg22x = ax * 13573;
+                    bool lm;
+                    if (ay < tg22x) {
+                        lm = m > s_mag[my][mx - 1] && m >= s_mag[my][mx + 1];
+                    } else {
+                        const int tg67x = tg22x + (ax << 16);
+                        if (ay > tg67x) {
+                            lm = m > s_mag[my - 1][mx] && m >= s_mag[my + 1][mx];
+                        } else {
+                            const int s = ((dx ^ dy) < 0) ? -1 : 1;
+                            lm = m > s_mag[my - 1][mx - s] && m > s_mag[my + 1][mx + s];
+                        }
+                    }
+                    if (lm) out = m > a.high ? 2 : 1;
+                }
+                a.map[(size_t)y * a.mpitch + x] = out;
+            }
+        }
     }
 }
 
@@ -114,20 +125,20 @@ __global__ void __launch_bounds__(CN_NT) k_canny_nms(const CannyArgs a) {
 // hysteresis: one cooperative launch; per tile a breadth-first frontier in shared memory, tiles whose
 // neighbourhood changed are revisited after a grid-wide barrier until nothing changes anywhere
 // ---------------------------------------------------------------------------------------------------
-constexpr int HY_T = 64, HY_NT = 256, HY_P = HY_T + 2;
+constexpr int HY_TW = 128, HY_TH = 64, HY_NT = 256, HY_PW = HY_TW + 4, HY_PH = HY_TH + 2;   // halo 1 (row pitch padded to 4)
 
 struct HystArgs {
     uint8_t* map; size_t mpitch; int w, h;
     int tiles_x, tiles_y;
     unsigned char* dirty;          // 2 * ntiles flags (ping-pong); dirty[0..ntiles) preset to 1 by the host memset
-    unsigned* again;               // 2 counters (ping-pong), zeroed by the host memset
+    unsigned* again;               // 3 rotating counters, zeroed by the host memset
 };
 
 __global__ void __launch_bounds__(HY_NT) k_canny_hyst(const HystArgs a) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
-    __shared__ int s_map[HY_P * HY_P];
-    __shared__ unsigned short s_q[2][HY_P * HY_P];
+    __shared__ __align__(16) uint8_t s_map[HY_PW * HY_PH];     // 0 none, 1 weak, >= 2 edge (promotion ORs in bit 1)
+    __shared__ unsigned short s_q[2][HY_PW * HY_PH];
     __shared__ int s_n[2];
     __shared__ int s_changed;
     const int tid = threadIdx.x;
@@ -138,16 +149,20 @@ __global__ void __launch_bounds__(HY_NT) k_canny_hyst(const HystArgs a) {
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             if (!*(volatile unsigned char*)&dcur[t]) continue;
             const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
-            const int x0 = tx * HY_T - 1, y0 = ty * HY_T - 1;     // origin of the halo tile
+            const int x0 = tx * HY_TW - 1, y0 = ty * HY_TH - 1;   // origin of the halo tile
             if (tid == 0) { s_n[0] = 0; s_n[1] = 0; s_changed = 0; }
             __syncthreads();
-            for (int i = tid; i < HY_P * HY_P; i += HY_NT) {
-                const int py = i / HY_P, px = i - py * HY_P;
-                const int x = x0 + px, y = y0 + py;
-                int v = 0;
-                if (x >= 0 && x < a.w && y >= 0 && y < a.h) v = __ldcg(a.map + (size_t)y * a.mpitch + x);   // L2: other CTAs write it
-                s_map[i] = v;
-                if (v == 2) s_q[0][atomicAdd(&s_n[0], 1)] = (unsigned short)i;
+            for (int py = tid >> 5; py < HY_PH; py += HY_NT / 32) {       // warp per row, lanes along x
+                const int y = y0 + py;
+                const bool yin = y >= 0 && y < a.h;
+                for (int px = tid & 31; px < HY_PW; px += 32) {
+                    const int x = x0 + px;
+                    int v = 0;
+                    if (yin && px < HY_TW + 2 && x >= 0 && x < a.w) v = __ldcg(a.map + (size_t)y * a.mpitch + x);   // L2: other CTAs write it
+                    const int i = py * HY_PW + px;
+                    s_map[i] = (uint8_t)v;
+                    if (v >= 2) s_q[0][atomicAdd(&s_n[0], 1)] = (unsigned short)i;
+                }
             }
             __syncthreads();
             int cur = 0;
@@ -156,18 +171,22 @@ __global__ void __launch_bounds__(HY_NT) k_canny_hyst(const HystArgs a) {
                 if (n == 0) break;
                 for (int k = tid; k < n; k += HY_NT) {
                     const int i = s_q[cur][k];
-                    const int py = i / HY_P, px = i - py * HY_P;
+                    const int py = i / HY_PW, px = i - py * HY_PW;
 #pragma unroll
                     for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
                         for (int dx = -1; dx <= 1; ++dx) {
                             const int qy = py + dy, qx = px + dx;
                             // only interior pixels are owned (and written back) by this tile
-                            if ((dx | dy) != 0 && qy >= 1 && qy <= HY_T && qx >= 1 && qx <= HY_T) {
-                                const int j = qy * HY_P + qx;
-                                if (s_map[j] == 1 && atomicCAS(&s_map[j], 1, 2) == 1) {
-                                    s_q[cur ^ 1][atomicAdd(&s_n[cur ^ 1], 1)] = (unsigned short)j;
-                                    s_changed = 1;
+                            if ((dx | dy) != 0 && qy >= 1 && qy <= HY_TH && qx >= 1 && qx <= HY_TW) {
+                                const int j = qy * HY_PW + qx;
+                                if (s_map[j] == 1) {
+                                    const int sh = (j & 3) * 8;
+                                    const unsigned old = atomicOr(reinterpret_cast<unsigned*>(s_map + (j & ~3)), 2u << sh);
+                                    if (((old >> sh) & 0xff) == 1) {          // this thread promoted it
+                                        s_q[cur ^ 1][atomicAdd(&s_n[cur ^ 1], 1)] = (unsigned short)j;
+                                        s_changed = 1;
+                                    }
                                 }
                             }
                         }
@@ -178,26 +197,29 @@ __global__ void __launch_bounds__(HY_NT) k_canny_hyst(const HystArgs a) {
                 __syncthreads();
             }
             if (s_changed) {
-                for (int i = tid; i < HY_T * HY_T; i += HY_NT) {
-                    const int py = i / HY_T + 1, px = (i & (HY_T - 1)) + 1;
-                    const int x = x0 + px, y = y0 + py;
-                    if (x < a.w && y < a.h && s_map[py * HY_P + px] == 2) a.map[(size_t)y * a.mpitch + x] = 2;
+                for (int py = 1 + (tid >> 5); py <= HY_TH; py += HY_NT / 32) {
+                    const int y = y0 + py;
+                    if (y >= a.h) break;
+                    for (int px = 1 + (tid & 31); px <= HY_TW; px += 32) {
+                        const int x = x0 + px;
+                        if (x < a.w && s_map[py * HY_PW + px] == 3) a.map[(size_t)y * a.mpitch + x] = 2;   // 1|2: promoted here
+                    }
                 }
                 if (tid < 9) {                                  // neighbours must look again
                     const int ny = ty + tid / 3 - 1, nx = tx + tid % 3 - 1;
                     if (tid != 4 && ny >= 0 && ny < a.tiles_y && nx >= 0 && nx < a.tiles_x) dnext[ny * a.tiles_x + nx] = 1;
                 }
-                if (tid == 0) atomicAdd(&a.again[iter & 1], 1u);
+                if (tid == 0) atomicAdd(&a.again[iter % 3], 1u);
             }
             __syncthreads();
             if (tid == 0) dcur[t] = 0;
         }
         __threadfence();
         grid.sync();
-        const unsigned more = *(volatile unsigned*)&a.again[iter & 1];
-        if (blockIdx.x == 0 && tid == 0) a.again[(iter + 1) & 1] = 0;   // next iteration's counter
+        const unsigned more = *(volatile unsigned*)&a.again[iter % 3];
+        // again[(iter+2)%3] was last read after the previous barrier, i.e. before every CTA reached this one
+        if (blockIdx.x == 0 && tid == 0) a.again[(iter + 2) % 3] = 0;
         if (!more) break;
-        grid.sync();                                           // everyone has read `again[iter&1]` before it is reused
     }
 }
 

@@ -492,7 +492,7 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
     }
     if (g.bicubic_enhance) {
         c->map_pitch = align_up((size_t)g.dst_w, 256);
-        c->hy_tiles_x = (g.dst_w + HY_T - 1) / HY_T; c->hy_tiles_y = (g.dst_h + HY_T - 1) / HY_T;
+        c->hy_tiles_x = (g.dst_w + HY_TW - 1) / HY_TW; c->hy_tiles_y = (g.dst_h + HY_TH - 1) / HY_TH;
         c->dirty_bytes = align_up((size_t)2 * c->hy_tiles_x * c->hy_tiles_y, 16) + 16;
         int per_sm = 0;
         VP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canny_hyst, HY_NT, 0));
