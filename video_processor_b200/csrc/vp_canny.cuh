@@ -125,10 +125,13 @@ __global__ void __launch_bounds__(CN_NT) k_canny_nms(const CannyArgs a) {
 // hysteresis: one cooperative launch; per tile a breadth-first frontier in shared memory, tiles whose
 // neighbourhood changed are revisited after a grid-wide barrier until nothing changes anywhere
 // ---------------------------------------------------------------------------------------------------
-constexpr int HY_TW = 128, HY_TH = 64, HY_NT = 256, HY_PW = HY_TW + 4, HY_PH = HY_TH + 2;   // halo 1 (row pitch padded to 4)
+constexpr int HY_STACK = 8;
+constexpr int HY_TW = 128, HY_TH = 64, HY_NT = 256;
+constexpr int HY_X0 = 4;                                  // interior starts at column 4: rows are whole aligned words
+constexpr int HY_PW = HY_TW + 8, HY_PH = HY_TH + 2;      // columns [tx*128-4, tx*128+132), rows [ty*64-1, ty*64+65)
 
 struct HystArgs {
-    uint8_t* map; size_t mpitch; int w, h;
+    uint8_t* map; size_t mpitch; int w, h;                // mpitch % 4 == 0
     int tiles_x, tiles_y;
     unsigned char* dirty;          // 2 * ntiles flags (ping-pong); dirty[0..ntiles) preset to 1 by the host memset
     unsigned* again;               // 3 rotating counters, zeroed by the host memset
@@ -139,8 +142,9 @@ __global__ void __launch_bounds__(HY_NT) k_canny_hyst(const HystArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ __align__(16) uint8_t s_map[HY_PW * HY_PH];     // 0 none, 1 weak, >= 2 edge (promotion ORs in bit 1)
     __shared__ unsigned short s_q[2][HY_PW * HY_PH];
+    __shared__ unsigned short s_stack[HY_NT * HY_STACK];
     __shared__ int s_n[2];
-    __shared__ int s_changed;
+    __shared__ unsigned s_border;                              // which of the 8 neighbours saw a promotion on their halo
     const int tid = threadIdx.x;
     const int ntiles = a.tiles_x * a.tiles_y;
     for (int iter = 0;; ++iter) {
@@ -149,67 +153,92 @@ __global__ void __launch_bounds__(HY_NT) k_canny_hyst(const HystArgs a) {
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             if (!*(volatile unsigned char*)&dcur[t]) continue;
             const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
-            const int x0 = tx * HY_TW - 1, y0 = ty * HY_TH - 1;   // origin of the halo tile
-            if (tid == 0) { s_n[0] = 0; s_n[1] = 0; s_changed = 0; }
+            const int x0 = tx * HY_TW - HY_X0, y0 = ty * HY_TH - 1;   // image coordinates of s_map[0][0]
+            if (tid == 0) { s_n[0] = 0; s_n[1] = 0; s_border = 0; }
             __syncthreads();
-            for (int py = tid >> 5; py < HY_PH; py += HY_NT / 32) {       // warp per row, lanes along x
-                const int y = y0 + py;
-                const bool yin = y >= 0 && y < a.h;
-                for (int px = tid & 31; px < HY_PW; px += 32) {
-                    const int x = x0 + px;
-                    int v = 0;
-                    if (yin && px < HY_TW + 2 && x >= 0 && x < a.w) v = __ldcg(a.map + (size_t)y * a.mpitch + x);   // L2: other CTAs write it
-                    const int i = py * HY_PW + px;
-                    s_map[i] = (uint8_t)v;
-                    if (v >= 2) s_q[0][atomicAdd(&s_n[0], 1)] = (unsigned short)i;
+            // load whole words (4 map bytes); everything outside the image or outside the 1-pixel halo reads 0
+            constexpr int WPR = HY_PW / 4;
+            for (int i = tid; i < WPR * HY_PH; i += HY_NT) {
+                const int py = i / WPR, wx = i - py * WPR;
+                const int y = y0 + py, x = x0 + 4 * wx;
+                uint32_t v = 0;
+                if (y >= 0 && y < a.h && x + 3 >= 0 && x < a.w) {
+                    v = __ldcg(reinterpret_cast<const uint32_t*>(a.map + (size_t)y * a.mpitch + x));   // L2: other CTAs write it
+                    if (x + 3 >= a.w) v &= 0xffffffffu >> (8 * (x + 4 - a.w));      // bytes past the last column
+                }
+                if (wx == 0) v &= 0xff000000u;                        // only column 3 (= interior-1) is halo
+                if (wx == WPR - 1) v &= 0x000000ffu;                  // only column 132
+                reinterpret_cast<uint32_t*>(s_map)[i] = v;
+                if (v & 0x02020202u) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if ((v >> (8 * b)) & 2) s_q[0][atomicAdd(&s_n[0], 1)] = (unsigned short)(4 * i + b);
                 }
             }
             __syncthreads();
+            // Flood from the seeds without a barrier per step: a thread claims a seed and follows the chain of
+            // weak pixels itself (depth-first, small private stack in shared memory; what does not fit goes to
+            // the other queue and seeds the next pass).  atomicOr makes every pixel promoted exactly once.
             int cur = 0;
             while (true) {
                 const int n = s_n[cur];
                 if (n == 0) break;
+                unsigned short* stk = s_stack + tid * HY_STACK;
                 for (int k = tid; k < n; k += HY_NT) {
-                    const int i = s_q[cur][k];
-                    const int py = i / HY_PW, px = i - py * HY_PW;
+                    int sp = 0;
+                    stk[sp++] = s_q[cur][k];
+                    while (sp > 0) {
+                        const int i = stk[--sp];
+                        const int py = i / HY_PW, px = i - py * HY_PW;
 #pragma unroll
-                    for (int dy = -1; dy <= 1; ++dy)
+                        for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
-                        for (int dx = -1; dx <= 1; ++dx) {
-                            const int qy = py + dy, qx = px + dx;
-                            // only interior pixels are owned (and written back) by this tile
-                            if ((dx | dy) != 0 && qy >= 1 && qy <= HY_TH && qx >= 1 && qx <= HY_TW) {
-                                const int j = qy * HY_PW + qx;
-                                if (s_map[j] == 1) {
-                                    const int sh = (j & 3) * 8;
-                                    const unsigned old = atomicOr(reinterpret_cast<unsigned*>(s_map + (j & ~3)), 2u << sh);
-                                    if (((old >> sh) & 0xff) == 1) {          // this thread promoted it
-                                        s_q[cur ^ 1][atomicAdd(&s_n[cur ^ 1], 1)] = (unsigned short)j;
-                                        s_changed = 1;
+                            for (int dx = -1; dx <= 1; ++dx) {
+                                const int qy = py + dy, qx = px + dx;
+                                // only interior pixels are owned (and written back) by this tile
+                                if ((dx | dy) != 0 && qy >= 1 && qy <= HY_TH && qx >= HY_X0 && qx < HY_X0 + HY_TW) {
+                                    const int j = qy * HY_PW + qx;
+                                    if (s_map[j] == 1) {
+                                        const int sh = (j & 3) * 8;
+                                        const unsigned old = atomicOr(reinterpret_cast<unsigned*>(s_map + (j & ~3)), 2u << sh);
+                                        if (((old >> sh) & 0xff) == 1) {          // this thread promoted it
+                                            const unsigned top = qy == 1, bot = qy == HY_TH, lef = qx == HY_X0, rig = qx == HY_X0 + HY_TW - 1;
+                                            // bit k = neighbour (k/3-1, k%3-1) in (dy,dx) order; bit 4 = "something changed"
+                                            atomicOr(&s_border, 16u | (top << 1) | (bot << 7) | (lef << 3) | (rig << 5) |
+                                                                    ((top & lef) << 0) | ((top & rig) << 2) | ((bot & lef) << 6) | ((bot & rig) << 8));
+                                            if (sp < HY_STACK) stk[sp++] = (unsigned short)j;
+                                            else s_q[cur ^ 1][atomicAdd(&s_n[cur ^ 1], 1)] = (unsigned short)j;
+                                        }
                                     }
                                 }
                             }
-                        }
+                    }
                 }
                 __syncthreads();
                 if (tid == 0) s_n[cur] = 0;
                 cur ^= 1;
                 __syncthreads();
             }
-            if (s_changed) {
-                for (int py = 1 + (tid >> 5); py <= HY_TH; py += HY_NT / 32) {
-                    const int y = y0 + py;
-                    if (y >= a.h) break;
-                    for (int px = 1 + (tid & 31); px <= HY_TW; px += 32) {
-                        const int x = x0 + px;
-                        if (x < a.w && s_map[py * HY_PW + px] == 3) a.map[(size_t)y * a.mpitch + x] = 2;   // 1|2: promoted here
+            const unsigned border = s_border;
+            if (border) {
+                for (int i = tid; i < (HY_TW / 4) * HY_TH; i += HY_NT) {       // interior words
+                    const int py = 1 + i / (HY_TW / 4), wx = 1 + i % (HY_TW / 4);
+                    const int y = y0 + py, x = x0 + 4 * wx;
+                    if (y >= a.h || x >= a.w) continue;
+                    const uint32_t v = reinterpret_cast<const uint32_t*>(s_map)[py * WPR + wx];
+                    if (v & ((v >> 1) & 0x01010101u)) {                          // some byte == 3: promoted here
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                            if (((v >> (8 * b)) & 0xff) == 3 && x + b < a.w) a.map[(size_t)y * a.mpitch + x + b] = 2;
                     }
                 }
-                if (tid < 9) {                                  // neighbours must look again
+                if (tid < 9 && tid != 4 && ((border >> tid) & 1)) {              // neighbours whose halo changed look again
                     const int ny = ty + tid / 3 - 1, nx = tx + tid % 3 - 1;
-                    if (tid != 4 && ny >= 0 && ny < a.tiles_y && nx >= 0 && nx < a.tiles_x) dnext[ny * a.tiles_x + nx] = 1;
+                    if (ny >= 0 && ny < a.tiles_y && nx >= 0 && nx < a.tiles_x) {
+                        dnext[ny * a.tiles_x + nx] = 1;
+                        atomicAdd(&a.again[iter % 3], 1u);
+                    }
                 }
-                if (tid == 0) atomicAdd(&a.again[iter % 3], 1u);
             }
             __syncthreads();
             if (tid == 0) dcur[t] = 0;
