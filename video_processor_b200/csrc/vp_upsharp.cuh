@@ -278,7 +278,9 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
             }
         }
     } else {
-        const bool own_mask = (a.mask_in == nullptr);
+        // caller-supplied / exported masks exist only on the stage-wise (no-resize) entry points
+        constexpr bool MASKIO = !RESIZE;
+        const bool own_mask = !MASKIO || (a.mask_in == nullptr);
         constexpr int CW = US_TW + 4, CH = US_TH + 4;
         if (own_mask) {
             // ---- P3: Sobel / Laplacian magnitude -> sigmoid on (TW+4)x(TH+4); column walk, 3-row window ---
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
                     const int gx = min(x0 + x, a.dw - 1), gy = min(y0 + y, a.dh - 1);
                     e = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(a.mask_in) + (size_t)gy * a.mask_in_pitch + (size_t)gx * 4);
                 }
-                if (a.mask_out && x < vw && y < vh)
+                if (MASKIO && a.mask_out && x < vw && y < vh)
                     *reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a.mask_out) + (size_t)(y0 + y) * a.mask_out_pitch + (size_t)(x0 + x) * 4) = e;
                 bgw[(i + GK - 1) % GK] = s_rowbg[(y + GK - 1) * US_TW + x];
                 rw[(i + GK - 1) % GK] = s_rowr[(y + GK - 1) * US_TW + x];
