@@ -50,6 +50,38 @@ def test_chain_vs_oracle(vp, kind, temporal):
         assert mx <= 4, (mx, nd)
 
 
+@pytest.mark.parametrize("buffer_size", [1, 2, 3])
+def test_chain_temporal_buffer_sizes(vp, buffer_size):
+    sw, sh, n = 96, 64, 5
+    ocfg = RC.ChainConfig(dst_w=2 * sw, dst_h=2 * sh, temporal=RC.TEMPORAL_BLEND_FRAMES)
+    ocfg.temporal_cfg = RC.TemporalConfig(buffer_size=buffer_size, blend_strength=0.45)
+    frames = synth.clip("scene", sw, sh, n)
+    oracle = RC.Chain(RC.NumpyOps(), ocfg)
+    refs = [oracle.process(f) for f in frames]
+    outs, _ = run_chain_device(vp, ocfg, frames, sw, sh)
+    for o, r in zip(outs, refs):
+        mx, nd = G.diff_stats(o, r)
+        assert RC.psnr(o, r) >= 50.0 and mx <= 4, (buffer_size, mx, nd)
+
+
+@pytest.mark.parametrize("dst,ks,sigma,adaptive", [((384, 256), 3, 0.8, True), ((384, 256), 7, 2.5, False), ((96, 64), 5, 1.5, False),
+                                                   ((144, 100), 5, 1.5, True), ((288, 192), 5, 1.0, True)])
+def test_chain_other_ratios_and_configs(vp, dst, ks, sigma, adaptive):
+    """x4, x1 (no resize), x1.5-ish and x3 chains; 3/7-tap unsharp Gaussians; fixed (non-adaptive) bilateral parameters."""
+    sw, sh = 96, 64
+    ocfg = RC.ChainConfig(dst_w=dst[0], dst_h=dst[1], temporal=RC.TEMPORAL_MAIN_BLEND)
+    ocfg.sharpen = RC.SharpenConfig(0.7, 1.3, 0.3, 25.0, sigma, ks, True, True, False)
+    ocfg.pre = RC.BilateralConfig(RC.PRE_PROCESSING, True, adaptive, 5, 25.0, 12.0, False, 30.0, 1.5, 2.0, False, 3)
+    ocfg.post = RC.BilateralConfig(RC.POST_PROCESSING, True, adaptive, 7, 18.0, 40.0, False, 30.0, 1.2, 1.5, False, 2)
+    frames = synth.clip("scene", sw, sh, 3)
+    oracle = RC.Chain(RC.NumpyOps(), ocfg)
+    refs = [oracle.process(f) for f in frames]
+    outs, _ = run_chain_device(vp, ocfg, frames, sw, sh)
+    for o, r in zip(outs, refs):
+        mx, nd = G.diff_stats(o, r)
+        assert RC.psnr(o, r) >= 50.0 and mx <= 4, (dst, ks, mx, nd)
+
+
 def test_chain_stage_toggles(vp):
     sw, sh = 96, 64
     frames = synth.clip("scene", sw, sh, 3)
