@@ -266,6 +266,7 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=4, help="frames per step of the reference arm")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scene-detect", action="store_true", help="enable TemporalConsistency::detectSceneChange (blend becomes its own kernel)")
     ap.add_argument("--lanes", type=int, default=0, help="stream lanes of the batch API (0 = library default)")
     ap.add_argument("--per-frame", action="store_true", help="one vp_process_device call per frame on one stream (no batch API)")
     ap.add_argument("--latency-frames", type=int, default=None,
@@ -299,6 +300,8 @@ def main():
 
     wl = args.workload
     cfg, temporal = build_cfg(capi, wl, args.temporal)
+    if args.scene_detect:
+        cfg.temporal.scene_detect = 1
     sw, sh, dw, dh = WORKLOADS[wl][:4]
     chain_bytes, kbytes, inb, outb = algorithmic_bytes(wl, temporal, cfg)
     F = args.frames

@@ -75,6 +75,12 @@ typedef struct vp_temporal_config {
     int32_t buffer_size;       /* TemporalConsistency::Config::buffer_size (2 or 3)              */
     float blend_strength;      /* TemporalConsistency::Config::blend_strength                    */
     float main_weight;         /* current-frame weight of the main.cpp blend (0.6 / 0.7)         */
+    int32_t scene_detect;      /* VP_TEMPORAL_BLEND_FRAMES only: TemporalConsistency::detectSceneChange
+                                  (src/temporal_consistency.cpp:283-323: 64-bin histogram correlation + mean
+                                  absolute difference of the gray frames) - a cut clears the history and passes
+                                  the frame through (:100-112).  Needs a whole-frame reduction before the blend,
+                                  so the blend runs as its own kernel instead of in the POST epilogue.          */
+    float scene_change_threshold;   /* TemporalConsistency::Config::scene_change_threshold (100)  */
 } vp_temporal_config;
 
 /* The chain of Upscaler::upscale (src/upscaler.cpp:772-829) with step 2 = cv::resize(INTER_CUBIC)

@@ -78,6 +78,9 @@ class TemporalConfig:  # include/temporal_consistency.h:18-33 (flow parameters u
     motion_threshold: float = 15.0
     scene_change_threshold: float = 100.0
     use_gpu: bool = True
+    # oracle switch (not a reference field): run detectSceneChange (temporal_consistency.cpp:283-323) and
+    # reset the buffers on a cut (:100-105); off reproduces the blend alone
+    scene_detect: bool = False
 
 
 # ------------------------------------------------------------------------------------------------
@@ -125,6 +128,9 @@ class NumpyOps:
 
     def canny(self, gray, low, high):
         return R.canny_u8(gray, low, high)
+
+    def scene_metrics(self, prev_gray, cur_gray):
+        return R.scene_metrics(prev_gray, cur_gray)
 
     def dilate_2x2(self, edges):
         return R.dilate_2x2(edges)
@@ -180,6 +186,12 @@ class Cv2Ops:
 
     def canny(self, gray, low, high):
         return self.cv2.Canny(gray, low, high)
+
+    def scene_metrics(self, prev_gray, cur_gray):
+        cv2 = self.cv2
+        ph = cv2.normalize(cv2.calcHist([prev_gray], [0], None, [64], [0, 256]), None, 0, 1, cv2.NORM_MINMAX)
+        ch = cv2.normalize(cv2.calcHist([cur_gray], [0], None, [64], [0, 256]), None, 0, 1, cv2.NORM_MINMAX)
+        return cv2.compareHist(ph, ch, cv2.HISTCMP_CORREL), cv2.mean(cv2.absdiff(prev_gray, cur_gray))[0]
 
     def dilate_2x2(self, edges):
         return self.cv2.dilate(edges, self.cv2.getStructuringElement(self.cv2.MORPH_RECT, (2, 2)))
@@ -326,15 +338,23 @@ def blend_frames(frames, blend_strength, masks=None):
     return np.clip(np.rint(res), 0, 255).astype(np.uint8)
 
 
+def detect_scene_change(ops, prev_gray, cur_gray, threshold):
+    """TemporalConsistency::detectSceneChange, temporal_consistency.cpp:283-323."""
+    corr, mad = ops.scene_metrics(prev_gray, cur_gray)
+    combined = (1.0 - corr) * 100.0 + mad * 0.5
+    return combined > float(F32(threshold))
+
+
 class TemporalBlendState:
     """TemporalConsistency::process buffer policy (temporal_consistency.cpp:61-172) with the
-    flow/warp/scene-change front end out of scope: first frame passes through; afterwards the
-    current frame is blended with the up-to (buffer_size-1) most recent *unblended* inputs
-    (m_flow_buffer holds < buffer_size flows, :167-169); the unblended input is what is stored
-    (:158)."""
+    flow/warp front end out of scope: first frame passes through; afterwards the current frame is
+    blended with the up-to (buffer_size-1) most recent *unblended* inputs (m_flow_buffer holds
+    < buffer_size flows, :167-169); the unblended input is what is stored (:158).  With
+    cfg.scene_detect a detected cut clears the buffers and passes the frame through (:100-112)."""
 
-    def __init__(self, cfg=None):
+    def __init__(self, cfg=None, ops=None):
         self.cfg = cfg or TemporalConfig()
+        self.ops = ops
         self.frames = []
 
     def reset(self):
@@ -344,6 +364,11 @@ class TemporalBlendState:
         if not self.frames:
             self.frames.append(cur.copy())
             return cur.copy()
+        if self.cfg.scene_detect:
+            ops = self.ops or NumpyOps()
+            if detect_scene_change(ops, ops.bgr2gray(self.frames[-1]), ops.bgr2gray(cur), self.cfg.scene_change_threshold):
+                self.frames = [cur.copy()]
+                return cur.copy()
         nprev = min(len(self.frames), self.cfg.buffer_size - 1)
         fr = [cur] + [self.frames[-1 - i] for i in range(nprev)]
         out = blend_frames(fr, self.cfg.blend_strength) if len(fr) > 1 else cur.copy()
@@ -410,7 +435,7 @@ class Chain:
         if cfg.temporal == TEMPORAL_MAIN_BLEND:
             self.temporal = MainBlendState(ops, cfg.main_blend_weight)
         elif cfg.temporal == TEMPORAL_BLEND_FRAMES:
-            self.temporal = TemporalBlendState(cfg.temporal_cfg)
+            self.temporal = TemporalBlendState(cfg.temporal_cfg, ops)
         else:
             self.temporal = None
 

@@ -417,3 +417,35 @@ def dilate_2x2(edges):
     h, w = e.shape
     out = p[0:h, 0:w] | p[0:h, 1:w + 1] | p[1:h + 1, 0:w] | p[1:h + 1, 1:w + 1]
     return (out * 255).astype(np.uint8)
+
+
+# --------------------------------------------------------------------------------------------
+# TemporalConsistency::detectSceneChange primitives  -- temporal_consistency.cpp:283-323
+# --------------------------------------------------------------------------------------------
+def hist64(gray):
+    """cv::calcHist(gray8U, 64 bins over [0,256)): bin = v >> 2, counts as float32."""
+    return np.bincount((gray.reshape(-1) >> 2).astype(np.int64), minlength=64).astype(F32)
+
+
+def normalize_minmax01(h):
+    """cv::normalize(h, h, 0, 1, NORM_MINMAX) on CV_32F: scale/shift formed in double, applied in float32."""
+    smin, smax = float(h.min()), float(h.max())
+    scale = 1.0 / (smax - smin) if (smax - smin) > 2.220446049250313e-16 else 0.0
+    shift = 0.0 - smin * scale
+    return (h * F32(scale) + F32(shift)).astype(F32)
+
+
+def hist_correlation(h1, h2):
+    """cv::compareHist(HISTCMP_CORREL): double sums; 1 when a histogram is constant."""
+    a, b = h1.astype(np.float64), h2.astype(np.float64)
+    n = a.size
+    s1, s2, s11, s22, s12 = a.sum(), b.sum(), (a * a).sum(), (b * b).sum(), (a * b).sum()
+    num = s12 - s1 * s2 / n
+    den = (s11 - s1 * s1 / n) * (s22 - s2 * s2 / n)
+    return num / math.sqrt(den) if abs(den) > 2.220446049250313e-16 else 1.0
+
+
+def scene_metrics(prev_gray, cur_gray):
+    corr = hist_correlation(normalize_minmax01(hist64(prev_gray)), normalize_minmax01(hist64(cur_gray)))
+    mad = float(np.abs(prev_gray.astype(np.int64) - cur_gray.astype(np.int64)).sum()) / prev_gray.size
+    return corr, mad

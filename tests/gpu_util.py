@@ -70,5 +70,6 @@ def chain_cfg(vp, o, sw, sh):
     c.pre = bilateral_cfg(vp, o.pre)
     c.sharpen = sharpen_cfg(vp, o.sharpen)
     c.post = bilateral_cfg(vp, o.post)
-    c.temporal = vp.TemporalConfig(o.temporal, o.temporal_cfg.buffer_size, o.temporal_cfg.blend_strength, o.main_blend_weight)
+    c.temporal = vp.TemporalConfig(o.temporal, o.temporal_cfg.buffer_size, o.temporal_cfg.blend_strength, o.main_blend_weight,
+                                   int(getattr(o.temporal_cfg, "scene_detect", False)), o.temporal_cfg.scene_change_threshold)
     return c

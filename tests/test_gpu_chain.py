@@ -82,6 +82,30 @@ def test_chain_other_ratios_and_configs(vp, dst, ks, sigma, adaptive):
         assert RC.psnr(o, r) >= 50.0 and mx <= 4, (dst, ks, mx, nd)
 
 
+@pytest.mark.parametrize("use_post", [True, False])
+def test_scene_change_detection(vp, use_post):
+    """detectSceneChange on the device: a flat -> scene cut clears the history (the cut frame passes through
+    unblended) and blending resumes afterwards; frames without a cut blend as usual."""
+    sw, sh = 96, 64
+    frames = [synth.frame("flat", sw, sh, 0), synth.frame("flat", sw, sh, 1), synth.frame("flat", sw, sh, 2),
+              synth.frame("scene", sw, sh, 3), synth.frame("scene", sw, sh, 4), synth.frame("scene", sw, sh, 5)]
+    ocfg = RC.ChainConfig(dst_w=2 * sw, dst_h=2 * sh, temporal=RC.TEMPORAL_BLEND_FRAMES, use_post=use_post)
+    ocfg.temporal_cfg = RC.TemporalConfig(scene_detect=True)
+    oracle = RC.Chain(RC.NumpyOps(), ocfg)
+    refs = [oracle.process(f) for f in frames]
+    assert len(oracle.temporal.frames) == 3
+    spatial3 = RC.Chain(RC.NumpyOps(), RC.ChainConfig(dst_w=2 * sw, dst_h=2 * sh, temporal=RC.TEMPORAL_NONE, use_post=use_post)).process(frames[3])
+    assert np.array_equal(refs[3], spatial3)          # the oracle itself saw the cut at frame 3
+    outs, _ = run_chain_device(vp, ocfg, frames, sw, sh)
+    for i, (o, r) in enumerate(zip(outs, refs)):
+        mx, nd = G.diff_stats(o, r)
+        assert RC.psnr(o, r) >= 50.0 and mx <= 4, (i, mx, nd)
+    # and with the detector off the same clip blends across the cut
+    ocfg.temporal_cfg = RC.TemporalConfig(scene_detect=False)
+    outs2, _ = run_chain_device(vp, ocfg, frames, sw, sh)
+    assert RC.psnr(outs2[3], refs[3]) < 45.0
+
+
 def test_chain_stage_toggles(vp):
     sw, sh = 96, 64
     frames = synth.clip("scene", sw, sh, 3)

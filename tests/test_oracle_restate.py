@@ -95,6 +95,27 @@ def test_cpuimpl_bicubic_wrapper_numpy_vs_cv2(kind):
     assert np.array_equal(RC.cpuimpl_bicubic(RC.NumpyOps(), img, 240, 136), RC.cpuimpl_bicubic(RC.Cv2Ops(), img, 240, 136))
 
 
+@pytest.mark.parametrize("a,b", [(("scene", 0), ("scene", 1)), (("scene", 15), ("scene", 16)), (("flat", 0), ("scene", 3)),
+                                 (("scene", 0), ("noise", 0)), (("flat", 1), ("flat", 2))])
+def test_scene_metrics_match_cv2(a, b):
+    ga = cv2.cvtColor(synth.frame(a[0], 320, 180, a[1]), cv2.COLOR_BGR2GRAY)
+    gb = cv2.cvtColor(synth.frame(b[0], 320, 180, b[1]), cv2.COLOR_BGR2GRAY)
+    c1, m1 = R.scene_metrics(ga, gb)
+    c2, m2 = RC.Cv2Ops().scene_metrics(ga, gb)
+    assert abs(c1 - c2) < 1e-7 and m1 == m2
+    assert np.array_equal(R.normalize_minmax01(R.hist64(ga)),
+                          cv2.normalize(cv2.calcHist([ga], [0], None, [64], [0, 256]), None, 0, 1, cv2.NORM_MINMAX).ravel())
+
+
+def test_scene_change_resets_blend_state():
+    cfg = RC.TemporalConfig(scene_detect=True)
+    st = RC.TemporalBlendState(cfg, RC.NumpyOps())
+    f = [synth.frame("flat", 64, 48, 0), synth.frame("flat", 64, 48, 1), synth.frame("scene", 64, 48, 3), synth.frame("scene", 64, 48, 4)]
+    outs = [st.process(x) for x in f]
+    assert np.array_equal(outs[2], f[2])                       # cut flat -> scene: passthrough, history cleared
+    assert np.array_equal(outs[3], RC.blend_frames([f[3], f[2]], cfg.blend_strength))
+
+
 def test_mean_stddev_matches_cv2():
     img = synth.frame("scene", 160, 90, 0)
     m, s, _, _ = R.mean_stddev(img)

@@ -29,7 +29,7 @@ class SharpenConfig(C.Structure):
 
 class TemporalConfig(C.Structure):
     _fields_ = [("mode", C.c_int32), ("buffer_size", C.c_int32), ("blend_strength", C.c_float),
-                ("main_weight", C.c_float)]
+                ("main_weight", C.c_float), ("scene_detect", C.c_int32), ("scene_change_threshold", C.c_float)]
 
 
 class ChainConfig(C.Structure):

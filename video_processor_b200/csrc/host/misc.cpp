@@ -144,6 +144,7 @@ bool VideoEnhancer::enhance(const cv::Mat& input, cv::Mat& output) {
     c.use_pre = m_level >= MEDIUM;
     c.use_post = m_level >= STRONG;
     c.temporal.mode = m_level >= YOUTUBE ? VP_TEMPORAL_BLEND_FRAMES : VP_TEMPORAL_NONE;
+    c.temporal.scene_detect = 1;
     if (!m_impl->ctx || std::memcmp(&c, &m_impl->cfg, sizeof(c)) != 0) {
         if (m_impl->ctx) { vp_destroy(m_impl->ctx); m_impl->ctx = nullptr; }
         if (vp_create(&m_impl->ctx, 0, &c) != VP_OK) {

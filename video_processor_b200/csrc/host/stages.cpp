@@ -2,7 +2,7 @@
 // stage-wise entry points of the C ABI.  Error policy follows the reference: bool returns, nothing
 // throws; on a stage failure the input is copied through and false is returned
 // (src/selective_bilateral.cpp:77-81, src/adaptive_sharpening.cpp:100-104).
-#include <deque>
+#include <cstring>
 #include <mutex>
 
 #include "adaptive_sharpening.h"
@@ -119,15 +119,14 @@ bool AdaptiveSharpening::process(const cv::Mat& input, cv::Mat& output) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// TemporalConsistency
+// TemporalConsistency: a chain context with every spatial stage off - buffer policy, scene-change reset
+// and blendFrames all run on the device (src/temporal_consistency.cpp:61-172, :283-323, :355-444)
 // ------------------------------------------------------------------------------------------------
 struct TemporalConsistency::Impl {
-    StageRunner run;
-    std::deque<uint8_t*> frames;          // device copies of the previous unblended inputs, newest last
-    size_t pitch = 0;
-    int w = 0, h = 0;
-    void clear() { for (uint8_t* p : frames) cudaFree(p); frames.clear(); }
-    ~Impl() { clear(); }
+    vp_ctx* ctx = nullptr;
+    vp_chain_config cfg{};
+    bool available = false;
+    ~Impl() { if (ctx) vp_destroy(ctx); }
 };
 
 TemporalConsistency::TemporalConsistency() : m_impl(new Impl) {}
@@ -135,9 +134,9 @@ TemporalConsistency::TemporalConsistency(const Config& config) : m_config(config
 TemporalConsistency::~TemporalConsistency() = default;
 
 bool TemporalConsistency::initialize() {
-    std::string err;
-    if (!m_impl->run.create(0, &err)) {
-        std::cerr << "TemporalConsistency: no B200 context (" << err << "); this build has no CPU path" << std::endl;
+    m_impl->available = vp_device_count() > 0;
+    if (!m_impl->available) {
+        std::cerr << "TemporalConsistency: no B200 context (vp_create: no CUDA device); this build has no CPU path" << std::endl;
         m_initialized = false;
         return false;
     }
@@ -148,7 +147,7 @@ bool TemporalConsistency::initialize() {
 
 void TemporalConsistency::reset() {
     std::lock_guard<std::mutex> lock(m_buffer_mutex);
-    m_impl->clear();
+    if (m_impl->ctx) vp_reset_temporal(m_impl->ctx);
 }
 
 void TemporalConsistency::setConfig(const Config& config) { m_config = config; }
@@ -157,41 +156,40 @@ TemporalConsistency::Config TemporalConsistency::getConfig() const { return m_co
 bool TemporalConsistency::process(const cv::Mat& input, cv::Mat& output) {
     if (!m_initialized) {
         std::cerr << "Temporal consistency module not initialized" << std::endl;
+        if (!input.empty()) input.copyTo(output);
         return false;
     }
     if (input.empty()) {
-        std::cerr << "Empty input image" << std::endl;
+        std::cerr << "Empty input frame" << std::endl;
         return false;
     }
     std::lock_guard<std::mutex> lock(m_buffer_mutex);
+    vp_chain_config c{};
+    vp_default_chain_config(&c, input.cols, input.rows, input.cols, input.rows);
+    c.use_pre = c.use_sharpen = c.use_post = 0;
+    c.temporal.mode = VP_TEMPORAL_BLEND_FRAMES;
+    c.temporal.buffer_size = std::min(std::max(m_config.buffer_size, 1), 3);
+    c.temporal.blend_strength = m_config.blend_strength;
+    c.temporal.scene_detect = 1;
+    c.temporal.scene_change_threshold = m_config.scene_change_threshold;
     Impl& s = *m_impl;
-    StageRunner& r = s.run;
-    if (!vp_host_api::is_bgr8(input) || !r.upload(input, input.cols, input.rows, 3)) {
+    if (!s.ctx || std::memcmp(&c, &s.cfg, sizeof(c)) != 0) {
+        if (s.ctx) { vp_destroy(s.ctx); s.ctx = nullptr; }
+        if (vp_create(&s.ctx, 0, &c) != VP_OK) {
+            std::cerr << "Error in temporal consistency: " << vp_last_error(nullptr) << std::endl;
+            input.copyTo(output);
+            return false;
+        }
+        s.cfg = c;
+    }
+    output.create(input.rows, input.cols, CV_8UC3);
+    if (!vp_host_api::is_bgr8(input) ||
+        vp_process_host(s.ctx, input.data, input.step, output.data, output.step) != VP_OK) {
+        std::cerr << "Error in temporal consistency: " << vp_last_error(s.ctx) << std::endl;
         input.copyTo(output);
         return false;
     }
-    if (s.w != input.cols || s.h != input.rows) { s.clear(); s.w = input.cols; s.h = input.rows; s.pitch = r.in_pitch(); }
-    const int buffer = std::min(std::max(m_config.buffer_size, 1), 3);
-    const int nprev = std::min<int>((int)s.frames.size(), buffer - 1);
-    const uint8_t* ptrs[3] = {r.d_in(), nullptr, nullptr};
-    for (int i = 0; i < nprev; ++i) ptrs[1 + i] = s.frames[s.frames.size() - 1 - i];
-    bool ok = vp_temporal_blend(r.ctx(), ptrs, 1 + nprev, s.pitch, m_config.blend_strength, r.d_out(), r.out_pitch(),
-                                input.cols, input.rows, r.stream()) == VP_OK;
-    ok = ok && r.download(output, input.cols, input.rows, CV_8UC3, 3);
-    // keep the unblended input (src/temporal_consistency.cpp:158-159), trim to buffer_size (:162-169)
-    uint8_t* keep = nullptr;
-    if ((int)s.frames.size() >= buffer) { keep = s.frames.front(); s.frames.pop_front(); }
-    if (!keep && cudaMalloc(&keep, s.pitch * input.rows) != cudaSuccess) { cudaGetLastError(); keep = nullptr; }
-    if (keep) {
-        cudaMemcpy2DAsync(keep, s.pitch, r.d_in(), s.pitch, (size_t)input.cols * 3, input.rows, cudaMemcpyDeviceToDevice, (cudaStream_t)r.stream());
-        cudaStreamSynchronize((cudaStream_t)r.stream());
-        s.frames.push_back(keep);
-    }
-    if (!ok) {
-        std::cerr << "Error in temporal consistency: " << r.error() << std::endl;
-        input.copyTo(output);
-    }
-    return ok;
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------

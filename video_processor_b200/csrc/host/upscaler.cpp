@@ -117,6 +117,8 @@ bool Upscaler::ensureChain(int src_w, int src_h) {
         c.temporal.mode = m_use_temporal_consistency ? VP_TEMPORAL_BLEND_FRAMES : VP_TEMPORAL_NONE;
         c.temporal.buffer_size = std::min(std::max(tc.buffer_size, 1), 3);
         c.temporal.blend_strength = tc.blend_strength;
+        c.temporal.scene_detect = 1;                       // TemporalConsistency::process always checks for a cut (:96-105)
+        c.temporal.scene_change_threshold = tc.scene_change_threshold;
     }
     if (m_chain && m_chain->device == m_device && std::memcmp(&m_chain->cfg, &c, sizeof(c)) == 0) return true;
     if (m_chain && m_chain->ctx) {          // drain frames in flight before the context is replaced

@@ -16,6 +16,7 @@
 // number" form (0x4B0000xx - 2^23) instead of I2F so the conversion pipe is not the limiter.
 #pragma once
 #include "vp_common.cuh"
+#include "vp_scene.cuh"
 #include "vp_stats.cuh"
 
 namespace vp {
@@ -52,6 +53,9 @@ struct BilArgs {
     // CPUImpl::enhanceBicubicResult (src/upscaler.cpp:112-147): where the 2x2-dilated Canny edge map is set
     // the output is the 5-point sharpened source pixel (interior pixels) instead of the filtered one
     const uint8_t* emap; size_t epitch;
+    // detectSceneChange accumulators (src/temporal_consistency.cpp:283-323): 64-bin histogram of the gray output and
+    // sum |gray(out) - gray(previous unblended frame = blend.prev[0])|; null = off
+    SceneAccum* scene;
     BlendArgs blend;
 };
 
@@ -274,20 +278,28 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
 
     const BlendArgs& b = a.blend;
     const bool doblend = a.dst && b.mode != 0 && b.nprev > 0;
+    const bool scene_prev = a.scene && b.nprev > 0;          // previous frame needed for the gray difference
+    __shared__ unsigned s_hist[64];
+    __shared__ unsigned long long s_mad;
+    if (a.scene) {                                           // uniform across the grid
+        if (tid < 64) s_hist[tid] = 0;
+        if (tid == 0) s_mad = 0ull;
+        __syncthreads();
+    }
+    unsigned mad = 0;
     const int lx = (tid & 15) * BIL_PX;
     const int gx = x0 + lx;
-    if (gx >= a.w) return;
     const int npx = min(BIL_PX, a.w - gx);
     const size_t boff = (size_t)gx * 3;
-    for (int s = 0; s < a.ns; ++s) {
+    for (int s = 0; s < a.ns && gx < a.w; ++s) {
         const int ly = (tid >> 4) + s * BIL_TH;
         const int gy = y0 + ly;
         if (gy >= a.h) break;
         // previous frames of the temporal blend: issue the loads before the tap loop hides their latency
         uint32_t p0[3] = {0, 0, 0}, p1[3] = {0, 0, 0};
-        if (doblend) {
+        if (doblend || scene_prev) {
             load12(b.prev[0] + (size_t)gy * b.ppitch + boff, p0, npx);
-            if (b.nprev > 1) load12(b.prev[1] + (size_t)gy * b.ppitch + boff, p1, npx);
+            if (doblend && b.nprev > 1) load12(b.prev[1] + (size_t)gy * b.ppitch + boff, p1, npx);
         }
         uint32_t out[BIL_PX];
         switch (R) {
@@ -342,6 +354,19 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
         cur[1] = ((out[1] >> 8) & 0xffffu) | (out[2] << 16);
         cur[2] = ((out[2] >> 16) & 0xffu) | (out[3] << 8);
         if (b.state) store12(b.state + (size_t)gy * b.spitch + boff, cur, npx);
+        if (a.scene) {
+            // previous pixels of the strip, unpacked from the 12 packed bytes
+            const uint32_t q[BIL_PX] = {p0[0] & 0xffffffu, (p0[0] >> 24) | ((p0[1] & 0xffffu) << 8),
+                                        (p0[1] >> 16) | ((p0[2] & 0xffu) << 16), p0[2] >> 8};
+#pragma unroll
+            for (int j = 0; j < BIL_PX; ++j) {
+                if (j < npx) {
+                    const int g = gray_of(out[j]);
+                    atomicAdd(&s_hist[g >> 2], 1u);
+                    if (scene_prev) mad += abs(g - gray_of(q[j]));
+                }
+            }
+        }
         if (!a.dst) continue;
         uint8_t* dp = a.dst + (size_t)gy * a.dpitch + boff;
         if (doblend) {
@@ -352,6 +377,13 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
         } else {
             store12(dp, cur, npx);
         }
+    }
+    if (a.scene) {
+        if (mad) atomicAdd(&s_mad, (unsigned long long)mad);
+        __syncthreads();
+        const int copy = (blockIdx.x + blockIdx.y) % SC_COPIES;
+        if (tid < 64 && s_hist[tid]) atomicAdd(&a.scene->hist[copy][tid], s_hist[tid]);
+        if (tid == 0 && s_mad) atomicAdd(&a.scene->mad, s_mad);
     }
 }
 

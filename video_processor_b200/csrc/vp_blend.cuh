@@ -13,10 +13,18 @@ struct BlendKArgs {
     uint8_t* dst; size_t dpitch;      // may be null: state-only update
     int row_bytes, h;
     BlendArgs blend;                  // prev[], state, weights
+    // scene detection: k_scene_decide's verdict caps the number of previous frames (0 = pass-through);
+    // inv_wsum_n[n-1] is 1/(w0+..+wn) for n previous frames.  Null = use blend.nprev as given.
+    const int* use_dev;
+    float inv_wsum_n[2];
 };
 
 __global__ void __launch_bounds__(256) k_blend(const BlendKArgs a) {
-    const BlendArgs& b = a.blend;
+    BlendArgs b = a.blend;
+    if (a.use_dev) {
+        b.nprev = min(b.nprev, *a.use_dev);
+        if (b.nprev > 0) b.inv_wsum = a.inv_wsum_n[b.nprev - 1];
+    }
     const bool doblend = (b.mode != 0 && b.nprev > 0 && a.dst);
     bool al = aligned16(a.cur, a.cpitch);
     if (a.dst) al = al && aligned16(a.dst, a.dpitch);

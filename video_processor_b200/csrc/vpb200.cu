@@ -23,6 +23,7 @@
 #include "vp_bilateral.cuh"
 #include "vp_blend.cuh"
 #include "vp_canny.cuh"
+#include "vp_scene.cuh"
 #include "vp_stats.cuh"
 #include "vp_tables.h"
 #include "vp_upsharp.cuh"
@@ -70,6 +71,8 @@ struct vp_ctx {
     int last_lane = 0;
     size_t map_pitch = 0; int hy_tiles_x = 0, hy_tiles_y = 0, hy_grid = 0; size_t dirty_bytes = 0;
     BilCand* d_cand_be = nullptr; int cand_be_rad[3] = {0, 0, 0};
+    // scene-change detection (temporal.scene_detect)
+    SceneAccum* d_scene_acc = nullptr; SceneState* d_scene_state = nullptr; int* d_use = nullptr; bool scene_reset = true;
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     bool has_chain = false;
     vp_chain_config cfg{};
@@ -402,7 +405,7 @@ int vp_default_chain_config(vp_chain_config* cfg, int src_w, int src_h, int dst_
     cfg->pre = vp_bilateral_config{VP_STAGE_PRE, 1, 7, 0, 30.0, 30.0};          // src/upscaler.cpp:668-682
     cfg->sharpen = vp_sharpen_config{0.8f, 1.2f, 0.4f, 30.0f, 1.5f, 5, 1};      // :691-702
     cfg->post = vp_bilateral_config{VP_STAGE_POST, 1, 5, 0, 20.0, 20.0};        // :711-725
-    cfg->temporal = vp_temporal_config{VP_TEMPORAL_BLEND_FRAMES, 3, 0.6f, 0.6f}; // :734-748, main.cpp:282
+    cfg->temporal = vp_temporal_config{VP_TEMPORAL_BLEND_FRAMES, 3, 0.6f, 0.6f, 0, 100.0f}; // :734-748, main.cpp:282; scene_detect is opt-in
     return VP_OK;
 }
 
@@ -424,7 +427,7 @@ void vp_destroy(vp_ctx* c) {
     }
     if (c->ev_batch) cudaEventDestroy(c->ev_batch);
     for (auto& p : c->d_state) cudaFree(p);
-    cudaFree(c->d_cand_be);
+    cudaFree(c->d_cand_be); cudaFree(c->d_scene_acc); cudaFree(c->d_scene_state); cudaFree(c->d_use);
     cudaFree(c->d_cand_pre); cudaFree(c->d_cand_post); cudaFree(c->d_cand_tmp); cudaFree(c->d_cand_sel);
     free_resize(c->rc_chain); free_resize(c->rc_tmp);
     cudaFree(c->d_siglut); cudaFree(c->d_siglut_tmp);
@@ -489,6 +492,14 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
     if (g.dst_w != g.src_w || g.dst_h != g.src_h) {
         int rc = ensure_resize(c, c->rc_chain, g.src_w, g.src_h, g.dst_w, g.dst_h, c->s_compute);
         if (rc) return rc;
+    }
+    if (g.temporal.mode == VP_TEMPORAL_BLEND_FRAMES && g.temporal.scene_detect) {
+        VP_CUDA(c, cudaMalloc(&c->d_scene_acc, sizeof(SceneAccum)));
+        VP_CUDA(c, cudaMemset(c->d_scene_acc, 0, sizeof(SceneAccum)));
+        VP_CUDA(c, cudaMalloc(&c->d_scene_state, sizeof(SceneState)));
+        VP_CUDA(c, cudaMemset(c->d_scene_state, 0, sizeof(SceneState)));
+        VP_CUDA(c, cudaMalloc(&c->d_use, sizeof(int)));
+        VP_CUDA(c, cudaMemset(c->d_use, 0, sizeof(int)));
     }
     if (g.bicubic_enhance) {
         c->map_pitch = align_up((size_t)g.dst_w, 256);
@@ -576,6 +587,7 @@ int vp_reset_temporal(vp_ctx* c) {
     if (!c) return VP_ERR_INVALID_ARG;
     c->nvalid = 0;
     c->head = 0;
+    c->scene_reset = true;
     return VP_OK;
 }
 
@@ -720,6 +732,43 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
     BlendArgs bl{};
     temporal_args(c, temporal, bl);
     if (temporal && temporal_dep) VP_CUDA(c, cudaStreamWaitEvent(st, temporal_dep, 0));
+    const bool scene = temporal && c->d_scene_acc != nullptr;
+    if (scene) {
+        // detectSceneChange needs the whole unblended frame before any pixel may be blended: the producer
+        // accumulates the histogram / gray difference, k_scene_decide rules, k_blend blends (or passes through)
+        const uint8_t* blend_cur = cur; size_t blend_cur_pitch = cur_pitch;
+        if (g.use_post) {
+            BilArgs a{};
+            a.src = cur; a.spitch = cur_pitch; a.dst = nullptr; a.dpitch = 0; a.w = g.dst_w; a.h = g.dst_h;
+            a.cand = c->d_cand_post; a.sel = need_post_stats ? L.d_sel + 1 : nullptr;
+            a.blend = bl;                         // state store + previous frame for the gray difference
+            a.scene = c->d_scene_acc;
+            rc = launch_bilateral(c, a, c->cand_post_rad, st, K_BIL_POST); if (rc) return rc;
+            blend_cur = bl.state; blend_cur_pitch = c->frame_pitch;
+        } else {
+            if (cur == d_src && (g.dst_w != g.src_w || g.dst_h != g.src_h))
+                return fail(c, VP_ERR_STATE, "internal: chain produced no frame");
+            SceneAccumArgs sa{cur, cur_pitch, bl.nprev > 0 ? bl.prev[0] : nullptr, c->frame_pitch, g.dst_w, g.dst_h, c->d_scene_acc};
+            ProfScope ps(c, K_BLEND, st);
+            k_scene_accum<<<c->sm_count * 8, 256, 0, st>>>(sa);
+            VP_CUDA(c, cudaGetLastError());
+            c->launches++;
+        }
+        k_scene_decide<<<1, 64, 0, st>>>(c->d_scene_acc, c->d_scene_state, c->d_use, (double)g.dst_w * g.dst_h,
+                                         g.temporal.scene_change_threshold, g.temporal.buffer_size, c->scene_reset ? 1 : 0);
+        VP_CUDA(c, cudaGetLastError());
+        c->launches++;
+        c->scene_reset = false;
+        if (d_dst || !g.use_post) {
+            BlendKArgs a{};
+            a.cur = blend_cur; a.cpitch = blend_cur_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.row_bytes = g.dst_w * 3; a.h = g.dst_h;
+            a.blend = bl;
+            if (g.use_post) a.blend.state = nullptr;      // POST already stored the unblended frame
+            a.use_dev = c->d_use;
+            for (int n = 1; n <= 2; ++n) { BlendArgs t{}; blend_weights(g.temporal, n, t); a.inv_wsum_n[n - 1] = t.inv_wsum; }
+            rc = launch_blend(c, a, st); if (rc) return rc;
+        }
+    } else
     // 4+5. SelectiveBilateral POST with the temporal blend in its epilogue
     if (g.use_post) {
         BilArgs a{};
@@ -1045,7 +1094,7 @@ int vp_temporal_blend(vp_ctx* c, const uint8_t* const* d_frames, int nframes, si
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
     BlendKArgs a{};
     a.cur = d_frames[0]; a.cpitch = pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.row_bytes = 3 * w; a.h = h;
-    vp_temporal_config t{VP_TEMPORAL_BLEND_FRAMES, 3, blend_strength, 0.6f};
+    vp_temporal_config t{VP_TEMPORAL_BLEND_FRAMES, 3, blend_strength, 0.6f, 0, 100.0f};
     blend_weights(t, nframes - 1, a.blend);
     for (int i = 1; i < nframes; ++i) a.blend.prev[i - 1] = d_frames[i];
     a.blend.ppitch = pitch;
