@@ -280,10 +280,10 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
     const bool doblend = a.dst && b.mode != 0 && b.nprev > 0;
     const bool scene_prev = a.scene && b.nprev > 0;          // previous frame needed for the gray difference
     __shared__ unsigned s_hist[64];
-    __shared__ unsigned long long s_mad;
+    __shared__ unsigned s_mad;                               // <= 2048 px * 255 per tile: fits 32 bits (native atomic)
     if (a.scene) {                                           // uniform across the grid
         if (tid < 64) s_hist[tid] = 0;
-        if (tid == 0) s_mad = 0ull;
+        if (tid == 0) s_mad = 0u;
         __syncthreads();
     }
     unsigned mad = 0;
@@ -360,11 +360,12 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
                                         (p0[1] >> 16) | ((p0[2] & 0xffu) << 16), p0[2] >> 8};
 #pragma unroll
             for (int j = 0; j < BIL_PX; ++j) {
-                if (j < npx) {
-                    const int g = gray_of(out[j]);
-                    atomicAdd(&s_hist[g >> 2], 1u);
-                    if (scene_prev) mad += abs(g - gray_of(q[j]));
-                }
+                // one shared-memory atomic per distinct bin per warp: neighbouring pixels share bins
+                const int g = j < npx ? gray_of(out[j]) : -4;
+                const int bin = g >> 2;                                  // -1 for lanes without a pixel
+                const unsigned same = __match_any_sync(__activemask(), bin);
+                if (bin >= 0 && (int)(__ffs(same) - 1) == (tid & 31)) atomicAdd(&s_hist[bin], (unsigned)__popc(same));
+                if (scene_prev && j < npx) mad += abs(g - gray_of(q[j]));
             }
         }
         if (!a.dst) continue;
@@ -379,11 +380,13 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
         }
     }
     if (a.scene) {
-        if (mad) atomicAdd(&s_mad, (unsigned long long)mad);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mad += __shfl_xor_sync(0xffffffffu, mad, o);
+        if ((tid & 31) == 0 && mad) atomicAdd(&s_mad, mad);
         __syncthreads();
-        const int copy = (blockIdx.x + blockIdx.y) % SC_COPIES;
+        const int copy = (blockIdx.x + blockIdx.y * gridDim.x) % SC_COPIES;
         if (tid < 64 && s_hist[tid]) atomicAdd(&a.scene->hist[copy][tid], s_hist[tid]);
-        if (tid == 0 && s_mad) atomicAdd(&a.scene->mad, s_mad);
+        if (tid == 0 && s_mad) atomicAdd(&a.scene->mad, (unsigned long long)s_mad);
     }
 }
 

@@ -10,7 +10,7 @@
 
 namespace vp {
 
-constexpr int SC_COPIES = 8;                      // privatised global histograms (spread the atomics)
+constexpr int SC_COPIES = 128;                    // privatised global histograms: same-line L2 atomics serialise, spread them
 
 struct SceneAccum {                               // device memory, zeroed by k_scene_decide after use
     unsigned hist[SC_COPIES][64];
@@ -96,7 +96,12 @@ __global__ void __launch_bounds__(256) k_scene_accum(const SceneAccumArgs a) {
             mad += abs(g - gray_of((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16)));
         }
     }
-    if (mad) atomicAdd(&s_mad, (unsigned long long)mad);
+    {   // per-thread sums fit 32 bits only for short strides: widen before the warp reduction
+        unsigned long long m = mad;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_mad, m);
+    }
     __syncthreads();
     if (threadIdx.x < 64 && s_hist[threadIdx.x]) atomicAdd(&a.acc->hist[blockIdx.x % SC_COPIES][threadIdx.x], s_hist[threadIdx.x]);
     if (threadIdx.x == 0 && s_mad) atomicAdd(&a.acc->mad, s_mad);
