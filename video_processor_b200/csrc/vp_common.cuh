@@ -99,21 +99,25 @@ __device__ __forceinline__ bool aligned16(const void* p, size_t pitch) {
     return ((((uintptr_t)p) | pitch) & 15) == 0;
 }
 
-// warp reduction of 6 uint32 partial sums into the CTA's shared uint64 accumulators
-__device__ __forceinline__ void reduce_sums6(const unsigned v[6], unsigned long long* s_red) {
-    const int lane = threadIdx.x & 31;
-    unsigned long long w[6];
+// CTA reduction of 6 uint32 per-thread partial sums without shared-memory atomics (64-bit shared atomics
+// are CAS loops): warp shuffles, one slot per warp, then threads 0..5 add the slots.  `s_part` holds
+// (blockDim.x / 32) * 6 entries; the result lands in s_tot[0..5] after the function's barrier.
+__device__ __forceinline__ void reduce_sums6(const unsigned v[6], unsigned long long* s_part, unsigned long long* s_tot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         unsigned long long x = v[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        w[k] = x;
+        if (lane == 0) s_part[warp * 6 + k] = x;
     }
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) atomicAdd(&s_red[k], w[k]);
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        unsigned long long t = 0;
+        for (int w = 0; w < nwarps; ++w) t += s_part[w * 6 + threadIdx.x];
+        s_tot[threadIdx.x] = t;
     }
+    __syncthreads();
 }
 
 }  // namespace vp

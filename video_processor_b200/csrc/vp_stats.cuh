@@ -75,12 +75,10 @@ __device__ __forceinline__ void acc12(uint32_t a, uint32_t b, uint32_t c, unsign
 // CTA per accumulator finish the reduction.
 __global__ void __launch_bounds__(256) k_stats(const uint8_t* __restrict__ src, size_t pitch, int w, int h,
                                                unsigned long long* __restrict__ sums, const SelOut fin) {
-    __shared__ unsigned long long s_red[6];
-    if (threadIdx.x < 6) s_red[threadIdx.x] = 0ull;
-    __syncthreads();
+    __shared__ unsigned long long s_red[6], s_part[8 * 6];
     const int row_bytes = 3 * w;
     unsigned acc[6] = {0, 0, 0, 0, 0, 0};
-    unsigned long long tail[6] = {0, 0, 0, 0, 0, 0};
+    unsigned* tail = acc;      // byte tails: a few dozen bytes per thread at most, same 32-bit accumulators
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
     if (pitch == (size_t)row_bytes && ((uintptr_t)src & 15) == 0) {
         const long long total = (long long)row_bytes * h;
@@ -125,11 +123,7 @@ __global__ void __launch_bounds__(256) k_stats(const uint8_t* __restrict__ src, 
             }
         }
     }
-#pragma unroll
-    for (int k = 0; k < 6; ++k)
-        if (tail[k]) atomicAdd(&s_red[k], tail[k]);
-    reduce_sums6(acc, s_red);
-    __syncthreads();
+    reduce_sums6(acc, s_part, s_red);
     flush_and_finalize(s_red, sums, fin, gridDim.x);
 }
 

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
     constexpr int EW = US_TW + 2 * HALO, EH = US_TH + 2 * HALO;
     constexpr int GR = GK / 2;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ unsigned long long s_red[6];
+    __shared__ unsigned long long s_red[6], s_part[(US_NT / 32) * 6];
     const int tid = threadIdx.x;
     const UpsharpSmem L = upsharp_layout(RESIZE, SHARPEN, a.max_src_rows, a.max_src_cols);
     uint8_t* s_raw = smem + L.raw;
@@ -125,7 +125,6 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
     float* s_lut = reinterpret_cast<float*>(tp);
 
     const int x0 = blockIdx.x * US_TW, y0 = blockIdx.y * US_TH;
-    if (tid < 6) s_red[tid] = 0ull;
 
     // ---- P0: tables for this tile + source window -------------------------------------------------
     const int dxa = max(0, x0 - HALO), dxb = min(a.dw - 1, x0 + US_TW - 1 + HALO);
@@ -416,7 +415,7 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
             }
         }
     }
-    if (a.sums) reduce_sums6(acc6, s_red);
+    if (a.sums) reduce_sums6(acc6, s_part, s_red);
     fence_proxy_async();    // staged tile (generic-proxy writes) -> visible to the TMA store engine
     __syncthreads();
 
