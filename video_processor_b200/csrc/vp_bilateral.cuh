@@ -175,6 +175,34 @@ struct BilRowSwitch<R, -1> {
                                                unsigned long long (&)[BIL_PX]) {}
 };
 
+// half-width of tap row i of a radius-R window: taps (i,j) with i*i + j*j <= R*R  (the host's BilCand::xmax)
+__host__ __device__ constexpr int bil_xmax(int R, int i) {
+    int x = 0;
+    while ((x + 1) * (x + 1) + i * i <= R * R) ++x;
+    return x;
+}
+
+// small windows: every tap row unrolled with its compile-time half-width (no row switch, no xmax loads)
+template <int R, int ROW>
+__device__ __forceinline__ void bil_rows_unrolled(const uint32_t* __restrict__ s_tile, const float* __restrict__ s_sw,
+                                                  const float* __restrict__ s_cw, int lx, int ly, const uint32_t (&ctr)[BIL_PX],
+                                                  unsigned long long (&abg)[BIL_PX], unsigned long long (&arw)[BIL_PX]) {
+    if constexpr (ROW <= 2 * R) {
+        constexpr int TP = BilGeom<R>::TP, NSEG = BilGeom<R>::NSEG, D = BilGeom<R>::D;
+        const uint4* rowp = reinterpret_cast<const uint4*>(s_tile + (ly + ROW) * TP + lx);
+        uint32_t seg[NSEG];
+#pragma unroll
+        for (int q = 0; q < NSEG / 4; ++q) {
+            const uint4 v = rowp[q];
+            seg[4 * q] = v.x; seg[4 * q + 1] = v.y; seg[4 * q + 2] = v.z; seg[4 * q + 3] = v.w;
+        }
+        bil_row<R, bil_xmax(R, ROW - R)>(seg, s_sw + ROW * D, s_cw, ctr, abg, arw);
+        bil_rows_unrolled<R, ROW + 1>(s_tile, s_sw, s_cw, lx, ly, ctr, abg, arw);
+    }
+}
+
+constexpr int BIL_UNROLL_RMAX = 3;
+
 template <int R>
 __device__ __forceinline__ void bil_strip(const uint32_t* __restrict__ s_tile, const float* __restrict__ s_sw,
                                        const float* __restrict__ s_cw, const int* __restrict__ s_xm,
@@ -187,16 +215,20 @@ __device__ __forceinline__ void bil_strip(const uint32_t* __restrict__ s_tile, c
         ctr[j] = s_tile[(ly + R) * TP + lx + R + j];
         abg[j] = arw[j] = 0ull;
     }
+    if constexpr (R <= BIL_UNROLL_RMAX) {
+        bil_rows_unrolled<R, 0>(s_tile, s_sw, s_cw, lx, ly, ctr, abg, arw);
+    } else {
 #pragma unroll 1
-    for (int row = 0; row < D; ++row) {
-        const uint4* rowp = reinterpret_cast<const uint4*>(s_tile + (ly + row) * TP + lx);
-        uint32_t seg[NSEG];
+        for (int row = 0; row < D; ++row) {
+            const uint4* rowp = reinterpret_cast<const uint4*>(s_tile + (ly + row) * TP + lx);
+            uint32_t seg[NSEG];
 #pragma unroll
-        for (int q = 0; q < NSEG / 4; ++q) {
-            const uint4 v = rowp[q];
-            seg[4 * q] = v.x; seg[4 * q + 1] = v.y; seg[4 * q + 2] = v.z; seg[4 * q + 3] = v.w;
+            for (int q = 0; q < NSEG / 4; ++q) {
+                const uint4 v = rowp[q];
+                seg[4 * q] = v.x; seg[4 * q + 1] = v.y; seg[4 * q + 2] = v.z; seg[4 * q + 3] = v.w;
+            }
+            BilRowSwitch<R, R>::run(s_xm[row], seg, s_sw + row * D, s_cw, ctr, abg, arw);
         }
-        BilRowSwitch<R, R>::run(s_xm[row], seg, s_sw + row * D, s_cw, ctr, abg, arw);
     }
 #pragma unroll
     for (int j = 0; j < BIL_PX; ++j) {
@@ -251,9 +283,32 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
     stage_rows(s_raw, RP, a.src, a.spitch, 3 * a.w, vy0, vy1, bx0, bx1, fast, bar);
 
     // expand raw bytes -> BGR0 words with BORDER_REFLECT_101 resolved; warp per row, lanes along x
-    {
+    const bool simple = (a.w > R) && (a.h > R);          // one mirror step suffices
+    if (fast && simple && x0 >= R && x0 + BIL_TW + R <= a.w) {
+        // no horizontal mirroring in this tile: a lane turns 12 raw bytes (4 pixels, any byte phase) into four
+        // BGR1 words with funnel shifts and byte permutes and stores them as one 128-bit word
+        const int c0 = 3 * vx0 - bx0;                    // byte offset of tile column 0 inside a raw row, 0..15
+        const int sh = 8 * (c0 & 3);
+        const int ng = TP >> 2;
+        const int lane = tid & 31, wrp = tid >> 5;
+        for (int ty = wrp; ty < TROWS; ty += BIL_NT / 32) {
+            int sy = y0 - R + ty;
+            sy = sy < 0 ? -sy : sy; sy = sy >= a.h ? 2 * a.h - 2 - sy : sy;
+            if (lane >= ng) continue;
+            uint4 o = make_uint4(0x01000000u, 0x01000000u, 0x01000000u, 0x01000000u);
+            if (sy >= vy0 && sy < vy1) {                 // false only for unused rows of bottom-edge tiles
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(s_raw + (sy - vy0) * RP + (c0 & ~3)) + 3 * lane;
+                const uint32_t r0 = q[0], r1 = q[1], r2 = q[2], r3 = q[3];
+                const uint32_t w0 = __funnelshift_r(r0, r1, sh), w1 = __funnelshift_r(r1, r2, sh), w2 = __funnelshift_r(r2, r3, sh);
+                o.x = __byte_perm(w0, 0x01010101u, 0x4210);
+                o.y = (__byte_perm(w0, w1, 0x3543) & 0x00ffffffu) | 0x01000000u;
+                o.z = (__byte_perm(w1, w2, 0x3432) & 0x00ffffffu) | 0x01000000u;
+                o.w = __byte_perm(w2, 0x01010101u, 0x4321);
+            }
+            *reinterpret_cast<uint4*>(s_tile + ty * TP + 4 * lane) = o;
+        }
+    } else {
         const int TWH = BIL_TW + 2 * R;
-        const bool simple = (a.w > R) && (a.h > R);      // one mirror step suffices
         const int lane = tid & 31, wrp = tid >> 5;
         for (int ty = wrp; ty < TROWS; ty += BIL_NT / 32) {
             int sy = y0 - R + ty;
