@@ -99,11 +99,11 @@ __device__ __forceinline__ bool aligned16(const void* p, size_t pitch) {
     return ((((uintptr_t)p) | pitch) & 15) == 0;
 }
 
-// CTA reduction of 6 uint32 per-thread partial sums without shared-memory atomics (64-bit shared atomics
-// are CAS loops): warp shuffles, one slot per warp, then threads 0..5 add the slots.  `s_part` holds
-// (blockDim.x / 32) * 6 entries; the result lands in s_tot[0..5] after the function's barrier.
-__device__ __forceinline__ void reduce_sums6(const unsigned v[6], unsigned long long* s_part, unsigned long long* s_tot) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+// First half of the CTA reduction of 6 uint32 per-thread partial sums (no shared-memory atomics: 64-bit shared
+// atomics are CAS loops): warp shuffles, then lane 0 of every warp stores its 6 totals to s_part[warp*6 ..].
+// The caller's next __syncthreads() publishes them; one warp then finishes with warp_flush_and_finalize().
+__device__ __forceinline__ void warp_partials6(const unsigned v[6], unsigned long long* s_part) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         unsigned long long x = v[k];
@@ -111,13 +111,6 @@ __device__ __forceinline__ void reduce_sums6(const unsigned v[6], unsigned long 
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if (lane == 0) s_part[warp * 6 + k] = x;
     }
-    __syncthreads();
-    if (threadIdx.x < 6) {
-        unsigned long long t = 0;
-        for (int w = 0; w < nwarps; ++w) t += s_part[w * 6 + threadIdx.x];
-        s_tot[threadIdx.x] = t;
-    }
-    __syncthreads();
 }
 
 }  // namespace vp

@@ -30,26 +30,28 @@ struct SelOut {
     double npx;
 };
 
-// Flush this CTA's shared partial sums, then let the last CTA of the grid evaluate the class once
-// (threadfence-reduction pattern) so the consumer does no double-precision work.
-__device__ __forceinline__ void flush_and_finalize(unsigned long long* s_red, unsigned long long* __restrict__ sums,
-                                                   const SelOut f, unsigned nblocks) {
-    __shared__ bool s_last;
-    if (threadIdx.x < 6) {
-        if (s_red[threadIdx.x]) atomicAdd(&sums[threadIdx.x], s_red[threadIdx.x]);
-        if (f.counter) __threadfence();      // only the threads that published need the fence
+// Second half of the reduction, run by ONE whole warp after the barrier that published s_part: lanes 0..5 add the
+// per-warp partials and flush them with one 64-bit global atomic each, then the last CTA of the grid evaluates
+// the class once (threadfence-reduction pattern at warp scope) so the consumer does no double-precision work.
+// Only this warp waits for the atomics and the fence; the CTA's other warps carry on (stores) or exit.
+__device__ __forceinline__ void warp_flush_and_finalize(const unsigned long long* s_part, int nwarps,
+                                                        unsigned long long* __restrict__ sums, const SelOut f, unsigned nblocks) {
+    const int lane = threadIdx.x & 31;
+    if (lane < 6) {
+        unsigned long long t = 0;
+        for (int w = 0; w < nwarps; ++w) t += s_part[w * 6 + lane];
+        if (t) atomicAdd(&sums[lane], t);
+        if (f.counter) __threadfence();
     }
     if (!f.counter) return;
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    __syncwarp();
+    if (lane == 0) {
         const unsigned ticket = atomicAdd(f.counter, 1u);
-        s_last = (ticket == nblocks - 1);
-    }
-    __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-        __threadfence();
-        *f.sel = noise_class_from_sums(sums, f.npx);
-        *f.counter = 0u;
+        if (ticket == nblocks - 1) {
+            __threadfence();
+            *f.sel = noise_class_from_sums(sums, f.npx);
+            *f.counter = 0u;
+        }
     }
 }
 
@@ -71,11 +73,11 @@ __device__ __forceinline__ void acc12(uint32_t a, uint32_t b, uint32_t c, unsign
 
 // Fast path: the frame is one contiguous, 16-byte aligned run of 3*w*h bytes (pitch == 3*w): it is
 // streamed as 48-byte groups (three 128-bit loads = 16 pixels) with a grid-stride loop.  Otherwise rows
-// are walked in 12-byte groups (4-byte aligned) or bytes.  Warp shuffles + one 64-bit atomic per
-// CTA per accumulator finish the reduction.
+// are walked in 12-byte groups (4-byte aligned) or bytes.  Warp shuffles, one barrier and one 64-bit atomic
+// per CTA per accumulator (issued by warp 0) finish the reduction.
 __global__ void __launch_bounds__(256) k_stats(const uint8_t* __restrict__ src, size_t pitch, int w, int h,
                                                unsigned long long* __restrict__ sums, const SelOut fin) {
-    __shared__ unsigned long long s_red[6], s_part[8 * 6];
+    __shared__ unsigned long long s_part[8 * 6];
     const int row_bytes = 3 * w;
     unsigned acc[6] = {0, 0, 0, 0, 0, 0};
     unsigned* tail = acc;      // byte tails: a few dozen bytes per thread at most, same 32-bit accumulators
@@ -123,8 +125,9 @@ __global__ void __launch_bounds__(256) k_stats(const uint8_t* __restrict__ src, 
             }
         }
     }
-    reduce_sums6(acc, s_part, s_red);
-    flush_and_finalize(s_red, sums, fin, gridDim.x);
+    warp_partials6(acc, s_part);
+    __syncthreads();
+    if (threadIdx.x < 32) warp_flush_and_finalize(s_part, 8, sums, fin, gridDim.x);
 }
 
 }  // namespace vp

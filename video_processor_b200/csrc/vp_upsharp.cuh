@@ -75,7 +75,7 @@ __host__ __device__ inline UpsharpSmem upsharp_layout(bool resize, bool sharpen,
     L.raw_pitch = ((max_src_cols * 3 + 15 + 15) & ~15) + 16;
     // region U: raw source bytes + BGR0 source words (dead after P1 / the expand), later the sigmoid
     // image (68 x 36 f32, P3-P4) and finally the staged output tile (US_TH x US_TW*3 bytes, P5-P6)
-    L.src_pitch = max_src_cols + 1;
+    L.src_pitch = (max_src_cols + 4) & ~3;      // whole 128-bit words per row (the word-wise expand stores uint4s)
     const int rawb = L.raw_pitch * max_src_rows;
     const int srcb = resize ? ((L.src_pitch * max_src_rows * 4 + 15) & ~15) : 0;
     const int sig = sharpen ? (US_TW + 4) * (US_TH + 4) * 4 : 0;
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
     constexpr int EW = US_TW + 2 * HALO, EH = US_TH + 2 * HALO;
     constexpr int GR = GK / 2;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ unsigned long long s_red[6], s_part[(US_NT / 32) * 6];
+    __shared__ unsigned long long s_part[(US_NT / 32) * 6];
     const int tid = threadIdx.x;
     const UpsharpSmem L = upsharp_layout(RESIZE, SHARPEN, a.max_src_rows, a.max_src_cols);
     uint8_t* s_raw = smem + L.raw;
@@ -155,8 +155,26 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
         const int SP = L.src_pitch;
         const int ncols = ux1 - ux0 + 1, nrows = uy1 - uy0 + 1;
         // raw bytes -> BGR0 words, replicate border materialised; warp per row, lanes along x
-        {
-            const int lane = tid & 31, wrp = tid >> 5;
+        const int lane = tid & 31, wrp = tid >> 5;
+        if (ux0 >= 0 && ux1 < a.sw && aligned16(a.src, a.spitch)) {
+            // no horizontal clamping in this tile: a lane turns 12 raw bytes (4 pixels, any byte phase) into four
+            // BGR0 words with funnel shifts and byte permutes and stores them as one 128-bit word
+            const int c0 = 3 * ux0 - bx0;               // byte offset of window column 0 inside a raw row, 0..15
+            const int sh = 8 * (c0 & 3);
+            const int ng = (ncols + 3) >> 2;
+            for (int rr = wrp; rr < nrows; rr += US_NT / 32) {
+                if (lane >= ng) continue;
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(s_raw + (clampi(uy0 + rr, 0, a.sh - 1) - sy0) * RP + (c0 & ~3)) + 3 * lane;
+                const uint32_t r0 = q[0], r1 = q[1], r2 = q[2], r3 = q[3];
+                const uint32_t w0 = __funnelshift_r(r0, r1, sh), w1 = __funnelshift_r(r1, r2, sh), w2 = __funnelshift_r(r2, r3, sh);
+                uint4 o;
+                o.x = w0 & 0x00ffffffu;
+                o.y = __byte_perm(w0, w1, 0x7543) & 0x00ffffffu;
+                o.z = __byte_perm(w1, w2, 0x7432) & 0x00ffffffu;
+                o.w = w2 >> 8;
+                *reinterpret_cast<uint4*>(s_src + rr * SP + 4 * lane) = o;
+            }
+        } else {
             for (int rr = wrp; rr < nrows; rr += US_NT / 32) {
                 const uint8_t* rrow = s_raw + (clampi(uy0 + rr, 0, a.sh - 1) - sy0) * RP - bx0;
                 for (int cc = lane; cc < ncols; cc += 32) {
@@ -415,9 +433,11 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
             }
         }
     }
-    if (a.sums) reduce_sums6(acc6, s_part, s_red);
+    if (a.sums) warp_partials6(acc6, s_part);
     fence_proxy_async();    // staged tile (generic-proxy writes) -> visible to the TMA store engine
     __syncthreads();
+    // warp 1 publishes the statistics (global atomics, fence, ticket) while warp 0 drives the tile's TMA stores
+    if (a.sums && (tid >> 5) == 1) warp_flush_and_finalize(s_part, US_NT / 32, a.sums, a.fin, gridDim.x * gridDim.y);
 
     // ---- P6: staged tile -> HBM: one TMA bulk store per row (16-byte aligned frames), else bytes ----
     if (a.dst) {
@@ -437,7 +457,6 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
         }
         if (nb16 && tid < vh) bulk_wait_read0();
     }
-    if (a.sums) flush_and_finalize(s_red, a.sums, a.fin, gridDim.x * gridDim.y);
 }
 
 }  // namespace vp
