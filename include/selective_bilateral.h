@@ -1,11 +1,11 @@
 // selective_bilateral.h - SelectiveBilateral with the reference's interface
 // (reference include/selective_bilateral.h:12-153), executed by libvpb200's CUDA bilateral kernel.
 //
-// Built branch: SelectiveBilateral::applyBilateralFilter (src/selective_bilateral.cpp:84-119) with
-// calculateAdaptiveParams (:315-371).  use_multiscale / selective are accepted but take the same
-// branch: in the reference their bodies call cv::sqrt on a CV_8U Mat (:276, undefined behaviour) and
-// its own GPU multiscale path ends in `return applyBilateralFilter(input, output)` through the
-// exception fallback (:164-176, :232-235).  DESIGN.md lists this under "reference defects".
+// process() dispatches as the reference does (src/selective_bilateral.cpp:57-82): use_multiscale ->
+// applyMultiscaleBilateral (:138-237), else selective -> applySelectiveBilateral (:121-136, :373-439), else
+// applyBilateralFilter (:84-119) with calculateAdaptiveParams (:315-371).  The first two run with REPAIRED
+// semantics: createDetailMask calls cv::sqrt on a CV_8U Mat in the reference (:276, undefined behaviour); here
+// local_var is converted to float32 first (oracle/ref_chain.py:create_detail_mask).
 #pragma once
 #include <memory>
 #include "vp/mat.h"

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VPB200_ABI_VERSION 1
+#define VPB200_ABI_VERSION 2
 
 typedef enum vp_status {
     VP_OK = 0,
@@ -40,9 +40,13 @@ typedef enum vp_status {
     VP_ERR_NOMEM = -6
 } vp_status;
 
-/* SelectiveBilateral::Config (include/selective_bilateral.h:20-40), plain branch only:
- * use_multiscale=false, selective=false (the other branches call cv::sqrt on CV_8U,
- * src/selective_bilateral.cpp:276 - undefined behaviour). */
+/* SelectiveBilateral::Config (include/selective_bilateral.h:20-40).  process() dispatches as the reference does
+ * (src/selective_bilateral.cpp:57-82): use_multiscale -> applyMultiscaleBilateral (:138-237, the config's diameter at
+ * every scale, sigmas x (1 + 0.5 i), pyrDown / pyrUp, detail-weighted coarse-to-fine blend); else selective ->
+ * applySelectiveBilateral (:121-136: createDetailMask :239-313 + applyJointBilateral :373-439); else the plain
+ * applyBilateralFilter (:84-119).  The two detail-mask branches run with REPAIRED semantics: the literal code
+ * calls cv::sqrt on a CV_8U Mat (:276, undefined behaviour); here local_var is converted to float32 first and a zero
+ * maximum normalises to 0 instead of NaN.  Fields after sigma_space default to 0 = plain. */
 enum { VP_STAGE_PRE = 0, VP_STAGE_POST = 1 };   /* SelectiveBilateral::ProcessingStage */
 typedef struct vp_bilateral_config {
     int32_t stage;             /* VP_STAGE_PRE / VP_STAGE_POST                                    */
@@ -51,6 +55,12 @@ typedef struct vp_bilateral_config {
     int32_t reserved_;         /* keeps the doubles 8-byte aligned on every ABI                   */
     double sigma_color;        /* double in the reference's Config                                */
     double sigma_space;
+    int32_t selective;         /* Config::selective                                               */
+    int32_t use_multiscale;    /* Config::use_multiscale                                          */
+    int32_t num_scales;        /* Config::num_scales, clamped to 1..5 as initialize() does (:40-43) */
+    int32_t reserved2_;
+    double detail_threshold;   /* Config::detail_threshold (0..255 scale, :291)                   */
+    double edge_preserve;      /* Config::edge_preserve (:392)                                    */
 } vp_bilateral_config;
 
 /* AdaptiveSharpening::Config (include/adaptive_sharpening.h:14-24), adaptive_sigma=false branch
@@ -168,10 +178,19 @@ int vp_bicubic(vp_ctx* ctx, const uint8_t* d_src, size_t src_pitch, int src_w, i
 /* cv::bilateralFilter(src, dst, d, sigma_color, sigma_space) - src/selective_bilateral.cpp:110 */
 int vp_bilateral(vp_ctx* ctx, const uint8_t* d_src, size_t src_pitch, uint8_t* d_dst, size_t dst_pitch,
                  int w, int h, int d, double sigma_color, double sigma_space, void* stream);
-/* SelectiveBilateral::process, plain branch (src/selective_bilateral.cpp:57-119): adaptive
- * parameters from the frame's own mean/std-dev, then the bilateral filter. */
+/* SelectiveBilateral::process (src/selective_bilateral.cpp:57-82) in the mode `cfg` selects: plain (adaptive
+ * parameters from the frame's own mean/std-dev, then the bilateral filter), selective or multi-scale. */
 int vp_selective_bilateral(vp_ctx* ctx, const vp_bilateral_config* cfg, const uint8_t* d_src, size_t src_pitch,
                            uint8_t* d_dst, size_t dst_pitch, int w, int h, void* stream);
+/* SelectiveBilateral::createDetailMask (src/selective_bilateral.cpp:239-313, repaired semantics): float32 mask,
+ * pitch in bytes */
+int vp_detail_mask(vp_ctx* ctx, double detail_threshold, const uint8_t* d_src, size_t src_pitch,
+                   float* d_mask, size_t mask_pitch, int w, int h, void* stream);
+/* cv::pyrDown / cv::pyrUp on CV_8UC3 (src/selective_bilateral.cpp:148-150, :188); pyrUp takes dst = 2*src or 2*src-1 */
+int vp_pyr_down(vp_ctx* ctx, const uint8_t* d_src, size_t src_pitch, int src_w, int src_h,
+                uint8_t* d_dst, size_t dst_pitch, void* stream);
+int vp_pyr_up(vp_ctx* ctx, const uint8_t* d_src, size_t src_pitch, int src_w, int src_h,
+              uint8_t* d_dst, size_t dst_pitch, int dst_w, int dst_h, void* stream);
 /* cv::meanStdDev sums (src/selective_bilateral.cpp:321-322): d_sums[0..2] = sum x per channel,
  * d_sums[3..5] = sum x^2 per channel (uint64, device memory, overwritten). */
 int vp_mean_stddev_sums(vp_ctx* ctx, const uint8_t* d_src, size_t src_pitch, int w, int h,

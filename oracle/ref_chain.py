@@ -14,8 +14,10 @@ import this module.  The product path never does: it fails loudly if libvpb200.s
 
 Scope decisions where the literal reference code is undefined behaviour (SURVEY.md section 8(c),
 Appendix B) -- each is an oracle decision, stated here once:
-  * SelectiveBilateral: only the plain branch (use_multiscale=false, selective=false) is in scope;
-    createDetailMask calls cv::sqrt on a CV_8U Mat (selective_bilateral.cpp:276).
+  * SelectiveBilateral: the plain branch (use_multiscale=false, selective=false) is the north-star path;
+    createDetailMask calls cv::sqrt on a CV_8U Mat (selective_bilateral.cpp:276), so the selective and
+    multi-scale branches are restated with REPAIRED semantics (local_var -> float32 before the sqrt, a zero
+    maximum normalises to 0) - see create_detail_mask below.
   * AdaptiveSharpening: only adaptive_sigma=false is in scope; calculateTextureMap has the same
     defect (adaptive_sharpening.cpp:386).
   * TemporalConsistency::blendFrames writes Vec3f into a CV_8UC3 Mat (temporal_consistency.cpp:367
@@ -135,6 +137,21 @@ class NumpyOps:
     def dilate_2x2(self, edges):
         return R.dilate_2x2(edges)
 
+    def box_blur5(self, img):
+        return R.box_blur5_u8(img)
+
+    def pyr_down(self, img):
+        return R.pyr_down_u8(img)
+
+    def pyr_up(self, img, dw, dh):
+        return R.pyr_up_u8(img, dw, dh)
+
+    def sobel_magnitude(self, gray):
+        return R.sobel_magnitude_f32(gray)
+
+    def add_weighted_f32(self, a, alpha, b, beta):
+        return (a.astype(np.float64) * alpha + b.astype(np.float64) * beta).astype(F32)
+
 
 class Cv2Ops:
     name = "cv2"
@@ -196,6 +213,22 @@ class Cv2Ops:
     def dilate_2x2(self, edges):
         return self.cv2.dilate(edges, self.cv2.getStructuringElement(self.cv2.MORPH_RECT, (2, 2)))
 
+    def box_blur5(self, img):
+        return self.cv2.blur(img, (5, 5))
+
+    def pyr_down(self, img):
+        return self.cv2.pyrDown(img)
+
+    def pyr_up(self, img, dw, dh):
+        return self.cv2.pyrUp(img, dstsize=(dw, dh))
+
+    def sobel_magnitude(self, gray):
+        cv2 = self.cv2
+        return cv2.magnitude(cv2.Sobel(gray, cv2.CV_32F, 1, 0, ksize=3), cv2.Sobel(gray, cv2.CV_32F, 0, 1, ksize=3))
+
+    def add_weighted_f32(self, a, alpha, b, beta):
+        return self.cv2.addWeighted(a, alpha, b, beta, 0)
+
 
 # ------------------------------------------------------------------------------------------------
 # SelectiveBilateral (plain branch)
@@ -235,6 +268,87 @@ def bilateral_plain(ops, img, cfg):
     if cfg.adaptive_params:
         d, sc, ss = adaptive_params(ops, img, cfg)
     return ops.bilateral(img, d, sc, ss)
+
+
+# ------------------------------------------------------------------------------------------------
+# SelectiveBilateral, selective and multiscale branches with REPAIRED semantics.
+# The literal code calls cv::sqrt on the CV_8U `local_var` (selective_bilateral.cpp:276, undefined
+# behaviour: the float kernel runs over a byte buffer); the repair converts `local_var` to float32 first
+# and keeps everything else as written, including the saturating u8 subtract / multiply (:268-269).
+# "Parity unpinned": no run of the reference can produce these numbers.
+# ------------------------------------------------------------------------------------------------
+def create_detail_mask(ops, img, cfg):
+    """SelectiveBilateral::createDetailMask, selective_bilateral.cpp:239-313."""
+    gray = ops.bgr2gray(img)                                        # :245
+    magnitude = ops.sobel_magnitude(gray)                           # :250-256
+    local_mean = ops.box_blur5(gray)                                # :263
+    diff = ops.subtract(gray, local_mean)                           # :267-268 (u8, saturating)
+    d16 = diff.astype(np.uint16)
+    diff_sq = np.minimum(d16 * d16, 255).astype(np.uint8)           # :269 cv::multiply on u8 saturates
+    local_var = ops.box_blur5(diff_sq)                              # :272
+    texture = np.sqrt(local_var.astype(F32)).astype(F32)            # :276 REPAIRED: float32 before cv::sqrt
+    # :281-285  Mat / double == convertTo(alpha = 1/max): a float32 multiply by (float)(1.0 / max)
+    # REPAIRED as well: a zero maximum (flat frame) would make this 0 * inf = NaN and the output black; it yields 0
+    mm, tm = float(magnitude.max()), float(texture.max())
+    norm_mag = (magnitude * F32(1.0 / mm)).astype(F32) if mm > 0 else np.zeros_like(magnitude)
+    norm_tex = (texture * F32(1.0 / tm)).astype(F32) if tm > 0 else np.zeros_like(texture)
+    detail = ops.add_weighted_f32(norm_mag, 0.7, norm_tex, 0.3)    # :288
+    mask = R.detail_sigmoid_f32(detail, cfg.detail_threshold)       # :291-303
+    return ops.gaussian_f32(mask, 5, 1.0)                           # :306
+
+
+def joint_blend(img, filtered, mask, edge_preserve):
+    """applyJointBilateral's per-pixel loop, selective_bilateral.cpp:412-428: float32 arithmetic
+    `orig * d * p + filt * (1 - d * p)`, saturate_cast<uchar>."""
+    d = mask.astype(F32)[:, :, None]
+    # `float preservation = 1.0f + detail_value * (m_config.edge_preserve - 1.0f)`: edge_preserve is a double, so the
+    # right-hand side is evaluated in double and rounded once on the store
+    p = (1.0 + d.astype(np.float64) * (float(edge_preserve) - 1.0)).astype(F32)
+    dp = (d * p).astype(F32)
+    a = ((img.astype(F32) * d).astype(F32) * p).astype(F32)
+    b = (filtered.astype(F32) * (F32(1.0) - dp).astype(F32)).astype(F32)
+    return np.clip(np.rint((a + b).astype(F32)), 0, 255).astype(np.uint8)
+
+
+def bilateral_selective(ops, img, cfg):
+    """SelectiveBilateral::applySelectiveBilateral, selective_bilateral.cpp:121-136 -> applyJointBilateral :373-439."""
+    mask = create_detail_mask(ops, img, cfg)
+    filtered = bilateral_plain(ops, img, cfg)
+    return joint_blend(img, filtered, mask, cfg.edge_preserve)
+
+
+def multiscale_blend(fine, coarse_up, mask):
+    """selective_bilateral.cpp:198-228: result = saturate_cast<uchar>(fine * d + coarse * (1 - d)), float32."""
+    d = mask.astype(F32)[:, :, None]
+    cw = (F32(1.0) - d).astype(F32)
+    v = ((fine.astype(F32) * d).astype(F32) + (coarse_up.astype(F32) * cw).astype(F32)).astype(F32)
+    return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+
+
+def bilateral_multiscale(ops, img, cfg):
+    """SelectiveBilateral::applyMultiscaleBilateral, selective_bilateral.cpp:138-237, CPU branch (:178): the
+    config's diameter at every scale (no adaptive parameters here), sigmas x (1 + 0.5 i)."""
+    n = max(1, min(int(cfg.num_scales), 5))                         # initialize(), :40-43
+    scales = [img]
+    for i in range(1, n):
+        scales.append(ops.pyr_down(scales[i - 1]))                  # :146-151
+    done = [ops.bilateral(s, cfg.diameter, cfg.sigma_color * (1.0 + 0.5 * i), cfg.sigma_space * (1.0 + 0.5 * i))
+            for i, s in enumerate(scales)]                          # :155-182
+    for i in range(n - 1, 0, -1):                                   # :185-230
+        h, w = done[i - 1].shape[:2]
+        up = ops.pyr_up(done[i], w, h)
+        mask = create_detail_mask(ops, done[i - 1], cfg)
+        done[i - 1] = multiscale_blend(done[i - 1], up, mask)
+    return done[0]
+
+
+def selective_bilateral_process(ops, img, cfg):
+    """SelectiveBilateral::process dispatch, selective_bilateral.cpp:57-82."""
+    if cfg.use_multiscale:
+        return bilateral_multiscale(ops, img, cfg)
+    if cfg.selective:
+        return bilateral_selective(ops, img, cfg)
+    return bilateral_plain(ops, img, cfg)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -448,7 +562,7 @@ class Chain:
         ops, cfg = self.ops, self.cfg
         if cfg.bicubic_enhance:
             return cpuimpl_bicubic(ops, frame, cfg.dst_w, cfg.dst_h)
-        x = bilateral_plain(ops, frame, cfg.pre) if cfg.use_pre else frame
+        x = selective_bilateral_process(ops, frame, cfg.pre) if cfg.use_pre else frame
         if stages is not None:
             stages["pre"] = x
         x = ops.resize_cubic(x, cfg.dst_w, cfg.dst_h)
@@ -459,7 +573,7 @@ class Chain:
         if stages is not None:
             stages["sharp"] = x
         if cfg.use_post:
-            x = bilateral_plain(ops, x, cfg.post)
+            x = selective_bilateral_process(ops, x, cfg.post)
         if stages is not None:
             stages["post"] = x
         return x

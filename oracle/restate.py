@@ -449,3 +449,71 @@ def scene_metrics(prev_gray, cur_gray):
     corr = hist_correlation(normalize_minmax01(hist64(prev_gray)), normalize_minmax01(hist64(cur_gray)))
     mad = float(np.abs(prev_gray.astype(np.int64) - cur_gray.astype(np.int64)).sum()) / prev_gray.size
     return corr, mad
+
+
+# --------------------------------------------------------------------------------------------
+# SelectiveBilateral's multiscale / selective branches
+# -- selective_bilateral.cpp:138-313 (pyrDown/pyrUp :148-150,:188; blur :263,:272; Sobel/magnitude :251-256)
+# --------------------------------------------------------------------------------------------
+def box_blur5_u8(img):
+    """cv::blur(img8U, out, Size(5,5)): normalised box filter, BORDER_REFLECT_101, dst = round(sum / 25)
+    (sum / 25 never lands on .5, so every rounding mode agrees)."""
+    img = np.asarray(img)
+    h, w = img.shape[:2]
+    p = pad_reflect101(img, 2).astype(np.int64)
+    s = sum(p[dy:dy + h, dx:dx + w] for dy in range(5) for dx in range(5))
+    return ((2 * s + 25) // 50).astype(np.uint8)
+
+
+def pyr_down_u8(img):
+    """cv::pyrDown on CV_8U: [1 4 6 4 1] x [1 4 6 4 1], BORDER_REFLECT_101, (v + 128) >> 8 at even (y, x);
+    dst = ((W+1)/2, (H+1)/2)."""
+    img = np.asarray(img)
+    k = (1, 4, 6, 4, 1)
+    h, w = img.shape[:2]
+    p = pad_reflect101(img, 2).astype(np.int64)
+    row = sum(p[:, i:i + w] * k[i] for i in range(5))
+    col = sum(row[i:i + h] * k[i] for i in range(5))
+    return ((col + 128) >> 8)[::2, ::2].astype(np.uint8)
+
+
+def pyr_up_u8(img, dst_w, dst_h):
+    """cv::pyrUp(img8U, out, Size(dst_w, dst_h)) for dst = 2*src or 2*src - 1 per axis (the sizes
+    applyMultiscaleBilateral produces, selective_bilateral.cpp:188).  Even outputs: s[i-1] + 6 s[i] + s[i+1],
+    odd outputs: 4 (s[i] + s[i+1]); the low neighbour is reflect-101 (s[-1] = s[1]), the high neighbour
+    replicates (s[n] = s[n-1]); both axes, then (v + 32) >> 6."""
+    src = np.asarray(img)
+    H, W = src.shape[:2]
+    assert dst_w in (2 * W, 2 * W - 1) and dst_h in (2 * H, 2 * H - 1)
+    s = src.astype(np.int64)
+    xm = np.arange(W) - 1
+    xm[0] = 1 if W > 1 else 0
+    xp = np.minimum(np.arange(W) + 1, W - 1)
+    row = np.empty((H, 2 * W) + s.shape[2:], dtype=np.int64)
+    row[:, 0::2] = s[:, xm] + 6 * s + s[:, xp]
+    row[:, 1::2] = 4 * (s + s[:, xp])
+    ym = np.arange(H) - 1
+    ym[0] = 1 if H > 1 else 0
+    yp = np.minimum(np.arange(H) + 1, H - 1)
+    out = np.empty((2 * H, 2 * W) + s.shape[2:], dtype=np.int64)
+    out[0::2] = row[ym] + 6 * row + row[yp]
+    out[1::2] = 4 * (row + row[yp])
+    return ((out + 32) >> 6).astype(np.uint8)[:dst_h, :dst_w]
+
+
+def sobel_magnitude_f32(gray):
+    """cv::Sobel(gray, CV_32F, 1,0,3) / (0,1,3) + cv::magnitude (selective_bilateral.cpp:251-256): the
+    derivatives are exact integers, gx^2 + gy^2 < 2^24 is exact, so this is one correctly rounded sqrt
+    (cv2's own magnitude deviates from it by at most 1 ulp)."""
+    gx = sobel_x(gray).astype(np.int64)
+    gy = sobel_y(gray).astype(np.int64)
+    return np.sqrt((gx * gx + gy * gy).astype(F32)).astype(F32)
+
+
+def detail_sigmoid_f32(detail, detail_threshold):
+    """selective_bilateral.cpp:293-303: mask = 1.0f / (1.0f + std::exp(-(v - threshold) * 10.0f)) with
+    `threshold` a double (detail_threshold / 255.0), so the expression is evaluated in double and rounded
+    to float32 on the store."""
+    thr = float(detail_threshold) / 255.0
+    v = np.asarray(detail, dtype=F32).astype(np.float64)
+    return (1.0 / (1.0 + np.exp(-(v - thr) * 10.0))).astype(F32)

@@ -58,7 +58,8 @@ def sharpen_cfg(vp, o):
 
 
 def bilateral_cfg(vp, o):
-    return vp.BilateralConfig(o.stage, int(o.adaptive_params), o.diameter, 0, o.sigma_color, o.sigma_space)
+    return vp.BilateralConfig(o.stage, int(o.adaptive_params), o.diameter, 0, o.sigma_color, o.sigma_space,
+                              int(o.selective), int(o.use_multiscale), o.num_scales, 0, o.detail_threshold, o.edge_preserve)
 
 
 def chain_cfg(vp, o, sw, sh):

@@ -37,6 +37,14 @@ def run(driver, tmp_path, mode, frames, tw, th):
     return np.frombuffer(outp.read_bytes(), np.uint8).reshape(len(frames), th, tw, 3)
 
 
+def ref_defaults(**kw):
+    """Upscaler::initializeEnhancements as the reference writes it (src/upscaler.cpp:666-758): selective and
+    multi-scale on for both bilateral stages (repaired semantics); adaptive_sigma routes to the unsharp mask."""
+    return RC.ChainConfig(
+        pre=RC.BilateralConfig(RC.PRE_PROCESSING, True, True, 7, 30.0, 30.0, True, 30.0, 1.5, 2.0, True, 3),
+        post=RC.BilateralConfig(RC.POST_PROCESSING, True, True, 5, 20.0, 20.0, True, 30.0, 1.2, 1.5, True, 2), **kw)
+
+
 def close(o, r):
     d = np.abs(o.astype(int) - r.astype(int))
     return RC.psnr(o, r) >= 50.0 and d.max() <= 4
@@ -46,7 +54,8 @@ def close(o, r):
 def test_upscaler_chain_modes(driver, tmp_path, mode):
     frames = synth.clip("scene", SW, SH, N)
     outs = run(driver, tmp_path, mode, frames, 2 * SW, 2 * SH)
-    oracle = RC.Chain(RC.NumpyOps(), RC.ChainConfig(dst_w=2 * SW, dst_h=2 * SH, temporal=RC.TEMPORAL_BLEND_FRAMES))
+    mk = RC.ChainConfig if mode == "stages" else ref_defaults     # the stage objects of "stages" carry plain configs
+    oracle = RC.Chain(RC.NumpyOps(), mk(dst_w=2 * SW, dst_h=2 * SH, temporal=RC.TEMPORAL_BLEND_FRAMES))
     for o, f in zip(outs, frames):
         assert close(o, oracle.process(f))
 
@@ -73,13 +82,14 @@ def test_upscaler_toggles(driver, tmp_path):
     frames = synth.clip("scene", SW, SH, 3)
     outs = run(driver, tmp_path, "toggles", frames, 2 * SW, 2 * SH)
     for i, (o, f) in enumerate(zip(outs, frames)):
-        cfg = RC.ChainConfig(dst_w=2 * SW, dst_h=2 * SH, temporal=RC.TEMPORAL_NONE, use_pre=i < 1, use_post=i < 1, use_sharpen=i < 2)
+        cfg = ref_defaults(dst_w=2 * SW, dst_h=2 * SH, temporal=RC.TEMPORAL_NONE, use_pre=i < 1, use_post=i < 1, use_sharpen=i < 2)
         assert close(o, RC.Chain(RC.NumpyOps(), cfg).process(f)), i
 
 
 def test_video_enhancer_facade(driver, tmp_path):
     frames = synth.clip("scene", SW, SH, 3)
     outs = run(driver, tmp_path, "enhancer", frames, SW, SH)
+    # the facade runs the north-star chain (plain branches) at the input resolution
     oracle = RC.Chain(RC.NumpyOps(), RC.ChainConfig(dst_w=SW, dst_h=SH, temporal=RC.TEMPORAL_BLEND_FRAMES))
     for o, f in zip(outs, frames):
         assert close(o, oracle.process(f))

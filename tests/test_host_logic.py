@@ -35,17 +35,19 @@ def test_library_exports_every_declared_symbol(vp):
     assert declared == set(vp.PROTOTYPES), declared ^ set(vp.PROTOTYPES)
     for name in declared:
         assert hasattr(vp.lib, name)
-    assert vp.lib.vp_abi_version() == 1
+    assert vp.lib.vp_abi_version() == 2
 
 
 def test_struct_layout_matches_header(vp):
     import ctypes as C
     # doubles 8-aligned behind the reserved word; the chain config is a plain concatenation
-    assert C.sizeof(vp.BilateralConfig) == 32 and vp.BilateralConfig.sigma_color.offset == 16
+    assert C.sizeof(vp.BilateralConfig) == 64 and vp.BilateralConfig.sigma_color.offset == 16
+    assert vp.BilateralConfig.selective.offset == 32 and vp.BilateralConfig.detail_threshold.offset == 48
     assert C.sizeof(vp.SharpenConfig) == 28 and C.sizeof(vp.TemporalConfig) == 24
-    assert vp.ChainConfig.pre.offset == 32 and vp.ChainConfig.post.offset == 96
+    assert vp.ChainConfig.pre.offset == 32 and vp.ChainConfig.post.offset == 128
     cfg = vp.default_chain_config(1920, 1080, 3840, 2160)
     assert (cfg.pre.diameter, cfg.pre.sigma_color, cfg.post.diameter, cfg.post.sigma_space) == (7, 30.0, 5, 20.0)
+    assert (cfg.pre.selective, cfg.pre.use_multiscale, cfg.post.selective, cfg.post.use_multiscale) == (0, 0, 0, 0)
     assert (cfg.sharpen.kernel_size, cfg.temporal.mode, cfg.temporal.buffer_size) == (5, vp.VP_TEMPORAL_BLEND_FRAMES, 3)
     assert abs(cfg.sharpen.strength - 0.8) < 1e-7 and abs(cfg.temporal.blend_strength - 0.6) < 1e-7
 

@@ -165,3 +165,51 @@ def test_golden_vectors():
     # the same vectors out of the real OpenCV kernels
     assert np.array_equal(g["bicubic_x2"], cv2.resize(img, (96, 64), interpolation=cv2.INTER_CUBIC))
     assert np.array_equal(g["bicubic_x4"], cv2.resize(img, (192, 128), interpolation=cv2.INTER_CUBIC))
+
+
+# ---- SelectiveBilateral's selective / multi-scale branches --------------------------------
+@pytest.mark.parametrize("size", [(37, 53), (64, 64), (5, 7), (3, 3), (1, 9), (120, 200)])
+def test_box_blur5_bit_exact(size):
+    g = np.random.default_rng(1).integers(0, 256, size, dtype=np.uint8)
+    assert np.array_equal(R.box_blur5_u8(g), cv2.blur(g, (5, 5)))
+
+
+@pytest.mark.parametrize("size", [(37, 53), (64, 64), (5, 7), (3, 3), (120, 200), (135, 240), (2, 2)])
+def test_pyr_down_up_bit_exact(size):
+    h, w = size
+    img = np.random.default_rng(2).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    down = R.pyr_down_u8(img)
+    assert np.array_equal(down, cv2.pyrDown(img))
+    assert np.array_equal(R.pyr_up_u8(down, w, h), cv2.pyrUp(down, dstsize=(w, h)))
+
+
+def test_sobel_magnitude_within_1ulp():
+    g = np.random.default_rng(3).integers(0, 256, (97, 131), dtype=np.uint8)
+    ref = cv2.magnitude(cv2.Sobel(g, cv2.CV_32F, 1, 0, ksize=3), cv2.Sobel(g, cv2.CV_32F, 0, 1, ksize=3))
+    mine = R.sobel_magnitude_f32(g)
+    assert np.abs(mine.view(np.int32) - ref.view(np.int32)).max() <= 1
+
+
+@pytest.mark.parametrize("kind", ["noise", "scene", "flat"])
+def test_detail_mask_numpy_vs_cv2(kind):
+    img = synth.frame(kind, 160, 96, 1)
+    cfg = RC.BilateralConfig()
+    a = RC.create_detail_mask(RC.NumpyOps(), img, cfg)
+    b = RC.create_detail_mask(RC.Cv2Ops(), img, cfg)
+    assert a.dtype == np.float32 and np.abs(a - b).max() <= 2e-6 and 0.0 <= a.min() and a.max() <= 1.0
+
+
+@pytest.mark.parametrize("mode", [dict(use_multiscale=False, selective=True), dict(use_multiscale=True, num_scales=3)])
+def test_selective_modes_numpy_vs_cv2(mode):
+    img = synth.frame("scene", 160, 96, 1)
+    cfg = RC.BilateralConfig(**mode)
+    a = RC.selective_bilateral_process(RC.NumpyOps(), img, cfg)
+    b = RC.selective_bilateral_process(RC.Cv2Ops(), img, cfg)
+    d = np.abs(a.astype(int) - b.astype(int))
+    assert d.max() <= 2 and (d > 0).mean() < 0.02
+
+
+def test_detail_mask_of_a_constant_frame_is_finite():
+    img = np.full((20, 30, 3), 77, np.uint8)
+    m = RC.create_detail_mask(RC.NumpyOps(), img, RC.BilateralConfig())
+    assert np.isfinite(m).all()

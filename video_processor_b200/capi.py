@@ -18,7 +18,9 @@ VP_TEMPORAL_NONE, VP_TEMPORAL_MAIN_BLEND, VP_TEMPORAL_BLEND_FRAMES = 0, 1, 2
 
 class BilateralConfig(C.Structure):
     _fields_ = [("stage", C.c_int32), ("adaptive_params", C.c_int32), ("diameter", C.c_int32),
-                ("reserved_", C.c_int32), ("sigma_color", C.c_double), ("sigma_space", C.c_double)]
+                ("reserved_", C.c_int32), ("sigma_color", C.c_double), ("sigma_space", C.c_double),
+                ("selective", C.c_int32), ("use_multiscale", C.c_int32), ("num_scales", C.c_int32),
+                ("reserved2_", C.c_int32), ("detail_threshold", C.c_double), ("edge_preserve", C.c_double)]
 
 
 class SharpenConfig(C.Structure):
@@ -69,6 +71,9 @@ PROTOTYPES = {
     "vp_bicubic": (C.c_int, [_vp, _u8p, _sz, C.c_int, C.c_int, _u8p, _sz, C.c_int, C.c_int, C.c_void_p]),
     "vp_bilateral": (C.c_int, [_vp, _u8p, _sz, _u8p, _sz, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]),
     "vp_selective_bilateral": (C.c_int, [_vp, C.POINTER(BilateralConfig), _u8p, _sz, _u8p, _sz, C.c_int, C.c_int, C.c_void_p]),
+    "vp_detail_mask": (C.c_int, [_vp, C.c_double, _u8p, _sz, C.c_void_p, _sz, C.c_int, C.c_int, C.c_void_p]),
+    "vp_pyr_down": (C.c_int, [_vp, _u8p, _sz, C.c_int, C.c_int, _u8p, _sz, C.c_void_p]),
+    "vp_pyr_up": (C.c_int, [_vp, _u8p, _sz, C.c_int, C.c_int, _u8p, _sz, C.c_int, C.c_int, C.c_void_p]),
     "vp_mean_stddev_sums": (C.c_int, [_vp, _u8p, _sz, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "vp_edge_mask": (C.c_int, [_vp, C.POINTER(SharpenConfig), _u8p, _sz, C.c_void_p, _sz, C.c_int, C.c_int, C.c_void_p]),
     "vp_unsharp": (C.c_int, [_vp, C.POINTER(SharpenConfig), _u8p, _sz, C.c_void_p, _sz, _u8p, _sz, C.c_int, C.c_int, C.c_void_p]),

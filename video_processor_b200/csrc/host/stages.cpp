@@ -47,8 +47,8 @@ bool SelectiveBilateral::process(const cv::Mat& input, cv::Mat& output) {
         return false;
     }
     if ((m_config.use_multiscale || m_config.selective) && !m_impl->warned) {
-        std::cerr << "SelectiveBilateral: multiscale/selective modes run the plain bilateral branch "
-                     "(the reference's own bodies are undefined behaviour, see DESIGN.md)" << std::endl;
+        std::cerr << "SelectiveBilateral: the multiscale/selective branches run with repaired semantics (the reference "
+                     "calls cv::sqrt on a CV_8U Mat, src/selective_bilateral.cpp:276; see DESIGN.md)" << std::endl;
         m_impl->warned = true;
     }
     StageRunner& r = m_impl->run;
@@ -58,6 +58,11 @@ bool SelectiveBilateral::process(const cv::Mat& input, cv::Mat& output) {
     c.diameter = m_config.diameter;
     c.sigma_color = m_config.sigma_color;
     c.sigma_space = m_config.sigma_space;
+    c.selective = m_config.selective;
+    c.use_multiscale = m_config.use_multiscale;
+    c.num_scales = m_config.num_scales;
+    c.detail_threshold = m_config.detail_threshold;
+    c.edge_preserve = m_config.edge_preserve;
     bool ok = vp_host_api::is_bgr8(input) && r.upload(input, input.cols, input.rows, 3);
     ok = ok && vp_selective_bilateral(r.ctx(), &c, r.d_in(), r.in_pitch(), r.d_out(), r.out_pitch(), input.cols, input.rows, r.stream()) == VP_OK;
     ok = ok && r.download(output, input.cols, input.rows, CV_8UC3, 3);

@@ -109,9 +109,11 @@ bool Upscaler::ensureChain(int src_w, int src_h) {
         c.use_pre = c.use_post = m_use_selective_bilateral ? 1 : 0;
         c.use_sharpen = m_use_adaptive_sharpening ? 1 : 0;
         c.pre = vp_bilateral_config{pre.stage == SelectiveBilateral::POST_PROCESSING ? VP_STAGE_POST : VP_STAGE_PRE,
-                                    pre.adaptive_params, pre.diameter, 0, pre.sigma_color, pre.sigma_space};
+                                    pre.adaptive_params, pre.diameter, 0, pre.sigma_color, pre.sigma_space,
+                                    pre.selective, pre.use_multiscale, pre.num_scales, 0, pre.detail_threshold, pre.edge_preserve};
         c.post = vp_bilateral_config{post.stage == SelectiveBilateral::POST_PROCESSING ? VP_STAGE_POST : VP_STAGE_PRE,
-                                     post.adaptive_params, post.diameter, 0, post.sigma_color, post.sigma_space};
+                                     post.adaptive_params, post.diameter, 0, post.sigma_color, post.sigma_space,
+                                     post.selective, post.use_multiscale, post.num_scales, 0, post.detail_threshold, post.edge_preserve};
         c.sharpen = vp_sharpen_config{sh.strength, sh.edge_strength, sh.smooth_strength, sh.edge_threshold, sh.sigma,
                                       sh.kernel_size, sh.preserve_tone ? 1 : 0};
         c.temporal.mode = m_use_temporal_consistency ? VP_TEMPORAL_BLEND_FRAMES : VP_TEMPORAL_NONE;

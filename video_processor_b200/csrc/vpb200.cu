@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <deque>
@@ -23,12 +24,17 @@
 #include "vp_bilateral.cuh"
 #include "vp_blend.cuh"
 #include "vp_canny.cuh"
+#include "vp_detail.cuh"
 #include "vp_scene.cuh"
 #include "vp_stats.cuh"
 #include "vp_tables.h"
 #include "vp_upsharp.cuh"
 
 using namespace vp;
+
+// layout the ctypes / FFI stubs rely on (tests/test_host_logic.py::test_struct_layout_matches_header)
+static_assert(sizeof(vp_bilateral_config) == 64 && offsetof(vp_bilateral_config, detail_threshold) == 48, "vp_bilateral_config layout");
+static_assert(offsetof(vp_chain_config, pre) == 32 && offsetof(vp_chain_config, post) == 128, "vp_chain_config layout");
 
 namespace {
 
@@ -51,6 +57,16 @@ struct HostSlot {
 
 }  // namespace
 
+struct MsScratch {                  // SelectiveBilateral's selective / multi-scale branches: one frame size's buffers
+    int w = 0, h = 0, n = 0; bool p0 = false;
+    uint8_t* lvl[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};    // pyrDown levels 1..n-1 (level 0 is the caller's frame)
+    uint8_t* proc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // filtered levels (proc[0] only when the caller's dst is not used)
+    size_t pitch[5] = {0, 0, 0, 0, 0};
+    int lw[5] = {0, 0, 0, 0, 0}, lh[5] = {0, 0, 0, 0, 0};
+    float* mask = nullptr; size_t mpitch = 0;
+    vp::DetailMax* mx = nullptr;
+};
+
 struct Lane {                       // per-frame intermediates; two lanes let consecutive frames overlap
     cudaStream_t st = nullptr;      // lane 1's own stream (lane 0 runs on the caller's / the compute stream)
     uint8_t* d_pre = nullptr;       // PRE-filtered frame, src resolution
@@ -61,6 +77,8 @@ struct Lane {                       // per-frame intermediates; two lanes let co
     cudaEvent_t ev_done = nullptr;
     uint8_t* d_map = nullptr;       // Canny map (bicubic_enhance chains): 0 none, 1 weak, 2 edge
     unsigned char* d_dirty = nullptr;   // hysteresis tile flags (2 x ntiles) followed by the 2 `again` counters
+    MsScratch ms_pre, ms_post;      // selective / multi-scale SelectiveBilateral stages of the chain
+    uint8_t* d_post = nullptr;      // their POST output (the plain POST filter writes the caller's frame directly)
 };
 
 struct vp_ctx {
@@ -91,6 +109,10 @@ struct vp_ctx {
     int tmp_d = -1; double tmp_sc = 0, tmp_ss = 0; int tmp_r = 0;
     vp_bilateral_config tmp_sel_cfg{}; bool tmp_sel_valid = false; int tmp_sel_rad[3] = {0, 0, 0};
     BilCand* d_cand_sel = nullptr;
+    // per-scale tables of the multi-scale branch: chain PRE / POST stages and the stage-wise entry point
+    BilCand* d_cand_ms_pre = nullptr; BilCand* d_cand_ms_post = nullptr; BilCand* d_cand_ms_tmp = nullptr;
+    int ms_pre_rad[5] = {0, 0, 0, 0, 0}, ms_post_rad[5] = {0, 0, 0, 0, 0}, ms_tmp_rad[5] = {0, 0, 0, 0, 0};
+    MsScratch ms_tmp;               // stage-wise scratch
     ResizeCache rc_chain, rc_tmp;
     float* d_siglut = nullptr; float siglut_thr = -1e30f; bool siglut_valid = false;
     float* d_siglut_tmp = nullptr; float siglut_tmp_thr = 0; bool siglut_tmp_valid = false;
@@ -264,6 +286,129 @@ int launch_bilateral(vp_ctx* c, BilArgs& a, const int radius[3], cudaStream_t st
     return VP_OK;
 }
 
+// ---- SelectiveBilateral's selective / multi-scale branches (vp_detail.cuh) ------------------------------------
+inline bool bil_has_modes(const vp_bilateral_config& b) { return b.use_multiscale || b.selective; }
+inline int bil_num_scales(const vp_bilateral_config& b) { return std::max(1, std::min(b.num_scales, 5)); }   // initialize(), :40-43
+
+void free_ms_scratch(MsScratch& S) {
+    for (int i = 0; i < 5; ++i) { cudaFree(S.lvl[i]); cudaFree(S.proc[i]); }
+    cudaFree(S.mask); cudaFree(S.mx);
+    S = MsScratch();
+}
+
+int ensure_ms_scratch(vp_ctx* c, MsScratch& S, int w, int h, int n, bool p0) {
+    if (S.w == w && S.h == h && S.n == n && S.p0 == p0 && S.mask) return VP_OK;
+    VP_CUDA(c, cudaDeviceSynchronize());
+    free_ms_scratch(S);
+    S.w = w; S.h = h; S.n = n; S.p0 = p0;
+    int lw = w, lh = h;
+    for (int i = 0; i < n; ++i) {
+        S.lw[i] = lw; S.lh[i] = lh; S.pitch[i] = align_up((size_t)lw * 3, 256);
+        if (i > 0) VP_CUDA(c, cudaMalloc(&S.lvl[i], S.pitch[i] * lh));
+        if (i > 0 || p0) VP_CUDA(c, cudaMalloc(&S.proc[i], S.pitch[i] * lh));
+        lw = (lw + 1) / 2; lh = (lh + 1) / 2;
+    }
+    S.mpitch = align_up((size_t)w * 4, 256);
+    VP_CUDA(c, cudaMalloc(&S.mask, S.mpitch * h));
+    VP_CUDA(c, cudaMalloc(&S.mx, sizeof(DetailMax)));
+    return VP_OK;
+}
+
+// one BilCand per scale: the config's diameter, sigmas x (1 + 0.5 i) (src/selective_bilateral.cpp:157-160)
+int build_multiscale_cands(vp_ctx* c, const vp_bilateral_config& cfg, BilCand** d_cand, int rad[5], cudaStream_t st) {
+    const int n = bil_num_scales(cfg);
+    std::vector<BilCand> hc(5);
+    for (int i = 0; i < n; ++i) {
+        vp_host::BilateralTables t = vp_host::bilateral_tables(cfg.diameter, cfg.sigma_color * (1.0 + 0.5 * i), cfg.sigma_space * (1.0 + 0.5 * i));
+        if (t.radius > BIL_RMAX) return fail(c, VP_ERR_UNSUPPORTED, "bilateral radius > 7 (diameter > 15) is not built");
+        fill_cand(hc[i], t);
+        rad[i] = t.radius;
+    }
+    if (!*d_cand) VP_CUDA(c, cudaMalloc(d_cand, 5 * sizeof(BilCand)));
+    VP_CUDA(c, cudaMemcpyAsync(*d_cand, hc.data(), 5 * sizeof(BilCand), cudaMemcpyHostToDevice, st));
+    VP_CUDA(c, cudaStreamSynchronize(st));
+    return VP_OK;
+}
+
+int launch_detail_mask(vp_ctx* c, const uint8_t* src, size_t pitch, int w, int h, double detail_threshold,
+                       DetailMax* mx, float* mask, size_t mpitch, cudaStream_t st) {
+    ProfScope ps(c, K_BIL_OTHER, st);
+    VP_CUDA(c, cudaMemsetAsync(mx, 0, sizeof(DetailMax), st));
+    const dim3 grid((w + DT_TW - 1) / DT_TW, (h + DT_TH - 1) / DT_TH);
+    k_detail_max<<<grid, DT_NT, 0, st>>>(src, pitch, w, h, mx);
+    DetailMaskArgs a{};
+    a.src = src; a.pitch = pitch; a.w = w; a.h = h; a.mx = mx;
+    a.thr = detail_threshold / 255.0;
+    const std::vector<double> g = vp_host::gaussian_kernel_f64(5, 1.0);   // literal Size(5,5), 1.0 at :306
+    for (int i = 0; i < 5; ++i) a.gf[i] = (float)g[i];
+    a.mask = mask; a.mpitch = mpitch;
+    k_detail_mask<<<grid, DT_NT, 0, st>>>(a);
+    VP_CUDA(c, cudaGetLastError());
+    c->launches += 2;
+    return VP_OK;
+}
+
+struct StatsRes { unsigned long long* sums; unsigned* counter; int* sel; };   // calculateAdaptiveParams' reduction slots
+
+// SelectiveBilateral::process in the selective or multi-scale mode (src/selective_bilateral.cpp:57-82).
+// `cand3` / `rad3`: the plain filter's candidates (selective mode); `cand_ms` / `rad_ms`: one candidate per scale.
+int run_bilateral_modes(vp_ctx* c, MsScratch& S, const vp_bilateral_config& cfg, const BilCand* cand3, const int rad3[3],
+                        const BilCand* cand_ms, const int* rad_ms, const StatsRes& sr,
+                        const uint8_t* src, size_t spitch, uint8_t* dst, size_t dpitch, int w, int h, cudaStream_t st, int kind) {
+    const dim3 eb(256);
+    int rc;
+    if (cfg.use_multiscale) {
+        const int n = bil_num_scales(cfg);
+        rc = ensure_ms_scratch(c, S, w, h, n, false); if (rc) return rc;
+        const uint8_t* lvl[5]; size_t lp[5]; uint8_t* proc[5]; size_t pp[5];
+        lvl[0] = src; lp[0] = spitch; proc[0] = dst; pp[0] = dpitch;
+        for (int i = 1; i < n; ++i) { lvl[i] = S.lvl[i]; lp[i] = S.pitch[i]; proc[i] = S.proc[i]; pp[i] = S.pitch[i]; }
+        for (int i = 1; i < n; ++i) {                                            // :146-151
+            ProfScope ps(c, K_BIL_OTHER, st);
+            const dim3 grid((S.lw[i] + 31) / 32, (S.lh[i] + 7) / 8);
+            k_pyr_down<<<grid, eb, 0, st>>>(lvl[i - 1], lp[i - 1], S.lw[i - 1], S.lh[i - 1], S.lvl[i], S.pitch[i], S.lw[i], S.lh[i]);
+            VP_CUDA(c, cudaGetLastError());
+            c->launches++;
+        }
+        for (int i = 0; i < n; ++i) {                                            // :155-182
+            BilArgs a{};
+            a.src = lvl[i]; a.spitch = lp[i]; a.dst = proc[i]; a.dpitch = pp[i]; a.w = S.lw[i]; a.h = S.lh[i];
+            a.cand = cand_ms + i;
+            const int rad[3] = {rad_ms[i], rad_ms[i], rad_ms[i]};
+            rc = launch_bilateral(c, a, rad, st, i == 0 ? kind : K_BIL_OTHER); if (rc) return rc;
+        }
+        for (int i = n - 1; i > 0; --i) {                                        // :185-230
+            rc = launch_detail_mask(c, proc[i - 1], pp[i - 1], S.lw[i - 1], S.lh[i - 1], cfg.detail_threshold, S.mx, S.mask, S.mpitch, st);
+            if (rc) return rc;
+            MsBlendArgs b{proc[i - 1], pp[i - 1], S.lw[i - 1], S.lh[i - 1], proc[i], pp[i], S.lw[i], S.lh[i], S.mask, S.mpitch};
+            ProfScope ps(c, K_BIL_OTHER, st);
+            const dim3 grid((S.lw[i - 1] + 31) / 32, (S.lh[i - 1] + 7) / 8);
+            k_ms_blend<<<grid, eb, 0, st>>>(b);
+            VP_CUDA(c, cudaGetLastError());
+            c->launches++;
+        }
+        return VP_OK;
+    }
+    // selective: detail mask of the input, the plain (adaptive) filter, the joint blend (:121-136, :373-439)
+    rc = ensure_ms_scratch(c, S, w, h, 1, true); if (rc) return rc;
+    rc = launch_detail_mask(c, src, spitch, w, h, cfg.detail_threshold, S.mx, S.mask, S.mpitch, st); if (rc) return rc;
+    if (cfg.adaptive_params) {
+        VP_CUDA(c, cudaMemsetAsync(sr.sums, 0, 6 * sizeof(unsigned long long), st));
+        rc = launch_stats(c, src, spitch, w, h, sr.sums, SelOut{sr.counter, sr.sel, (double)w * h}, st); if (rc) return rc;
+    }
+    BilArgs a{};
+    a.src = src; a.spitch = spitch; a.dst = S.proc[0]; a.dpitch = S.pitch[0]; a.w = w; a.h = h;
+    a.cand = cand3; a.sel = cfg.adaptive_params ? sr.sel : nullptr;
+    rc = launch_bilateral(c, a, rad3, st, kind); if (rc) return rc;
+    JointBlendArgs j{src, spitch, S.proc[0], S.pitch[0], S.mask, S.mpitch, dst, dpitch, w, h, cfg.edge_preserve - 1.0};
+    ProfScope ps(c, K_BIL_OTHER, st);
+    const dim3 grid((w + 31) / 32, (h + 7) / 8);
+    k_joint_blend<<<grid, eb, 0, st>>>(j);
+    VP_CUDA(c, cudaGetLastError());
+    c->launches++;
+    return VP_OK;
+}
+
 int fill_sharpen_args(vp_ctx* c, UpsharpArgs& a, const vp_sharpen_config& s) {
     if (s.kernel_size != 3 && s.kernel_size != 5 && s.kernel_size != 7)
         return fail(c, VP_ERR_UNSUPPORTED, "AdaptiveSharpening kernel_size must be 3, 5 or 7");
@@ -421,7 +566,8 @@ void vp_destroy(vp_ctx* c) {
     for (auto& e : c->prof_pool) cudaEventDestroy(e);
     for (Lane& L : c->lanes) {
         cudaFree(L.d_pre); cudaFree(L.d_sharp); cudaFree(L.d_sums); cudaFree(L.d_sel); cudaFree(L.d_counter);
-        cudaFree(L.d_map); cudaFree(L.d_dirty);
+        cudaFree(L.d_map); cudaFree(L.d_dirty); cudaFree(L.d_post);
+        free_ms_scratch(L.ms_pre); free_ms_scratch(L.ms_post);
         if (L.ev_done) cudaEventDestroy(L.ev_done);
         if (L.st) cudaStreamDestroy(L.st);
     }
@@ -429,6 +575,8 @@ void vp_destroy(vp_ctx* c) {
     for (auto& p : c->d_state) cudaFree(p);
     cudaFree(c->d_cand_be); cudaFree(c->d_scene_acc); cudaFree(c->d_scene_state); cudaFree(c->d_use);
     cudaFree(c->d_cand_pre); cudaFree(c->d_cand_post); cudaFree(c->d_cand_tmp); cudaFree(c->d_cand_sel);
+    cudaFree(c->d_cand_ms_pre); cudaFree(c->d_cand_ms_post); cudaFree(c->d_cand_ms_tmp);
+    free_ms_scratch(c->ms_tmp);
     free_resize(c->rc_chain); free_resize(c->rc_tmp);
     cudaFree(c->d_siglut); cudaFree(c->d_siglut_tmp);
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
@@ -479,11 +627,14 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
         VP_CUDA(c, cudaMalloc(&c->d_cand_pre, 3 * sizeof(BilCand)));
         int rc = build_selective_cands(c, g.pre, c->d_cand_pre, c->cand_pre_rad, c->s_compute);
         if (rc) return rc;
+        if (g.pre.use_multiscale) { rc = build_multiscale_cands(c, g.pre, &c->d_cand_ms_pre, c->ms_pre_rad, c->s_compute); if (rc) return rc; }
     }
     if (g.use_post && !g.bicubic_enhance) {
         VP_CUDA(c, cudaMalloc(&c->d_cand_post, 3 * sizeof(BilCand)));
         int rc = build_selective_cands(c, g.post, c->d_cand_post, c->cand_post_rad, c->s_compute);
         if (rc) return rc;
+        if (g.post.use_multiscale) { rc = build_multiscale_cands(c, g.post, &c->d_cand_ms_post, c->ms_post_rad, c->s_compute); if (rc) return rc; }
+        if (bil_has_modes(g.post)) VP_CUDA(c, cudaMalloc(&c->lanes[0].d_post, c->frame_pitch * g.dst_h));
     }
     VP_CUDA(c, cudaMalloc(&c->lanes[0].d_sharp, c->frame_pitch * g.dst_h));
     c->nring = g.temporal.mode == VP_TEMPORAL_MAIN_BLEND ? 2
@@ -681,14 +832,22 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
     if (!d_dst && !temporal) return VP_OK;   // warm-up frame of a chain without temporal state: nothing to do
 
     if (g.bicubic_enhance) return process_frame_enhance(c, L, st, temporal_dep, temporal, d_src, src_pitch, d_dst, dst_pitch);
-    const bool need_pre_stats = g.use_pre && g.pre.adaptive_params;
-    const bool need_post_stats = g.use_post && g.post.adaptive_params;
+    // selective / multi-scale SelectiveBilateral stages run as their own kernel sequence (run_bilateral_modes)
+    const bool pre_modes = g.use_pre && bil_has_modes(g.pre), post_modes = g.use_post && bil_has_modes(g.post);
+    const bool plain_post = g.use_post && !post_modes;
+    const bool need_pre_stats = g.use_pre && g.pre.adaptive_params && !pre_modes;
+    const bool need_post_stats = plain_post && g.post.adaptive_params;
     if (need_pre_stats || need_post_stats)
         VP_CUDA(c, cudaMemsetAsync(L.d_sums, 0, 12 * sizeof(unsigned long long), st));
 
     const uint8_t* cur = d_src; size_t cur_pitch = src_pitch;
     // 1. SelectiveBilateral PRE (src resolution)
-    if (g.use_pre) {
+    if (pre_modes) {
+        rc = run_bilateral_modes(c, L.ms_pre, g.pre, c->d_cand_pre, c->cand_pre_rad, c->d_cand_ms_pre, c->ms_pre_rad,
+                                 StatsRes{L.d_sums, L.d_counter, L.d_sel}, cur, cur_pitch, L.d_pre, c->pre_pitch, g.src_w, g.src_h, st, K_BIL_PRE);
+        if (rc) return rc;
+        cur = L.d_pre; cur_pitch = c->pre_pitch;
+    } else if (g.use_pre) {
         if (need_pre_stats) {
             rc = launch_stats(c, cur, cur_pitch, g.src_w, g.src_h, L.d_sums, SelOut{L.d_counter, L.d_sel, (double)g.src_w * g.src_h}, st);
             if (rc) return rc;
@@ -701,7 +860,7 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
     }
     // 2+3. bicubic resize + AdaptiveSharpening (dst resolution)
     const bool do_resize = (g.dst_w != g.src_w || g.dst_h != g.src_h);
-    const bool last_is_upsharp = !g.use_post && !temporal;
+    const bool last_is_upsharp = !g.use_post && !temporal;     // (a POST stage of either kind reads the lane buffer)
     if (do_resize && !g.use_sharpen && !need_post_stats) {
         uint8_t* out = last_is_upsharp ? d_dst : L.d_sharp;
         const size_t opitch = last_is_upsharp ? dst_pitch : c->frame_pitch;
@@ -729,6 +888,15 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
         rc = launch_stats(c, cur, cur_pitch, g.dst_w, g.dst_h, L.d_sums + 6, SelOut{L.d_counter + 1, L.d_sel + 1, (double)g.dst_w * g.dst_h}, st);
         if (rc) return rc;
     }
+    if (post_modes) {
+        // the temporal stage (if any) then runs as the stand-alone blend, exactly as for a chain without POST
+        uint8_t* out = temporal ? L.d_post : d_dst;
+        const size_t opitch = temporal ? c->frame_pitch : dst_pitch;
+        rc = run_bilateral_modes(c, L.ms_post, g.post, c->d_cand_post, c->cand_post_rad, c->d_cand_ms_post, c->ms_post_rad,
+                                 StatsRes{L.d_sums + 6, L.d_counter + 1, L.d_sel + 1}, cur, cur_pitch, out, opitch, g.dst_w, g.dst_h, st, K_BIL_POST);
+        if (rc) return rc;
+        cur = out; cur_pitch = opitch;
+    }
     BlendArgs bl{};
     temporal_args(c, temporal, bl);
     if (temporal && temporal_dep) VP_CUDA(c, cudaStreamWaitEvent(st, temporal_dep, 0));
@@ -737,7 +905,7 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
         // detectSceneChange needs the whole unblended frame before any pixel may be blended: the producer
         // accumulates the histogram / gray difference, k_scene_decide rules, k_blend blends (or passes through)
         const uint8_t* blend_cur = cur; size_t blend_cur_pitch = cur_pitch;
-        if (g.use_post) {
+        if (plain_post) {
             BilArgs a{};
             a.src = cur; a.spitch = cur_pitch; a.dst = nullptr; a.dpitch = 0; a.w = g.dst_w; a.h = g.dst_h;
             a.cand = c->d_cand_post; a.sel = need_post_stats ? L.d_sel + 1 : nullptr;
@@ -759,18 +927,18 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
         VP_CUDA(c, cudaGetLastError());
         c->launches++;
         c->scene_reset = false;
-        if (d_dst || !g.use_post) {
+        if (d_dst || !plain_post) {
             BlendKArgs a{};
             a.cur = blend_cur; a.cpitch = blend_cur_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.row_bytes = g.dst_w * 3; a.h = g.dst_h;
             a.blend = bl;
-            if (g.use_post) a.blend.state = nullptr;      // POST already stored the unblended frame
+            if (plain_post) a.blend.state = nullptr;      // POST already stored the unblended frame
             a.use_dev = c->d_use;
             for (int n = 1; n <= 2; ++n) { BlendArgs t{}; blend_weights(g.temporal, n, t); a.inv_wsum_n[n - 1] = t.inv_wsum; }
             rc = launch_blend(c, a, st); if (rc) return rc;
         }
     } else
     // 4+5. SelectiveBilateral POST with the temporal blend in its epilogue
-    if (g.use_post) {
+    if (plain_post) {
         BilArgs a{};
         a.src = cur; a.spitch = cur_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.w = g.dst_w; a.h = g.dst_h;
         a.cand = c->d_cand_post; a.sel = need_post_stats ? L.d_sel + 1 : nullptr;
@@ -802,6 +970,7 @@ static int ensure_lane(vp_ctx* c, int ln) {
     VP_CUDA(c, cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
     if (g.use_pre && !g.bicubic_enhance) VP_CUDA(c, cudaMalloc(&L.d_pre, c->pre_pitch * g.src_h));
     VP_CUDA(c, cudaMalloc(&L.d_sharp, c->frame_pitch * g.dst_h));
+    if (g.use_post && !g.bicubic_enhance && bil_has_modes(g.post)) VP_CUDA(c, cudaMalloc(&L.d_post, c->frame_pitch * g.dst_h));
     VP_CUDA(c, cudaMalloc(&L.d_sums, 18 * sizeof(unsigned long long)));
     VP_CUDA(c, cudaMalloc(&L.d_sel, 4 * sizeof(int)));
     VP_CUDA(c, cudaMemset(L.d_sel, 0, 4 * sizeof(int)));
@@ -1007,9 +1176,13 @@ int vp_selective_bilateral(vp_ctx* c, const vp_bilateral_config* cfg, const uint
         VP_CUDA(c, cudaStreamSynchronize(st));
         c->tmp_sel_valid = false;
         rc = build_selective_cands(c, *cfg, c->d_cand_sel, c->tmp_sel_rad, st); if (rc) return rc;
+        if (cfg->use_multiscale) { rc = build_multiscale_cands(c, *cfg, &c->d_cand_ms_tmp, c->ms_tmp_rad, st); if (rc) return rc; }
         c->tmp_sel_cfg = *cfg; c->tmp_sel_valid = true;
     }
     unsigned long long* sums = c->lanes[0].d_sums + 12;
+    if (bil_has_modes(*cfg))
+        return run_bilateral_modes(c, c->ms_tmp, *cfg, c->d_cand_sel, c->tmp_sel_rad, c->d_cand_ms_tmp, c->ms_tmp_rad,
+                                   StatsRes{sums, c->lanes[0].d_counter + 2, c->lanes[0].d_sel + 2}, d_src, src_pitch, d_dst, dst_pitch, w, h, st, K_BIL_OTHER);
     if (cfg->adaptive_params) {
         VP_CUDA(c, cudaMemsetAsync(sums, 0, 6 * sizeof(unsigned long long), st));
         rc = launch_stats(c, d_src, src_pitch, w, h, sums, SelOut{c->lanes[0].d_counter + 2, c->lanes[0].d_sel + 2, (double)w * h}, st); if (rc) return rc;
@@ -1018,6 +1191,47 @@ int vp_selective_bilateral(vp_ctx* c, const vp_bilateral_config* cfg, const uint
     a.src = d_src; a.spitch = src_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.w = w; a.h = h;
     a.cand = c->d_cand_sel; a.sel = cfg->adaptive_params ? c->lanes[0].d_sel + 2 : nullptr;
     return launch_bilateral(c, a, c->tmp_sel_rad, st);
+}
+
+int vp_detail_mask(vp_ctx* c, double detail_threshold, const uint8_t* d_src, size_t src_pitch, float* d_mask, size_t mask_pitch,
+                   int w, int h, void* stream) {
+    if (!c || !d_mask) return VP_ERR_INVALID_ARG;
+    int rc = check_frame(c, d_src, src_pitch, w, h, "vp_detail_mask(src)"); if (rc) return rc;
+    if (mask_pitch < (size_t)w * 4) return fail(c, VP_ERR_INVALID_ARG, "vp_detail_mask: mask pitch < 4*width");
+    VP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    if (!c->ms_tmp.mx) VP_CUDA(c, cudaMalloc(&c->ms_tmp.mx, sizeof(DetailMax)));
+    return launch_detail_mask(c, d_src, src_pitch, w, h, detail_threshold, c->ms_tmp.mx, d_mask, mask_pitch, st);
+}
+
+int vp_pyr_down(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, int src_w, int src_h, uint8_t* d_dst, size_t dst_pitch, void* stream) {
+    if (!c) return VP_ERR_INVALID_ARG;
+    const int dw = (src_w + 1) / 2, dh = (src_h + 1) / 2;
+    int rc = check_frame(c, d_src, src_pitch, src_w, src_h, "vp_pyr_down(src)"); if (rc) return rc;
+    rc = check_frame(c, d_dst, dst_pitch, dw, dh, "vp_pyr_down(dst)"); if (rc) return rc;
+    VP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    ProfScope ps(c, K_BIL_OTHER, st);
+    k_pyr_down<<<dim3((dw + 31) / 32, (dh + 7) / 8), 256, 0, st>>>(d_src, src_pitch, src_w, src_h, d_dst, dst_pitch, dw, dh);
+    VP_CUDA(c, cudaGetLastError());
+    c->launches++;
+    return VP_OK;
+}
+
+int vp_pyr_up(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, int src_w, int src_h, uint8_t* d_dst, size_t dst_pitch,
+              int dst_w, int dst_h, void* stream) {
+    if (!c) return VP_ERR_INVALID_ARG;
+    int rc = check_frame(c, d_src, src_pitch, src_w, src_h, "vp_pyr_up(src)"); if (rc) return rc;
+    rc = check_frame(c, d_dst, dst_pitch, dst_w, dst_h, "vp_pyr_up(dst)"); if (rc) return rc;
+    if ((dst_w != 2 * src_w && dst_w != 2 * src_w - 1) || (dst_h != 2 * src_h && dst_h != 2 * src_h - 1))
+        return fail(c, VP_ERR_UNSUPPORTED, "vp_pyr_up: dst must be 2*src or 2*src-1 per axis");
+    VP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    ProfScope ps(c, K_BIL_OTHER, st);
+    k_pyr_up<<<dim3((dst_w + 31) / 32, (dst_h + 7) / 8), 256, 0, st>>>(d_src, src_pitch, src_w, src_h, d_dst, dst_pitch, dst_w, dst_h);
+    VP_CUDA(c, cudaGetLastError());
+    c->launches++;
+    return VP_OK;
 }
 
 int vp_mean_stddev_sums(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, int w, int h, uint64_t* d_sums, void* stream) {
