@@ -152,6 +152,22 @@ def traffic_for(kernel):
         return None
 
 
+BILATERAL_MODE = "plain"     # --bilateral-mode: plain (north-star chain) | selective | multiscale (repaired semantics)
+
+
+def apply_bilateral_mode(pre, post):
+    """Upscaler::initializeEnhancements' own flags (src/upscaler.cpp:668-725) on a pair of bilateral configs
+    (ctypes structs or the oracle's dataclasses: same field names)."""
+    if BILATERAL_MODE == "plain":
+        return
+    for b, ep, ns in ((pre, 2.0, 3), (post, 1.5, 2)):
+        b.selective = 1
+        b.use_multiscale = int(BILATERAL_MODE == "multiscale")
+        b.num_scales = ns
+        b.detail_threshold = 30.0
+        b.edge_preserve = ep
+
+
 def build_cfg(capi, wl, temporal):
     sw, sh, dw, dh, pre, sharpen, post, tdef = WORKLOADS[wl]
     cfg = capi.default_chain_config(sw, sh, dw, dh)
@@ -159,6 +175,7 @@ def build_cfg(capi, wl, temporal):
     cfg.bicubic_enhance = 1 if wl in ENHANCE else 0
     t = temporal or tdef
     cfg.temporal.mode = {"none": capi.VP_TEMPORAL_NONE, "main": capi.VP_TEMPORAL_MAIN_BLEND, "frames": capi.VP_TEMPORAL_BLEND_FRAMES}[t]
+    apply_bilateral_mode(cfg.pre, cfg.post)
     return cfg, t
 
 
@@ -192,6 +209,7 @@ def cpu_chain_fps(wl, temporal, nframes, kind, threads=None):
     ocfg = RC.ChainConfig(dst_w=dw, dst_h=dh, use_pre=bool(pre), use_sharpen=bool(sharpen), use_post=bool(post),
                           temporal={"none": RC.TEMPORAL_NONE, "main": RC.TEMPORAL_MAIN_BLEND, "frames": RC.TEMPORAL_BLEND_FRAMES}[t],
                           bicubic_enhance=wl in ENHANCE)
+    apply_bilateral_mode(ocfg.pre, ocfg.post)
     ops = RC.Cv2Ops(threads=threads or os.cpu_count())
     chain = RC.Chain(ops, ocfg)
     frames = synth.clip(kind, sw, sh, nframes, SEED)
@@ -216,6 +234,7 @@ def run_reference(args, rank):
     ocfg = RC.ChainConfig(dst_w=dw, dst_h=dh, use_pre=bool(pre), use_sharpen=bool(sharpen), use_post=bool(post),
                           temporal={"none": RC.TEMPORAL_NONE, "main": RC.TEMPORAL_MAIN_BLEND, "frames": RC.TEMPORAL_BLEND_FRAMES}[t],
                           bicubic_enhance=wl in ENHANCE)
+    apply_bilateral_mode(ocfg.pre, ocfg.post)
     chain = RC.Chain(RC.Cv2Ops(threads=os.cpu_count()), ocfg)
     frames = synth.clip(args.kind, sw, sh, per_step, SEED)
     for _ in range(args.warmup):
@@ -249,7 +268,8 @@ def workload_name(wl, temporal):
         return f"{wl.upper()}: {sw}x{sh}->{dw}x{dh} BGR8 Upscaler(BICUBIC) " + "+".join(stages)
     stages = (["bilateral_pre"] if pre else []) + ["bicubic"] + (["adaptive_sharpen"] if sharpen else []) + \
              (["bilateral_post"] if post else []) + ([f"temporal_{temporal}"] if temporal != "none" else [])
-    return f"{wl.upper()}: {sw}x{sh}->{dw}x{dh} BGR8 " + "+".join(stages)
+    mode = "" if BILATERAL_MODE == "plain" else f" [SelectiveBilateral {BILATERAL_MODE} branch, repaired semantics]"
+    return f"{wl.upper()}: {sw}x{sh}->{dw}x{dh} BGR8 " + "+".join(stages) + mode
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -271,7 +291,11 @@ def main():
     ap.add_argument("--per-frame", action="store_true", help="one vp_process_device call per frame on one stream (no batch API)")
     ap.add_argument("--latency-frames", type=int, default=None,
                     help="single-frame latency sample (p50/p99); default 1000 for workload c5, else 0")
+    ap.add_argument("--bilateral-mode", default="plain", choices=["plain", "selective", "multiscale"],
+                    help="SelectiveBilateral branch of both bilateral stages (default: the north-star plain branch)")
     args = ap.parse_args()
+    global BILATERAL_MODE
+    BILATERAL_MODE = args.bilateral_mode
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -395,7 +419,7 @@ def main():
                 us = tms_k / n * 1e3
                 kernels[k] = {"launches_per_step": n, "avg_us": round(us, 2), "share": round(tms_k / tot, 4),
                               "alg_bytes": kbytes.get(k), "achieved_gbs": round(kbytes[k] / (us * 1e-6) / 1e9, 1) if k in kbytes else None}
-        dom = max(kernels, key=lambda k: kernels[k]["share"])
+        dom = max((k for k in kernels if kernels[k]["achieved_gbs"] is not None), key=lambda k: kernels[k]["share"])
         traffic = traffic_for(dom)
         ach = kernels[dom]["achieved_gbs"]
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
