@@ -152,6 +152,7 @@ def traffic_for(kernel):
         return None
 
 
+ADAPTIVE_SIGMA = False       # --adaptive-sigma: AdaptiveSharpening's variable-sigma branch (repaired semantics)
 BILATERAL_MODE = "plain"     # --bilateral-mode: plain (north-star chain) | selective | multiscale (repaired semantics)
 
 
@@ -176,6 +177,7 @@ def build_cfg(capi, wl, temporal):
     t = temporal or tdef
     cfg.temporal.mode = {"none": capi.VP_TEMPORAL_NONE, "main": capi.VP_TEMPORAL_MAIN_BLEND, "frames": capi.VP_TEMPORAL_BLEND_FRAMES}[t]
     apply_bilateral_mode(cfg.pre, cfg.post)
+    cfg.sharpen.adaptive_sigma = int(ADAPTIVE_SIGMA)
     return cfg, t
 
 
@@ -210,6 +212,7 @@ def cpu_chain_fps(wl, temporal, nframes, kind, threads=None):
                           temporal={"none": RC.TEMPORAL_NONE, "main": RC.TEMPORAL_MAIN_BLEND, "frames": RC.TEMPORAL_BLEND_FRAMES}[t],
                           bicubic_enhance=wl in ENHANCE)
     apply_bilateral_mode(ocfg.pre, ocfg.post)
+    ocfg.sharpen.adaptive_sigma = bool(ADAPTIVE_SIGMA)
     ops = RC.Cv2Ops(threads=threads or os.cpu_count())
     chain = RC.Chain(ops, ocfg)
     frames = synth.clip(kind, sw, sh, nframes, SEED)
@@ -235,6 +238,7 @@ def run_reference(args, rank):
                           temporal={"none": RC.TEMPORAL_NONE, "main": RC.TEMPORAL_MAIN_BLEND, "frames": RC.TEMPORAL_BLEND_FRAMES}[t],
                           bicubic_enhance=wl in ENHANCE)
     apply_bilateral_mode(ocfg.pre, ocfg.post)
+    ocfg.sharpen.adaptive_sigma = bool(ADAPTIVE_SIGMA)
     chain = RC.Chain(RC.Cv2Ops(threads=os.cpu_count()), ocfg)
     frames = synth.clip(args.kind, sw, sh, per_step, SEED)
     for _ in range(args.warmup):
@@ -269,6 +273,8 @@ def workload_name(wl, temporal):
     stages = (["bilateral_pre"] if pre else []) + ["bicubic"] + (["adaptive_sharpen"] if sharpen else []) + \
              (["bilateral_post"] if post else []) + ([f"temporal_{temporal}"] if temporal != "none" else [])
     mode = "" if BILATERAL_MODE == "plain" else f" [SelectiveBilateral {BILATERAL_MODE} branch, repaired semantics]"
+    if ADAPTIVE_SIGMA:
+        mode += " [AdaptiveSharpening adaptive_sigma branch, repaired semantics]"
     return f"{wl.upper()}: {sw}x{sh}->{dw}x{dh} BGR8 " + "+".join(stages) + mode
 
 
@@ -293,9 +299,11 @@ def main():
                     help="single-frame latency sample (p50/p99); default 1000 for workload c5, else 0")
     ap.add_argument("--bilateral-mode", default="plain", choices=["plain", "selective", "multiscale"],
                     help="SelectiveBilateral branch of both bilateral stages (default: the north-star plain branch)")
+    ap.add_argument("--adaptive-sigma", action="store_true", help="AdaptiveSharpening's adaptive_sigma branch (default: the north-star unsharp mask)")
     args = ap.parse_args()
-    global BILATERAL_MODE
+    global BILATERAL_MODE, ADAPTIVE_SIGMA
     BILATERAL_MODE = args.bilateral_mode
+    ADAPTIVE_SIGMA = args.adaptive_sigma
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -2,9 +2,10 @@
 // (reference include/adaptive_sharpening.h:12-126), executed by libvpb200's fused edge-mask +
 // unsharp-mask + tone-preservation kernel.
 //
-// Built branch: createEdgeMask + applyUnsharpMask (src/adaptive_sharpening.cpp:107-355).
-// adaptive_sigma is accepted but takes the same branch: calculateTextureMap calls cv::sqrt on a
-// CV_8U Mat (:386, undefined behaviour in the reference).
+// adaptive_sigma = false: createEdgeMask + applyUnsharpMask (src/adaptive_sharpening.cpp:107-355), one fused kernel.
+// adaptive_sigma = true: calculateTextureMap + calculateAdaptiveSigma + applyVariableSigmaUnsharpMask (:357-592) with
+// REPAIRED semantics - the reference calls cv::sqrt on a CV_8U Mat (:386, undefined behaviour); here local_var is
+// converted to float32 first (oracle/ref_chain.py:sharpen_variable_sigma).
 #pragma once
 #include <memory>
 #include "vp/mat.h"

@@ -63,8 +63,11 @@ typedef struct vp_bilateral_config {
     double edge_preserve;      /* Config::edge_preserve (:392)                                    */
 } vp_bilateral_config;
 
-/* AdaptiveSharpening::Config (include/adaptive_sharpening.h:14-24), adaptive_sigma=false branch
- * (createEdgeMask + applyUnsharpMask, src/adaptive_sharpening.cpp:107-355). */
+/* AdaptiveSharpening::Config (include/adaptive_sharpening.h:14-24).  adaptive_sigma = 0: createEdgeMask +
+ * applyUnsharpMask (src/adaptive_sharpening.cpp:107-355), the north-star branch.  adaptive_sigma = 1:
+ * calculateTextureMap + calculateAdaptiveSigma + applyVariableSigmaUnsharpMask (:357-592) with REPAIRED semantics
+ * (the literal code calls cv::sqrt on a CV_8U Mat, :386; local_var is converted to float32 first, degenerate
+ * ranges give 0 instead of NaN - DESIGN.md section 4f). */
 typedef struct vp_sharpen_config {
     float strength;
     float edge_strength;
@@ -73,6 +76,7 @@ typedef struct vp_sharpen_config {
     float sigma;
     int32_t kernel_size;       /* odd, 3..7 */
     int32_t preserve_tone;
+    int32_t adaptive_sigma;    /* Config::adaptive_sigma */
 } vp_sharpen_config;
 
 /* Temporal stage.  VP_TEMPORAL_MAIN_BLEND = src/main.cpp:269-292 (addWeighted(cur,w,prev,1-w) on
@@ -201,9 +205,13 @@ int vp_edge_mask(vp_ctx* ctx, const vp_sharpen_config* cfg, const uint8_t* d_src
 /* AdaptiveSharpening::applyUnsharpMask (src/adaptive_sharpening.cpp:232-355) with a caller-supplied mask */
 int vp_unsharp(vp_ctx* ctx, const vp_sharpen_config* cfg, const uint8_t* d_src, size_t src_pitch,
                const float* d_mask, size_t mask_pitch, uint8_t* d_dst, size_t dst_pitch, int w, int h, void* stream);
-/* AdaptiveSharpening::process, adaptive_sigma=false (src/adaptive_sharpening.cpp:51-105) */
+/* AdaptiveSharpening::process (src/adaptive_sharpening.cpp:51-105), either branch (cfg->adaptive_sigma) */
 int vp_sharpen(vp_ctx* ctx, const vp_sharpen_config* cfg, const uint8_t* d_src, size_t src_pitch,
                uint8_t* d_dst, size_t dst_pitch, int w, int h, void* stream);
+/* AdaptiveSharpening::calculateTextureMap + calculateAdaptiveSigma (src/adaptive_sharpening.cpp:357-440, repaired
+ * semantics): the blurred float32 sigma map, pitch in bytes */
+int vp_sigma_map(vp_ctx* ctx, const uint8_t* d_src, size_t src_pitch, float* d_sigma, size_t sigma_pitch,
+                 int w, int h, void* stream);
 /* cv::addWeighted(a, alpha, b, beta, 0, dst) on CV_8UC3 - src/main.cpp:286-290 */
 int vp_add_weighted(vp_ctx* ctx, const uint8_t* d_a, size_t a_pitch, double alpha,
                     const uint8_t* d_b, size_t b_pitch, double beta,

@@ -140,6 +140,9 @@ class NumpyOps:
     def box_blur5(self, img):
         return R.box_blur5_u8(img)
 
+    def box_mean7(self, img):
+        return R.box_mean7_u8(img)
+
     def pyr_down(self, img):
         return R.pyr_down_u8(img)
 
@@ -215,6 +218,9 @@ class Cv2Ops:
 
     def box_blur5(self, img):
         return self.cv2.blur(img, (5, 5))
+
+    def box_mean7(self, img):
+        return self.cv2.filter2D(img, -1, np.ones((7, 7), F32) / F32(49.0))
 
     def pyr_down(self, img):
         return self.cv2.pyrDown(img)
@@ -378,7 +384,13 @@ def unsharp_mask(ops, img, mask, cfg):
     """AdaptiveSharpening::applyUnsharpMask, adaptive_sharpening.cpp:232-355 (3-channel branch).
     All float32, no FMA contraction (the reference is built without -O / -mfma)."""
     blurred = ops.gaussian_u8(img, cfg.kernel_size, float(F32(cfg.sigma)))
-    um = ops.subtract(img, blurred)  # saturating: negative lobes dropped (:265)
+    return unsharp_from_blur(ops, img, blurred, mask, cfg)
+
+
+def unsharp_from_blur(ops, img, blurred, mask, cfg):
+    """The part applyUnsharpMask (:262-347) and applyVariableSigmaUnsharpMask (:503-585) share: one-sided
+    unsharp mask, edge-adaptive strength, tone preservation."""
+    um = ops.subtract(img, blurred)  # saturating: negative lobes dropped (:265, :505)
     e = mask.astype(F32)
     st, es, ss = F32(cfg.strength), F32(cfg.edge_strength), F32(cfg.smooth_strength)
     t1 = (e * es).astype(F32)
@@ -396,8 +408,79 @@ def unsharp_mask(ops, img, mask, cfg):
     return out
 
 
-def sharpen(ops, img, cfg):
-    """AdaptiveSharpening::process with adaptive_sigma=false, adaptive_sharpening.cpp:51-105."""
+# ---- adaptive_sigma = true with REPAIRED semantics -------------------------------------------
+# calculateTextureMap calls cv::sqrt on the CV_8U `local_var` (adaptive_sharpening.cpp:386, undefined behaviour);
+# the repair converts it to float32 first.  Degenerate ranges (max == min, a constant frame) divide by zero in the
+# reference and send NaN through static_cast<uchar>; the repair maps them to 0.  "Parity unpinned".
+def texture_map(ops, img):
+    """AdaptiveSharpening::calculateTextureMap, adaptive_sharpening.cpp:357-403."""
+    gray = ops.bgr2gray(img)
+    local_mean = ops.box_mean7(gray)                                # :373 filter2D(gray, -1, ones(7,7)/49)
+    diff = ops.subtract(gray, local_mean)                           # :377 u8, saturating
+    d16 = diff.astype(np.uint16)
+    diff_sq = np.minimum(d16 * d16, 255).astype(np.uint8)           # :379 cv::multiply on u8 saturates
+    local_var = ops.box_mean7(diff_sq)                              # :383
+    tex = np.sqrt(local_var.astype(F32)).astype(F32)                # :386 REPAIRED: float32 before cv::sqrt
+    mn, mx = float(tex.min()), float(tex.max())                     # :390
+    if mx <= mn:
+        return np.zeros_like(tex)                                   # REPAIRED: 0/0
+    # :391 (t - min) / (max - min) is one MatExpr: convertTo(alpha = 1/(max-min), beta = -min/(max-min)) in float32
+    a, b = F32(1.0 / (mx - mn)), F32(-mn * (1.0 / (mx - mn)))
+    return (tex.astype(np.float64) * np.float64(a) + np.float64(b)).astype(F32)
+
+
+def adaptive_sigma_map(ops, tex):
+    """AdaptiveSharpening::calculateAdaptiveSigma, adaptive_sharpening.cpp:405-440."""
+    min_sigma, max_sigma = F32(0.8), F32(2.5)
+    span = F32(max_sigma - min_sigma)
+    sigma = (max_sigma - (tex * span).astype(F32)).astype(F32)      # :423
+    return ops.gaussian_f32(sigma, 5, 1.0)                          # :431
+
+
+SIGMA_LEVELS = 5
+
+
+def variable_sigma_blur(ops, img, sigma_map, kernel_size):
+    """The blur of applyVariableSigmaUnsharpMask, adaptive_sharpening.cpp:442-500: five Gaussian levels between the
+    sigma map's extremes, per-pixel linear interpolation in float32, static_cast<uchar> (truncation)."""
+    L = SIGMA_LEVELS
+    mn, mx = F32(sigma_map.min()), F32(sigma_map.max())             # :457-460
+    span = F32(mx - mn)
+    levels = [F32(mn + F32(F32(span * F32(i)) / F32(L - 1))) for i in range(L)]                                           # :465
+    blurred = [ops.gaussian_u8(img, kernel_size, float(lv)) for lv in levels]                                               # :466-468
+    s = sigma_map.astype(F32)
+    if span > 0:
+        r = (((s - mn).astype(F32) / span).astype(F32) * F32(L - 1)).astype(F32)
+        idx = np.clip(np.trunc(r).astype(np.int64), 0, L - 2)       # :477-478
+    else:
+        idx = np.zeros(s.shape, np.int64)                           # REPAIRED: 0/0
+    lo = (mn + ((span * idx.astype(F32)).astype(F32) / F32(L - 1)).astype(F32)).astype(F32)          # :482
+    hi = (mn + ((span * (idx + 1).astype(F32)).astype(F32) / F32(L - 1)).astype(F32)).astype(F32)    # :483
+    den = (hi - lo).astype(F32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        alpha = np.where(den > 0, ((s - lo).astype(F32) / den).astype(F32), F32(0.0)).astype(F32)    # :486 (REPAIRED 0/0)
+    stack = np.stack(blurred)                                       # L x H x W x 3
+    yy, xx = np.indices(s.shape)
+    p_lo = stack[idx, yy, xx].astype(F32)
+    p_hi = stack[idx + 1, yy, xx].astype(F32)
+    a3 = alpha[..., None]
+    v = ((p_lo * (F32(1.0) - a3).astype(F32)).astype(F32) + (p_hi * a3).astype(F32)).astype(F32)     # :496-498
+    return np.clip(np.trunc(v), 0, 255).astype(np.uint8)            # static_cast<uchar>
+
+
+def sharpen_variable_sigma(ops, img, cfg):
+    """AdaptiveSharpening::process with adaptive_sigma=true, adaptive_sharpening.cpp:70-90."""
+    mask = edge_mask(ops, img, cfg)
+    sigma_map = adaptive_sigma_map(ops, texture_map(ops, img))
+    blurred = variable_sigma_blur(ops, img, sigma_map, cfg.kernel_size)
+    return unsharp_from_blur(ops, img, blurred, mask, cfg)
+
+
+def sharpen(ops, img, cfg, honour_adaptive_sigma=False):
+    """AdaptiveSharpening::process, adaptive_sharpening.cpp:51-105.  The north-star branch is adaptive_sigma=false;
+    the adaptive_sigma=true body is the repaired restatement above and is used only when asked for."""
+    if honour_adaptive_sigma and cfg.adaptive_sigma:
+        return sharpen_variable_sigma(ops, img, cfg)
     return unsharp_mask(ops, img, edge_mask(ops, img, cfg), cfg)
 
 
@@ -569,7 +652,7 @@ class Chain:
         if stages is not None:
             stages["up"] = x
         if cfg.use_sharpen:
-            x = sharpen(ops, x, cfg.sharpen)
+            x = sharpen(ops, x, cfg.sharpen, honour_adaptive_sigma=True)
         if stages is not None:
             stages["sharp"] = x
         if cfg.use_post:

@@ -465,6 +465,16 @@ def box_blur5_u8(img):
     return ((2 * s + 25) // 50).astype(np.uint8)
 
 
+def box_mean7_u8(img):
+    """cv::filter2D(img8U, out, -1, ones(7,7)/49.f) (adaptive_sharpening.cpp:369-373): float32 accumulation then
+    saturate_cast<uchar>; sum/49 is never within 0.01 of .5, so it equals round(sum / 49) whatever the summation order."""
+    img = np.asarray(img)
+    h, w = img.shape[:2]
+    p = pad_reflect101(img, 3).astype(np.int64)
+    s = sum(p[dy:dy + h, dx:dx + w] for dy in range(7) for dx in range(7))
+    return ((2 * s + 49) // 98).astype(np.uint8)
+
+
 def pyr_down_u8(img):
     """cv::pyrDown on CV_8U: [1 4 6 4 1] x [1 4 6 4 1], BORDER_REFLECT_101, (v + 128) >> 8 at even (y, x);
     dst = ((W+1)/2, (H+1)/2)."""

@@ -54,7 +54,7 @@ def run_bilateral(vp, ctx, img, d, sc, ss):
 
 def sharpen_cfg(vp, o):
     return vp.SharpenConfig(o.strength, o.edge_strength, o.smooth_strength, o.edge_threshold, o.sigma,
-                            o.kernel_size, int(o.preserve_tone))
+                            o.kernel_size, int(o.preserve_tone), int(o.adaptive_sigma))
 
 
 def bilateral_cfg(vp, o):

@@ -39,10 +39,11 @@ def run(driver, tmp_path, mode, frames, tw, th):
 
 def ref_defaults(**kw):
     """Upscaler::initializeEnhancements as the reference writes it (src/upscaler.cpp:666-758): selective and
-    multi-scale on for both bilateral stages (repaired semantics); adaptive_sigma routes to the unsharp mask."""
+    multi-scale on for both bilateral stages, adaptive_sigma on for the sharpening (all with repaired semantics)."""
     return RC.ChainConfig(
         pre=RC.BilateralConfig(RC.PRE_PROCESSING, True, True, 7, 30.0, 30.0, True, 30.0, 1.5, 2.0, True, 3),
-        post=RC.BilateralConfig(RC.POST_PROCESSING, True, True, 5, 20.0, 20.0, True, 30.0, 1.2, 1.5, True, 2), **kw)
+        post=RC.BilateralConfig(RC.POST_PROCESSING, True, True, 5, 20.0, 20.0, True, 30.0, 1.2, 1.5, True, 2),
+        sharpen=RC.SharpenConfig(0.8, 1.2, 0.4, 30.0, 1.5, 5, True, True, True), **kw)
 
 
 def close(o, r):

@@ -213,3 +213,30 @@ def test_detail_mask_of_a_constant_frame_is_finite():
     img = np.full((20, 30, 3), 77, np.uint8)
     m = RC.create_detail_mask(RC.NumpyOps(), img, RC.BilateralConfig())
     assert np.isfinite(m).all()
+
+
+# ---- AdaptiveSharpening, adaptive_sigma = true ----------------------------------------------
+@pytest.mark.parametrize("size", [(37, 53), (64, 64), (7, 9), (3, 3), (120, 200)])
+def test_box_mean7_bit_exact(size):
+    g = np.random.default_rng(5).integers(0, 256, size, dtype=np.uint8)
+    assert np.array_equal(R.box_mean7_u8(g), cv2.filter2D(g, -1, np.ones((7, 7), np.float32) / np.float32(49.0)))
+
+
+@pytest.mark.parametrize("kind", ["noise", "scene", "flat"])
+def test_variable_sigma_numpy_vs_cv2(kind):
+    img = synth.frame(kind, 160, 96, 1)
+    cfg = RC.SharpenConfig()
+    ta, tb = RC.texture_map(RC.NumpyOps(), img), RC.texture_map(RC.Cv2Ops(), img)
+    assert np.array_equal(ta, tb)
+    sa, sb = RC.adaptive_sigma_map(RC.NumpyOps(), ta), RC.adaptive_sigma_map(RC.Cv2Ops(), tb)
+    assert np.abs(sa - sb).max() <= 2e-6 and 0.8 - 1e-5 <= sa.min() and sa.max() <= 2.5 + 1e-5
+    a = RC.sharpen_variable_sigma(RC.NumpyOps(), img, cfg)
+    b = RC.sharpen_variable_sigma(RC.Cv2Ops(), img, cfg)
+    d = np.abs(a.astype(int) - b.astype(int))
+    assert d.max() <= 2 and (d > 0).mean() < 0.01
+
+
+def test_variable_sigma_constant_frame_is_passthrough_safe():
+    img = np.full((20, 30, 3), 77, np.uint8)
+    out = RC.sharpen_variable_sigma(RC.NumpyOps(), img, RC.SharpenConfig())
+    assert out.shape == img.shape and np.abs(out.astype(int) - 77).max() <= 1

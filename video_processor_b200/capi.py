@@ -26,7 +26,7 @@ class BilateralConfig(C.Structure):
 class SharpenConfig(C.Structure):
     _fields_ = [("strength", C.c_float), ("edge_strength", C.c_float), ("smooth_strength", C.c_float),
                 ("edge_threshold", C.c_float), ("sigma", C.c_float), ("kernel_size", C.c_int32),
-                ("preserve_tone", C.c_int32)]
+                ("preserve_tone", C.c_int32), ("adaptive_sigma", C.c_int32)]
 
 
 class TemporalConfig(C.Structure):
@@ -78,6 +78,7 @@ PROTOTYPES = {
     "vp_edge_mask": (C.c_int, [_vp, C.POINTER(SharpenConfig), _u8p, _sz, C.c_void_p, _sz, C.c_int, C.c_int, C.c_void_p]),
     "vp_unsharp": (C.c_int, [_vp, C.POINTER(SharpenConfig), _u8p, _sz, C.c_void_p, _sz, _u8p, _sz, C.c_int, C.c_int, C.c_void_p]),
     "vp_sharpen": (C.c_int, [_vp, C.POINTER(SharpenConfig), _u8p, _sz, _u8p, _sz, C.c_int, C.c_int, C.c_void_p]),
+    "vp_sigma_map": (C.c_int, [_vp, _u8p, _sz, C.c_void_p, _sz, C.c_int, C.c_int, C.c_void_p]),
     "vp_add_weighted": (C.c_int, [_vp, _u8p, _sz, C.c_double, _u8p, _sz, C.c_double, _u8p, _sz, C.c_int, C.c_int, C.c_void_p]),
     "vp_temporal_blend": (C.c_int, [_vp, C.POINTER(C.c_void_p), C.c_int, _sz, C.c_float, _u8p, _sz, C.c_int, C.c_int, C.c_void_p]),
 }

@@ -106,13 +106,13 @@ bool AdaptiveSharpening::process(const cv::Mat& input, cv::Mat& output) {
         return false;
     }
     if (m_config.adaptive_sigma && !m_impl->warned) {
-        std::cerr << "AdaptiveSharpening: adaptive_sigma runs the unsharp-mask branch (the reference's "
-                     "variable-sigma body is undefined behaviour, see DESIGN.md)" << std::endl;
+        std::cerr << "AdaptiveSharpening: the adaptive_sigma branch runs with repaired semantics (the reference calls "
+                     "cv::sqrt on a CV_8U Mat, src/adaptive_sharpening.cpp:386; see DESIGN.md)" << std::endl;
         m_impl->warned = true;
     }
     StageRunner& r = m_impl->run;
     vp_sharpen_config c{m_config.strength, m_config.edge_strength, m_config.smooth_strength, m_config.edge_threshold,
-                        m_config.sigma, m_config.kernel_size, m_config.preserve_tone ? 1 : 0};
+                        m_config.sigma, m_config.kernel_size, m_config.preserve_tone ? 1 : 0, m_config.adaptive_sigma ? 1 : 0};
     bool ok = vp_host_api::is_bgr8(input) && r.upload(input, input.cols, input.rows, 3);
     ok = ok && vp_sharpen(r.ctx(), &c, r.d_in(), r.in_pitch(), r.d_out(), r.out_pitch(), input.cols, input.rows, r.stream()) == VP_OK;
     ok = ok && r.download(output, input.cols, input.rows, CV_8UC3, 3);

@@ -115,7 +115,7 @@ bool Upscaler::ensureChain(int src_w, int src_h) {
                                      post.adaptive_params, post.diameter, 0, post.sigma_color, post.sigma_space,
                                      post.selective, post.use_multiscale, post.num_scales, 0, post.detail_threshold, post.edge_preserve};
         c.sharpen = vp_sharpen_config{sh.strength, sh.edge_strength, sh.smooth_strength, sh.edge_threshold, sh.sigma,
-                                      sh.kernel_size, sh.preserve_tone ? 1 : 0};
+                                      sh.kernel_size, sh.preserve_tone ? 1 : 0, sh.adaptive_sigma ? 1 : 0};
         c.temporal.mode = m_use_temporal_consistency ? VP_TEMPORAL_BLEND_FRAMES : VP_TEMPORAL_NONE;
         c.temporal.buffer_size = std::min(std::max(tc.buffer_size, 1), 3);
         c.temporal.blend_strength = tc.blend_strength;

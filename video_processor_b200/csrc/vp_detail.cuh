@@ -32,39 +32,49 @@ __device__ __forceinline__ void load_gray_tile(const uint8_t* __restrict__ src, 
     }
 }
 
-// 5-tap row sums of a u8 plane: out[y][x] = sum in[y][x..x+4], x < iw-4
-__device__ __forceinline__ void row_sum5(const uint8_t* __restrict__ in, int iw, int ih, uint16_t* __restrict__ out) {
-    const int ow = iw - 4;
+// K-tap row sums of a u8 plane: out[y][x] = sum in[y][x..x+K-1], x < iw-K+1
+template <int K>
+__device__ __forceinline__ void row_sum(const uint8_t* __restrict__ in, int iw, int ih, uint16_t* __restrict__ out) {
+    const int ow = iw - (K - 1);
     for (int i = threadIdx.x; i < ow * ih; i += DT_NT) {
         const int y = i / ow, x = i - y * ow;
         const uint8_t* p = in + y * iw + x;
-        out[y * ow + x] = (uint16_t)(p[0] + p[1] + p[2] + p[3] + p[4]);
+        unsigned s = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) s += p[k];
+        out[y * ow + x] = (uint16_t)s;
     }
 }
-// cv::blur 5x5 on u8 at (x, y) of the row-sum plane: round(sum / 25); sum/25 never lands on .5
-__device__ __forceinline__ int box5_at(const uint16_t* __restrict__ rs, int rw, int x, int y) {
+// normalised KxK box filter on u8 (cv::blur / cv::filter2D with ones/K^2) at (x, y) of the row-sum plane:
+// round(sum / K^2); sum / K^2 never lands on .5 for odd K
+template <int K>
+__device__ __forceinline__ int box_at(const uint16_t* __restrict__ rs, int rw, int x, int y) {
     const uint16_t* p = rs + y * rw + x;
-    const unsigned s = p[0] + p[rw] + p[2 * rw] + p[3 * rw] + p[4 * rw];
-    return (int)((2u * s + 25u) / 50u);
+    unsigned s = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) s += p[k * rw];
+    return (int)((2u * s + (unsigned)(K * K)) / (unsigned)(2 * K * K));
 }
 
 struct DetailMax { int g2; int var; };   // max gx^2+gy^2 (Sobel), max local_var; zeroed before k_detail_max
 
-// shared by both kernels: gray tile (halo H) -> diff_sq plane of (DT_TW + 2*(H-2)) x (DT_TH + 2*(H-2)) -> its row sums
-template <int HALO>
+// gray tile (halo H) -> local mean (KxK box) -> saturating diff^2 plane of (DT_TW + 2*H - K + 1) x (DT_TH + 2*H - K + 1)
+// -> its row sums: the "local variance" front end createDetailMask (K = 5, src/selective_bilateral.cpp:262-272) and
+// calculateTextureMap (K = 7, src/adaptive_sharpening.cpp:368-383) share
+template <int HALO, int K>
 __device__ __forceinline__ void detail_variance_rows(const uint8_t* s_gray, uint16_t* s_rs1, uint8_t* s_dsq, uint16_t* s_rs2) {
     constexpr int GW = DT_TW + 2 * HALO, GH = DT_TH + 2 * HALO;
-    constexpr int MW = GW - 4, MH = GH - 4;            // local_mean / diff_sq plane
-    row_sum5(s_gray, GW, GH, s_rs1);
+    constexpr int MW = GW - (K - 1), MH = GH - (K - 1);            // local_mean / diff_sq plane
+    row_sum<K>(s_gray, GW, GH, s_rs1);
     __syncthreads();
     for (int i = threadIdx.x; i < MW * MH; i += DT_NT) {
         const int y = i / MW, x = i - y * MW;
-        const int mean = box5_at(s_rs1, MW, x, y);                             // :263 cv::blur
-        const int d = max((int)s_gray[(y + 2) * GW + x + 2] - mean, 0);        // :268 cv::subtract on u8 saturates
-        s_dsq[i] = (uint8_t)min(d * d, 255);                                   // :269 cv::multiply on u8 saturates
+        const int mean = box_at<K>(s_rs1, MW, x, y);
+        const int d = max((int)s_gray[(y + K / 2) * GW + x + K / 2] - mean, 0);   // cv::subtract on u8 saturates
+        s_dsq[i] = (uint8_t)min(d * d, 255);                                       // cv::multiply on u8 saturates
     }
     __syncthreads();
-    row_sum5(s_dsq, MW, MH, s_rs2);
+    row_sum<K>(s_dsq, MW, MH, s_rs2);
     __syncthreads();
 }
 
@@ -85,12 +95,12 @@ __global__ void __launch_bounds__(DT_NT) k_detail_max(const uint8_t* __restrict_
     if (threadIdx.x < 2) s_max[threadIdx.x] = 0;
     load_gray_tile<HALO>(src, pitch, w, h, x0, y0, s_gray);
     __syncthreads();
-    detail_variance_rows<HALO>(s_gray, s_rs1, s_dsq, s_rs2);
+    detail_variance_rows<HALO, 5>(s_gray, s_rs1, s_dsq, s_rs2);
     int g2 = 0, var = 0;
     for (int i = threadIdx.x; i < DT_TW * DT_TH; i += DT_NT) {
         const int y = i / DT_TW, x = i - y * DT_TW;
         if (x0 + x < w && y0 + y < h) {
-            var = max(var, box5_at(s_rs2, VW, x, y));                          // :272 local_var
+            var = max(var, box_at<5>(s_rs2, VW, x, y));                          // :272 local_var
             g2 = max(g2, sobel_g2(s_gray + (y + HALO) * GW + x + HALO, GW));   // :251-256
         }
     }
@@ -127,10 +137,10 @@ __global__ void __launch_bounds__(DT_NT) k_detail_mask(const DetailMaskArgs a) {
     const float inv_mag = magmax > 0.f ? (float)(1.0 / (double)magmax) : 0.f;
     const float inv_tex = texmax > 0.f ? (float)(1.0 / (double)texmax) : 0.f;
     __syncthreads();
-    detail_variance_rows<HALO>(s_gray, s_rs1, s_dsq, s_rs2);
+    detail_variance_rows<HALO, 5>(s_gray, s_rs1, s_dsq, s_rs2);
     for (int i = threadIdx.x; i < VW * VH; i += DT_NT) {
         const int y = i / VW, x = i - y * VW;
-        const float tex = __fsqrt_rn((float)box5_at(s_rs2, VW, x, y));                          // :272,:276 (repaired)
+        const float tex = __fsqrt_rn((float)box_at<5>(s_rs2, VW, x, y));                          // :272,:276 (repaired)
         const float mag = __fsqrt_rn((float)sobel_g2(s_gray + (y + 4) * GW + x + 4, GW));       // :251-256
         const float nm = __fmul_rn(mag, inv_mag), nt = __fmul_rn(tex, inv_tex);
         const float detail = (float)((double)nm * 0.7 + (double)nt * 0.3);                      // :288

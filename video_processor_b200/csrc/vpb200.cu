@@ -29,11 +29,13 @@
 #include "vp_stats.cuh"
 #include "vp_tables.h"
 #include "vp_upsharp.cuh"
+#include "vp_varsharp.cuh"
 
 using namespace vp;
 
 // layout the ctypes / FFI stubs rely on (tests/test_host_logic.py::test_struct_layout_matches_header)
 static_assert(sizeof(vp_bilateral_config) == 64 && offsetof(vp_bilateral_config, detail_threshold) == 48, "vp_bilateral_config layout");
+static_assert(sizeof(vp_sharpen_config) == 32, "vp_sharpen_config layout");
 static_assert(offsetof(vp_chain_config, pre) == 32 && offsetof(vp_chain_config, post) == 128, "vp_chain_config layout");
 
 namespace {
@@ -67,6 +69,13 @@ struct MsScratch {                  // SelectiveBilateral's selective / multi-sc
     vp::DetailMax* mx = nullptr;
 };
 
+struct VsScratch {                  // AdaptiveSharpening, adaptive_sigma branch: one frame size's buffers
+    int w = 0, h = 0;
+    float* emask = nullptr; float* sigma = nullptr; size_t fpitch = 0;   // edge mask / sigma map planes
+    vp::SigmaStats* st = nullptr; vp::SigmaLevels* lv = nullptr;
+    uint8_t* up = nullptr; size_t upitch = 0;                            // chain only: the bicubic output
+};
+
 struct Lane {                       // per-frame intermediates; two lanes let consecutive frames overlap
     cudaStream_t st = nullptr;      // lane 1's own stream (lane 0 runs on the caller's / the compute stream)
     uint8_t* d_pre = nullptr;       // PRE-filtered frame, src resolution
@@ -79,6 +88,7 @@ struct Lane {                       // per-frame intermediates; two lanes let co
     unsigned char* d_dirty = nullptr;   // hysteresis tile flags (2 x ntiles) followed by the 2 `again` counters
     MsScratch ms_pre, ms_post;      // selective / multi-scale SelectiveBilateral stages of the chain
     uint8_t* d_post = nullptr;      // their POST output (the plain POST filter writes the caller's frame directly)
+    VsScratch vs;                   // adaptive_sigma sharpening of the chain
 };
 
 struct vp_ctx {
@@ -113,6 +123,7 @@ struct vp_ctx {
     BilCand* d_cand_ms_pre = nullptr; BilCand* d_cand_ms_post = nullptr; BilCand* d_cand_ms_tmp = nullptr;
     int ms_pre_rad[5] = {0, 0, 0, 0, 0}, ms_post_rad[5] = {0, 0, 0, 0, 0}, ms_tmp_rad[5] = {0, 0, 0, 0, 0};
     MsScratch ms_tmp;               // stage-wise scratch
+    VsScratch vs_tmp;
     ResizeCache rc_chain, rc_tmp;
     float* d_siglut = nullptr; float siglut_thr = -1e30f; bool siglut_valid = false;
     float* d_siglut_tmp = nullptr; float siglut_tmp_thr = 0; bool siglut_tmp_valid = false;
@@ -409,6 +420,79 @@ int run_bilateral_modes(vp_ctx* c, MsScratch& S, const vp_bilateral_config& cfg,
     return VP_OK;
 }
 
+void free_vs_scratch(VsScratch& S) {
+    cudaFree(S.emask); cudaFree(S.sigma); cudaFree(S.st); cudaFree(S.lv); cudaFree(S.up);
+    S = VsScratch();
+}
+
+int ensure_vs_scratch(vp_ctx* c, VsScratch& S, int w, int h, bool with_up) {
+    if (S.w == w && S.h == h && S.emask && (!with_up || S.up)) return VP_OK;
+    VP_CUDA(c, cudaDeviceSynchronize());
+    free_vs_scratch(S);
+    S.w = w; S.h = h;
+    S.fpitch = align_up((size_t)w * 4, 256);
+    VP_CUDA(c, cudaMalloc(&S.emask, S.fpitch * h));
+    VP_CUDA(c, cudaMalloc(&S.sigma, S.fpitch * h));
+    VP_CUDA(c, cudaMalloc(&S.st, sizeof(SigmaStats)));
+    VP_CUDA(c, cudaMalloc(&S.lv, sizeof(SigmaLevels)));
+    if (with_up) {
+        S.upitch = align_up((size_t)w * 3, 256);
+        VP_CUDA(c, cudaMalloc(&S.up, S.upitch * h));
+    }
+    return VP_OK;
+}
+
+// calculateTextureMap + calculateAdaptiveSigma (src/adaptive_sharpening.cpp:357-440) -> sigma plane, and the extremes of
+// that plane in S.st for k_sigma_levels
+int launch_sigma_map(vp_ctx* c, SigmaStats* st_dev, const uint8_t* src, size_t pitch, int w, int h, float* sigma, size_t spitch, cudaStream_t st) {
+    static const SigmaStats init{0x7fffffff, 0, 0x7f800000, 0};
+    ProfScope ps(c, K_UPSHARP, st);
+    VP_CUDA(c, cudaMemcpyAsync(st_dev, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+    const dim3 grid((w + DT_TW - 1) / DT_TW, (h + DT_TH - 1) / DT_TH);
+    k_texture_minmax<<<grid, DT_NT, 0, st>>>(src, pitch, w, h, st_dev);
+    SigmaMapArgs a{};
+    a.src = src; a.pitch = pitch; a.w = w; a.h = h; a.st = st_dev;
+    const std::vector<double> g = vp_host::gaussian_kernel_f64(5, 1.0);   // literal Size(5,5), 1.0 at :431
+    for (int i = 0; i < 5; ++i) a.gf[i] = (float)g[i];
+    a.sigma = sigma; a.spitch = spitch;
+    k_sigma_map<<<grid, DT_NT, 0, st>>>(a);
+    VP_CUDA(c, cudaGetLastError());
+    c->launches += 2;
+    return VP_OK;
+}
+
+int launch_upsharp(vp_ctx* c, UpsharpArgs& a, bool do_resize, bool do_sharpen, cudaStream_t st);
+int fill_sharpen_args(vp_ctx* c, UpsharpArgs& a, const vp_sharpen_config& s);
+
+// AdaptiveSharpening::process with adaptive_sigma = true (src/adaptive_sharpening.cpp:70-90) on a frame that is already
+// at its final size: edge mask (k_upsharp's mask-only form), sigma map, levels, variable-sigma unsharp mask
+int run_varsharp(vp_ctx* c, VsScratch& S, const vp_sharpen_config& cfg, const float* siglut, const uint8_t* src, size_t spitch,
+                 uint8_t* dst, size_t dpitch, int w, int h, unsigned long long* sums, const SelOut& fin, cudaStream_t st) {
+    if (w < 8 || h < 8) return fail(c, VP_ERR_UNSUPPORTED, "AdaptiveSharpening needs frames of at least 8x8");
+    UpsharpArgs m{};
+    int rc = fill_sharpen_args(c, m, cfg); if (rc) return rc;
+    m.sig_lut = siglut;
+    m.src = src; m.spitch = spitch; m.sw = w; m.sh = h; m.dst = nullptr; m.dpitch = 0; m.dw = w; m.dh = h;
+    m.max_src_rows = US_TH + 2 * US_HALO; m.max_src_cols = US_TW + 2 * US_HALO;
+    m.mask_out = S.emask; m.mask_out_pitch = S.fpitch;
+    rc = launch_upsharp(c, m, false, true, st); if (rc) return rc;
+    rc = launch_sigma_map(c, S.st, src, spitch, w, h, S.sigma, S.fpitch, st); if (rc) return rc;
+    ProfScope ps(c, K_UPSHARP, st);
+    k_sigma_levels<<<1, 32, 0, st>>>(S.st, cfg.kernel_size, S.lv);
+    VarSharpArgs a{};
+    a.src = src; a.spitch = spitch; a.w = w; a.h = h;
+    a.emask = S.emask; a.epitch = S.fpitch; a.sigma = S.sigma; a.gpitch = S.fpitch; a.lv = S.lv;
+    a.gk = cfg.kernel_size;
+    a.strength = cfg.strength; a.edge_strength = cfg.edge_strength; a.smooth_strength = cfg.smooth_strength;
+    a.preserve_tone = cfg.preserve_tone;
+    a.dst = dst; a.dpitch = dpitch; a.sums = sums; a.fin = fin;
+    const dim3 grid((w + VS_TW - 1) / VS_TW, (h + VS_TH - 1) / VS_TH);
+    k_varsharp<<<grid, VS_NT, 0, st>>>(a);
+    VP_CUDA(c, cudaGetLastError());
+    c->launches += 2;
+    return VP_OK;
+}
+
 int fill_sharpen_args(vp_ctx* c, UpsharpArgs& a, const vp_sharpen_config& s) {
     if (s.kernel_size != 3 && s.kernel_size != 5 && s.kernel_size != 7)
         return fail(c, VP_ERR_UNSUPPORTED, "AdaptiveSharpening kernel_size must be 3, 5 or 7");
@@ -567,7 +651,7 @@ void vp_destroy(vp_ctx* c) {
     for (Lane& L : c->lanes) {
         cudaFree(L.d_pre); cudaFree(L.d_sharp); cudaFree(L.d_sums); cudaFree(L.d_sel); cudaFree(L.d_counter);
         cudaFree(L.d_map); cudaFree(L.d_dirty); cudaFree(L.d_post);
-        free_ms_scratch(L.ms_pre); free_ms_scratch(L.ms_post);
+        free_ms_scratch(L.ms_pre); free_ms_scratch(L.ms_post); free_vs_scratch(L.vs);
         if (L.ev_done) cudaEventDestroy(L.ev_done);
         if (L.st) cudaStreamDestroy(L.st);
     }
@@ -576,7 +660,7 @@ void vp_destroy(vp_ctx* c) {
     cudaFree(c->d_cand_be); cudaFree(c->d_scene_acc); cudaFree(c->d_scene_state); cudaFree(c->d_use);
     cudaFree(c->d_cand_pre); cudaFree(c->d_cand_post); cudaFree(c->d_cand_tmp); cudaFree(c->d_cand_sel);
     cudaFree(c->d_cand_ms_pre); cudaFree(c->d_cand_ms_post); cudaFree(c->d_cand_ms_tmp);
-    free_ms_scratch(c->ms_tmp);
+    free_ms_scratch(c->ms_tmp); free_vs_scratch(c->vs_tmp);
     free_resize(c->rc_chain); free_resize(c->rc_tmp);
     cudaFree(c->d_siglut); cudaFree(c->d_siglut_tmp);
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
@@ -861,7 +945,22 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
     // 2+3. bicubic resize + AdaptiveSharpening (dst resolution)
     const bool do_resize = (g.dst_w != g.src_w || g.dst_h != g.src_h);
     const bool last_is_upsharp = !g.use_post && !temporal;     // (a POST stage of either kind reads the lane buffer)
-    if (do_resize && !g.use_sharpen && !need_post_stats) {
+    if (g.use_sharpen && g.sharpen.adaptive_sigma) {
+        // adaptive_sigma branch: bicubic on its own, then the four-kernel variable-sigma stage (run_varsharp)
+        rc = ensure_vs_scratch(c, L.vs, g.dst_w, g.dst_h, do_resize); if (rc) return rc;
+        if (do_resize) {
+            rc = launch_bicubic(c, cur, cur_pitch, g.src_w, g.src_h, L.vs.up, L.vs.upitch, g.dst_w, g.dst_h, c->rc_chain, st);
+            if (rc) return rc;
+            cur = L.vs.up; cur_pitch = L.vs.upitch;
+        }
+        uint8_t* out = last_is_upsharp ? d_dst : L.d_sharp;
+        const size_t opitch = last_is_upsharp ? dst_pitch : c->frame_pitch;
+        rc = run_varsharp(c, L.vs, g.sharpen, c->d_siglut, cur, cur_pitch, out, opitch, g.dst_w, g.dst_h,
+                          need_post_stats ? L.d_sums + 6 : nullptr,
+                          need_post_stats ? SelOut{L.d_counter + 1, L.d_sel + 1, (double)g.dst_w * g.dst_h} : SelOut{nullptr, nullptr, 0.0}, st);
+        if (rc) return rc;
+        cur = out; cur_pitch = opitch;
+    } else if (do_resize && !g.use_sharpen && !need_post_stats) {
         uint8_t* out = last_is_upsharp ? d_dst : L.d_sharp;
         const size_t opitch = last_is_upsharp ? dst_pitch : c->frame_pitch;
         rc = launch_bicubic(c, cur, cur_pitch, g.src_w, g.src_h, out, opitch, g.dst_w, g.dst_h, c->rc_chain, st);
@@ -1256,6 +1355,10 @@ static int sharpen_common(vp_ctx* c, const vp_sharpen_config* cfg, const uint8_t
     UpsharpArgs a{};
     rc = fill_sharpen_args(c, a, *cfg); if (rc) return rc;
     rc = ensure_siglut(c, &c->d_siglut_tmp, &c->siglut_tmp_thr, &c->siglut_tmp_valid, cfg->edge_threshold, st); if (rc) return rc;
+    if (cfg->adaptive_sigma && d_dst && !mask_in && !mask_out) {      // vp_sharpen, adaptive_sigma branch
+        rc = ensure_vs_scratch(c, c->vs_tmp, w, h, false); if (rc) return rc;
+        return run_varsharp(c, c->vs_tmp, *cfg, c->d_siglut_tmp, d_src, src_pitch, d_dst, dst_pitch, w, h, nullptr, SelOut{nullptr, nullptr, 0.0}, st);
+    }
     a.sig_lut = c->d_siglut_tmp;
     a.src = d_src; a.spitch = src_pitch; a.sw = w; a.sh = h;
     a.dst = d_dst; a.dpitch = dst_pitch; a.dw = w; a.dh = h;
@@ -1280,6 +1383,16 @@ int vp_sharpen(vp_ctx* c, const vp_sharpen_config* cfg, const uint8_t* d_src, si
                uint8_t* d_dst, size_t dst_pitch, int w, int h, void* stream) {
     if (!d_dst) return VP_ERR_INVALID_ARG;
     return sharpen_common(c, cfg, d_src, src_pitch, nullptr, 0, nullptr, 0, d_dst, dst_pitch, w, h, stream, "vp_sharpen");
+}
+
+int vp_sigma_map(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, float* d_sigma, size_t sigma_pitch, int w, int h, void* stream) {
+    if (!c || !d_sigma) return VP_ERR_INVALID_ARG;
+    int rc = check_frame(c, d_src, src_pitch, w, h, "vp_sigma_map(src)"); if (rc) return rc;
+    if (sigma_pitch < (size_t)w * 4) return fail(c, VP_ERR_INVALID_ARG, "vp_sigma_map: sigma pitch < 4*width");
+    VP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    if (!c->vs_tmp.st) VP_CUDA(c, cudaMalloc(&c->vs_tmp.st, sizeof(SigmaStats)));
+    return launch_sigma_map(c, c->vs_tmp.st, d_src, src_pitch, w, h, d_sigma, sigma_pitch, st);
 }
 
 int vp_add_weighted(vp_ctx* c, const uint8_t* d_a, size_t a_pitch, double alpha, const uint8_t* d_b, size_t b_pitch, double beta,
