@@ -185,7 +185,7 @@ def algorithmic_bytes(wl, temporal, cfg):
     """in + out (+ state reads + state write when the temporal stage is on), per frame."""
     sw, sh, dw, dh = WORKLOADS[wl][:4]
     inb, outb = sw * sh * 3, dw * dh * 3
-    nprev = {"none": 0, "main": 1, "frames": max(cfg.temporal.buffer_size - 1, 0)}[temporal]
+    nprev = {"none": 0, "main": 1, "frames": max(cfg.temporal.buffer_size, 0)}[temporal]
     chain = inb + outb + (nprev * outb + outb if nprev else 0)
     if wl in ENHANCE:   # profile kinds are reused: stats = gauss3, upsharp = bicubic, blend = canny (nms + hysteresis)
         return chain, {"stats": 2 * inb, "upsharp": inb + outb, "blend": outb + 2 * (outb // 3),
@@ -521,7 +521,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload_name(wl, temporal), "clip": args.kind, "frames_per_step_per_gpu": F,
-                       "temporal_warmup_frames_rank_gt0": {"none": 0, "main": 1, "frames": max(cfg.temporal.buffer_size - 1, 0)}[temporal],
+                       "temporal_warmup_frames_rank_gt0": {"none": 0, "main": 1, "frames": max(cfg.temporal.buffer_size, 0)}[temporal],
                        "sharding": "contiguous frame segments, no collective",
                        "l2": f"inputs ({F}x{inb >> 20} MiB) and output ring ({NOUT}x{outb >> 20} MiB) exceed the 126 MB L2",
                        "roofline_pass": "per-kernel CUDA events in a separate pass of one step, one stream, one frame at a time",

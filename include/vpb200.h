@@ -81,12 +81,14 @@ typedef struct vp_sharpen_config {
 
 /* Temporal stage.  VP_TEMPORAL_MAIN_BLEND = src/main.cpp:269-292 (addWeighted(cur,w,prev,1-w) on
  * the history of unblended frames).  VP_TEMPORAL_BLEND_FRAMES = TemporalConsistency::blendFrames
- * (src/temporal_consistency.cpp:355-444) over the current and up to buffer_size-1 previous
- * unblended frames, masks == 1, float32 accumulator. */
+ * (src/temporal_consistency.cpp:355-444) over the current frame and every buffered unblended frame - up to
+ * buffer_size of them: m_frame_buffer keeps the last buffer_size inputs (:162-165) and m_flow_buffer reaches
+ * buffer_size entries once the new flow is pushed (:97; it is trimmed to buffer_size-1 only after the blend,
+ * :167-169), so the loop of :127 runs over buffer_size previous frames.  Masks == 1, float32 accumulator. */
 enum { VP_TEMPORAL_NONE = 0, VP_TEMPORAL_MAIN_BLEND = 1, VP_TEMPORAL_BLEND_FRAMES = 2 };
 typedef struct vp_temporal_config {
     int32_t mode;
-    int32_t buffer_size;       /* TemporalConsistency::Config::buffer_size (2 or 3)              */
+    int32_t buffer_size;       /* TemporalConsistency::Config::buffer_size (1..3)                */
     float blend_strength;      /* TemporalConsistency::Config::blend_strength                    */
     float main_weight;         /* current-frame weight of the main.cpp blend (0.6 / 0.7)         */
     int32_t scene_detect;      /* VP_TEMPORAL_BLEND_FRAMES only: TemporalConsistency::detectSceneChange
@@ -217,7 +219,7 @@ int vp_add_weighted(vp_ctx* ctx, const uint8_t* d_a, size_t a_pitch, double alph
                     const uint8_t* d_b, size_t b_pitch, double beta,
                     uint8_t* d_dst, size_t dst_pitch, int w, int h, void* stream);
 /* TemporalConsistency::blendFrames (src/temporal_consistency.cpp:355-444): frames[0] = current,
- * frames[i] = i-th previous; nframes in 1..3; all frames share `pitch`. */
+ * frames[i] = i-th previous; nframes in 1..4; all frames share `pitch`. */
 int vp_temporal_blend(vp_ctx* ctx, const uint8_t* const* d_frames, int nframes, size_t pitch,
                       float blend_strength, uint8_t* d_dst, size_t dst_pitch, int w, int h, void* stream);
 

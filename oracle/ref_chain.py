@@ -545,8 +545,10 @@ def detect_scene_change(ops, prev_gray, cur_gray, threshold):
 class TemporalBlendState:
     """TemporalConsistency::process buffer policy (temporal_consistency.cpp:61-172) with the
     flow/warp front end out of scope: first frame passes through; afterwards the current frame is
-    blended with the up-to (buffer_size-1) most recent *unblended* inputs (m_flow_buffer holds
-    < buffer_size flows, :167-169); the unblended input is what is stored (:158).  With
+    blended with EVERY buffered *unblended* input - up to buffer_size of them: m_frame_buffer keeps the
+    last buffer_size inputs (:162-165) and m_flow_buffer, trimmed to buffer_size-1 only after the blend
+    (:167-169), holds buffer_size flows once the new one is pushed (:97), so the loop bound of :127 is
+    min(frames, flows) = len(frames); the unblended input is what is stored (:158).  With
     cfg.scene_detect a detected cut clears the buffers and passes the frame through (:100-112)."""
 
     def __init__(self, cfg=None, ops=None):
@@ -566,7 +568,7 @@ class TemporalBlendState:
             if detect_scene_change(ops, ops.bgr2gray(self.frames[-1]), ops.bgr2gray(cur), self.cfg.scene_change_threshold):
                 self.frames = [cur.copy()]
                 return cur.copy()
-        nprev = min(len(self.frames), self.cfg.buffer_size - 1)
+        nprev = min(len(self.frames), self.cfg.buffer_size)
         fr = [cur] + [self.frames[-1 - i] for i in range(nprev)]
         out = blend_frames(fr, self.cfg.blend_strength) if len(fr) > 1 else cur.copy()
         self.frames.append(cur.copy())

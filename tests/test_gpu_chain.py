@@ -122,7 +122,7 @@ def test_chain_stage_toggles(vp):
                 assert mx == 0   # bicubic + addWeighted only: bit-exact
 
 
-@pytest.mark.parametrize("temporal,warm", [(RC.TEMPORAL_MAIN_BLEND, 1), (RC.TEMPORAL_BLEND_FRAMES, 2)])
+@pytest.mark.parametrize("temporal,warm", [(RC.TEMPORAL_MAIN_BLEND, 1), (RC.TEMPORAL_BLEND_FRAMES, 3)])
 def test_segment_sharding_is_bit_identical(vp, temporal, warm):
     """file/--fast mode partitioning (DESIGN.md multi-GPU): a segment started with `warm` warm-up frames
     (d_dst = NULL) reproduces the single-context outputs exactly."""

@@ -168,7 +168,7 @@ def test_add_weighted_all_pairs(vp, ctx):
     assert np.array_equal(dst.cpu().numpy(), R.add_weighted_u8(a3, 0.6, b3, 0.4))
 
 
-@pytest.mark.parametrize("nframes", [1, 2, 3])
+@pytest.mark.parametrize("nframes", [1, 2, 3, 4])
 def test_temporal_blend(vp, ctx, nframes):
     w, h = 176, 50
     frames = [synth.frame("noise", w, h, t) for t in range(nframes)]

@@ -142,7 +142,7 @@ def test_segments_cover_clip():
             assert segs[0][0] == 0 and segs[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(segs, segs[1:]))
     assert S.plan(300, 8, 0, "frames", 3) == (0, 0, 0, 37)
-    assert S.plan(300, 8, 3, "frames", 3) == (110, 2, 112, 150)
+    assert S.plan(300, 8, 3, "frames", 3) == (109, 3, 112, 150)     # every buffered frame is blended: buffer_size warm-up frames
     assert S.plan(300, 8, 3, "main") == (111, 1, 112, 150)
     assert S.plan(4, 4, 1, "frames", 3) == (0, 1, 1, 2)      # warm-up clipped at the start of the clip
 

@@ -33,13 +33,13 @@ struct BilCand {                   // one (d, sigma) parameter set, device memor
 
 struct BlendArgs {
     int mode;                      // VP_TEMPORAL_*
-    int nprev;                     // previous frames available (0 = pass-through)
-    const uint8_t* prev[2];        // prev[0] = t-1, prev[1] = t-2 (unblended states)
+    int nprev;                     // previous frames available (0 = pass-through), at most 3
+    const uint8_t* prev[3];        // prev[0] = t-1, prev[1] = t-2, prev[2] = t-3 (unblended states)
     size_t ppitch;
     uint8_t* state;                // where the unblended current frame is stored (may be null)
     size_t spitch;
-    float w[3];                    // main blend: w[0]=alpha, w[1]=beta; blend_frames: per-frame weights
-    float inv_wsum;                // blend_frames: 1.f / (w0+w1(+w2)) as accumulated in float32
+    float w[4];                    // main blend: w[0]=alpha, w[1]=beta; blend_frames: per-frame weights
+    float inv_wsum;                // blend_frames: 1.f / (w0+w1(+w2(+w3))) as accumulated in float32
 };
 
 struct BilArgs {
@@ -70,18 +70,19 @@ __device__ __forceinline__ uint32_t f2u8(float v) {
     return r;
 }
 
-__device__ __forceinline__ uint32_t blend_byte(const BlendArgs& b, float cur, float p0, float p1) {
+__device__ __forceinline__ uint32_t blend_byte(const BlendArgs& b, float cur, float p0, float p1, float p2) {
     if (b.mode == 1)               // cv::addWeighted AVX2 form: fma(cur, alpha, prev*beta)
         return f2u8(__fmaf_rn(cur, b.w[0], __fmul_rn(p0, b.w[1])));
     float acc = __fmul_rn(b.w[0], cur);
     acc = __fadd_rn(acc, __fmul_rn(b.w[1], p0));
     if (b.nprev > 1) acc = __fadd_rn(acc, __fmul_rn(b.w[2], p1));
+    if (b.nprev > 2) acc = __fadd_rn(acc, __fmul_rn(b.w[3], p2));
     return f2u8(__fmul_rn(acc, b.inv_wsum));
 }
-__device__ __forceinline__ uint32_t blend_word(const BlendArgs& b, uint32_t cur, uint32_t p0, uint32_t p1) {
+__device__ __forceinline__ uint32_t blend_word(const BlendArgs& b, uint32_t cur, uint32_t p0, uint32_t p1, uint32_t p2) {
     uint32_t r = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) r |= blend_byte(b, u8f(cur, k), u8f(p0, k), u8f(p1, k)) << (8 * k);
+    for (int k = 0; k < 4; ++k) r |= blend_byte(b, u8f(cur, k), u8f(p0, k), u8f(p1, k), u8f(p2, k)) << (8 * k);
     return r;
 }
 
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
         const int gy = y0 + ly;
         if (gy >= a.h) break;
         // previous frames of the temporal blend: issue the loads before the tap loop hides their latency
-        uint32_t p0[3] = {0, 0, 0}, p1[3] = {0, 0, 0};
+        uint32_t p0[3] = {0, 0, 0}, p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0};
         if (doblend || scene_prev) {
             load12(b.prev[0] + (size_t)gy * b.ppitch + boff, p0, npx);
             if (doblend && b.nprev > 1) load12(b.prev[1] + (size_t)gy * b.ppitch + boff, p1, npx);
@@ -426,9 +427,11 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
         if (!a.dst) continue;
         uint8_t* dp = a.dst + (size_t)gy * a.dpitch + boff;
         if (doblend) {
+            // the third previous frame is fetched late: holding 9 prefetched words across the tap loop spills
+            if (b.nprev > 2) load12(b.prev[2] + (size_t)gy * b.ppitch + boff, p2, npx);
             uint32_t o[3];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) o[q] = blend_word(b, cur[q], p0[q], b.nprev > 1 ? p1[q] : p0[q]);
+            for (int q = 0; q < 3; ++q) o[q] = blend_word(b, cur[q], p0[q], p1[q], p2[q]);
             store12(dp, o, npx);
         } else {
             store12(dp, cur, npx);

@@ -16,7 +16,7 @@ struct BlendKArgs {
     // scene detection: k_scene_decide's verdict caps the number of previous frames (0 = pass-through);
     // inv_wsum_n[n-1] is 1/(w0+..+wn) for n previous frames.  Null = use blend.nprev as given.
     const int* use_dev;
-    float inv_wsum_n[2];
+    float inv_wsum_n[3];
 };
 
 __global__ void __launch_bounds__(256) k_blend(const BlendKArgs a) {
@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256) k_blend(const BlendKArgs a) {
     if (doblend) {
         al = al && aligned16(b.prev[0], b.ppitch);
         if (b.nprev > 1) al = al && aligned16(b.prev[1], b.ppitch);
+        if (b.nprev > 2) al = al && aligned16(b.prev[2], b.ppitch);
     }
     const int nv = al ? a.row_bytes >> 4 : 0;
     const long long nvec = (long long)nv * a.h;
@@ -45,9 +46,10 @@ __global__ void __launch_bounds__(256) k_blend(const BlendKArgs a) {
         if (doblend) {
             const uint4 p0 = *reinterpret_cast<const uint4*>(b.prev[0] + (size_t)y * b.ppitch + off);
             const uint4 p1 = b.nprev > 1 ? *reinterpret_cast<const uint4*>(b.prev[1] + (size_t)y * b.ppitch + off) : p0;
+            const uint4 p2 = b.nprev > 2 ? *reinterpret_cast<const uint4*>(b.prev[2] + (size_t)y * b.ppitch + off) : p0;
             uint32_t r[4];
-            r[0] = blend_word(b, c.x, p0.x, p1.x); r[1] = blend_word(b, c.y, p0.y, p1.y);
-            r[2] = blend_word(b, c.z, p0.z, p1.z); r[3] = blend_word(b, c.w, p0.w, p1.w);
+            r[0] = blend_word(b, c.x, p0.x, p1.x, p2.x); r[1] = blend_word(b, c.y, p0.y, p1.y, p2.y);
+            r[2] = blend_word(b, c.z, p0.z, p1.z, p2.z); r[3] = blend_word(b, c.w, p0.w, p1.w, p2.w);
             o = make_uint4(r[0], r[1], r[2], r[3]);
         }
         *reinterpret_cast<uint4*>(a.dst + (size_t)y * a.dpitch + off) = o;
@@ -65,7 +67,8 @@ __global__ void __launch_bounds__(256) k_blend(const BlendKArgs a) {
         if (doblend) {
             const int p0 = b.prev[0][(size_t)y * b.ppitch + off];
             const int p1 = b.nprev > 1 ? b.prev[1][(size_t)y * b.ppitch + off] : p0;
-            o = (int)blend_byte(b, (float)c, (float)p0, (float)p1);
+            const int p2 = b.nprev > 2 ? b.prev[2][(size_t)y * b.ppitch + off] : p0;
+            o = (int)blend_byte(b, (float)c, (float)p0, (float)p1, (float)p2);
         }
         a.dst[(size_t)y * a.dpitch + off] = (uint8_t)o;
     }

@@ -61,7 +61,7 @@ __global__ void k_scene_decide(SceneAccum* __restrict__ acc, SceneState* __restr
             const double mad = (double)acc->mad / npx;
             const double combined = (1.0 - corr) * 100.0 + mad * 0.5;
             if (combined > (double)threshold) nframes = 0;          // cut: history cleared, frame passes through
-            else use = min(nframes, buffer_size - 1);
+            else use = min(nframes, buffer_size);                   // every buffered frame has a flow slot (:127, :167-169)
         }
         st->nframes = min(nframes + 1, buffer_size);
         acc->mad = 0ull;

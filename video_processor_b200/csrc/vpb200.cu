@@ -111,7 +111,7 @@ struct vp_ctx {
     // chain buffers
     size_t pre_pitch = 0;
     size_t frame_pitch = 0;                                 // pitch of dst-sized intermediates / states
-    uint8_t* d_state[3] = {nullptr, nullptr, nullptr};
+    uint8_t* d_state[4] = {nullptr, nullptr, nullptr, nullptr};
     int nring = 0, head = 0, nvalid = 0;                    // temporal ring
     BilCand* d_cand_pre = nullptr; BilCand* d_cand_post = nullptr; BilCand* d_cand_tmp = nullptr;
     int cand_pre_rad[3] = {0, 0, 0}, cand_post_rad[3] = {0, 0, 0};
@@ -559,11 +559,11 @@ void blend_weights(const vp_temporal_config& t, int nprev, BlendArgs& b) {
     if (t.mode == VP_TEMPORAL_MAIN_BLEND) {
         volatile float cw = t.main_weight;
         volatile float pw = 1.0f - cw;
-        b.w[0] = cw; b.w[1] = pw; b.w[2] = 0.f; b.inv_wsum = 1.f;
+        b.w[0] = cw; b.w[1] = pw; b.w[2] = 0.f; b.w[3] = 0.f; b.inv_wsum = 1.f;
     } else {
         // frame_weights[i] = std::exp(-(float)i / 2.0f) (float overload, correctly rounded here through double)
         volatile float wsum = 0.f;
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < 4; ++i) {
             volatile float arg = -(float)i / 2.0f;
             volatile float fw = (float)std::exp((double)arg);
             volatile float bf = i == 0 ? 1.0f : t.blend_strength;
@@ -722,7 +722,7 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
     }
     VP_CUDA(c, cudaMalloc(&c->lanes[0].d_sharp, c->frame_pitch * g.dst_h));
     c->nring = g.temporal.mode == VP_TEMPORAL_MAIN_BLEND ? 2
-             : g.temporal.mode == VP_TEMPORAL_BLEND_FRAMES ? std::max(1, g.temporal.buffer_size) : 0;
+             : g.temporal.mode == VP_TEMPORAL_BLEND_FRAMES ? std::max(1, g.temporal.buffer_size) + 1 : 0;
     for (int i = 0; i < c->nring; ++i) VP_CUDA(c, cudaMalloc(&c->d_state[i], c->frame_pitch * g.dst_h));
     if (g.dst_w != g.src_w || g.dst_h != g.src_h) {
         int rc = ensure_resize(c, c->rc_chain, g.src_w, g.src_h, g.dst_w, g.dst_h, c->s_compute);
@@ -831,12 +831,14 @@ int vp_reset_temporal(vp_ctx* c) {
 static void temporal_args(vp_ctx* c, bool temporal, BlendArgs& bl) {
     const vp_chain_config& g = c->cfg;
     if (!temporal) return;
-    const int maxprev = g.temporal.mode == VP_TEMPORAL_MAIN_BLEND ? 1 : g.temporal.buffer_size - 1;
+    // TemporalConsistency::process blends the current frame with EVERY buffered frame: m_frame_buffer holds the last
+    // buffer_size inputs (:162-165) and m_flow_buffer is trimmed to buffer_size-1 only after the blend (:167-169), so with
+    // the flow pushed at :97 the loop bound min(flows, frames) of :127 reaches buffer_size
+    const int maxprev = g.temporal.mode == VP_TEMPORAL_MAIN_BLEND ? 1 : g.temporal.buffer_size;
     const int nprev = std::min(c->nvalid, maxprev);
     blend_weights(g.temporal, nprev, bl);
     for (int i = 0; i < nprev; ++i) bl.prev[i] = c->d_state[(c->head - 1 - i + 2 * c->nring) % c->nring];
     bl.ppitch = c->frame_pitch;
-    // with a single ring slot (buffer_size 1) nothing is ever blended and no state is kept
     bl.state = c->nring > 1 ? c->d_state[c->head] : nullptr;
     bl.spitch = c->frame_pitch;
 }
@@ -1032,7 +1034,7 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
             a.blend = bl;
             if (plain_post) a.blend.state = nullptr;      // POST already stored the unblended frame
             a.use_dev = c->d_use;
-            for (int n = 1; n <= 2; ++n) { BlendArgs t{}; blend_weights(g.temporal, n, t); a.inv_wsum_n[n - 1] = t.inv_wsum; }
+            for (int n = 1; n <= 3; ++n) { BlendArgs t{}; blend_weights(g.temporal, n, t); a.inv_wsum_n[n - 1] = t.inv_wsum; }
             rc = launch_blend(c, a, st); if (rc) return rc;
         }
     } else
@@ -1413,7 +1415,7 @@ int vp_add_weighted(vp_ctx* c, const uint8_t* d_a, size_t a_pitch, double alpha,
 int vp_temporal_blend(vp_ctx* c, const uint8_t* const* d_frames, int nframes, size_t pitch, float blend_strength,
                       uint8_t* d_dst, size_t dst_pitch, int w, int h, void* stream) {
     if (!c || !d_frames) return VP_ERR_INVALID_ARG;
-    if (nframes < 1 || nframes > 3) return fail(c, VP_ERR_UNSUPPORTED, "vp_temporal_blend: 1..3 frames");
+    if (nframes < 1 || nframes > 4) return fail(c, VP_ERR_UNSUPPORTED, "vp_temporal_blend: 1..4 frames");
     int rc = VP_OK;
     for (int i = 0; i < nframes; ++i) { rc = check_frame(c, d_frames[i], pitch, w, h, "vp_temporal_blend(frame)"); if (rc) return rc; }
     rc = check_frame(c, d_dst, dst_pitch, w, h, "vp_temporal_blend(dst)"); if (rc) return rc;

@@ -1,7 +1,8 @@
 """File / --fast mode frame partitioning across GPUs (multi-GPU): contiguous segments, each
 preceded by the temporal warm-up frames its first output depends on.  No collective is involved: the
 temporal stage only looks back `warmup` unblended frames (src/main.cpp:277: 1 frame;
-TemporalConsistency with buffer_size b: b-1 frames, src/temporal_consistency.cpp:127,167-169)."""
+TemporalConsistency with buffer_size b: b frames - every buffered frame is blended,
+src/temporal_consistency.cpp:127 with :97, :162-169)."""
 
 
 def segment(n_frames, world, rank):
@@ -15,7 +16,7 @@ def warmup_frames(temporal_mode, buffer_size=3):
         return 0
     if temporal_mode in (1, "main"):
         return 1
-    return max(int(buffer_size) - 1, 0)
+    return max(int(buffer_size), 0)
 
 
 def plan(n_frames, world, rank, temporal_mode, buffer_size=3):
