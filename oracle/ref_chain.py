@@ -21,9 +21,9 @@ Appendix B) -- each is an oracle decision, stated here once:
   * AdaptiveSharpening: only adaptive_sigma=false is in scope; calculateTextureMap has the same
     defect (adaptive_sharpening.cpp:386).
   * TemporalConsistency::blendFrames writes Vec3f into a CV_8UC3 Mat (temporal_consistency.cpp:367
-    vs :408); the oracle uses the evidently intended float32 accumulator.  Optical flow / warp /
-    scene-change / reliability masks are out of scope: previous frames enter the blend unwarped
-    with mask == 1.
+    vs :408); the oracle uses the evidently intended float32 accumulator.  The north-star blend takes
+    previous frames unwarped with mask == 1 (TemporalBlendState); the motion-compensated front end
+    (Farneback flow, remap warp, reliability masks) is TemporalConsistencyFull.
 Parity status: the reference has no golden vectors and cannot be compiled here, so this glue is
 "parity unpinned" against a reference binary; the arithmetic underneath is pinned against real
 OpenCV (tests/test_oracle_restate.py) and frozen in tests/golden/.
@@ -74,15 +74,25 @@ class SharpenConfig:  # include/adaptive_sharpening.h:14-24
 
 
 @dataclass
-class TemporalConfig:  # include/temporal_consistency.h:18-33 (flow parameters unused: out of scope)
+class TemporalConfig:  # include/temporal_consistency.h:18-33
     buffer_size: int = 3
     blend_strength: float = 0.6
     motion_threshold: float = 15.0
     scene_change_threshold: float = 100.0
     use_gpu: bool = True
-    # oracle switch (not a reference field): run detectSceneChange (temporal_consistency.cpp:283-323) and
-    # reset the buffers on a cut (:100-105); off reproduces the blend alone
+    pyr_scale: float = 0.5
+    levels: int = 3
+    winsize: int = 15
+    iterations: int = 3
+    poly_n: int = 5
+    poly_sigma: float = 1.2
+    flags: int = 0
+    # oracle switches (not reference fields).  scene_detect: run detectSceneChange (temporal_consistency.cpp:283-323) and
+    # reset the buffers on a cut (:100-105); off reproduces the blend alone.  use_flow: the motion-compensated front end
+    # (Farneback flow, remap warp, reliability masks, :94-150) - TemporalConsistencyFull below; off = the north-star blend
+    # of unwarped frames with unit masks (TemporalBlendState).
     scene_detect: bool = False
+    use_flow: bool = False
 
 
 # ------------------------------------------------------------------------------------------------
@@ -154,6 +164,13 @@ class NumpyOps:
 
     def add_weighted_f32(self, a, alpha, b, beta):
         return (a.astype(np.float64) * alpha + b.astype(np.float64) * beta).astype(F32)
+
+    def farneback(self, prev_gray, cur_gray, t):
+        return R.farneback(prev_gray, cur_gray, t.pyr_scale, t.levels, t.winsize, t.iterations, t.poly_n, t.poly_sigma)
+
+    def remap_flow(self, frame, flow):
+        mx, my = R.flow_to_maps(flow)
+        return R.remap_linear_replicate_u8(frame, mx, my)
 
 
 class Cv2Ops:
@@ -234,6 +251,14 @@ class Cv2Ops:
 
     def add_weighted_f32(self, a, alpha, b, beta):
         return self.cv2.addWeighted(a, alpha, b, beta, 0)
+
+    def farneback(self, prev_gray, cur_gray, t):
+        return self.cv2.calcOpticalFlowFarneback(prev_gray, cur_gray, None, t.pyr_scale, t.levels, t.winsize, t.iterations,
+                                                 t.poly_n, t.poly_sigma, t.flags)
+
+    def remap_flow(self, frame, flow):
+        mx, my = R.flow_to_maps(flow)
+        return self.cv2.remap(frame, mx, my, self.cv2.INTER_LINEAR, borderMode=self.cv2.BORDER_REPLICATE)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -577,6 +602,52 @@ class TemporalBlendState:
         return out
 
 
+def flow_reliability_mask(ops, flow, motion_threshold):
+    """TemporalConsistency::calculateFlowReliabilityMask, temporal_consistency.cpp:325-353."""
+    return ops.gaussian_f32(R.flow_reliability_raw(flow, motion_threshold), 15, 5.0)   # :347
+
+
+class TemporalConsistencyFull:
+    """TemporalConsistency::process exactly as written, temporal_consistency.cpp:61-172 (CPU branches): gray buffer,
+    scene-change reset, Farneback flow prev->cur, every buffered frame warped with ITS OWN stored flow (frame t-1-i
+    with the flow computed when frame t-i arrived, :127-131 - not a flow composed up to the current frame) and weighted
+    by that flow's reliability mask, blendFrames with the float32 accumulator."""
+
+    def __init__(self, cfg=None, ops=None):
+        self.cfg = cfg or TemporalConfig()
+        self.ops = ops or NumpyOps()
+        self.reset()
+
+    def reset(self):
+        self.frames, self.grays, self.flows = [], [], []
+
+    def process(self, cur, debug=None):
+        ops, cfg = self.ops, self.cfg
+        gray = ops.bgr2gray(cur)                                           # :74
+        if not self.frames:                                                # :79-86
+            self.frames.append(cur.copy()); self.grays.append(gray)
+            return cur.copy()
+        if detect_scene_change(ops, self.grays[-1], gray, cfg.scene_change_threshold):   # :89-92, :100-112
+            self.frames, self.grays, self.flows = [cur.copy()], [gray], []
+            return cur.copy()
+        flow = ops.farneback(self.grays[-1], gray, cfg)                    # :95-97
+        self.flows.append(flow)
+        frames, masks = [cur], [None]                                      # :121-124 (identity mask)
+        for i in range(min(len(self.flows), len(self.frames))):            # :127
+            fl = self.flows[-1 - i]
+            frames.append(ops.remap_flow(self.frames[-1 - i], fl))         # :133-135
+            masks.append(flow_reliability_mask(ops, fl, cfg.motion_threshold))   # :137-138
+        if debug is not None:
+            debug.update(flow=flow, frames=frames, masks=masks)
+        out = blend_frames(frames, cfg.blend_strength, masks)              # :147-148
+        self.frames.append(cur.copy()); self.grays.append(gray)            # :158-159
+        while len(self.frames) > cfg.buffer_size:                          # :162-165
+            self.frames.pop(0); self.grays.pop(0)
+        while len(self.flows) >= cfg.buffer_size:                          # :167-169
+            self.flows.pop(0)
+        return out
+
+
 class MainBlendState:
     """main.cpp:269-292: history of processed (unblended) frames; from the second frame on
     out = addWeighted(cur, w, prev, 1-w), w = 0.6 (bicubic) / 0.7 (super-res)."""
@@ -634,7 +705,7 @@ class Chain:
         if cfg.temporal == TEMPORAL_MAIN_BLEND:
             self.temporal = MainBlendState(ops, cfg.main_blend_weight)
         elif cfg.temporal == TEMPORAL_BLEND_FRAMES:
-            self.temporal = TemporalBlendState(cfg.temporal_cfg, ops)
+            self.temporal = (TemporalConsistencyFull if cfg.temporal_cfg.use_flow else TemporalBlendState)(cfg.temporal_cfg, ops)
         else:
             self.temporal = None
 

@@ -527,3 +527,232 @@ def detail_sigmoid_f32(detail, detail_threshold):
     thr = float(detail_threshold) / 255.0
     v = np.asarray(detail, dtype=F32).astype(np.float64)
     return (1.0 / (1.0 + np.exp(-(v - thr) * 10.0))).astype(F32)
+
+
+# --------------------------------------------------------------------------------------------
+# TemporalConsistency's motion-compensated front end:
+# cv::calcOpticalFlowFarneback (temporal_consistency.cpp:211-216), cv::remap (:261-273).  The Farneback
+# restatement follows OpenCV's published algorithm (modules/video/src/optflowgf.cpp: FarnebackPrepareGaussian,
+# FarnebackPolyExp, FarnebackUpdateMatrices, FarnebackUpdateFlow_Blur and the pyramid loop of
+# FarnebackOpticalFlowImpl::calc) including its float / double mix; tests pin it against cv2 to 1e-4 px.
+# --------------------------------------------------------------------------------------------
+def cv_round(x):
+    return int(np.rint(x))
+
+def resize_linear_f32(src, dw, dh):
+    """cv::resize(INTER_LINEAR) on CV_32F (any channel count)."""
+    sh, sw = src.shape[:2]
+    def tabs(sn, dn):
+        scale = float(sn) / float(dn)
+        ofs = np.zeros(dn, np.int64); a = np.zeros(dn, F32)
+        for d in range(dn):
+            fx = F32((d + 0.5) * scale - 0.5)
+            sx = int(math.floor(fx)); fx = F32(fx - F32(sx))
+            if sx < 0: fx = F32(0); sx = 0
+            if sx >= sn - 1: fx = F32(0); sx = sn - 1
+            ofs[d] = sx; a[d] = fx
+        return ofs, a
+    xo, xa = tabs(sw, dw); yo, ya = tabs(sh, dh)
+    s = src.astype(F32)
+    x1 = np.minimum(xo + 1, sw - 1)
+    a1 = xa.reshape((1, dw) + (1,) * (s.ndim - 2)); a0 = (F32(1) - a1).astype(F32)
+    h = ((s[:, xo] * a0).astype(F32) + (s[:, x1] * a1).astype(F32)).astype(F32)
+    y1 = np.minimum(yo + 1, sh - 1)
+    b1 = ya.reshape((dh, 1) + (1,) * (s.ndim - 2)); b0 = (F32(1) - b1).astype(F32)
+    return ((h[yo] * b0).astype(F32) + (h[y1] * b1).astype(F32)).astype(F32)
+
+def prepare_gaussian(n, sigma):
+    if sigma < np.finfo(np.float32).eps: sigma = n * 0.3
+    xs = np.arange(-n, n + 1)
+    g = np.exp(-xs * xs / (2 * sigma * sigma)).astype(F32)
+    s = 1.0 / float(g.astype(np.float64).sum())
+    g = (g.astype(np.float64) * s).astype(F32)
+    xg = (xs.astype(F32) * g).astype(F32)
+    xxg = ((xs * xs).astype(F32) * g).astype(F32)
+    G = np.zeros((6, 6))
+    for y in range(-n, n + 1):
+        for x in range(-n, n + 1):
+            w = float(F32(g[y + n] * g[x + n]))     # float*float in float
+            G[0, 0] += w; G[1, 1] += w * x * x; G[3, 3] += w * x * x * x * x; G[5, 5] += w * x * x * y * y
+    G[2, 2] = G[0, 3] = G[0, 4] = G[3, 0] = G[4, 0] = G[1, 1]
+    G[4, 4] = G[3, 3]; G[3, 4] = G[4, 3] = G[5, 5]
+    inv = np.linalg.inv(G)
+    return g, xg, xxg, inv[1, 1], inv[0, 3], inv[3, 3], inv[5, 5]
+
+def poly_exp(src, n, sigma):
+    h, w = src.shape
+    g, xg, xxg, ig11, ig03, ig33, ig55 = prepare_gaussian(n, sigma)
+    c = n  # centre index
+    s = src.astype(F32)
+    ys = np.arange(h)
+    row0 = (s * g[c]).astype(F32); row1 = np.zeros_like(s); row2 = np.zeros_like(s)
+    for k in range(1, n + 1):
+        a = s[np.maximum(ys - k, 0)]; b = s[np.minimum(ys + k, h - 1)]
+        p = (a + b).astype(F32)
+        row0 = (row0 + (g[c + k] * p).astype(F32)).astype(F32)
+        row1 = (row1 + (xg[c + k] * (b - a).astype(F32)).astype(F32)).astype(F32)
+        row2 = (row2 + (xxg[c + k] * p).astype(F32)).astype(F32)
+    xs = np.arange(w)
+    def at(r, k):
+        return r[:, np.clip(xs + k, 0, w - 1)]
+    b1 = (row0 * g[c]).astype(F32).astype(np.float64); b3 = (row1 * g[c]).astype(F32).astype(np.float64); b5 = (row2 * g[c]).astype(F32).astype(np.float64)
+    b2 = np.zeros((h, w)); b4 = np.zeros((h, w)); b6 = np.zeros((h, w))
+    for k in range(1, n + 1):
+        tg = (at(row0, k) + at(row0, -k)).astype(F32).astype(np.float64)
+        g0 = float(g[c + k])
+        b1 += tg * g0; b4 += tg * float(xxg[c + k])
+        b2 += ((at(row0, k) - at(row0, -k)).astype(F32) * xg[c + k]).astype(F32).astype(np.float64)
+        b3 += ((at(row1, k) + at(row1, -k)).astype(F32) * g[c + k]).astype(F32).astype(np.float64)
+        b6 += ((at(row1, k) - at(row1, -k)).astype(F32) * xg[c + k]).astype(F32).astype(np.float64)
+        b5 += ((at(row2, k) + at(row2, -k)).astype(F32) * g[c + k]).astype(F32).astype(np.float64)
+    out = np.empty((h, w, 5), F32)
+    out[..., 1] = (b2 * ig11).astype(F32); out[..., 0] = (b3 * ig11).astype(F32)
+    out[..., 3] = (b1 * ig03 + b4 * ig33).astype(F32); out[..., 2] = (b1 * ig03 + b5 * ig33).astype(F32)
+    out[..., 4] = (b6 * ig55).astype(F32)
+    return out
+
+BORDER = np.array([0.14, 0.14, 0.4472, 0.4472, 0.4472], F32)
+
+def update_matrices(R0, R1, flow):
+    h, w = flow.shape[:2]
+    xs = np.arange(w, dtype=F32)[None, :]; ys = np.arange(h, dtype=F32)[:, None]
+    dx = flow[..., 0]; dy = flow[..., 1]
+    fx = (xs + dx).astype(F32); fy = (ys + dy).astype(F32)
+    x1 = np.floor(fx).astype(np.int64); y1 = np.floor(fy).astype(np.int64)
+    fx = (fx - x1.astype(F32)).astype(F32); fy = (fy - y1.astype(F32)).astype(F32)
+    inside = (x1 >= 0) & (x1 < w - 1) & (y1 >= 0) & (y1 < h - 1)
+    xc = np.clip(x1, 0, w - 2); yc = np.clip(y1, 0, h - 2)
+    a00 = ((F32(1) - fx) * (F32(1) - fy)).astype(F32); a01 = (fx * (F32(1) - fy)).astype(F32)
+    a10 = ((F32(1) - fx) * fy).astype(F32); a11 = (fx * fy).astype(F32)
+    def interp(c):
+        p = R1[..., c]
+        v = (a00 * p[yc, xc]).astype(F32)
+        v = (v + (a01 * p[yc, xc + 1]).astype(F32)).astype(F32)
+        v = (v + (a10 * p[yc + 1, xc]).astype(F32)).astype(F32)
+        v = (v + (a11 * p[yc + 1, xc + 1]).astype(F32)).astype(F32)
+        return v
+    r2 = interp(0); r3 = interp(1); r4 = interp(2); r5 = interp(3); r6 = interp(4)
+    r4 = ((R0[..., 2] + r4).astype(F32) * F32(0.5)).astype(F32)
+    r5 = ((R0[..., 3] + r5).astype(F32) * F32(0.5)).astype(F32)
+    r6 = ((R0[..., 4] + r6).astype(F32) * F32(0.25)).astype(F32)
+    r2 = np.where(inside, r2, F32(0)); r3 = np.where(inside, r3, F32(0))
+    r4 = np.where(inside, r4, R0[..., 2]); r5 = np.where(inside, r5, R0[..., 3])
+    r6 = np.where(inside, r6, (R0[..., 4] * F32(0.5)).astype(F32))
+    r2 = ((R0[..., 0] - r2).astype(F32) * F32(0.5)).astype(F32)
+    r3 = ((R0[..., 1] - r3).astype(F32) * F32(0.5)).astype(F32)
+    r2 = (r2 + ((r4 * dy).astype(F32) + (r6 * dx).astype(F32)).astype(F32)).astype(F32)
+    r3 = (r3 + ((r6 * dy).astype(F32) + (r5 * dx).astype(F32)).astype(F32)).astype(F32)
+    # :BORDER scale factors of the five outermost rows / columns
+    sx = np.ones(w, F32); sy = np.ones(h, F32)
+    for k in range(5):
+        if k < w: sx[k] = BORDER[k]
+    sxr = np.ones(w, F32)
+    for k in range(5):
+        if w - 1 - k >= 0: sxr[w - 1 - k] = BORDER[k]
+    for k in range(5):
+        if k < h: sy[k] = BORDER[k]
+    syr = np.ones(h, F32)
+    for k in range(5):
+        if h - 1 - k >= 0: syr[h - 1 - k] = BORDER[k]
+    scale = (((sx * sxr).astype(F32)[None, :] * sy[:, None]).astype(F32) * syr[:, None]).astype(F32)
+    r2 = (r2 * scale).astype(F32); r3 = (r3 * scale).astype(F32); r4 = (r4 * scale).astype(F32); r5 = (r5 * scale).astype(F32); r6 = (r6 * scale).astype(F32)
+    M = np.empty((h, w, 5), F32)
+    M[..., 0] = ((r4 * r4).astype(F32) + (r6 * r6).astype(F32)).astype(F32)
+    M[..., 1] = ((r4 + r5).astype(F32) * r6).astype(F32)
+    M[..., 2] = ((r5 * r5).astype(F32) + (r6 * r6).astype(F32)).astype(F32)
+    M[..., 3] = ((r4 * r2).astype(F32) + (r6 * r3).astype(F32)).astype(F32)
+    M[..., 4] = ((r6 * r2).astype(F32) + (r5 * r3).astype(F32)).astype(F32)
+    return M
+
+def update_flow_blur(M, block):
+    h, w = M.shape[:2]
+    m = block // 2
+    ys = np.arange(h); xs = np.arange(w)
+    Md = M.astype(np.float64)
+    v = np.zeros((h, w, 5))
+    for k in range(-m, m + 1):
+        v += Md[np.clip(ys + k, 0, h - 1)]
+    s = np.zeros((h, w, 5))
+    for k in range(-m, m + 1):
+        s += v[:, np.clip(xs + k, 0, w - 1)]
+    s *= 1.0 / (block * block)
+    g11, g12, g22, h1, h2 = [s[..., i] for i in range(5)]
+    idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3)
+    flow = np.empty((h, w, 2), F32)
+    flow[..., 0] = ((g11 * h2 - g12 * h1) * idet).astype(F32)
+    flow[..., 1] = ((g22 * h1 - g12 * h2) * idet).astype(F32)
+    return flow
+
+def farneback(prev, nxt, pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2):
+    h0, w0 = prev.shape
+    min_size = 32
+    k = 0; scale = 1.0
+    while k < levels:
+        scale *= pyr_scale
+        if w0 * scale < min_size or h0 * scale < min_size: break
+        k += 1
+    levels = k
+    prev_flow = None
+    for k in range(levels, -1, -1):
+        scale = 1.0
+        for i in range(k): scale *= pyr_scale
+        sigma = (1.0 / scale - 1) * 0.5
+        smooth_sz = cv_round(sigma * 5) | 1
+        smooth_sz = max(smooth_sz, 3)
+        width = cv_round(w0 * scale); height = cv_round(h0 * scale)
+        if prev_flow is None:
+            flow = np.zeros((height, width, 2), F32)
+        else:
+            flow = (resize_linear_f32(prev_flow, width, height) * F32(1.0 / pyr_scale)).astype(F32)
+        Rs = []
+        for img in (prev, nxt):
+            f = img.astype(F32)
+            f = gaussian_blur_f32(f, smooth_sz, sigma)
+            I = resize_linear_f32(f, width, height)
+            Rs.append(poly_exp(I, poly_n, poly_sigma))
+        M = update_matrices(Rs[0], Rs[1], flow)
+        for i in range(iterations):
+            flow = update_flow_blur(M, winsize)
+            if i < iterations - 1:
+                M = update_matrices(Rs[0], Rs[1], flow)
+        prev_flow = flow
+    return flow
+
+
+def remap_linear_replicate_u8(img, map_x, map_y):
+    """cv::remap(img8U, out, map_x, map_y, INTER_LINEAR, BORDER_REPLICATE) (temporal_consistency.cpp:273): the maps are
+    rounded to 1/32 pixel (cvRound(v * 32)), the four taps are clamped into the image, integer weights
+    32 * (32-fx) * (32-fy) ... summing to 2^15, dst = (sum + 2^14) >> 15.  Bit-exact against cv2."""
+    h, w = img.shape[:2]
+    sx = np.rint((np.asarray(map_x, F32) * F32(32)).astype(F32)).astype(np.int64)
+    sy = np.rint((np.asarray(map_y, F32) * F32(32)).astype(F32)).astype(np.int64)
+    fx, fy = sx & 31, sy & 31
+    ix, iy = np.clip(sx >> 5, -32768, 32767), np.clip(sy >> 5, -32768, 32767)
+    x0, x1 = np.clip(ix, 0, w - 1), np.clip(ix + 1, 0, w - 1)
+    y0, y1 = np.clip(iy, 0, h - 1), np.clip(iy + 1, 0, h - 1)
+    w00 = (32 * (32 - fx) * (32 - fy))[..., None]
+    w01 = (32 * fx * (32 - fy))[..., None]
+    w10 = (32 * (32 - fx) * fy)[..., None]
+    w11 = (32 * fx * fy)[..., None]
+    p = img.astype(np.int64)
+    v = p[y0, x0] * w00 + p[y0, x1] * w01 + p[y1, x0] * w10 + p[y1, x1] * w11
+    return np.clip((v + (1 << 14)) >> 15, 0, 255).astype(np.uint8)
+
+
+def flow_to_maps(flow):
+    """temporal_consistency.cpp:262-270: map_x = x + f[0], map_y = y + f[1] in float32."""
+    h, w = flow.shape[:2]
+    xs = np.arange(w, dtype=F32)[None, :]
+    ys = np.arange(h, dtype=F32)[:, None]
+    return (xs + flow[..., 0]).astype(F32), (ys + flow[..., 1]).astype(F32)
+
+
+def flow_reliability_raw(flow, motion_threshold):
+    """calculateFlowReliabilityMask before its blur, temporal_consistency.cpp:325-345: float32 magnitude (no FMA),
+    1 where |f| <= threshold, else clamp(expf(-(|f| - thr) / 10.f), 0, 1)."""
+    fx, fy = flow[..., 0].astype(F32), flow[..., 1].astype(F32)
+    mag = np.sqrt(((fx * fx).astype(F32) + (fy * fy).astype(F32)).astype(F32)).astype(F32)
+    thr = F32(motion_threshold)
+    rel = np.exp((-(mag - thr).astype(F32) / F32(10.0)).astype(F32).astype(np.float64)).astype(F32)
+    rel = np.clip(rel, F32(0), F32(1))
+    return np.where(mag > thr, rel, F32(1.0)).astype(F32)
