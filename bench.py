@@ -152,6 +152,7 @@ def traffic_for(kernel):
         return None
 
 
+USE_FLOW = False             # --flow
 ADAPTIVE_SIGMA = False       # --adaptive-sigma: AdaptiveSharpening's variable-sigma branch (repaired semantics)
 BILATERAL_MODE = "plain"     # --bilateral-mode: plain (north-star chain) | selective | multiscale (repaired semantics)
 
@@ -178,6 +179,9 @@ def build_cfg(capi, wl, temporal):
     cfg.temporal.mode = {"none": capi.VP_TEMPORAL_NONE, "main": capi.VP_TEMPORAL_MAIN_BLEND, "frames": capi.VP_TEMPORAL_BLEND_FRAMES}[t]
     apply_bilateral_mode(cfg.pre, cfg.post)
     cfg.sharpen.adaptive_sigma = int(ADAPTIVE_SIGMA)
+    if USE_FLOW:
+        cfg.temporal.use_flow = 1
+        cfg.temporal.scene_detect = 1
     return cfg, t
 
 
@@ -213,6 +217,9 @@ def cpu_chain_fps(wl, temporal, nframes, kind, threads=None):
                           bicubic_enhance=wl in ENHANCE)
     apply_bilateral_mode(ocfg.pre, ocfg.post)
     ocfg.sharpen.adaptive_sigma = bool(ADAPTIVE_SIGMA)
+    if USE_FLOW:
+        ocfg.temporal_cfg.use_flow = True
+        ocfg.temporal_cfg.scene_detect = True
     ops = RC.Cv2Ops(threads=threads or os.cpu_count())
     chain = RC.Chain(ops, ocfg)
     frames = synth.clip(kind, sw, sh, nframes, SEED)
@@ -239,6 +246,9 @@ def run_reference(args, rank):
                           bicubic_enhance=wl in ENHANCE)
     apply_bilateral_mode(ocfg.pre, ocfg.post)
     ocfg.sharpen.adaptive_sigma = bool(ADAPTIVE_SIGMA)
+    if USE_FLOW:
+        ocfg.temporal_cfg.use_flow = True
+        ocfg.temporal_cfg.scene_detect = True
     chain = RC.Chain(RC.Cv2Ops(threads=os.cpu_count()), ocfg)
     frames = synth.clip(args.kind, sw, sh, per_step, SEED)
     for _ in range(args.warmup):
@@ -275,6 +285,8 @@ def workload_name(wl, temporal):
     mode = "" if BILATERAL_MODE == "plain" else f" [SelectiveBilateral {BILATERAL_MODE} branch, repaired semantics]"
     if ADAPTIVE_SIGMA:
         mode += " [AdaptiveSharpening adaptive_sigma branch, repaired semantics]"
+    if USE_FLOW:
+        mode += " [TemporalConsistency with Farneback flow, warp and reliability masks]"
     return f"{wl.upper()}: {sw}x{sh}->{dw}x{dh} BGR8 " + "+".join(stages) + mode
 
 
@@ -299,11 +311,13 @@ def main():
                     help="single-frame latency sample (p50/p99); default 1000 for workload c5, else 0")
     ap.add_argument("--bilateral-mode", default="plain", choices=["plain", "selective", "multiscale"],
                     help="SelectiveBilateral branch of both bilateral stages (default: the north-star plain branch)")
+    ap.add_argument("--flow", action="store_true", help="TemporalConsistency's Farneback / warp / reliability-mask front end (SURVEY 8(f)3)")
     ap.add_argument("--adaptive-sigma", action="store_true", help="AdaptiveSharpening's adaptive_sigma branch (default: the north-star unsharp mask)")
     args = ap.parse_args()
-    global BILATERAL_MODE, ADAPTIVE_SIGMA
+    global BILATERAL_MODE, ADAPTIVE_SIGMA, USE_FLOW
     BILATERAL_MODE = args.bilateral_mode
     ADAPTIVE_SIGMA = args.adaptive_sigma
+    USE_FLOW = args.flow
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VPB200_ABI_VERSION 2
+#define VPB200_ABI_VERSION 3
 
 typedef enum vp_status {
     VP_OK = 0,
@@ -97,6 +97,20 @@ typedef struct vp_temporal_config {
                                   the frame through (:100-112).  Needs a whole-frame reduction before the blend,
                                   so the blend runs as its own kernel instead of in the POST epilogue.          */
     float scene_change_threshold;   /* TemporalConsistency::Config::scene_change_threshold (100)  */
+    /* VP_TEMPORAL_BLEND_FRAMES only: the motion-compensated front end of TemporalConsistency::process
+     * (src/temporal_consistency.cpp:94-150) - Farneback flow prev->cur (:211-216), every buffered frame warped by
+     * cv::remap with its own stored flow (:261-273) and weighted by that flow's reliability mask (:325-353).  Implies
+     * scene_detect.  0 = the north-star blend of unwarped frames with unit masks. */
+    int32_t use_flow;
+    float motion_threshold;    /* Config::motion_threshold (15)                                   */
+    double pyr_scale;          /* Config::pyr_scale (0.5)                                         */
+    double poly_sigma;         /* Config::poly_sigma (1.2)                                        */
+    int32_t levels;            /* Config::levels (3)                                              */
+    int32_t winsize;           /* Config::winsize (15), odd                                       */
+    int32_t iterations;        /* Config::iterations (3)                                          */
+    int32_t poly_n;            /* Config::poly_n (5), <= 7                                        */
+    int32_t flags;             /* Config::flags: only 0 is built (no initial flow, box window)    */
+    int32_t reserved3_;
 } vp_temporal_config;
 
 /* The chain of Upscaler::upscale (src/upscaler.cpp:772-829) with step 2 = cv::resize(INTER_CUBIC)
@@ -214,6 +228,18 @@ int vp_sharpen(vp_ctx* ctx, const vp_sharpen_config* cfg, const uint8_t* d_src, 
  * semantics): the blurred float32 sigma map, pitch in bytes */
 int vp_sigma_map(vp_ctx* ctx, const uint8_t* d_src, size_t src_pitch, float* d_sigma, size_t sigma_pitch,
                  int w, int h, void* stream);
+/* cv::calcOpticalFlowFarneback(gray(prev), gray(cur), flow, ...) as TemporalConsistency::calculateOpticalFlow calls it
+ * (src/temporal_consistency.cpp:211-216), parameters from `cfg` (pyr_scale .. flags).  The flow is returned as two
+ * float32 planes (x and y displacement), pitch in bytes. */
+int vp_optical_flow(vp_ctx* ctx, const vp_temporal_config* cfg, const uint8_t* d_prev, const uint8_t* d_cur, size_t pitch,
+                    float* d_flow_x, float* d_flow_y, size_t flow_pitch, int w, int h, void* stream);
+/* TemporalConsistency::warpFrame (src/temporal_consistency.cpp:261-273): cv::remap(frame, (x, y) + flow, INTER_LINEAR,
+ * BORDER_REPLICATE) */
+int vp_warp_flow(vp_ctx* ctx, const uint8_t* d_src, size_t src_pitch, const float* d_flow_x, const float* d_flow_y,
+                 size_t flow_pitch, uint8_t* d_dst, size_t dst_pitch, int w, int h, void* stream);
+/* TemporalConsistency::calculateFlowReliabilityMask (src/temporal_consistency.cpp:325-353): float32 mask, pitch in bytes */
+int vp_flow_reliability(vp_ctx* ctx, const float* d_flow_x, const float* d_flow_y, size_t flow_pitch, float motion_threshold,
+                        float* d_mask, size_t mask_pitch, int w, int h, void* stream);
 /* cv::addWeighted(a, alpha, b, beta, 0, dst) on CV_8UC3 - src/main.cpp:286-290 */
 int vp_add_weighted(vp_ctx* ctx, const uint8_t* d_a, size_t a_pitch, double alpha,
                     const uint8_t* d_b, size_t b_pitch, double beta,

@@ -71,6 +71,15 @@ def chain_cfg(vp, o, sw, sh):
     c.pre = bilateral_cfg(vp, o.pre)
     c.sharpen = sharpen_cfg(vp, o.sharpen)
     c.post = bilateral_cfg(vp, o.post)
-    c.temporal = vp.TemporalConfig(o.temporal, o.temporal_cfg.buffer_size, o.temporal_cfg.blend_strength, o.main_blend_weight,
-                                   int(getattr(o.temporal_cfg, "scene_detect", False)), o.temporal_cfg.scene_change_threshold)
+    t = o.temporal_cfg
+    c.temporal = vp.TemporalConfig(o.temporal, t.buffer_size, t.blend_strength, o.main_blend_weight,
+                                   int(getattr(t, "scene_detect", False)), t.scene_change_threshold,
+                                   int(getattr(t, "use_flow", False)), t.motion_threshold, t.pyr_scale, t.poly_sigma,
+                                   t.levels, t.winsize, t.iterations, t.poly_n, t.flags, 0)
     return c
+
+
+def temporal_cfg(vp, t):
+    """oracle TemporalConfig -> capi.TemporalConfig (flow parameters for the stage-wise flow entry points)"""
+    return vp.TemporalConfig(vp.VP_TEMPORAL_BLEND_FRAMES, t.buffer_size, t.blend_strength, 0.6, 1, t.scene_change_threshold,
+                             1, t.motion_threshold, t.pyr_scale, t.poly_sigma, t.levels, t.winsize, t.iterations, t.poly_n, t.flags, 0)

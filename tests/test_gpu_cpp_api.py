@@ -39,11 +39,13 @@ def run(driver, tmp_path, mode, frames, tw, th):
 
 def ref_defaults(**kw):
     """Upscaler::initializeEnhancements as the reference writes it (src/upscaler.cpp:666-758): selective and
-    multi-scale on for both bilateral stages, adaptive_sigma on for the sharpening (all with repaired semantics)."""
+    multi-scale on for both bilateral stages, adaptive_sigma on for the sharpening (all with repaired semantics), and
+    TemporalConsistency::process with its Farneback flow / warp / reliability-mask front end."""
     return RC.ChainConfig(
         pre=RC.BilateralConfig(RC.PRE_PROCESSING, True, True, 7, 30.0, 30.0, True, 30.0, 1.5, 2.0, True, 3),
         post=RC.BilateralConfig(RC.POST_PROCESSING, True, True, 5, 20.0, 20.0, True, 30.0, 1.2, 1.5, True, 2),
-        sharpen=RC.SharpenConfig(0.8, 1.2, 0.4, 30.0, 1.5, 5, True, True, True), **kw)
+        sharpen=RC.SharpenConfig(0.8, 1.2, 0.4, 30.0, 1.5, 5, True, True, True),
+        temporal_cfg=RC.TemporalConfig(use_flow=True, scene_detect=True), **kw)
 
 
 def close(o, r):
@@ -55,8 +57,12 @@ def close(o, r):
 def test_upscaler_chain_modes(driver, tmp_path, mode):
     frames = synth.clip("scene", SW, SH, N)
     outs = run(driver, tmp_path, mode, frames, 2 * SW, 2 * SH)
-    mk = RC.ChainConfig if mode == "stages" else ref_defaults     # the stage objects of "stages" carry plain configs
-    oracle = RC.Chain(RC.NumpyOps(), mk(dst_w=2 * SW, dst_h=2 * SH, temporal=RC.TEMPORAL_BLEND_FRAMES))
+    if mode == "stages":      # the stage objects of "stages" carry plain configs; TemporalConsistency always runs its flow front end
+        ocfg = RC.ChainConfig(dst_w=2 * SW, dst_h=2 * SH, temporal=RC.TEMPORAL_BLEND_FRAMES,
+                              temporal_cfg=RC.TemporalConfig(use_flow=True, scene_detect=True))
+    else:
+        ocfg = ref_defaults(dst_w=2 * SW, dst_h=2 * SH, temporal=RC.TEMPORAL_BLEND_FRAMES)
+    oracle = RC.Chain(RC.NumpyOps(), ocfg)
     for o, f in zip(outs, frames):
         assert close(o, oracle.process(f))
 

@@ -1,0 +1,167 @@
+"""TemporalConsistency's motion-compensated front end through the C ABI against the oracle:
+Farneback flow within 2e-3 px of cv2.calcOpticalFlowFarneback (float / double summation order), remap bit-exact,
+reliability mask within 1e-5, the whole TemporalConsistency::process within +-1 LSB on a small fraction."""
+import numpy as np
+import pytest
+
+from oracle import ref_chain as RC
+from oracle import restate as R
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from tests import gpu_util as G  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ctx(vp):
+    c = vp.Context()
+    yield c
+    c.close()
+
+
+def gpu_flow(vp, ctx, f0, f1, tcfg):
+    h, w = f0.shape[:2]
+    a, b = G.to_dev(f0), G.to_dev(f1)
+    fx = torch.empty((h, w), dtype=torch.float32, device="cuda")
+    fy = torch.empty((h, w), dtype=torch.float32, device="cuda")
+    ctx.call("vp_optical_flow", G.temporal_cfg(vp, tcfg), a.data_ptr(), b.data_ptr(), G.pitch(a), fx.data_ptr(), fy.data_ptr(), G.pitch(fx), w, h, None)
+    G.sync()
+    return np.stack([fx.cpu().numpy(), fy.cpu().numpy()], axis=-1)
+
+
+def shifted_pair(w, h, dx, dy):
+    """a textured frame and the same texture moved by (dx, dy): a flow field with known sign and size"""
+    big = synth.frame("scene", w + 32, h + 32, 5)
+    import cv2
+    big = cv2.GaussianBlur(big, (7, 7), 2.0)
+    return np.ascontiguousarray(big[16:16 + h, 16:16 + w]), np.ascontiguousarray(big[16 - dy:16 - dy + h, 16 - dx:16 - dx + w])
+
+
+@pytest.mark.parametrize("size", [(160, 96), (131, 67), (320, 180), (64, 48)])
+@pytest.mark.parametrize("levels,iters,win", [(3, 3, 15), (0, 1, 15), (2, 2, 9)])
+def test_farneback_matches_cv2(vp, ctx, size, levels, iters, win):
+    import cv2
+    w, h = size
+    f0, f1 = synth.frame("scene", w, h, 3), synth.frame("scene", w, h, 4)
+    t = RC.TemporalConfig(levels=levels, iterations=iters, winsize=win)
+    flow = gpu_flow(vp, ctx, f0, f1, t)
+    g0, g1 = cv2.cvtColor(f0, cv2.COLOR_BGR2GRAY), cv2.cvtColor(f1, cv2.COLOR_BGR2GRAY)
+    ref = cv2.calcOpticalFlowFarneback(g0, g1, None, t.pyr_scale, levels, win, iters, t.poly_n, t.poly_sigma, 0)
+    assert np.abs(flow - ref).max() <= 2e-3, np.abs(flow - ref).max()
+    mine = R.farneback(R.bgr2gray(f0), R.bgr2gray(f1), t.pyr_scale, levels, win, iters, t.poly_n, t.poly_sigma)
+    assert np.abs(flow - mine).max() <= 2e-3
+
+
+def test_farneback_recovers_a_translation(vp, ctx):
+    f0, f1 = shifted_pair(256, 144, 3, -2)
+    flow = gpu_flow(vp, ctx, f0, f1, RC.TemporalConfig())
+    core = flow[32:-32, 32:-32]
+    assert abs(np.median(core[..., 0]) - 3.0) < 0.5 and abs(np.median(core[..., 1]) + 2.0) < 0.5
+
+
+@pytest.mark.parametrize("size", [(160, 96), (131, 67), (17, 9)])
+def test_warp_bit_exact(vp, ctx, size):
+    import cv2
+    w, h = size
+    img = synth.frame("noise", w, h, 1)
+    rng = np.random.default_rng(0)
+    flow = (rng.standard_normal((h, w, 2)) * 6).astype(np.float32)
+    flow[0:3] *= 40            # far outside the frame: BORDER_REPLICATE
+    flow[5] = np.rint(flow[5])  # integer displacements
+    src = G.to_dev(img)
+    fx, fy = G.to_dev(flow[..., 0].copy()), G.to_dev(flow[..., 1].copy())
+    dst = G.dev_empty(h, w)
+    ctx.call("vp_warp_flow", src.data_ptr(), G.pitch(src), fx.data_ptr(), fy.data_ptr(), G.pitch(fx), dst.data_ptr(), G.pitch(dst), w, h, None)
+    G.sync()
+    mx, my = R.flow_to_maps(flow)
+    assert np.array_equal(dst.cpu().numpy(), cv2.remap(img, mx, my, cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE))
+    assert np.array_equal(dst.cpu().numpy(), R.remap_linear_replicate_u8(img, mx, my))
+
+
+@pytest.mark.parametrize("size", [(160, 96), (131, 67), (40, 20)])
+def test_reliability_mask(vp, ctx, size):
+    w, h = size
+    rng = np.random.default_rng(1)
+    flow = (rng.standard_normal((h, w, 2)) * 14).astype(np.float32)      # magnitudes on both sides of the threshold
+    fx, fy = G.to_dev(flow[..., 0].copy()), G.to_dev(flow[..., 1].copy())
+    mask = torch.empty((h, w), dtype=torch.float32, device="cuda")
+    ctx.call("vp_flow_reliability", fx.data_ptr(), fy.data_ptr(), G.pitch(fx), 15.0, mask.data_ptr(), G.pitch(mask), w, h, None)
+    G.sync()
+    for ops in (RC.NumpyOps(), RC.Cv2Ops()):
+        ref = RC.flow_reliability_mask(ops, flow, 15.0)
+        assert np.abs(mask.cpu().numpy() - ref).max() <= 1e-5
+
+
+def run_tc(vp, frames, tcfg, sw, sh):
+    ocfg = RC.ChainConfig(dst_w=sw, dst_h=sh, use_pre=False, use_sharpen=False, use_post=False, temporal=RC.TEMPORAL_BLEND_FRAMES, temporal_cfg=tcfg)
+    outs = []
+    with vp.Context(G.chain_cfg(vp, ocfg, sw, sh)) as ctx:
+        for f in frames:
+            src = G.to_dev(f)
+            dst = G.dev_empty(sh, sw)
+            ctx.call("vp_process_device", src.data_ptr(), sw * 3, dst.data_ptr(), G.pitch(dst), None)
+            G.sync()
+            outs.append(dst.cpu().numpy())
+    return outs
+
+
+@pytest.mark.parametrize("kind", ["scene", "noise"])
+@pytest.mark.parametrize("buffer_size", [3, 2])
+def test_temporal_consistency_full(vp, kind, buffer_size):
+    """TemporalConsistency::process as written: flow, warp, masks, blendFrames over every buffered frame"""
+    sw, sh = 160, 96
+    frames = synth.clip(kind, sw, sh, 7)
+    t = RC.TemporalConfig(buffer_size=buffer_size, use_flow=True, scene_detect=True)
+    outs = run_tc(vp, frames, t, sw, sh)
+    for ops in (RC.NumpyOps(), RC.Cv2Ops()):
+        oracle = RC.TemporalConsistencyFull(t, ops)
+        for i, (o, f) in enumerate(zip(outs, frames)):
+            ref = oracle.process(f)
+            mx, n = G.diff_stats(o, ref)
+            assert mx <= 1 and n <= o.size * 0.01, (ops.name, i, mx, n)
+
+
+def test_temporal_consistency_full_scene_cut(vp):
+    sw, sh = 128, 72
+    frames = synth.clip("flat", sw, sh, 4) + synth.clip("scene", sw, sh, 4, t0=3)      # a flat -> scene cut at frame 4
+    t = RC.TemporalConfig(use_flow=True, scene_detect=True)
+    outs = run_tc(vp, frames, t, sw, sh)
+    oracle = RC.TemporalConsistencyFull(t, RC.NumpyOps())
+    refs = [oracle.process(f) for f in frames]
+    assert np.array_equal(refs[4], frames[4])          # the oracle sees the cut
+    for i, (o, r) in enumerate(zip(outs, refs)):
+        mx, n = G.diff_stats(o, r)
+        assert mx <= 1 and n <= o.size * 0.01, (i, mx, n)
+    assert np.array_equal(outs[4], frames[4])
+
+
+def test_chain_with_flow_temporal(vp):
+    """the whole chain in front of the flow-based temporal stage, batch API included"""
+    import ctypes as C
+    sw, sh = 128, 72
+    t = RC.TemporalConfig(use_flow=True, scene_detect=True)
+    ocfg = RC.ChainConfig(dst_w=2 * sw, dst_h=2 * sh, temporal=RC.TEMPORAL_BLEND_FRAMES, temporal_cfg=t)
+    frames = synth.clip("scene", sw, sh, 5)
+    oracle = RC.Chain(RC.NumpyOps(), ocfg)
+    refs = [oracle.process(f) for f in frames]
+    for batch in (False, True):
+        with vp.Context(G.chain_cfg(vp, ocfg, sw, sh)) as ctx:
+            srcs = [G.to_dev(f) for f in frames]
+            dsts = [G.dev_empty(2 * sh, 2 * sw) for _ in frames]
+            if batch:
+                sp = (C.c_void_p * len(frames))(*[s.data_ptr() for s in srcs])
+                dp = (C.c_void_p * len(frames))(*[d.data_ptr() for d in dsts])
+                ctx.call("vp_process_batch_device", len(frames), sp, sw * 3, dp, G.pitch(dsts[0]), None)
+            else:
+                for s, d in zip(srcs, dsts):
+                    ctx.call("vp_process_device", s.data_ptr(), sw * 3, d.data_ptr(), G.pitch(d), None)
+            ctx.call("vp_synchronize")
+            for d, r in zip(dsts, refs):
+                o = d.cpu().numpy()
+                mx, _ = G.diff_stats(o, r)
+                assert RC.psnr(o, r) >= 50.0 and mx <= 4, (batch, RC.psnr(o, r), mx)

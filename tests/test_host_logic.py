@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(vp):
     assert declared == set(vp.PROTOTYPES), declared ^ set(vp.PROTOTYPES)
     for name in declared:
         assert hasattr(vp.lib, name)
-    assert vp.lib.vp_abi_version() == 2
+    assert vp.lib.vp_abi_version() == 3
 
 
 def test_struct_layout_matches_header(vp):
@@ -43,7 +43,7 @@ def test_struct_layout_matches_header(vp):
     # doubles 8-aligned behind the reserved word; the chain config is a plain concatenation
     assert C.sizeof(vp.BilateralConfig) == 64 and vp.BilateralConfig.sigma_color.offset == 16
     assert vp.BilateralConfig.selective.offset == 32 and vp.BilateralConfig.detail_threshold.offset == 48
-    assert C.sizeof(vp.SharpenConfig) == 32 and C.sizeof(vp.TemporalConfig) == 24
+    assert C.sizeof(vp.SharpenConfig) == 32 and C.sizeof(vp.TemporalConfig) == 72 and vp.TemporalConfig.pyr_scale.offset == 32
     assert vp.ChainConfig.pre.offset == 32 and vp.ChainConfig.post.offset == 128
     cfg = vp.default_chain_config(1920, 1080, 3840, 2160)
     assert (cfg.pre.diameter, cfg.pre.sigma_color, cfg.post.diameter, cfg.post.sigma_space) == (7, 30.0, 5, 20.0)

@@ -31,7 +31,10 @@ class SharpenConfig(C.Structure):
 
 class TemporalConfig(C.Structure):
     _fields_ = [("mode", C.c_int32), ("buffer_size", C.c_int32), ("blend_strength", C.c_float),
-                ("main_weight", C.c_float), ("scene_detect", C.c_int32), ("scene_change_threshold", C.c_float)]
+                ("main_weight", C.c_float), ("scene_detect", C.c_int32), ("scene_change_threshold", C.c_float),
+                ("use_flow", C.c_int32), ("motion_threshold", C.c_float), ("pyr_scale", C.c_double),
+                ("poly_sigma", C.c_double), ("levels", C.c_int32), ("winsize", C.c_int32), ("iterations", C.c_int32),
+                ("poly_n", C.c_int32), ("flags", C.c_int32), ("reserved3_", C.c_int32)]
 
 
 class ChainConfig(C.Structure):
@@ -79,6 +82,9 @@ PROTOTYPES = {
     "vp_unsharp": (C.c_int, [_vp, C.POINTER(SharpenConfig), _u8p, _sz, C.c_void_p, _sz, _u8p, _sz, C.c_int, C.c_int, C.c_void_p]),
     "vp_sharpen": (C.c_int, [_vp, C.POINTER(SharpenConfig), _u8p, _sz, _u8p, _sz, C.c_int, C.c_int, C.c_void_p]),
     "vp_sigma_map": (C.c_int, [_vp, _u8p, _sz, C.c_void_p, _sz, C.c_int, C.c_int, C.c_void_p]),
+    "vp_optical_flow": (C.c_int, [_vp, C.POINTER(TemporalConfig), _u8p, _u8p, _sz, C.c_void_p, C.c_void_p, _sz, C.c_int, C.c_int, C.c_void_p]),
+    "vp_warp_flow": (C.c_int, [_vp, _u8p, _sz, C.c_void_p, C.c_void_p, _sz, _u8p, _sz, C.c_int, C.c_int, C.c_void_p]),
+    "vp_flow_reliability": (C.c_int, [_vp, C.c_void_p, C.c_void_p, _sz, C.c_float, C.c_void_p, _sz, C.c_int, C.c_int, C.c_void_p]),
     "vp_add_weighted": (C.c_int, [_vp, _u8p, _sz, C.c_double, _u8p, _sz, C.c_double, _u8p, _sz, C.c_int, C.c_int, C.c_void_p]),
     "vp_temporal_blend": (C.c_int, [_vp, C.POINTER(C.c_void_p), C.c_int, _sz, C.c_float, _u8p, _sz, C.c_int, C.c_int, C.c_void_p]),
 }

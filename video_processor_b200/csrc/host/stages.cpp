@@ -177,6 +177,16 @@ bool TemporalConsistency::process(const cv::Mat& input, cv::Mat& output) {
     c.temporal.blend_strength = m_config.blend_strength;
     c.temporal.scene_detect = 1;
     c.temporal.scene_change_threshold = m_config.scene_change_threshold;
+    // the motion-compensated front end, :94-150 (flow, warp, reliability masks)
+    c.temporal.use_flow = 1;
+    c.temporal.motion_threshold = m_config.motion_threshold;
+    c.temporal.pyr_scale = m_config.pyr_scale;
+    c.temporal.poly_sigma = m_config.poly_sigma;
+    c.temporal.levels = m_config.levels;
+    c.temporal.winsize = m_config.winsize;
+    c.temporal.iterations = m_config.iterations;
+    c.temporal.poly_n = m_config.poly_n;
+    c.temporal.flags = m_config.flags;
     Impl& s = *m_impl;
     if (!s.ctx || std::memcmp(&c, &s.cfg, sizeof(c)) != 0) {
         if (s.ctx) { vp_destroy(s.ctx); s.ctx = nullptr; }

@@ -121,6 +121,11 @@ bool Upscaler::ensureChain(int src_w, int src_h) {
         c.temporal.blend_strength = tc.blend_strength;
         c.temporal.scene_detect = 1;                       // TemporalConsistency::process always checks for a cut (:96-105)
         c.temporal.scene_change_threshold = tc.scene_change_threshold;
+        c.temporal.use_flow = 1;                           // ... and warps every buffered frame along its Farneback flow (:94-150)
+        c.temporal.motion_threshold = tc.motion_threshold;
+        c.temporal.pyr_scale = tc.pyr_scale; c.temporal.poly_sigma = tc.poly_sigma;
+        c.temporal.levels = tc.levels; c.temporal.winsize = tc.winsize; c.temporal.iterations = tc.iterations;
+        c.temporal.poly_n = tc.poly_n; c.temporal.flags = tc.flags;
     }
     if (m_chain && m_chain->device == m_device && std::memcmp(&m_chain->cfg, &c, sizeof(c)) == 0) return true;
     if (m_chain && m_chain->ctx) {          // drain frames in flight before the context is replaced

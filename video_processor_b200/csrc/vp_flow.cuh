@@ -1,0 +1,260 @@
+// vp_flow.cuh - TemporalConsistency's motion-compensated front end:
+//   calculateOpticalFlow          src/temporal_consistency.cpp:174-225  (cv::calcOpticalFlowFarneback :211-216)
+//   warpFrame                     src/temporal_consistency.cpp:227-281  (cv::remap INTER_LINEAR / BORDER_REPLICATE :273)
+//   calculateFlowReliabilityMask  src/temporal_consistency.cpp:325-353
+//   blendFrames with masks        src/temporal_consistency.cpp:355-444
+// The Farneback kernels follow OpenCV's published algorithm (modules/video/src/optflowgf.cpp, restated and pinned
+// against cv2 in oracle/restate.py:farneback) including its float / double mix: the polynomial expansion's row pass
+// and the 15x15 box sums accumulate in double (the 2x2 solve cancels catastrophically in float on edges).
+//
+// Planes are planar float32 (`ps` = plane stride in floats, `p` = row pitch in floats): R = 5 polynomial coefficients,
+// M = 5 structure-tensor entries, flow = 2.  Every kernel is a 32x8 thread block over output pixels; these are
+// streaming / small-stencil passes whose operands sit in L2 between launches (HBM-bound at worst).
+#pragma once
+#include "vp_bilateral.cuh"   // f2u8
+#include "vp_common.cuh"
+#include "vp_scene.cuh"       // gray_of
+
+namespace vp {
+
+#define VP_FLOW_XY                                                                          \
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5); \
+    if (x >= w || y >= h) return
+
+// BGR8 -> gray float32 (:74 cv::cvtColor, then convertTo(CV_32F) inside calcOpticalFlowFarneback)
+__global__ void __launch_bounds__(256) k_gray_f32(const uint8_t* __restrict__ src, size_t spitch, float* __restrict__ dst, int p, int w, int h) {
+    VP_FLOW_XY;
+    const uint8_t* q = src + (size_t)y * spitch + (size_t)x * 3;
+    dst[(size_t)y * p + x] = (float)gray_of((uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16));
+}
+
+struct GaussTaps { int ksize; float k[19]; };
+
+// separable float32 Gaussian, BORDER_REFLECT_101, accumulation left to right without FMA (cv::GaussianBlur on CV_32F)
+template <bool ROWS>
+__global__ void __launch_bounds__(256) k_gauss_f32(const float* __restrict__ src, int sp, float* __restrict__ dst, int dp, int w, int h, const GaussTaps t) {
+    VP_FLOW_XY;
+    const int r = t.ksize >> 1;
+    float acc = 0.f;
+    for (int i = 0; i < t.ksize; ++i) {
+        const float v = ROWS ? src[(size_t)y * sp + reflect101(x + i - r, w)] : src[(size_t)reflect101(y + i - r, h) * sp + x];
+        acc = i == 0 ? __fmul_rn(v, t.k[0]) : __fadd_rn(acc, __fmul_rn(v, t.k[i]));
+    }
+    dst[(size_t)y * dp + x] = acc;
+}
+
+// cv::resize(INTER_LINEAR) on CV_32F planes (nch planes, plane strides sps / dps), optional scale of the result
+// (`flow *= 1 / pyr_scale`).  Horizontal interpolation of both rows first, then vertical, all float32 without FMA.
+__device__ __forceinline__ void linear_tap(int d, double scale, int sn, int& s0, float& f) {
+    float fx = (float)(((double)d + 0.5) * scale - 0.5);
+    int sx = (int)floorf(fx);
+    fx = __fsub_rn(fx, (float)sx);
+    if (sx < 0) { fx = 0.f; sx = 0; }
+    if (sx >= sn - 1) { fx = 0.f; sx = sn - 1; }
+    s0 = sx; f = fx;
+}
+__global__ void __launch_bounds__(256) k_resize_linear_f32(const float* __restrict__ src, int sp, size_t sps, int sw, int sh,
+                                                           float* __restrict__ dst, int dp, size_t dps, int w, int h, int nch, float mul) {
+    VP_FLOW_XY;
+    int x0, y0; float fx, fy;
+    linear_tap(x, (double)sw / (double)w, sw, x0, fx);
+    linear_tap(y, (double)sh / (double)h, sh, y0, fy);
+    const int x1 = min(x0 + 1, sw - 1), y1 = min(y0 + 1, sh - 1);
+    const float a0 = __fsub_rn(1.f, fx), b0 = __fsub_rn(1.f, fy);
+    for (int c = 0; c < nch; ++c) {
+        const float* s = src + c * sps;
+        const float h0 = __fadd_rn(__fmul_rn(s[(size_t)y0 * sp + x0], a0), __fmul_rn(s[(size_t)y0 * sp + x1], fx));
+        const float h1 = __fadd_rn(__fmul_rn(s[(size_t)y1 * sp + x0], a0), __fmul_rn(s[(size_t)y1 * sp + x1], fx));
+        const float v = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, fy));
+        dst[c * dps + (size_t)y * dp + x] = mul == 1.f ? v : __fmul_rn(v, mul);
+    }
+}
+
+struct PolyTaps { int n; float g[8], xg[8], xxg[8]; double ig11, ig03, ig33, ig55; };   // FarnebackPrepareGaussian, taps 0..n
+
+// FarnebackPolyExp, vertical part: three float32 moment rows per pixel (rows clamp at the border)
+__global__ void __launch_bounds__(256) k_polyexp_v(const float* __restrict__ src, int sp, float* __restrict__ tmp, int tp, size_t tps, int w, int h, const PolyTaps t) {
+    VP_FLOW_XY;
+    const float s0 = src[(size_t)y * sp + x];
+    float r0 = __fmul_rn(s0, t.g[0]), r1 = 0.f, r2 = 0.f;
+    for (int k = 1; k <= t.n; ++k) {
+        const float a = src[(size_t)max(y - k, 0) * sp + x], b = src[(size_t)min(y + k, h - 1) * sp + x];
+        const float p = __fadd_rn(a, b);
+        r0 = __fadd_rn(r0, __fmul_rn(t.g[k], p));
+        r1 = __fadd_rn(r1, __fmul_rn(t.xg[k], __fsub_rn(b, a)));
+        r2 = __fadd_rn(r2, __fmul_rn(t.xxg[k], p));
+    }
+    const size_t o = (size_t)y * tp + x;
+    tmp[o] = r0; tmp[tps + o] = r1; tmp[2 * tps + o] = r2;
+}
+// horizontal part: double accumulators over float32 partial products exactly as the C++ mixes them; columns replicate
+__global__ void __launch_bounds__(256) k_polyexp_h(const float* __restrict__ tmp, int tp, size_t tps, float* __restrict__ R, int rp, size_t rps, int w, int h, const PolyTaps t) {
+    VP_FLOW_XY;
+    const float* r0 = tmp + (size_t)y * tp;
+    const float* r1 = r0 + tps;
+    const float* r2 = r0 + 2 * tps;
+    double b1 = (double)__fmul_rn(r0[x], t.g[0]), b2 = 0, b3 = (double)__fmul_rn(r1[x], t.g[0]), b4 = 0, b5 = (double)__fmul_rn(r2[x], t.g[0]), b6 = 0;
+    for (int k = 1; k <= t.n; ++k) {
+        const int xp = min(x + k, w - 1), xm = max(x - k, 0);
+        const double tg = (double)__fadd_rn(r0[xp], r0[xm]);
+        b1 += tg * (double)t.g[k];
+        b4 += tg * (double)t.xxg[k];
+        b2 += (double)__fmul_rn(__fsub_rn(r0[xp], r0[xm]), t.xg[k]);
+        b3 += (double)__fmul_rn(__fadd_rn(r1[xp], r1[xm]), t.g[k]);
+        b6 += (double)__fmul_rn(__fsub_rn(r1[xp], r1[xm]), t.xg[k]);
+        b5 += (double)__fmul_rn(__fadd_rn(r2[xp], r2[xm]), t.g[k]);
+    }
+    const size_t o = (size_t)y * rp + x;
+    R[rps + o] = (float)(b2 * t.ig11);
+    R[o] = (float)(b3 * t.ig11);
+    R[3 * rps + o] = (float)(b1 * t.ig03 + b4 * t.ig33);
+    R[2 * rps + o] = (float)(b1 * t.ig03 + b5 * t.ig33);
+    R[4 * rps + o] = (float)(b6 * t.ig55);
+}
+
+// FarnebackUpdateMatrices: the second frame's expansion sampled at x + flow (bilinear), structure tensor M
+__global__ void __launch_bounds__(256) k_update_matrices(const float* __restrict__ R0, const float* __restrict__ R1, int rp, size_t rps,
+                                                         const float* __restrict__ flow, int fp, size_t fps,
+                                                         float* __restrict__ M, int mp, size_t mps, int w, int h) {
+    VP_FLOW_XY;
+    const size_t o = (size_t)y * rp + x;
+    const float dx = flow[(size_t)y * fp + x], dy = flow[fps + (size_t)y * fp + x];
+    float fx = __fadd_rn((float)x, dx), fy = __fadd_rn((float)y, dy);
+    const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
+    fx = __fsub_rn(fx, (float)x1); fy = __fsub_rn(fy, (float)y1);
+    float r2, r3, r4, r5, r6;
+    if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+        const float a00 = __fmul_rn(__fsub_rn(1.f, fx), __fsub_rn(1.f, fy)), a01 = __fmul_rn(fx, __fsub_rn(1.f, fy));
+        const float a10 = __fmul_rn(__fsub_rn(1.f, fx), fy), a11 = __fmul_rn(fx, fy);
+        const size_t q = (size_t)y1 * rp + x1;
+        float v[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const float* p = R1 + c * rps + q;
+            float s = __fmul_rn(a00, p[0]);
+            s = __fadd_rn(s, __fmul_rn(a01, p[1]));
+            s = __fadd_rn(s, __fmul_rn(a10, p[rp]));
+            v[c] = __fadd_rn(s, __fmul_rn(a11, p[rp + 1]));
+        }
+        r2 = v[0]; r3 = v[1];
+        r4 = __fmul_rn(__fadd_rn(R0[2 * rps + o], v[2]), 0.5f);
+        r5 = __fmul_rn(__fadd_rn(R0[3 * rps + o], v[3]), 0.5f);
+        r6 = __fmul_rn(__fadd_rn(R0[4 * rps + o], v[4]), 0.25f);
+    } else {
+        r2 = r3 = 0.f;
+        r4 = R0[2 * rps + o]; r5 = R0[3 * rps + o]; r6 = __fmul_rn(R0[4 * rps + o], 0.5f);
+    }
+    r2 = __fmul_rn(__fsub_rn(R0[o], r2), 0.5f);
+    r3 = __fmul_rn(__fsub_rn(R0[rps + o], r3), 0.5f);
+    r2 = __fadd_rn(r2, __fadd_rn(__fmul_rn(r4, dy), __fmul_rn(r6, dx)));
+    r3 = __fadd_rn(r3, __fadd_rn(__fmul_rn(r6, dy), __fmul_rn(r5, dx)));
+    if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
+        const float border[5] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f};
+        float scale = x < 5 ? border[x] : 1.f;
+        scale = __fmul_rn(scale, x >= w - 5 ? border[w - x - 1] : 1.f);
+        scale = __fmul_rn(scale, y < 5 ? border[y] : 1.f);
+        scale = __fmul_rn(scale, y >= h - 5 ? border[h - y - 1] : 1.f);
+        r2 = __fmul_rn(r2, scale); r3 = __fmul_rn(r3, scale); r4 = __fmul_rn(r4, scale); r5 = __fmul_rn(r5, scale); r6 = __fmul_rn(r6, scale);
+    }
+    const size_t m = (size_t)y * mp + x;
+    M[m] = __fadd_rn(__fmul_rn(r4, r4), __fmul_rn(r6, r6));
+    M[mps + m] = __fmul_rn(__fadd_rn(r4, r5), r6);
+    M[2 * mps + m] = __fadd_rn(__fmul_rn(r5, r5), __fmul_rn(r6, r6));
+    M[3 * mps + m] = __fadd_rn(__fmul_rn(r4, r2), __fmul_rn(r6, r3));
+    M[4 * mps + m] = __fadd_rn(__fmul_rn(r6, r2), __fmul_rn(r5, r3));
+}
+
+// FarnebackUpdateFlow_Blur: (2m+1)^2 box sums of M in double (rows / columns replicate), then the 2x2 solve
+__global__ void __launch_bounds__(256) k_box_v(const float* __restrict__ M, int mp, size_t mps, double* __restrict__ V, int vp_, size_t vps, int w, int h, int m) {
+    VP_FLOW_XY;
+    for (int c = 0; c < 5; ++c) {
+        const float* p = M + c * mps + x;
+        double s = 0.0;
+        for (int k = -m; k <= m; ++k) s += (double)p[(size_t)min(max(y + k, 0), h - 1) * mp];
+        V[c * vps + (size_t)y * vp_ + x] = s;
+    }
+}
+__global__ void __launch_bounds__(256) k_box_h_solve(const double* __restrict__ V, int vp_, size_t vps, float* __restrict__ flow, int fp, size_t fps,
+                                                     int w, int h, int m, double scale) {
+    VP_FLOW_XY;
+    double s[5];
+    for (int c = 0; c < 5; ++c) {
+        const double* p = V + c * vps + (size_t)y * vp_;
+        double a = 0.0;
+        for (int k = -m; k <= m; ++k) a += p[min(max(x + k, 0), w - 1)];
+        s[c] = a * scale;
+    }
+    const double idet = 1.0 / (s[0] * s[2] - s[1] * s[1] + 1e-3);
+    flow[(size_t)y * fp + x] = (float)((s[0] * s[4] - s[1] * s[3]) * idet);
+    flow[fps + (size_t)y * fp + x] = (float)((s[2] * s[3] - s[1] * s[4]) * idet);
+}
+
+// cv::remap(frame, map = (x, y) + flow, INTER_LINEAR, BORDER_REPLICATE) on BGR8, bit-exact: coordinates rounded to
+// 1/32 pixel, taps clamped into the image, integer weights summing to 2^15, (sum + 2^14) >> 15
+__global__ void __launch_bounds__(256) k_warp(const uint8_t* __restrict__ src, size_t spitch, const float* __restrict__ flow_x,
+                                              const float* __restrict__ flow_y, int fp, uint8_t* __restrict__ dst, size_t dpitch, int w, int h) {
+    VP_FLOW_XY;
+    const float mx = __fadd_rn((float)x, flow_x[(size_t)y * fp + x]), my = __fadd_rn((float)y, flow_y[(size_t)y * fp + x]);
+    const int sx = __float2int_rn(__fmul_rn(mx, 32.f)), sy = __float2int_rn(__fmul_rn(my, 32.f));
+    const int fx = sx & 31, fy = sy & 31;
+    const int ix = min(max(sx >> 5, -32768), 32767), iy = min(max(sy >> 5, -32768), 32767);
+    const int x0 = min(max(ix, 0), w - 1), x1 = min(max(ix + 1, 0), w - 1), y0 = min(max(iy, 0), h - 1), y1 = min(max(iy + 1, 0), h - 1);
+    const int w00 = 32 * (32 - fx) * (32 - fy), w01 = 32 * fx * (32 - fy), w10 = 32 * (32 - fx) * fy, w11 = 32 * fx * fy;
+    const uint8_t* r0 = src + (size_t)y0 * spitch;
+    const uint8_t* r1 = src + (size_t)y1 * spitch;
+    uint8_t* o = dst + (size_t)y * dpitch + (size_t)x * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int v = __ldg(r0 + 3 * x0 + c) * w00 + __ldg(r0 + 3 * x1 + c) * w01 + __ldg(r1 + 3 * x0 + c) * w10 + __ldg(r1 + 3 * x1 + c) * w11;
+        o[c] = (uint8_t)min(max((v + (1 << 14)) >> 15, 0), 255);
+    }
+}
+
+// calculateFlowReliabilityMask before its blur (:331-344): 1 where |f| <= threshold, else clamp(expf(-(|f| - thr) / 10), 0, 1)
+__global__ void __launch_bounds__(256) k_reliability(const float* __restrict__ flow_x, const float* __restrict__ flow_y, int fp,
+                                                     float* __restrict__ mask, int mp, int w, int h, float thr) {
+    VP_FLOW_XY;
+    const float fx = flow_x[(size_t)y * fp + x], fy = flow_y[(size_t)y * fp + x];
+    const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)));
+    float r = 1.f;
+    if (mag > thr) r = fminf(fmaxf(expf(__fdiv_rn(-__fsub_rn(mag, thr), 10.0f)), 0.f), 1.f);
+    mask[(size_t)y * mp + x] = r;
+}
+
+// blendFrames with reliability masks (:380-436): weight_i = e^{-i/2} * mask_i * blend_factor_i in float32, accumulation
+// in frame order, `pixel /= weight` (multiplication by 1.f / weight), convertTo RNE.  frames[0] = current (mask 1).
+struct MaskedBlendArgs {
+    const uint8_t* cur; size_t cpitch;
+    const uint8_t* prev[3]; size_t ppitch;      // warped previous frames
+    const float* mask[3]; int mp;               // their reliability masks (pitch in floats)
+    int nprev;
+    const int* use_dev;                         // scene verdict: caps nprev (0 = pass the frame through); may be null
+    float fw[4];                                // e^{-i/2} (float), blend_strength
+    float blend_strength;
+    uint8_t* dst; size_t dpitch;
+    int w, h;
+};
+__global__ void __launch_bounds__(256) k_blend_masked(const MaskedBlendArgs a) {
+    const int w = a.w, h = a.h;
+    VP_FLOW_XY;
+    int n = a.nprev;
+    if (a.use_dev) n = min(n, *a.use_dev);
+    const uint8_t* c = a.cur + (size_t)y * a.cpitch + (size_t)x * 3;
+    uint8_t* o = a.dst + (size_t)y * a.dpitch + (size_t)x * 3;
+    if (n <= 0) { o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; return; }
+    const float w0 = __fmul_rn(__fmul_rn(a.fw[0], 1.0f), 1.0f);
+    float acc[3] = {__fmul_rn(w0, (float)c[0]), __fmul_rn(w0, (float)c[1]), __fmul_rn(w0, (float)c[2])};
+    float wsum = w0;
+    for (int i = 0; i < n; ++i) {
+        const float wt = __fmul_rn(__fmul_rn(a.fw[i + 1], a.mask[i][(size_t)y * a.mp + x]), a.blend_strength);
+        const uint8_t* p = a.prev[i] + (size_t)y * a.ppitch + (size_t)x * 3;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) acc[ch] = __fadd_rn(acc[ch], __fmul_rn(wt, (float)p[ch]));
+        wsum = __fadd_rn(wsum, wt);
+    }
+    const float inv = __fdiv_rn(1.0f, wsum);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) o[ch] = (uint8_t)f2u8(wsum > 0.f ? __fmul_rn(acc[ch], inv) : (float)c[ch]);
+}
+
+}  // namespace vp

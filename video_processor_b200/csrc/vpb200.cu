@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cstddef>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <deque>
 #include <new>
@@ -25,6 +26,7 @@
 #include "vp_blend.cuh"
 #include "vp_canny.cuh"
 #include "vp_detail.cuh"
+#include "vp_flow.cuh"
 #include "vp_scene.cuh"
 #include "vp_stats.cuh"
 #include "vp_tables.h"
@@ -35,6 +37,7 @@ using namespace vp;
 
 // layout the ctypes / FFI stubs rely on (tests/test_host_logic.py::test_struct_layout_matches_header)
 static_assert(sizeof(vp_bilateral_config) == 64 && offsetof(vp_bilateral_config, detail_threshold) == 48, "vp_bilateral_config layout");
+static_assert(sizeof(vp_temporal_config) == 72 && offsetof(vp_temporal_config, pyr_scale) == 32, "vp_temporal_config layout");
 static_assert(sizeof(vp_sharpen_config) == 32, "vp_sharpen_config layout");
 static_assert(offsetof(vp_chain_config, pre) == 32 && offsetof(vp_chain_config, post) == 128, "vp_chain_config layout");
 
@@ -67,6 +70,34 @@ struct MsScratch {                  // SelectiveBilateral's selective / multi-sc
     int lw[5] = {0, 0, 0, 0, 0}, lh[5] = {0, 0, 0, 0, 0};
     float* mask = nullptr; size_t mpitch = 0;
     vp::DetailMax* mx = nullptr;
+};
+
+struct FlowLevel {                  // one pyramid level of the Farneback engine
+    int w = 0, h = 0, p = 0; size_t ps = 0;      // size, row pitch and plane stride in floats
+    int ksize = 3; double sigma = 0;             // pre-smoothing of the full-resolution image for this level
+    float* I = nullptr;                          // level image
+    float* R[2] = {nullptr, nullptr};            // polynomial expansions (5 planes), ping-pong previous / current frame
+    float* flow = nullptr;                       // 2 planes
+};
+struct FlowEngine {                 // cv::calcOpticalFlowFarneback for one frame size and parameter set
+    int w = 0, h = 0, nlev = 0;     // nlev = levels + 1 pyramid entries, [0] = full resolution
+    vp_temporal_config prm{};
+    FlowLevel lv[8];
+    float* gray = nullptr; float* blur_a = nullptr; float* blur_b = nullptr;   // full-resolution float planes
+    float* tmp = nullptr;           // polyexp row moments (3 planes)
+    float* M = nullptr;             // 5 planes
+    double* V = nullptr;            // 5 planes, double
+    vp::PolyTaps poly{};
+};
+struct FlowTemporal {               // TemporalConsistency::process with the flow front end: device state
+    FlowEngine eng;
+    int cur = 0;                    // which R[] holds the newest frame's expansions
+    bool have_prev = false;
+    uint8_t* raw_prev = nullptr; size_t rpitch = 0;          // the previous unblended input (:158)
+    uint8_t* warped[3] = {nullptr, nullptr, nullptr};        // remap(frame t-1-i, its flow): fixed once computed
+    float* mask[3] = {nullptr, nullptr, nullptr};            // that flow's reliability mask
+    float* mtmp = nullptr;
+    int head = 0, nvalid = 0;
 };
 
 struct VsScratch {                  // AdaptiveSharpening, adaptive_sigma branch: one frame size's buffers
@@ -122,6 +153,9 @@ struct vp_ctx {
     // per-scale tables of the multi-scale branch: chain PRE / POST stages and the stage-wise entry point
     BilCand* d_cand_ms_pre = nullptr; BilCand* d_cand_ms_post = nullptr; BilCand* d_cand_ms_tmp = nullptr;
     int ms_pre_rad[5] = {0, 0, 0, 0, 0}, ms_post_rad[5] = {0, 0, 0, 0, 0}, ms_tmp_rad[5] = {0, 0, 0, 0, 0};
+    FlowTemporal ftc;               // temporal.use_flow
+    FlowEngine flow_tmp;            // stage-wise vp_optical_flow
+    float* flow_tmp_mask = nullptr; size_t flow_tmp_mask_n = 0;
     MsScratch ms_tmp;               // stage-wise scratch
     VsScratch vs_tmp;
     ResizeCache rc_chain, rc_tmp;
@@ -420,6 +454,239 @@ int run_bilateral_modes(vp_ctx* c, MsScratch& S, const vp_bilateral_config& cfg,
     return VP_OK;
 }
 
+// ---- Farneback engine (vp_flow.cuh) ---------------------------------------------------------------------------
+void free_flow_engine(FlowEngine& E) {
+    for (FlowLevel& L : E.lv) { cudaFree(L.I); cudaFree(L.R[0]); cudaFree(L.R[1]); cudaFree(L.flow); }
+    cudaFree(E.gray); cudaFree(E.blur_a); cudaFree(E.blur_b); cudaFree(E.tmp); cudaFree(E.M); cudaFree(E.V);
+    E = FlowEngine();
+}
+void free_flow_temporal(FlowTemporal& T) {
+    free_flow_engine(T.eng);
+    cudaFree(T.raw_prev); cudaFree(T.mtmp);
+    for (int i = 0; i < 3; ++i) { cudaFree(T.warped[i]); cudaFree(T.mask[i]); }
+    T = FlowTemporal();
+}
+
+// FarnebackPrepareGaussian (optflowgf.cpp): float taps g, x g, x^2 g and the four entries of inv(G) the expansion uses
+int poly_taps(vp_ctx* c, int n, double sigma, PolyTaps& t) {
+    if (n < 1 || n > 7) return fail(c, VP_ERR_UNSUPPORTED, "Farneback poly_n must be 1..7");
+    if (sigma < 1.1920929e-07) sigma = n * 0.3;
+    std::vector<float> g(2 * n + 1), xg(2 * n + 1), xxg(2 * n + 1);
+    double s = 0.0;
+    for (int x = -n; x <= n; ++x) { g[x + n] = (float)std::exp(-x * x / (2 * sigma * sigma)); s += g[x + n]; }
+    s = 1.0 / s;
+    for (int x = -n; x <= n; ++x) {
+        g[x + n] = (float)(g[x + n] * s);
+        xg[x + n] = (float)(x * g[x + n]);
+        xxg[x + n] = (float)(x * x * g[x + n]);
+    }
+    double G[6][6] = {};
+    for (int y = -n; y <= n; ++y)
+        for (int x = -n; x <= n; ++x) {
+            const float gg = g[y + n] * g[x + n];
+            G[0][0] += gg;
+            G[1][1] += gg * x * x;
+            G[3][3] += gg * x * x * x * x;
+            G[5][5] += gg * x * x * y * y;
+        }
+    G[2][2] = G[0][3] = G[0][4] = G[3][0] = G[4][0] = G[1][1];
+    G[4][4] = G[3][3];
+    G[3][4] = G[4][3] = G[5][5];
+    double A[6][12];
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 12; ++j) A[i][j] = j < 6 ? G[i][j] : (j - 6 == i ? 1.0 : 0.0);
+    for (int i = 0; i < 6; ++i) {                      // Gauss-Jordan with partial pivoting (G is SPD, 6x6)
+        int piv = i;
+        for (int r = i + 1; r < 6; ++r) if (std::fabs(A[r][i]) > std::fabs(A[piv][i])) piv = r;
+        if (std::fabs(A[piv][i]) < 1e-300) return fail(c, VP_ERR_UNSUPPORTED, "Farneback: singular moment matrix");
+        if (piv != i) for (int j = 0; j < 12; ++j) std::swap(A[i][j], A[piv][j]);
+        const double d = A[i][i];
+        for (int j = 0; j < 12; ++j) A[i][j] /= d;
+        for (int r = 0; r < 6; ++r) if (r != i) { const double f = A[r][i]; if (f != 0.0) for (int j = 0; j < 12; ++j) A[r][j] -= f * A[i][j]; }
+    }
+    t.n = n;
+    for (int k = 0; k <= n; ++k) { t.g[k] = g[n + k]; t.xg[k] = xg[n + k]; t.xxg[k] = xxg[n + k]; }
+    t.ig11 = A[1][7]; t.ig03 = A[0][9]; t.ig33 = A[3][9]; t.ig55 = A[5][11];
+    return VP_OK;
+}
+
+bool same_flow_params(const vp_temporal_config& a, const vp_temporal_config& b) {
+    return a.pyr_scale == b.pyr_scale && a.poly_sigma == b.poly_sigma && a.levels == b.levels && a.winsize == b.winsize &&
+           a.iterations == b.iterations && a.poly_n == b.poly_n && a.flags == b.flags;
+}
+
+int ensure_flow_engine(vp_ctx* c, FlowEngine& E, int w, int h, const vp_temporal_config& prm) {
+    if (E.w == w && E.h == h && E.gray && same_flow_params(E.prm, prm)) return VP_OK;
+    if (prm.flags != 0) return fail(c, VP_ERR_UNSUPPORTED, "Farneback flags other than 0 are not built");
+    if (prm.winsize < 1 || !(prm.winsize & 1) || prm.winsize > 63) return fail(c, VP_ERR_UNSUPPORTED, "Farneback winsize must be odd, 1..63");
+    if (prm.iterations < 1 || prm.levels < 0 || prm.levels > 7 || !(prm.pyr_scale > 0.0 && prm.pyr_scale < 1.0))
+        return fail(c, VP_ERR_INVALID_ARG, "Farneback: iterations >= 1, levels 0..7, 0 < pyr_scale < 1");
+    VP_CUDA(c, cudaDeviceSynchronize());
+    free_flow_engine(E);
+    int rc = poly_taps(c, prm.poly_n, prm.poly_sigma, E.poly); if (rc) return rc;
+    E.w = w; E.h = h; E.prm = prm;
+    // levels actually used (FarnebackOpticalFlowImpl::calc): stop before a level smaller than 32 pixels
+    int levels = 0; double scale = 1.0;
+    for (; levels < prm.levels; ++levels) {
+        scale *= prm.pyr_scale;
+        if (w * scale < 32 || h * scale < 32) break;
+    }
+    E.nlev = levels + 1;
+    auto planes = [&](float** p, int n, const FlowLevel& L) { return cudaMalloc(p, (size_t)n * L.ps * sizeof(float)); };
+    for (int k = 0; k < E.nlev; ++k) {
+        FlowLevel& L = E.lv[k];
+        scale = 1.0;
+        for (int i = 0; i < k; ++i) scale *= prm.pyr_scale;
+        L.sigma = (1.0 / scale - 1) * 0.5;
+        L.ksize = std::max((int)std::lrint(L.sigma * 5) | 1, 3);
+        if (L.ksize > 19) return fail(c, VP_ERR_UNSUPPORTED, "Farneback: pyramid pre-smoothing kernel > 19 (pyr_scale^levels too small)");
+        L.w = (int)std::lrint(w * scale); L.h = (int)std::lrint(h * scale);
+        L.p = (int)align_up((size_t)L.w, 64); L.ps = (size_t)L.p * L.h;
+        VP_CUDA(c, planes(&L.I, 1, L)); VP_CUDA(c, planes(&L.R[0], 5, L)); VP_CUDA(c, planes(&L.R[1], 5, L)); VP_CUDA(c, planes(&L.flow, 2, L));
+    }
+    const FlowLevel& L0 = E.lv[0];
+    VP_CUDA(c, planes(&E.gray, 1, L0)); VP_CUDA(c, planes(&E.blur_a, 1, L0)); VP_CUDA(c, planes(&E.blur_b, 1, L0));
+    VP_CUDA(c, planes(&E.tmp, 3, L0)); VP_CUDA(c, planes(&E.M, 5, L0));
+    VP_CUDA(c, cudaMalloc(&E.V, 5 * L0.ps * sizeof(double)));
+    return VP_OK;
+}
+
+inline dim3 grid2d(int w, int h) { return dim3((w + 31) / 32, (h + 7) / 8); }
+
+GaussTaps gauss_taps(int ksize, double sigma) {
+    GaussTaps t{};
+    t.ksize = ksize;
+    const std::vector<double> g = vp_host::gaussian_kernel_f64(ksize, sigma);
+    for (int i = 0; i < ksize; ++i) t.k[i] = (float)g[i];
+    return t;
+}
+
+// gray -> per level: GaussianBlur(full resolution) -> resize(INTER_LINEAR) -> FarnebackPolyExp, into R[which]
+int flow_expand(vp_ctx* c, FlowEngine& E, const uint8_t* bgr, size_t pitch, int which, cudaStream_t st) {
+    ProfScope ps(c, K_BLEND, st);
+    const FlowLevel& L0 = E.lv[0];
+    k_gray_f32<<<grid2d(E.w, E.h), 256, 0, st>>>(bgr, pitch, E.gray, L0.p, E.w, E.h);
+    c->launches++;
+    for (int k = 0; k < E.nlev; ++k) {
+        FlowLevel& L = E.lv[k];
+        const GaussTaps t = gauss_taps(L.ksize, L.sigma);
+        k_gauss_f32<true><<<grid2d(E.w, E.h), 256, 0, st>>>(E.gray, L0.p, E.blur_a, L0.p, E.w, E.h, t);
+        k_gauss_f32<false><<<grid2d(E.w, E.h), 256, 0, st>>>(E.blur_a, L0.p, E.blur_b, L0.p, E.w, E.h, t);
+        k_resize_linear_f32<<<grid2d(L.w, L.h), 256, 0, st>>>(E.blur_b, L0.p, 0, E.w, E.h, L.I, L.p, 0, L.w, L.h, 1, 1.f);
+        k_polyexp_v<<<grid2d(L.w, L.h), 256, 0, st>>>(L.I, L.p, E.tmp, L.p, L.ps, L.w, L.h, E.poly);
+        k_polyexp_h<<<grid2d(L.w, L.h), 256, 0, st>>>(E.tmp, L.p, L.ps, L.R[which], L.p, L.ps, L.w, L.h, E.poly);
+        c->launches += 5;
+    }
+    VP_CUDA(c, cudaGetLastError());
+    return VP_OK;
+}
+
+// coarse-to-fine Farneback iterations between R[prev] and R[cur]; the result is lv[0].flow
+int flow_solve(vp_ctx* c, FlowEngine& E, int prev, int cur, cudaStream_t st) {
+    ProfScope ps(c, K_BLEND, st);
+    const int m = E.prm.winsize / 2;
+    const double scale = 1.0 / ((double)E.prm.winsize * E.prm.winsize);
+    for (int k = E.nlev - 1; k >= 0; --k) {
+        FlowLevel& L = E.lv[k];
+        const dim3 g = grid2d(L.w, L.h);
+        if (k == E.nlev - 1) VP_CUDA(c, cudaMemsetAsync(L.flow, 0, 2 * L.ps * sizeof(float), st));
+        else {
+            const FlowLevel& U = E.lv[k + 1];
+            k_resize_linear_f32<<<g, 256, 0, st>>>(U.flow, U.p, U.ps, U.w, U.h, L.flow, L.p, L.ps, L.w, L.h, 2, (float)(1.0 / E.prm.pyr_scale));
+            c->launches++;
+        }
+        k_update_matrices<<<g, 256, 0, st>>>(L.R[prev], L.R[cur], L.p, L.ps, L.flow, L.p, L.ps, E.M, L.p, L.ps, L.w, L.h);
+        c->launches++;
+        for (int i = 0; i < E.prm.iterations; ++i) {
+            k_box_v<<<g, 256, 0, st>>>(E.M, L.p, L.ps, E.V, L.p, L.ps, L.w, L.h, m);
+            k_box_h_solve<<<g, 256, 0, st>>>(E.V, L.p, L.ps, L.flow, L.p, L.ps, L.w, L.h, m, scale);
+            c->launches += 2;
+            if (i < E.prm.iterations - 1) {
+                k_update_matrices<<<g, 256, 0, st>>>(L.R[prev], L.R[cur], L.p, L.ps, L.flow, L.p, L.ps, E.M, L.p, L.ps, L.w, L.h);
+                c->launches++;
+            }
+        }
+    }
+    VP_CUDA(c, cudaGetLastError());
+    return VP_OK;
+}
+
+// calculateFlowReliabilityMask: raw mask then cv::GaussianBlur(15x15, sigma 5) (:347); tmp = one float plane
+int launch_reliability(vp_ctx* c, const float* fx, const float* fy, int fp, float thr, float* mask, int mp, float* tmp, int w, int h, cudaStream_t st) {
+    ProfScope ps(c, K_BLEND, st);
+    const GaussTaps t = gauss_taps(15, 5.0);
+    k_reliability<<<grid2d(w, h), 256, 0, st>>>(fx, fy, fp, mask, mp, w, h, thr);
+    k_gauss_f32<true><<<grid2d(w, h), 256, 0, st>>>(mask, mp, tmp, mp, w, h, t);
+    k_gauss_f32<false><<<grid2d(w, h), 256, 0, st>>>(tmp, mp, mask, mp, w, h, t);
+    VP_CUDA(c, cudaGetLastError());
+    c->launches += 3;
+    return VP_OK;
+}
+
+int ensure_flow_temporal(vp_ctx* c, FlowTemporal& T, int w, int h, const vp_temporal_config& prm) {
+    if (T.raw_prev && T.eng.w == w && T.eng.h == h && same_flow_params(T.eng.prm, prm)) return VP_OK;
+    VP_CUDA(c, cudaDeviceSynchronize());
+    free_flow_temporal(T);
+    int rc = ensure_flow_engine(c, T.eng, w, h, prm); if (rc) return rc;
+    T.rpitch = align_up((size_t)w * 3, 256);
+    VP_CUDA(c, cudaMalloc(&T.raw_prev, T.rpitch * h));
+    const FlowLevel& L0 = T.eng.lv[0];
+    for (int i = 0; i < 3; ++i) {
+        VP_CUDA(c, cudaMalloc(&T.warped[i], T.rpitch * h));
+        VP_CUDA(c, cudaMalloc(&T.mask[i], L0.ps * sizeof(float)));
+    }
+    VP_CUDA(c, cudaMalloc(&T.mtmp, L0.ps * sizeof(float)));
+    return VP_OK;
+}
+
+// TemporalConsistency::process (src/temporal_consistency.cpp:61-172) with the flow front end, all on the device.
+// The warped copy of a buffered frame and its reliability mask depend only on that frame and on the flow computed when
+// its successor arrived (:127-138), so both are computed once and kept in a ring instead of being redone every frame.
+// `use_dev` is k_scene_decide's verdict for this frame (how many buffered frames may be used; 0 = pass through).
+int run_flow_temporal(vp_ctx* c, FlowTemporal& T, const vp_temporal_config& t, const uint8_t* cur, size_t cur_pitch,
+                      uint8_t* dst, size_t dst_pitch, const int* use_dev, cudaStream_t st) {
+    FlowEngine& E = T.eng;
+    const int w = E.w, h = E.h;
+    const FlowLevel& L0 = E.lv[0];
+    const int nxt = T.cur ^ 1;
+    int rc = flow_expand(c, E, cur, cur_pitch, nxt, st); if (rc) return rc;
+    if (T.have_prev) {
+        rc = flow_solve(c, E, T.cur, nxt, st); if (rc) return rc;                       // :95 flow prev -> cur
+        const int slot = T.head;
+        {
+            ProfScope ps(c, K_BLEND, st);
+            k_warp<<<grid2d(w, h), 256, 0, st>>>(T.raw_prev, T.rpitch, L0.flow, L0.flow + L0.ps, L0.p, T.warped[slot], T.rpitch, w, h);   // :133
+            VP_CUDA(c, cudaGetLastError());
+            c->launches++;
+        }
+        rc = launch_reliability(c, L0.flow, L0.flow + L0.ps, L0.p, t.motion_threshold, T.mask[slot], L0.p, T.mtmp, w, h, st);             // :137
+        if (rc) return rc;
+        T.head = (T.head + 1) % 3;
+        T.nvalid = std::min(T.nvalid + 1, std::min(std::max(t.buffer_size, 1), 3));
+    }
+    if (dst) {
+        if (!T.have_prev) {
+            VP_CUDA(c, cudaMemcpy2DAsync(dst, dst_pitch, cur, cur_pitch, (size_t)w * 3, h, cudaMemcpyDeviceToDevice, st));   // :79-86
+        } else {
+            MaskedBlendArgs a{};
+            a.cur = cur; a.cpitch = cur_pitch; a.ppitch = T.rpitch; a.mp = L0.p;
+            a.nprev = T.nvalid;
+            for (int i = 0; i < T.nvalid; ++i) { const int s = (T.head - 1 - i + 6) % 3; a.prev[i] = T.warped[s]; a.mask[i] = T.mask[s]; }
+            a.use_dev = use_dev;
+            for (int i = 0; i < 4; ++i) { volatile float arg = -(float)i / 2.0f; a.fw[i] = (float)std::exp((double)arg); }
+            a.blend_strength = t.blend_strength;
+            a.dst = dst; a.dpitch = dst_pitch; a.w = w; a.h = h;
+            ProfScope ps(c, K_BLEND, st);
+            k_blend_masked<<<grid2d(w, h), 256, 0, st>>>(a);
+            VP_CUDA(c, cudaGetLastError());
+            c->launches++;
+        }
+    }
+    VP_CUDA(c, cudaMemcpy2DAsync(T.raw_prev, T.rpitch, cur, cur_pitch, (size_t)w * 3, h, cudaMemcpyDeviceToDevice, st));     // :158
+    T.cur = nxt;
+    T.have_prev = true;
+    return VP_OK;
+}
+
 void free_vs_scratch(VsScratch& S) {
     cudaFree(S.emask); cudaFree(S.sigma); cudaFree(S.st); cudaFree(S.lv); cudaFree(S.up);
     S = VsScratch();
@@ -634,7 +901,8 @@ int vp_default_chain_config(vp_chain_config* cfg, int src_w, int src_h, int dst_
     cfg->pre = vp_bilateral_config{VP_STAGE_PRE, 1, 7, 0, 30.0, 30.0};          // src/upscaler.cpp:668-682
     cfg->sharpen = vp_sharpen_config{0.8f, 1.2f, 0.4f, 30.0f, 1.5f, 5, 1};      // :691-702
     cfg->post = vp_bilateral_config{VP_STAGE_POST, 1, 5, 0, 20.0, 20.0};        // :711-725
-    cfg->temporal = vp_temporal_config{VP_TEMPORAL_BLEND_FRAMES, 3, 0.6f, 0.6f, 0, 100.0f}; // :734-748, main.cpp:282; scene_detect is opt-in
+    // :734-748, main.cpp:282; scene_detect and the flow front end (use_flow) are opt-in, their parameters carry the reference's values
+    cfg->temporal = vp_temporal_config{VP_TEMPORAL_BLEND_FRAMES, 3, 0.6f, 0.6f, 0, 100.0f, 0, 15.0f, 0.5, 1.2, 3, 15, 3, 5, 0, 0};
     return VP_OK;
 }
 
@@ -660,6 +928,7 @@ void vp_destroy(vp_ctx* c) {
     cudaFree(c->d_cand_be); cudaFree(c->d_scene_acc); cudaFree(c->d_scene_state); cudaFree(c->d_use);
     cudaFree(c->d_cand_pre); cudaFree(c->d_cand_post); cudaFree(c->d_cand_tmp); cudaFree(c->d_cand_sel);
     cudaFree(c->d_cand_ms_pre); cudaFree(c->d_cand_ms_post); cudaFree(c->d_cand_ms_tmp);
+    free_flow_temporal(c->ftc); free_flow_engine(c->flow_tmp); cudaFree(c->flow_tmp_mask);
     free_ms_scratch(c->ms_tmp); free_vs_scratch(c->vs_tmp);
     free_resize(c->rc_chain); free_resize(c->rc_tmp);
     cudaFree(c->d_siglut); cudaFree(c->d_siglut_tmp);
@@ -718,17 +987,24 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
         int rc = build_selective_cands(c, g.post, c->d_cand_post, c->cand_post_rad, c->s_compute);
         if (rc) return rc;
         if (g.post.use_multiscale) { rc = build_multiscale_cands(c, g.post, &c->d_cand_ms_post, c->ms_post_rad, c->s_compute); if (rc) return rc; }
-        if (bil_has_modes(g.post)) VP_CUDA(c, cudaMalloc(&c->lanes[0].d_post, c->frame_pitch * g.dst_h));
+        if (bil_has_modes(g.post) || (g.temporal.mode == VP_TEMPORAL_BLEND_FRAMES && g.temporal.use_flow))
+            VP_CUDA(c, cudaMalloc(&c->lanes[0].d_post, c->frame_pitch * g.dst_h));
     }
     VP_CUDA(c, cudaMalloc(&c->lanes[0].d_sharp, c->frame_pitch * g.dst_h));
     c->nring = g.temporal.mode == VP_TEMPORAL_MAIN_BLEND ? 2
              : g.temporal.mode == VP_TEMPORAL_BLEND_FRAMES ? std::max(1, g.temporal.buffer_size) + 1 : 0;
-    for (int i = 0; i < c->nring; ++i) VP_CUDA(c, cudaMalloc(&c->d_state[i], c->frame_pitch * g.dst_h));
+    const bool flow_tc = g.temporal.mode == VP_TEMPORAL_BLEND_FRAMES && g.temporal.use_flow;
+    if (flow_tc) {                       // the flow front end keeps its own state (FlowTemporal)
+        c->nring = 1;
+        int rc = ensure_flow_temporal(c, c->ftc, g.dst_w, g.dst_h, g.temporal); if (rc) return rc;
+    } else {
+        for (int i = 0; i < c->nring; ++i) VP_CUDA(c, cudaMalloc(&c->d_state[i], c->frame_pitch * g.dst_h));
+    }
     if (g.dst_w != g.src_w || g.dst_h != g.src_h) {
         int rc = ensure_resize(c, c->rc_chain, g.src_w, g.src_h, g.dst_w, g.dst_h, c->s_compute);
         if (rc) return rc;
     }
-    if (g.temporal.mode == VP_TEMPORAL_BLEND_FRAMES && g.temporal.scene_detect) {
+    if (g.temporal.mode == VP_TEMPORAL_BLEND_FRAMES && (g.temporal.scene_detect || flow_tc)) {
         VP_CUDA(c, cudaMalloc(&c->d_scene_acc, sizeof(SceneAccum)));
         VP_CUDA(c, cudaMemset(c->d_scene_acc, 0, sizeof(SceneAccum)));
         VP_CUDA(c, cudaMalloc(&c->d_scene_state, sizeof(SceneState)));
@@ -823,6 +1099,7 @@ int vp_reset_temporal(vp_ctx* c) {
     c->nvalid = 0;
     c->head = 0;
     c->scene_reset = true;
+    c->ftc.have_prev = false; c->ftc.nvalid = 0; c->ftc.head = 0;
     return VP_OK;
 }
 
@@ -998,6 +1275,29 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
         if (rc) return rc;
         cur = out; cur_pitch = opitch;
     }
+    if (temporal && g.temporal.mode == VP_TEMPORAL_BLEND_FRAMES && g.temporal.use_flow) {
+        // TemporalConsistency::process with its flow front end (run_flow_temporal): the unblended frame has to exist in
+        // memory first, so the plain POST filter runs without its blend epilogue
+        if (plain_post) {
+            BilArgs a{};
+            a.src = cur; a.spitch = cur_pitch; a.dst = L.d_post; a.dpitch = c->frame_pitch; a.w = g.dst_w; a.h = g.dst_h;
+            a.cand = c->d_cand_post; a.sel = need_post_stats ? L.d_sel + 1 : nullptr;
+            rc = launch_bilateral(c, a, c->cand_post_rad, st, K_BIL_POST); if (rc) return rc;
+            cur = L.d_post; cur_pitch = c->frame_pitch;
+        }
+        if (temporal_dep) VP_CUDA(c, cudaStreamWaitEvent(st, temporal_dep, 0));
+        {
+            SceneAccumArgs sa{cur, cur_pitch, c->ftc.have_prev ? c->ftc.raw_prev : nullptr, c->ftc.rpitch, g.dst_w, g.dst_h, c->d_scene_acc};
+            ProfScope ps(c, K_BLEND, st);
+            k_scene_accum<<<c->sm_count * 8, 256, 0, st>>>(sa);
+            k_scene_decide<<<1, 64, 0, st>>>(c->d_scene_acc, c->d_scene_state, c->d_use, (double)g.dst_w * g.dst_h,
+                                             g.temporal.scene_change_threshold, g.temporal.buffer_size, (c->scene_reset || !c->ftc.have_prev) ? 1 : 0);
+            VP_CUDA(c, cudaGetLastError());
+            c->launches += 2;
+            c->scene_reset = false;
+        }
+        return run_flow_temporal(c, c->ftc, g.temporal, cur, cur_pitch, d_dst, dst_pitch, c->d_use, st);
+    }
     BlendArgs bl{};
     temporal_args(c, temporal, bl);
     if (temporal && temporal_dep) VP_CUDA(c, cudaStreamWaitEvent(st, temporal_dep, 0));
@@ -1071,7 +1371,8 @@ static int ensure_lane(vp_ctx* c, int ln) {
     VP_CUDA(c, cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
     if (g.use_pre && !g.bicubic_enhance) VP_CUDA(c, cudaMalloc(&L.d_pre, c->pre_pitch * g.src_h));
     VP_CUDA(c, cudaMalloc(&L.d_sharp, c->frame_pitch * g.dst_h));
-    if (g.use_post && !g.bicubic_enhance && bil_has_modes(g.post)) VP_CUDA(c, cudaMalloc(&L.d_post, c->frame_pitch * g.dst_h));
+    if (g.use_post && !g.bicubic_enhance && (bil_has_modes(g.post) || (g.temporal.mode == VP_TEMPORAL_BLEND_FRAMES && g.temporal.use_flow)))
+        VP_CUDA(c, cudaMalloc(&L.d_post, c->frame_pitch * g.dst_h));
     VP_CUDA(c, cudaMalloc(&L.d_sums, 18 * sizeof(unsigned long long)));
     VP_CUDA(c, cudaMalloc(&L.d_sel, 4 * sizeof(int)));
     VP_CUDA(c, cudaMemset(L.d_sel, 0, 4 * sizeof(int)));
@@ -1395,6 +1696,58 @@ int vp_sigma_map(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, float* d_sig
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
     if (!c->vs_tmp.st) VP_CUDA(c, cudaMalloc(&c->vs_tmp.st, sizeof(SigmaStats)));
     return launch_sigma_map(c, c->vs_tmp.st, d_src, src_pitch, w, h, d_sigma, sigma_pitch, st);
+}
+
+int vp_optical_flow(vp_ctx* c, const vp_temporal_config* cfg, const uint8_t* d_prev, const uint8_t* d_cur, size_t pitch,
+                    float* d_flow_x, float* d_flow_y, size_t flow_pitch, int w, int h, void* stream) {
+    if (!c || !cfg || !d_flow_x || !d_flow_y) return VP_ERR_INVALID_ARG;
+    int rc = check_frame(c, d_prev, pitch, w, h, "vp_optical_flow(prev)"); if (rc) return rc;
+    rc = check_frame(c, d_cur, pitch, w, h, "vp_optical_flow(cur)"); if (rc) return rc;
+    if (flow_pitch < (size_t)w * 4) return fail(c, VP_ERR_INVALID_ARG, "vp_optical_flow: flow pitch < 4*width");
+    VP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    FlowEngine& E = c->flow_tmp;
+    rc = ensure_flow_engine(c, E, w, h, *cfg); if (rc) return rc;
+    rc = flow_expand(c, E, d_prev, pitch, 0, st); if (rc) return rc;
+    rc = flow_expand(c, E, d_cur, pitch, 1, st); if (rc) return rc;
+    rc = flow_solve(c, E, 0, 1, st); if (rc) return rc;
+    const FlowLevel& L0 = E.lv[0];
+    VP_CUDA(c, cudaMemcpy2DAsync(d_flow_x, flow_pitch, L0.flow, (size_t)L0.p * 4, (size_t)w * 4, h, cudaMemcpyDeviceToDevice, st));
+    VP_CUDA(c, cudaMemcpy2DAsync(d_flow_y, flow_pitch, L0.flow + L0.ps, (size_t)L0.p * 4, (size_t)w * 4, h, cudaMemcpyDeviceToDevice, st));
+    return VP_OK;
+}
+
+int vp_warp_flow(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, const float* d_flow_x, const float* d_flow_y, size_t flow_pitch,
+                 uint8_t* d_dst, size_t dst_pitch, int w, int h, void* stream) {
+    if (!c || !d_flow_x || !d_flow_y) return VP_ERR_INVALID_ARG;
+    int rc = check_frame(c, d_src, src_pitch, w, h, "vp_warp_flow(src)"); if (rc) return rc;
+    rc = check_frame(c, d_dst, dst_pitch, w, h, "vp_warp_flow(dst)"); if (rc) return rc;
+    if (flow_pitch < (size_t)w * 4 || (flow_pitch & 3)) return fail(c, VP_ERR_INVALID_ARG, "vp_warp_flow: flow pitch");
+    VP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    ProfScope ps(c, K_BLEND, st);
+    k_warp<<<grid2d(w, h), 256, 0, st>>>(d_src, src_pitch, d_flow_x, d_flow_y, (int)(flow_pitch / 4), d_dst, dst_pitch, w, h);
+    VP_CUDA(c, cudaGetLastError());
+    c->launches++;
+    return VP_OK;
+}
+
+int vp_flow_reliability(vp_ctx* c, const float* d_flow_x, const float* d_flow_y, size_t flow_pitch, float motion_threshold,
+                        float* d_mask, size_t mask_pitch, int w, int h, void* stream) {
+    if (!c || !d_flow_x || !d_flow_y || !d_mask || w <= 0 || h <= 0) return VP_ERR_INVALID_ARG;
+    if (flow_pitch < (size_t)w * 4 || (flow_pitch & 3) || mask_pitch < (size_t)w * 4 || (mask_pitch & 3))
+        return fail(c, VP_ERR_INVALID_ARG, "vp_flow_reliability: pitch");
+    VP_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    const size_t need = mask_pitch / 4 * (size_t)h;
+    if (c->flow_tmp_mask_n < need) {
+        VP_CUDA(c, cudaStreamSynchronize(st));
+        cudaFree(c->flow_tmp_mask); c->flow_tmp_mask = nullptr; c->flow_tmp_mask_n = 0;
+        VP_CUDA(c, cudaMalloc(&c->flow_tmp_mask, need * sizeof(float)));
+        c->flow_tmp_mask_n = need;
+    }
+    if (flow_pitch != mask_pitch) return fail(c, VP_ERR_UNSUPPORTED, "vp_flow_reliability: flow and mask planes must share a pitch");
+    return launch_reliability(c, d_flow_x, d_flow_y, (int)(flow_pitch / 4), motion_threshold, d_mask, (int)(mask_pitch / 4), c->flow_tmp_mask, w, h, st);
 }
 
 int vp_add_weighted(vp_ctx* c, const uint8_t* d_a, size_t a_pitch, double alpha, const uint8_t* d_b, size_t b_pitch, double beta,
