@@ -30,21 +30,7 @@ __global__ void __launch_bounds__(256) k_gray_f32(const uint8_t* __restrict__ sr
 
 struct GaussTaps { int ksize; float k[19]; };
 
-// separable float32 Gaussian, BORDER_REFLECT_101, accumulation left to right without FMA (cv::GaussianBlur on CV_32F)
-template <bool ROWS>
-__global__ void __launch_bounds__(256) k_gauss_f32(const float* __restrict__ src, int sp, float* __restrict__ dst, int dp, int w, int h, const GaussTaps t) {
-    VP_FLOW_XY;
-    const int r = t.ksize >> 1;
-    float acc = 0.f;
-    for (int i = 0; i < t.ksize; ++i) {
-        const float v = ROWS ? src[(size_t)y * sp + reflect101(x + i - r, w)] : src[(size_t)reflect101(y + i - r, h) * sp + x];
-        acc = i == 0 ? __fmul_rn(v, t.k[0]) : __fadd_rn(acc, __fmul_rn(v, t.k[i]));
-    }
-    dst[(size_t)y * dp + x] = acc;
-}
-
-// cv::resize(INTER_LINEAR) on CV_32F planes (nch planes, plane strides sps / dps), optional scale of the result
-// (`flow *= 1 / pyr_scale`).  Horizontal interpolation of both rows first, then vertical, all float32 without FMA.
+// one axis of cv::resize(INTER_LINEAR): source index and fraction behind destination index d
 __device__ __forceinline__ void linear_tap(int d, double scale, int sn, int& s0, float& f) {
     float fx = (float)(((double)d + 0.5) * scale - 0.5);
     int sx = (int)floorf(fx);
@@ -53,6 +39,79 @@ __device__ __forceinline__ void linear_tap(int d, double scale, int sn, int& s0,
     if (sx >= sn - 1) { fx = 0.f; sx = sn - 1; }
     s0 = sx; f = fx;
 }
+
+// separable float32 Gaussian, BORDER_REFLECT_101, accumulation left to right without FMA (cv::GaussianBlur on CV_32F)
+template <bool ROWS>
+__global__ void __launch_bounds__(256) k_gauss_f32(const float* __restrict__ src, int sp, float* __restrict__ dst, int dp, int w, int h, const GaussTaps t) {
+    VP_FLOW_XY;
+    const int r = t.ksize >> 1;
+    float acc = 0.f;
+    const int c = ROWS ? x : y, n = ROWS ? w : h;
+    if (c >= r && c + r < n) {                    // interior: no border map per tap
+        const float* p = ROWS ? src + (size_t)y * sp + (x - r) : src + (size_t)(y - r) * sp + x;
+        const size_t step = ROWS ? 1 : (size_t)sp;
+        for (int i = 0; i < t.ksize; ++i) {
+            const float v = p[i * step];
+            acc = i == 0 ? __fmul_rn(v, t.k[0]) : __fadd_rn(acc, __fmul_rn(v, t.k[i]));
+        }
+    } else {
+        for (int i = 0; i < t.ksize; ++i) {
+            const float v = ROWS ? src[(size_t)y * sp + reflect101(x + i - r, w)] : src[(size_t)reflect101(y + i - r, h) * sp + x];
+            acc = i == 0 ? __fmul_rn(v, t.k[0]) : __fadd_rn(acc, __fmul_rn(v, t.k[i]));
+        }
+    }
+    dst[(size_t)y * dp + x] = acc;
+}
+
+// Pyramid levels below full resolution only need the blurred image where cv::resize(INTER_LINEAR) samples it: two source
+// columns and two source rows per output pixel.  k_gauss_rows_at runs the row pass at those columns only (compact plane
+// of 2*w' columns), k_gauss_cols_resize runs the column pass at the four taps and interpolates - the same arithmetic per
+// sample as the full blur followed by the resize, on a fraction of the samples.
+__global__ void __launch_bounds__(256) k_gauss_rows_at(const float* __restrict__ src, int sp, int sw, int sh, float* __restrict__ dst, int dp,
+                                                       int dw, const GaussTaps t) {
+    const int w = 2 * dw, h = sh;
+    VP_FLOW_XY;
+    int x0; float fx;
+    linear_tap(x >> 1, (double)sw / (double)dw, sw, x0, fx);
+    const int sx = (x & 1) ? min(x0 + 1, sw - 1) : x0;
+    const int r = t.ksize >> 1;
+    const float* row = src + (size_t)y * sp;
+    float acc = 0.f;
+    for (int i = 0; i < t.ksize; ++i) {
+        const float v = row[reflect101(sx + i - r, sw)];
+        acc = i == 0 ? __fmul_rn(v, t.k[0]) : __fadd_rn(acc, __fmul_rn(v, t.k[i]));
+    }
+    dst[(size_t)y * dp + x] = acc;
+}
+__global__ void __launch_bounds__(256) k_gauss_cols_resize(const float* __restrict__ src, int sp, int sw, int sh, float* __restrict__ dst, int dp,
+                                                           int w, int h, const GaussTaps t) {
+    VP_FLOW_XY;
+    int x0, y0; float fx, fy;
+    linear_tap(x, (double)sw / (double)w, sw, x0, fx);
+    linear_tap(y, (double)sh / (double)h, sh, y0, fy);
+    const int y1 = min(y0 + 1, sh - 1);
+    const int r = t.ksize >> 1;
+    float v[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int yy = a ? y1 : y0;
+        float acc0 = 0.f, acc1 = 0.f;
+        for (int i = 0; i < t.ksize; ++i) {
+            const float* p = src + (size_t)reflect101(yy + i - r, sh) * sp + 2 * x;
+            const float2 q = *reinterpret_cast<const float2*>(p);
+            acc0 = i == 0 ? __fmul_rn(q.x, t.k[0]) : __fadd_rn(acc0, __fmul_rn(q.x, t.k[i]));
+            acc1 = i == 0 ? __fmul_rn(q.y, t.k[0]) : __fadd_rn(acc1, __fmul_rn(q.y, t.k[i]));
+        }
+        v[a][0] = acc0; v[a][1] = acc1;
+    }
+    const float a0 = __fsub_rn(1.f, fx), b0 = __fsub_rn(1.f, fy);
+    const float h0 = __fadd_rn(__fmul_rn(v[0][0], a0), __fmul_rn(v[0][1], fx));
+    const float h1 = __fadd_rn(__fmul_rn(v[1][0], a0), __fmul_rn(v[1][1], fx));
+    dst[(size_t)y * dp + x] = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, fy));
+}
+
+// cv::resize(INTER_LINEAR) on CV_32F planes (nch planes, plane strides sps / dps), optional scale of the result
+// (`flow *= 1 / pyr_scale`).  Horizontal interpolation of both rows first, then vertical, all float32 without FMA.
 __global__ void __launch_bounds__(256) k_resize_linear_f32(const float* __restrict__ src, int sp, size_t sps, int sw, int sh,
                                                            float* __restrict__ dst, int dp, size_t dps, int w, int h, int nch, float mul) {
     VP_FLOW_XY;
@@ -164,29 +223,47 @@ __global__ void __launch_bounds__(256) k_update_matrices(const float* __restrict
     M[4 * mps + m] = __fadd_rn(__fmul_rn(r6, r2), __fmul_rn(r5, r3));
 }
 
-// FarnebackUpdateFlow_Blur: (2m+1)^2 box sums of M in double (rows / columns replicate), then the 2x2 solve
-__global__ void __launch_bounds__(256) k_box_v(const float* __restrict__ M, int mp, size_t mps, double* __restrict__ V, int vp_, size_t vps, int w, int h, int m) {
-    VP_FLOW_XY;
-    for (int c = 0; c < 5; ++c) {
-        const float* p = M + c * mps + x;
+// FarnebackUpdateFlow_Blur: (2m+1)^2 box sums of M in double (rows / columns replicate), then the 2x2 solve.
+// One CTA per 32x32 tile.  Phase A: a thread per (column, plane) of the tile's 32+2m columns walks down its column with a
+// running double sum (one add, one subtract per row - OpenCV's own scheme) into shared memory; phase B: every thread
+// sums 2m+1 shared doubles per plane for its four pixels and solves.  M is read ~1.5 times, nothing is spilled to HBM.
+constexpr int BOX_T = 32;
+__global__ void __launch_bounds__(256) k_box_solve(const float* __restrict__ M, int mp, size_t mps, float* __restrict__ flow, int fp, size_t fps,
+                                                   int w, int h, int m, double scale) {
+    extern __shared__ double s_v[];                       // [5][BOX_T][cw], cw = BOX_T + 2m
+    const int cw = BOX_T + 2 * m;
+    const int x0 = blockIdx.x * BOX_T, y0 = blockIdx.y * BOX_T;
+    for (int task = threadIdx.x; task < 5 * cw; task += 256) {
+        const int c = task / cw, cx = task - c * cw;
+        const float* p = M + c * mps + min(max(x0 - m + cx, 0), w - 1);
         double s = 0.0;
-        for (int k = -m; k <= m; ++k) s += (double)p[(size_t)min(max(y + k, 0), h - 1) * mp];
-        V[c * vps + (size_t)y * vp_ + x] = s;
+        for (int k = -m; k <= m; ++k) s += (double)p[(size_t)min(max(y0 + k, 0), h - 1) * mp];
+        double* o = s_v + ((size_t)c * BOX_T) * cw + cx;
+        o[0] = s;
+        for (int r = 1; r < BOX_T; ++r) {
+            const int y = y0 + r;
+            s += (double)p[(size_t)min(y + m, h - 1) * mp];
+            s -= (double)p[(size_t)min(max(y - m - 1, 0), h - 1) * mp];
+            o[(size_t)r * cw] = s;
+        }
     }
-}
-__global__ void __launch_bounds__(256) k_box_h_solve(const double* __restrict__ V, int vp_, size_t vps, float* __restrict__ flow, int fp, size_t fps,
-                                                     int w, int h, int m, double scale) {
-    VP_FLOW_XY;
-    double s[5];
-    for (int c = 0; c < 5; ++c) {
-        const double* p = V + c * vps + (size_t)y * vp_;
-        double a = 0.0;
-        for (int k = -m; k <= m; ++k) a += p[min(max(x + k, 0), w - 1)];
-        s[c] = a * scale;
+    __syncthreads();
+    const int lx = threadIdx.x & 31, x = x0 + lx;
+    for (int ly = threadIdx.x >> 5; ly < BOX_T; ly += 8) {
+        const int y = y0 + ly;
+        if (x >= w || y >= h) continue;
+        double s[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const double* p = s_v + ((size_t)c * BOX_T + ly) * cw + lx;      // window columns lx .. lx + 2m
+            double a = 0.0;
+            for (int k = 0; k <= 2 * m; ++k) a += p[k];
+            s[c] = a * scale;
+        }
+        const double idet = 1.0 / (s[0] * s[2] - s[1] * s[1] + 1e-3);
+        flow[(size_t)y * fp + x] = (float)((s[0] * s[4] - s[1] * s[3]) * idet);
+        flow[fps + (size_t)y * fp + x] = (float)((s[2] * s[3] - s[1] * s[4]) * idet);
     }
-    const double idet = 1.0 / (s[0] * s[2] - s[1] * s[1] + 1e-3);
-    flow[(size_t)y * fp + x] = (float)((s[0] * s[4] - s[1] * s[3]) * idet);
-    flow[fps + (size_t)y * fp + x] = (float)((s[2] * s[3] - s[1] * s[4]) * idet);
 }
 
 // cv::remap(frame, map = (x, y) + flow, INTER_LINEAR, BORDER_REPLICATE) on BGR8, bit-exact: coordinates rounded to

@@ -86,7 +86,6 @@ struct FlowEngine {                 // cv::calcOpticalFlowFarneback for one fram
     float* gray = nullptr; float* blur_a = nullptr; float* blur_b = nullptr;   // full-resolution float planes
     float* tmp = nullptr;           // polyexp row moments (3 planes)
     float* M = nullptr;             // 5 planes
-    double* V = nullptr;            // 5 planes, double
     vp::PolyTaps poly{};
 };
 struct FlowTemporal {               // TemporalConsistency::process with the flow front end: device state
@@ -457,7 +456,7 @@ int run_bilateral_modes(vp_ctx* c, MsScratch& S, const vp_bilateral_config& cfg,
 // ---- Farneback engine (vp_flow.cuh) ---------------------------------------------------------------------------
 void free_flow_engine(FlowEngine& E) {
     for (FlowLevel& L : E.lv) { cudaFree(L.I); cudaFree(L.R[0]); cudaFree(L.R[1]); cudaFree(L.flow); }
-    cudaFree(E.gray); cudaFree(E.blur_a); cudaFree(E.blur_b); cudaFree(E.tmp); cudaFree(E.M); cudaFree(E.V);
+    cudaFree(E.gray); cudaFree(E.blur_a); cudaFree(E.blur_b); cudaFree(E.tmp); cudaFree(E.M);
     E = FlowEngine();
 }
 void free_flow_temporal(FlowTemporal& T) {
@@ -518,6 +517,7 @@ int ensure_flow_engine(vp_ctx* c, FlowEngine& E, int w, int h, const vp_temporal
     if (E.w == w && E.h == h && E.gray && same_flow_params(E.prm, prm)) return VP_OK;
     if (prm.flags != 0) return fail(c, VP_ERR_UNSUPPORTED, "Farneback flags other than 0 are not built");
     if (prm.winsize < 1 || !(prm.winsize & 1) || prm.winsize > 63) return fail(c, VP_ERR_UNSUPPORTED, "Farneback winsize must be odd, 1..63");
+    VP_CUDA(c, cudaFuncSetAttribute(k_box_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(5 * BOX_T * (BOX_T + 62) * sizeof(double))));
     if (prm.iterations < 1 || prm.levels < 0 || prm.levels > 7 || !(prm.pyr_scale > 0.0 && prm.pyr_scale < 1.0))
         return fail(c, VP_ERR_INVALID_ARG, "Farneback: iterations >= 1, levels 0..7, 0 < pyr_scale < 1");
     VP_CUDA(c, cudaDeviceSynchronize());
@@ -546,7 +546,6 @@ int ensure_flow_engine(vp_ctx* c, FlowEngine& E, int w, int h, const vp_temporal
     const FlowLevel& L0 = E.lv[0];
     VP_CUDA(c, planes(&E.gray, 1, L0)); VP_CUDA(c, planes(&E.blur_a, 1, L0)); VP_CUDA(c, planes(&E.blur_b, 1, L0));
     VP_CUDA(c, planes(&E.tmp, 3, L0)); VP_CUDA(c, planes(&E.M, 5, L0));
-    VP_CUDA(c, cudaMalloc(&E.V, 5 * L0.ps * sizeof(double)));
     return VP_OK;
 }
 
@@ -569,12 +568,18 @@ int flow_expand(vp_ctx* c, FlowEngine& E, const uint8_t* bgr, size_t pitch, int 
     for (int k = 0; k < E.nlev; ++k) {
         FlowLevel& L = E.lv[k];
         const GaussTaps t = gauss_taps(L.ksize, L.sigma);
-        k_gauss_f32<true><<<grid2d(E.w, E.h), 256, 0, st>>>(E.gray, L0.p, E.blur_a, L0.p, E.w, E.h, t);
-        k_gauss_f32<false><<<grid2d(E.w, E.h), 256, 0, st>>>(E.blur_a, L0.p, E.blur_b, L0.p, E.w, E.h, t);
-        k_resize_linear_f32<<<grid2d(L.w, L.h), 256, 0, st>>>(E.blur_b, L0.p, 0, E.w, E.h, L.I, L.p, 0, L.w, L.h, 1, 1.f);
-        k_polyexp_v<<<grid2d(L.w, L.h), 256, 0, st>>>(L.I, L.p, E.tmp, L.p, L.ps, L.w, L.h, E.poly);
+        const float* img = L.I;
+        if (L.w == E.w && L.h == E.h) {        // full resolution: the resize is the identity
+            k_gauss_f32<true><<<grid2d(E.w, E.h), 256, 0, st>>>(E.gray, L0.p, E.blur_a, L0.p, E.w, E.h, t);
+            k_gauss_f32<false><<<grid2d(E.w, E.h), 256, 0, st>>>(E.blur_a, L0.p, E.blur_b, L0.p, E.w, E.h, t);
+            img = E.blur_b;
+        } else {                               // blur only where the resize samples: row pass at 2 columns per output column ...
+            k_gauss_rows_at<<<grid2d(2 * L.w, E.h), 256, 0, st>>>(E.gray, L0.p, E.w, E.h, E.blur_a, L0.p, L.w, t);
+            k_gauss_cols_resize<<<grid2d(L.w, L.h), 256, 0, st>>>(E.blur_a, L0.p, E.w, E.h, L.I, L.p, L.w, L.h, t);   // ... column pass at 2 rows
+        }
+        k_polyexp_v<<<grid2d(L.w, L.h), 256, 0, st>>>(img, img == L.I ? L.p : L0.p, E.tmp, L.p, L.ps, L.w, L.h, E.poly);
         k_polyexp_h<<<grid2d(L.w, L.h), 256, 0, st>>>(E.tmp, L.p, L.ps, L.R[which], L.p, L.ps, L.w, L.h, E.poly);
-        c->launches += 5;
+        c->launches += 4;
     }
     VP_CUDA(c, cudaGetLastError());
     return VP_OK;
@@ -597,9 +602,9 @@ int flow_solve(vp_ctx* c, FlowEngine& E, int prev, int cur, cudaStream_t st) {
         k_update_matrices<<<g, 256, 0, st>>>(L.R[prev], L.R[cur], L.p, L.ps, L.flow, L.p, L.ps, E.M, L.p, L.ps, L.w, L.h);
         c->launches++;
         for (int i = 0; i < E.prm.iterations; ++i) {
-            k_box_v<<<g, 256, 0, st>>>(E.M, L.p, L.ps, E.V, L.p, L.ps, L.w, L.h, m);
-            k_box_h_solve<<<g, 256, 0, st>>>(E.V, L.p, L.ps, L.flow, L.p, L.ps, L.w, L.h, m, scale);
-            c->launches += 2;
+            const dim3 gb((L.w + BOX_T - 1) / BOX_T, (L.h + BOX_T - 1) / BOX_T);
+            k_box_solve<<<gb, 256, 5 * BOX_T * (BOX_T + 2 * m) * sizeof(double), st>>>(E.M, L.p, L.ps, L.flow, L.p, L.ps, L.w, L.h, m, scale);
+            c->launches++;
             if (i < E.prm.iterations - 1) {
                 k_update_matrices<<<g, 256, 0, st>>>(L.R[prev], L.R[cur], L.p, L.ps, L.flow, L.p, L.ps, E.M, L.p, L.ps, L.w, L.h);
                 c->launches++;
