@@ -224,42 +224,64 @@ __global__ void __launch_bounds__(256) k_update_matrices(const float* __restrict
 }
 
 // FarnebackUpdateFlow_Blur: (2m+1)^2 box sums of M in double (rows / columns replicate), then the 2x2 solve.
-// One CTA per 32x32 tile.  Phase A: a thread per (column, plane) of the tile's 32+2m columns walks down its column with a
-// running double sum (one add, one subtract per row - OpenCV's own scheme) into shared memory; phase B: every thread
-// sums 2m+1 shared doubles per plane for its four pixels and solves.  M is read ~1.5 times, nothing is spilled to HBM.
-constexpr int BOX_T = 32;
+// One CTA per 32x32 tile, one plane of M at a time: (1) the plane's (32+2m)^2 halo tile is staged in shared memory with
+// coalesced, independent loads; (2) a thread per (tile row, 8-column segment) forms the row sums with a running double sum
+// (one add, one subtract per step - OpenCV's own scheme); (3) every thread owns four vertically adjacent pixels and slides
+// the column window over the row sums.  ~10 shared-memory accesses per pixel and plane instead of 2 x (2m+1); the five sums
+// stay in registers, M is read ~2x, nothing is spilled to HBM.  Shared pitches are odd so lanes walking rows hit distinct banks.
+constexpr int BOX_T = 32, BOX_SEG = 8;
+__host__ __device__ inline size_t box_smem_bytes(int m) {
+    const int ch = BOX_T + 2 * m;
+    return (size_t)ch * (BOX_T + 1) * sizeof(double) + (size_t)ch * (ch | 1) * sizeof(float);
+}
 __global__ void __launch_bounds__(256) k_box_solve(const float* __restrict__ M, int mp, size_t mps, float* __restrict__ flow, int fp, size_t fps,
                                                    int w, int h, int m, double scale) {
-    extern __shared__ double s_v[];                       // [5][BOX_T][cw], cw = BOX_T + 2m
-    const int cw = BOX_T + 2 * m;
+    extern __shared__ double s_r[];                       // [ch][BOX_T + 1] row sums, then the float halo tile [ch][cp]
+    const int ch = BOX_T + 2 * m, cp = ch | 1, rp = BOX_T + 1, win = 2 * m;
+    float* s_m = reinterpret_cast<float*>(s_r + ch * rp);
     const int x0 = blockIdx.x * BOX_T, y0 = blockIdx.y * BOX_T;
-    for (int task = threadIdx.x; task < 5 * cw; task += 256) {
-        const int c = task / cw, cx = task - c * cw;
-        const float* p = M + c * mps + min(max(x0 - m + cx, 0), w - 1);
-        double s = 0.0;
-        for (int k = -m; k <= m; ++k) s += (double)p[(size_t)min(max(y0 + k, 0), h - 1) * mp];
-        double* o = s_v + ((size_t)c * BOX_T) * cw + cx;
-        o[0] = s;
-        for (int r = 1; r < BOX_T; ++r) {
-            const int y = y0 + r;
-            s += (double)p[(size_t)min(y + m, h - 1) * mp];
-            s -= (double)p[(size_t)min(max(y - m - 1, 0), h - 1) * mp];
-            o[(size_t)r * cw] = s;
+    const int lx = threadIdx.x & 31, r0 = (threadIdx.x >> 5) * 4;
+    double acc[4][5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        const float* p = M + c * mps;
+        for (int i = threadIdx.x; i < ch * ch; i += 256) {
+            const int ty = i / ch, tx = i - ty * ch;
+            s_m[ty * cp + tx] = p[(size_t)min(max(y0 - m + ty, 0), h - 1) * mp + min(max(x0 - m + tx, 0), w - 1)];
+        }
+        __syncthreads();
+        for (int task = threadIdx.x; task < ch * (BOX_T / BOX_SEG); task += 256) {
+            const int seg = task / ch, row = task - seg * ch;
+            const float* q = s_m + row * cp + seg * BOX_SEG;           // first column of the first window
+            double s = 0.0;
+            for (int k = 0; k <= win; ++k) s += (double)q[k];
+            double* o = s_r + row * rp + seg * BOX_SEG;
+            o[0] = s;
+#pragma unroll
+            for (int t = 1; t < BOX_SEG; ++t) {
+                s += (double)q[t + win];
+                s -= (double)q[t - 1];
+                o[t] = s;
+            }
+        }
+        __syncthreads();
+        const double* v = s_r + r0 * rp + lx;                          // window rows r0 .. r0 + 2m of the tile's halo rows
+        double a = 0.0;
+        for (int k = 0; k <= win; ++k) a += v[k * rp];
+        acc[0][c] = a * scale;
+#pragma unroll
+        for (int t = 1; t < 4; ++t) {
+            a += v[(t + win) * rp];
+            a -= v[(t - 1) * rp];
+            acc[t][c] = a * scale;
         }
     }
-    __syncthreads();
-    const int lx = threadIdx.x & 31, x = x0 + lx;
-    for (int ly = threadIdx.x >> 5; ly < BOX_T; ly += 8) {
-        const int y = y0 + ly;
-        if (x >= w || y >= h) continue;
-        double s[5];
+    const int x = x0 + lx;
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            const double* p = s_v + ((size_t)c * BOX_T + ly) * cw + lx;      // window columns lx .. lx + 2m
-            double a = 0.0;
-            for (int k = 0; k <= 2 * m; ++k) a += p[k];
-            s[c] = a * scale;
-        }
+    for (int t = 0; t < 4; ++t) {
+        const int y = y0 + r0 + t;
+        if (x >= w || y >= h) continue;
+        const double* s = acc[t];
         const double idet = 1.0 / (s[0] * s[2] - s[1] * s[1] + 1e-3);
         flow[(size_t)y * fp + x] = (float)((s[0] * s[4] - s[1] * s[3]) * idet);
         flow[fps + (size_t)y * fp + x] = (float)((s[2] * s[3] - s[1] * s[4]) * idet);
