@@ -234,9 +234,12 @@ __host__ __device__ inline size_t box_smem_bytes(int m) {
     const int ch = BOX_T + 2 * m;
     return (size_t)ch * (BOX_T + 1) * sizeof(double) + (size_t)ch * (ch | 1) * sizeof(float);
 }
+// MT > 0: window half-width known at compile time (the reference's winsize 15 -> MT = 7), loops unrolled, constant divisors
+template <int MT>
 __global__ void __launch_bounds__(256) k_box_solve(const float* __restrict__ M, int mp, size_t mps, float* __restrict__ flow, int fp, size_t fps,
-                                                   int w, int h, int m, double scale) {
+                                                   int w, int h, int m_rt, double scale) {
     extern __shared__ double s_r[];                       // [ch][BOX_T + 1] row sums, then the float halo tile [ch][cp]
+    const int m = MT > 0 ? MT : m_rt;
     const int ch = BOX_T + 2 * m, cp = ch | 1, rp = BOX_T + 1, win = 2 * m;
     float* s_m = reinterpret_cast<float*>(s_r + ch * rp);
     const int x0 = blockIdx.x * BOX_T, y0 = blockIdx.y * BOX_T;
@@ -254,6 +257,7 @@ __global__ void __launch_bounds__(256) k_box_solve(const float* __restrict__ M, 
             const int seg = task / ch, row = task - seg * ch;
             const float* q = s_m + row * cp + seg * BOX_SEG;           // first column of the first window
             double s = 0.0;
+#pragma unroll
             for (int k = 0; k <= win; ++k) s += (double)q[k];
             double* o = s_r + row * rp + seg * BOX_SEG;
             o[0] = s;
@@ -267,6 +271,7 @@ __global__ void __launch_bounds__(256) k_box_solve(const float* __restrict__ M, 
         __syncthreads();
         const double* v = s_r + r0 * rp + lx;                          // window rows r0 .. r0 + 2m of the tile's halo rows
         double a = 0.0;
+#pragma unroll
         for (int k = 0; k <= win; ++k) a += v[k * rp];
         acc[0][c] = a * scale;
 #pragma unroll
