@@ -340,6 +340,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints a banner)
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
     from video_processor_b200 import capi
