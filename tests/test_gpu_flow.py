@@ -165,3 +165,62 @@ def test_chain_with_flow_temporal(vp):
                 o = d.cpu().numpy()
                 mx, _ = G.diff_stats(o, r)
                 assert RC.psnr(o, r) >= 50.0 and mx <= 4, (batch, RC.psnr(o, r), mx)
+
+
+@pytest.mark.parametrize("size", [(20, 12), (131, 67), (33, 200)])
+def test_temporal_consistency_full_odd_sizes(vp, size):
+    """ragged and tiny frames: every pyramid level smaller than 32 px is dropped, windows larger than the frame clamp"""
+    sw, sh = size
+    frames = synth.clip("scene", sw, sh, 5)
+    t = RC.TemporalConfig(use_flow=True, scene_detect=True)
+    outs = run_tc(vp, frames, t, sw, sh)
+    oracle = RC.TemporalConsistencyFull(t, RC.Cv2Ops())
+    for i, (o, f) in enumerate(zip(outs, frames)):
+        ref = oracle.process(f)
+        mx, n = G.diff_stats(o, ref)
+        assert mx <= 1 and n <= max(o.size * 0.01, 8), (i, mx, n)
+
+
+def test_flow_temporal_through_the_host_api(vp):
+    """vp_process_host and the pipelined vp_submit_host / vp_wait drive the same device state as vp_process_device"""
+    sw, sh = 96, 64
+    t = RC.TemporalConfig(use_flow=True, scene_detect=True)
+    ocfg = RC.ChainConfig(dst_w=sw, dst_h=sh, use_pre=False, use_sharpen=False, use_post=False, temporal=RC.TEMPORAL_BLEND_FRAMES, temporal_cfg=t)
+    frames = synth.clip("scene", sw, sh, 6)
+    ref = run_tc(vp, frames, t, sw, sh)
+    with vp.Context(G.chain_cfg(vp, ocfg, sw, sh)) as ctx:
+        outs = [np.empty((sh, sw, 3), np.uint8) for _ in frames]
+        for f, o in zip(frames, outs):
+            ctx.call("vp_process_host", f.ctypes.data, sw * 3, o.ctypes.data, sw * 3)
+        for o, r in zip(outs, ref):
+            assert np.array_equal(o, r)
+    with vp.Context(G.chain_cfg(vp, ocfg, sw, sh)) as ctx:
+        outs = [np.empty((sh, sw, 3), np.uint8) for _ in frames]
+        depth = vp.lib.vp_pipeline_depth(ctx.handle)
+        inflight = 0
+        for f, o in zip(frames, outs):
+            if inflight == depth:
+                ctx.call("vp_wait"); inflight -= 1
+            ctx.call("vp_submit_host", f.ctypes.data, sw * 3, o.ctypes.data, sw * 3)
+            inflight += 1
+        while inflight:
+            ctx.call("vp_wait"); inflight -= 1
+        for o, r in zip(outs, ref):
+            assert np.array_equal(o, r)
+
+
+def test_flow_temporal_reset(vp):
+    sw, sh = 96, 64
+    t = RC.TemporalConfig(use_flow=True, scene_detect=True)
+    ocfg = RC.ChainConfig(dst_w=sw, dst_h=sh, use_pre=False, use_sharpen=False, use_post=False, temporal=RC.TEMPORAL_BLEND_FRAMES, temporal_cfg=t)
+    frames = synth.clip("scene", sw, sh, 4)
+    ref = run_tc(vp, frames, t, sw, sh)
+    with vp.Context(G.chain_cfg(vp, ocfg, sw, sh)) as ctx:
+        for rep in range(2):
+            for f, r in zip(frames, ref):
+                src = G.to_dev(f)
+                dst = G.dev_empty(sh, sw)
+                ctx.call("vp_process_device", src.data_ptr(), sw * 3, dst.data_ptr(), G.pitch(dst), None)
+                G.sync()
+                assert np.array_equal(dst.cpu().numpy(), r), rep
+            ctx.call("vp_reset_temporal")
