@@ -224,3 +224,35 @@ def test_flow_temporal_reset(vp):
                 G.sync()
                 assert np.array_equal(dst.cpu().numpy(), r), rep
             ctx.call("vp_reset_temporal")
+
+
+def test_against_frozen_opencv_vectors(vp, ctx):
+    """tests/golden/golden_widened.npz = output of the real OpenCV kernels (minted by make_golden_widened.py)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_widened.npz"))
+    img, nxt = synth.frame("scene", 96, 64, 5), synth.frame("scene", 96, 64, 6)
+    t = RC.TemporalConfig(use_flow=True, scene_detect=True)
+    assert np.abs(gpu_flow(vp, ctx, img, nxt, t) - g["farneback_flow"]).max() <= 2e-3
+    src = G.to_dev(img)
+    fx, fy = G.to_dev(g["farneback_flow"][..., 0].copy()), G.to_dev(g["farneback_flow"][..., 1].copy())
+    dst = G.dev_empty(64, 96)
+    ctx.call("vp_warp_flow", src.data_ptr(), G.pitch(src), fx.data_ptr(), fy.data_ptr(), G.pitch(fx), dst.data_ptr(), G.pitch(dst), 96, 64, None)
+    G.sync()
+    assert np.array_equal(dst.cpu().numpy(), g["warp"])
+    outs = run_tc(vp, synth.clip("scene", 96, 64, 5), t, 96, 64)
+    for k, o in enumerate(outs):
+        mx, n = G.diff_stats(o, g[f"tc_full_t{k}"])
+        assert mx <= 1 and n <= o.size * 0.01, (k, mx, n)
+    # pyramids and the detail / sigma planes of the other widened rows
+    down = G.dev_empty(32, 48)
+    ctx.call("vp_pyr_down", src.data_ptr(), G.pitch(src), 96, 64, down.data_ptr(), G.pitch(down), None)
+    up = G.dev_empty(64, 96)
+    ctx.call("vp_pyr_up", down.data_ptr(), G.pitch(down), 48, 32, up.data_ptr(), G.pitch(up), 96, 64, None)
+    mask = torch.empty((64, 96), dtype=torch.float32, device="cuda")
+    ctx.call("vp_detail_mask", 30.0, src.data_ptr(), G.pitch(src), mask.data_ptr(), G.pitch(mask), 96, 64, None)
+    sig = torch.empty((64, 96), dtype=torch.float32, device="cuda")
+    ctx.call("vp_sigma_map", src.data_ptr(), G.pitch(src), sig.data_ptr(), G.pitch(sig), 96, 64, None)
+    G.sync()
+    assert np.array_equal(down.cpu().numpy(), g["pyr_down"]) and np.array_equal(up.cpu().numpy(), g["pyr_up"])
+    assert np.abs(mask.cpu().numpy() - g["detail_mask"]).max() <= 5e-6
+    assert np.abs(sig.cpu().numpy() - g["sigma_map"]).max() <= 5e-6

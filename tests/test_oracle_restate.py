@@ -240,3 +240,32 @@ def test_variable_sigma_constant_frame_is_passthrough_safe():
     img = np.full((20, 30, 3), 77, np.uint8)
     out = RC.sharpen_variable_sigma(RC.NumpyOps(), img, RC.SharpenConfig())
     assert out.shape == img.shape and np.abs(out.astype(int) - 77).max() <= 1
+
+
+def test_golden_vectors_widened_rows():
+    """tests/golden/golden_widened.npz holds output of the REAL OpenCV kernels (cv2 backend) for the SURVEY 8(f) rows;
+    the numpy restatement must reproduce it: integer stages exactly, float stages / truncating stages within the bars
+    the GPU tests use."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_widened.npz"))
+    n = RC.NumpyOps()
+    img, nxt = synth.frame("scene", 96, 64, 5), synth.frame("scene", 96, 64, 6)
+    assert np.array_equal(g["pyr_down"], R.pyr_down_u8(img))
+    assert np.array_equal(g["pyr_up"], R.pyr_up_u8(g["pyr_down"], 96, 64))
+    assert np.abs(g["detail_mask"] - RC.create_detail_mask(n, img, RC.BilateralConfig())).max() <= 2e-6
+
+    def lsb(a, b, mx, frac):
+        d = np.abs(a.astype(int) - b.astype(int))
+        return d.max() <= mx and (d > 0).mean() <= frac
+    assert lsb(g["selective"], RC.selective_bilateral_process(n, img, RC.BilateralConfig(selective=True, use_multiscale=False)), 1, 0.01)
+    assert lsb(g["multiscale"], RC.selective_bilateral_process(n, img, RC.BilateralConfig(use_multiscale=True, num_scales=3)), 2, 0.02)
+    assert np.abs(g["sigma_map"] - RC.adaptive_sigma_map(n, RC.texture_map(n, img))).max() <= 2e-6
+    assert lsb(g["variable_sigma_sharpen"], RC.sharpen_variable_sigma(n, img, RC.SharpenConfig(adaptive_sigma=True)), 2, 0.01)
+    t = RC.TemporalConfig(use_flow=True, scene_detect=True)
+    flow = n.farneback(R.bgr2gray(img), R.bgr2gray(nxt), t)
+    assert np.abs(g["farneback_flow"] - flow).max() <= 1e-4
+    assert np.array_equal(g["warp"], n.remap_flow(img, g["farneback_flow"]))
+    big = (g["farneback_flow"] * np.float32(12.0)).astype(np.float32)
+    assert np.abs(g["reliability_mask"] - RC.flow_reliability_mask(n, big, t.motion_threshold)).max() <= 2e-6
+    tc = RC.TemporalConsistencyFull(t, n)
+    for k in range(5):
+        assert lsb(g[f"tc_full_t{k}"], tc.process(synth.frame("scene", 96, 64, k)), 1, 0.01)
