@@ -298,6 +298,7 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
         // caller-supplied / exported masks exist only on the stage-wise (no-resize) entry points
         constexpr bool MASKIO = !RESIZE;
         const bool own_mask = !MASKIO || (a.mask_in == nullptr);
+        const bool mask_only = MASKIO && own_mask && a.dst == nullptr && a.sums == nullptr && a.mask_out != nullptr;
         constexpr int CW = US_TW + 4, CH = US_TH + 4;
         if (own_mask) {
             // ---- P3: Sobel / Laplacian magnitude -> sigmoid on (TW+4)x(TH+4); column walk, 3-row window ---
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
                 }
             }
             // ---- P4b: Q8.8 row pass of the 8-bit Gaussian; B and G share one 32-bit accumulator ---
-            {
+            if (!mask_only) {
                 int q[GK];
 #pragma unroll
                 for (int k = 0; k < GK; ++k) q[k] = a.gq[k];
@@ -358,6 +359,19 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
             }
         }
         __syncthreads();
+        if (mask_only) {
+            // createEdgeMask alone (vp_edge_mask, the adaptive_sigma branch): column pass of the mask blur, nothing else
+            const int x = tid & 63, yb = (tid >> 6) * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int y = yb + i;
+                float e = __fmul_rn(s_rowf[y * US_TW + x], a.gf[0]);
+#pragma unroll
+                for (int k = 1; k < 5; ++k) e = __fadd_rn(e, __fmul_rn(s_rowf[(y + k) * US_TW + x], a.gf[k]));
+                if (x < vw && y < vh)
+                    *reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a.mask_out) + (size_t)(y0 + y) * a.mask_out_pitch + (size_t)(x0 + x) * 4) = e;
+            }
+        } else
         // ---- P5: column passes (sliding windows), unsharp blend, tone preservation ------------------
         {
             const int x = tid & 63, g = tid >> 6;
