@@ -170,25 +170,29 @@ struct VarSharpArgs {
     SelOut fin;
 };
 
-constexpr int VS_TW = 64, VS_TH = 32, VS_NT = 256, VS_R = 3;   // tile, threads, largest kernel radius
+constexpr int VS_TW = 64, VS_TH = 32, VS_NT = 256;   // tile, threads
 
+// The two Gaussian levels of a pixel are exact integer sums sum(p * q_a * q_b) < 2^24, so they are accumulated in float32
+// (FFMA is full rate, IMAD is not) as packed pairs: (b, g) x w_low, (b, g) x w_high and r x (w_low, w_high) - three FFMA2 per
+// tap, fed by one 128-bit pixel load and one 64-bit weight-pair load.
+template <int GK>
 __global__ void __launch_bounds__(VS_NT) k_varsharp(const VarSharpArgs a) {
-    constexpr int EW = VS_TW + 2 * VS_R, EH = VS_TH + 2 * VS_R;
-    __shared__ uint32_t s_px[EW * EH];                   // BGR0 words, reflect-101 padded
-    __shared__ int s_w2[VS_LEVELS][49];                  // q[a] * q[b] per level
+    constexpr int GR = GK / 2, EW = VS_TW + 2 * GR, EH = VS_TH + 2 * GR;
+    __shared__ float4 s_px[EW * EH];                     // (b, g, r, packed BGR0 bits), reflect-101 padded
+    __shared__ float2 s_wp[VS_LEVELS - 1][GK * GK];      // (q[l][a] q[l][b], q[l+1][a] q[l+1][b]) for adjacent levels
     __shared__ unsigned long long s_part[(VS_NT / 32) * 6];
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * VS_TW, y0 = blockIdx.y * VS_TH;
-    const int gk = a.gk, gr = gk / 2;
     for (int i = tid; i < EW * EH; i += VS_NT) {
         const int ty = i / EW, tx = i - ty * EW;
-        const int sx = reflect101(x0 - VS_R + tx, a.w), sy = reflect101(y0 - VS_R + ty, a.h);
+        const int sx = reflect101(x0 - GR + tx, a.w), sy = reflect101(y0 - GR + ty, a.h);
         const uint8_t* p = a.src + (size_t)sy * a.spitch + (size_t)sx * 3;
-        s_px[i] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+        const uint32_t b = __ldg(p), g = __ldg(p + 1), r = __ldg(p + 2);
+        s_px[i] = make_float4((float)b, (float)g, (float)r, __uint_as_float(b | (g << 8) | (r << 16)));
     }
-    for (int i = tid; i < VS_LEVELS * 49; i += VS_NT) {
-        const int l = i / 49, t = i - l * 49, ta = t / 7, tb = t - ta * 7;
-        s_w2[l][t] = a.lv->q[l][ta] * a.lv->q[l][tb];
+    for (int i = tid; i < (VS_LEVELS - 1) * GK * GK; i += VS_NT) {
+        const int l = i / (GK * GK), t = i - l * (GK * GK), ta = t / GK, tb = t - ta * GK;
+        s_wp[l][t] = make_float2((float)(a.lv->q[l][ta] * a.lv->q[l][tb]), (float)(a.lv->q[l + 1][ta] * a.lv->q[l + 1][tb]));
     }
     const float mn = a.lv->mn, span = a.lv->span;
     __syncthreads();
@@ -207,20 +211,27 @@ __global__ void __launch_bounds__(VS_NT) k_varsharp(const VarSharpArgs a) {
         const float den = __fsub_rn(shi, slo);
         const float alpha = den > 0.f ? __fdiv_rn(__fsub_rn(sigma, slo), den) : 0.f;
         // the two Gaussian levels at this pixel: exact Q8.16 sums, (v + 2^15) >> 16
-        unsigned lo[3] = {1u << 15, 1u << 15, 1u << 15}, hi[3] = {1u << 15, 1u << 15, 1u << 15};
-        const int* wl = s_w2[idx];
-        const int* wh = s_w2[idx + 1];
-        for (int ta = 0; ta < gk; ++ta) {
-            const uint32_t* row = s_px + (y + VS_R - gr + ta) * EW + (x + VS_R - gr);
-            for (int tb = 0; tb < gk; ++tb) {
-                const uint32_t px = row[tb];
-                const unsigned w0 = (unsigned)wl[ta * 7 + tb], w1 = (unsigned)wh[ta * 7 + tb];
-                const unsigned b = px & 0xff, g = (px >> 8) & 0xff, r = (px >> 16) & 0xff;
-                lo[0] += b * w0; lo[1] += g * w0; lo[2] += r * w0;
-                hi[0] += b * w1; hi[1] += g * w1; hi[2] += r * w1;
+        unsigned long long bg_lo = 0ull, bg_hi = 0ull, r_lh = 0ull;
+        const float2* wp = s_wp[idx];
+#pragma unroll
+        for (int ta = 0; ta < GK; ++ta) {
+            const float4* row = s_px + (y + ta) * EW + x;
+#pragma unroll
+            for (int tb = 0; tb < GK; ++tb) {
+                const float4 px = row[tb];
+                const float2 w = wp[ta * GK + tb];
+                const unsigned long long bg = pack2(__float_as_uint(px.x), __float_as_uint(px.y));
+                bg_lo = ffma2(bg, pack2(__float_as_uint(w.x), __float_as_uint(w.x)), bg_lo);
+                bg_hi = ffma2(bg, pack2(__float_as_uint(w.y), __float_as_uint(w.y)), bg_hi);
+                r_lh = ffma2(pack2(__float_as_uint(w.x), __float_as_uint(w.y)), pack2(__float_as_uint(px.z), __float_as_uint(px.z)), r_lh);
             }
         }
-        const uint32_t cpx = s_px[(y + VS_R) * EW + x + VS_R];
+        float fl[3], fh[3];
+        unpack2(bg_lo, fl[0], fl[1]); unpack2(bg_hi, fh[0], fh[1]); unpack2(r_lh, fl[2], fh[2]);
+        unsigned lo[3], hi[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) { lo[ch] = __float2uint_rz(fl[ch]) + (1u << 15); hi[ch] = __float2uint_rz(fh[ch]) + (1u << 15); }
+        const uint32_t cpx = __float_as_uint(s_px[(y + GR) * EW + x + GR].w);
         const int u[3] = {(int)(cpx & 0xff), (int)((cpx >> 8) & 0xff), (int)((cpx >> 16) & 0xff)};
         const float e = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(a.emask) + (size_t)gy * a.epitch + (size_t)gx * 4);
         const float t1 = __fmul_rn(e, a.edge_strength);

@@ -761,7 +761,9 @@ int run_varsharp(vp_ctx* c, VsScratch& S, const vp_sharpen_config& cfg, const fl
     a.preserve_tone = cfg.preserve_tone;
     a.dst = dst; a.dpitch = dpitch; a.sums = sums; a.fin = fin;
     const dim3 grid((w + VS_TW - 1) / VS_TW, (h + VS_TH - 1) / VS_TH);
-    k_varsharp<<<grid, VS_NT, 0, st>>>(a);
+    if (a.gk == 3) k_varsharp<3><<<grid, VS_NT, 0, st>>>(a);
+    else if (a.gk == 5) k_varsharp<5><<<grid, VS_NT, 0, st>>>(a);
+    else k_varsharp<7><<<grid, VS_NT, 0, st>>>(a);
     VP_CUDA(c, cudaGetLastError());
     c->launches += 2;
     return VP_OK;
