@@ -25,6 +25,7 @@ struct BicubicArgs {
     uint8_t* dst; size_t dpitch; int dw, dh;
     ResizeTables rt;
     int max_src_rows, max_src_cols;     // unclamped per-tile source window bounds
+    int yperiod;                        // S when dst_h == S * src_h with S = 2 or 4 (host-verified row tables), else 0
 };
 
 struct BicubicSmem { int raw, raw_pitch, src, src_pitch, tabs, total; };
@@ -40,6 +41,10 @@ __host__ __device__ inline BicubicSmem bicubic_layout(int max_src_rows, int max_
     return L;
 }
 
+// S = 0: any ratio (row tables read per row).  S = 2 / 4: the vertical tap origin advances exactly once every S output
+// rows, at (y % S) == S/2, and the S coefficient sets repeat - so the step is unrolled statically, the coefficients live
+// in registers, and the S rows that share a window are filtered two at a time with packed float32 FMAs.
+template <int S>
 __global__ void __launch_bounds__(BC_NT) k_bicubic(const BicubicArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x;
@@ -95,6 +100,64 @@ __global__ void __launch_bounds__(BC_NT) k_bicubic(const BicubicArgs a) {
     float w0[3], w1[3], w2[3], w3[3];
     int yo = s_yo[0];
     hrow(yo, w0); hrow(yo + 1, w1); hrow(yo + 2, w2); hrow(yo + 3, w3);
+    // one finished pixel of this column -> memory (quad repack through a shuffle: every lane of the warp must call it)
+    auto emit = [&](int y, const uint32_t (&v)[3]) {
+        const uint32_t px = v[0] | (v[1] << 8) | (v[2] << 16);
+        const uint32_t nxt = __shfl_down_sync(0xffffffffu, px, 1);
+        if (y >= vh) return;
+        uint8_t* row = a.dst + (size_t)(y0 + y) * a.dpitch;
+        if (quad_ok) {
+            if (q != 3) {
+                const uint32_t lo = px | (nxt << 24), hi = nxt >> 8;
+                *reinterpret_cast<uint32_t*>(row + (size_t)(gx - q) * 3 + 4 * q) = __funnelshift_r(lo, hi, 8 * q);
+            }
+        } else if (col_ok) {
+            uint8_t* o = row + (size_t)gx * 3;
+            o[0] = (uint8_t)v[0]; o[1] = (uint8_t)v[1]; o[2] = (uint8_t)v[2];
+        }
+    };
+    if constexpr (S > 0) {
+        // rows y0 + y with y % S == j use coefficient set j (y0 is a multiple of BC_TH, hence of S)
+        float4 bj[S];
+#pragma unroll
+        for (int j = 0; j < S; ++j) bj[j] = s_yc[j];
+        auto row1 = [&](int y, const float4& b) {
+            uint32_t v[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+                v[ch] = f2u8(__fadd_rn(__fmaf_rn(w0[ch], b.x, __fmul_rn(w1[ch], b.y)), __fmaf_rn(w2[ch], b.z, __fmul_rn(w3[ch], b.w))));
+            emit(y, v);
+        };
+        // two rows that share the window: the same four products per channel as row1, as f32x2 lanes (row A, row B)
+        auto row2 = [&](int y, const float4& ba, const float4& bb) {
+            const unsigned long long bx = pack2(__float_as_uint(ba.x), __float_as_uint(bb.x)), by = pack2(__float_as_uint(ba.y), __float_as_uint(bb.y));
+            const unsigned long long bz = pack2(__float_as_uint(ba.z), __float_as_uint(bb.z)), bw = pack2(__float_as_uint(ba.w), __float_as_uint(bb.w));
+            uint32_t va[3], vb[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const unsigned long long p0 = pack2(__float_as_uint(w0[ch]), __float_as_uint(w0[ch])), p1 = pack2(__float_as_uint(w1[ch]), __float_as_uint(w1[ch]));
+                const unsigned long long p2 = pack2(__float_as_uint(w2[ch]), __float_as_uint(w2[ch])), p3 = pack2(__float_as_uint(w3[ch]), __float_as_uint(w3[ch]));
+                const unsigned long long t = fadd2(ffma2(p0, bx, fmul2(p1, by)), ffma2(p2, bz, fmul2(p3, bw)));
+                float ta, tb;
+                unpack2(t, ta, tb);
+                va[ch] = f2u8(ta); vb[ch] = f2u8(tb);
+            }
+            emit(y, va);
+            emit(y + 1, vb);
+        };
+        // rows before the first step (phases 0 .. S/2-1) share the initial window
+        if constexpr (S == 2) row1(0, bj[0]);
+        else row2(0, bj[0], bj[1]);
+        for (int yb = S / 2; yb < vh; yb += S) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) { w0[ch] = w1[ch]; w1[ch] = w2[ch]; w2[ch] = w3[ch]; }
+            yo += 1;
+            hrow(yo + 3, w3);
+            if constexpr (S == 2) row2(yb, bj[1], bj[0]);
+            else { row2(yb, bj[2], bj[3]); row2(yb + 2, bj[0], bj[1]); }
+        }
+        return;
+    }
     for (int y = 0; y < vh; ++y) {
         const int yn = s_yo[y];           // uniform across the CTA: no divergence below
         const int d = yn - yo;
@@ -112,18 +175,7 @@ __global__ void __launch_bounds__(BC_NT) k_bicubic(const BicubicArgs a) {
         for (int ch = 0; ch < 3; ++ch)
             v[ch] = f2u8(__fadd_rn(__fmaf_rn(w0[ch], b.x, __fmul_rn(w1[ch], b.y)),
                                    __fmaf_rn(w2[ch], b.z, __fmul_rn(w3[ch], b.w))));
-        const uint32_t px = v[0] | (v[1] << 8) | (v[2] << 16);
-        const uint32_t nxt = __shfl_down_sync(0xffffffffu, px, 1);
-        uint8_t* row = a.dst + (size_t)(y0 + y) * a.dpitch;
-        if (quad_ok) {
-            if (q != 3) {
-                const uint32_t lo = px | (nxt << 24), hi = nxt >> 8;
-                *reinterpret_cast<uint32_t*>(row + (size_t)(gx - q) * 3 + 4 * q) = __funnelshift_r(lo, hi, 8 * q);
-            }
-        } else if (col_ok) {
-            uint8_t* o = row + (size_t)gx * 3;
-            o[0] = (uint8_t)v[0]; o[1] = (uint8_t)v[1]; o[2] = (uint8_t)v[2];
-        }
+        emit(y, v);
     }
 }
 

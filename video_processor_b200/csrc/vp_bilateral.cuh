@@ -125,6 +125,9 @@ __device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& 
 __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
     unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
 }
+__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b) {
+    unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
 __device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
     unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
 }

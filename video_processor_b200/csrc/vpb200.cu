@@ -50,6 +50,7 @@ struct ResizeCache {
     int* xofs = nullptr; int4* xcoef = nullptr; int* yofs = nullptr; float4* ycoef = nullptr;
     int max_rows[2] = {0, 0}, max_cols[2] = {0, 0};   // [0] halo 0, [1] halo US_HALO (k_upsharp tiles)
     int bc_rows = 0, bc_cols = 0;                     // k_bicubic tiles
+    int yperiod = 0;                                  // 2 / 4 when the row tables are periodic with an integer ratio (k_bicubic<S>)
 };
 
 struct HostSlot {
@@ -289,6 +290,17 @@ int ensure_resize(vp_ctx* c, ResizeCache& rc, int sw, int sh, int dw, int dh, cu
     }
     rc.bc_cols = tile_span(tx.ofs, dw, BC_TW, 0);
     rc.bc_rows = tile_span(ty.ofs, dh, BC_TH, 0);
+    // integer vertical ratio S: the tap origin advances exactly at y % S == S/2 and the taps repeat with period S
+    rc.yperiod = 0;
+    for (int S : {2, 4}) {
+        if (dh != S * sh) continue;
+        bool ok = true;
+        for (int y = 0; y < dh && ok; ++y) {
+            if (y + 1 < dh && ty.ofs[y + 1] - ty.ofs[y] != (((y + 1) % S) == S / 2 ? 1 : 0)) ok = false;
+            if (y >= S && std::memcmp(&yb[(size_t)y * 4], &yb[(size_t)(y - S) * 4], 4 * sizeof(float)) != 0) ok = false;
+        }
+        if (ok) rc.yperiod = S;
+    }
     rc.sw = sw; rc.sh = sh; rc.dw = dw; rc.dh = dh;
     return VP_OK;
 }
@@ -813,7 +825,10 @@ int launch_bicubic(vp_ctx* c, const uint8_t* src, size_t spitch, int sw, int sh,
     if (L.total > 200 * 1024) return fail(c, VP_ERR_UNSUPPORTED, "resize ratio needs more shared memory than a CTA has");
     const dim3 grid((dw + BC_TW - 1) / BC_TW, (dh + BC_TH - 1) / BC_TH);
     ProfScope ps(c, K_UPSHARP, st);
-    k_bicubic<<<grid, BC_NT, L.total, st>>>(a);
+    a.yperiod = rcache.yperiod;
+    if (a.yperiod == 2) k_bicubic<2><<<grid, BC_NT, L.total, st>>>(a);
+    else if (a.yperiod == 4) k_bicubic<4><<<grid, BC_NT, L.total, st>>>(a);
+    else k_bicubic<0><<<grid, BC_NT, L.total, st>>>(a);
     VP_CUDA(c, cudaGetLastError());
     c->launches++;
     return VP_OK;
@@ -955,7 +970,9 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
     VP_CUDA(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
     VP_CUDA(c, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
     VP_CUDA(c, cudaFuncSetAttribute(k_bilateral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(bil_smem_bytes(BIL_RMAX, 1), bil_smem_bytes(3, 2))));
-    VP_CUDA(c, cudaFuncSetAttribute(k_bicubic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VP_CUDA(c, cudaFuncSetAttribute(k_bicubic<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VP_CUDA(c, cudaFuncSetAttribute(k_bicubic<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VP_CUDA(c, cudaFuncSetAttribute(k_bicubic<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
