@@ -28,7 +28,7 @@ struct BicubicArgs {
     int yperiod;                        // S when dst_h == S * src_h with S = 2 or 4 (host-verified row tables), else 0
 };
 
-struct BicubicSmem { int raw, raw_pitch, src, src_pitch, tabs, total; };
+struct BicubicSmem { int raw, raw_pitch, src, src_pitch, tabs, out, total; };
 
 __host__ __device__ inline BicubicSmem bicubic_layout(int max_src_rows, int max_src_cols) {
     BicubicSmem L{};
@@ -37,6 +37,7 @@ __host__ __device__ inline BicubicSmem bicubic_layout(int max_src_rows, int max_
     L.raw = o; o += L.raw_pitch * max_src_rows;
     L.src_pitch = 0; L.src = o;
     L.tabs = o; o += BC_TH * 16 + BC_TH * 4 + 16;      // ycoef float4[TH], yofs int[TH], mbarrier
+    L.out = (o + 15) & ~15; o = L.out + BC_TH * BC_TW * 3;   // staged output tile (integer-ratio path, TMA bulk stores)
     L.total = o;
     return L;
 }
@@ -121,40 +122,93 @@ __global__ void __launch_bounds__(BC_NT) k_bicubic(const BicubicArgs a) {
         float4 bj[S];
 #pragma unroll
         for (int j = 0; j < S; ++j) bj[j] = s_yc[j];
-        auto row1 = [&](int y, const float4& b) {
+        // 16-byte aligned frames: pixels are staged in shared memory and each tile row leaves as one TMA bulk store;
+        // otherwise the quad-shuffle path of the generic kernel
+        uint8_t* s_out = smem + L.out;
+        const bool staged = aligned16(a.dst, a.dpitch);
+        auto put = [&](int y, const uint32_t (&v)[3]) {
+            if (staged) {
+                if (y < vh) { uint8_t* o = s_out + y * (BC_TW * 3) + tid * 3; o[0] = (uint8_t)v[0]; o[1] = (uint8_t)v[1]; o[2] = (uint8_t)v[2]; }
+            } else emit(y, v);
+        };
+        // the four taps are 12 consecutive bytes unless the column touches the replicate border
+        const bool contig = (o1 == o0 + 3) && (o2 == o0 + 6) && (o3 == o0 + 9);
+        auto hrow_s = [&](int rr, float (&h)[3]) {
+            const uint8_t* row = s_raw + (min(max(rr, ylo), yhi) - ylo) * RP;
+            if (contig) {
+                const uint8_t* p = row + o0;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const int v = (int)p[ch] * kx.x + (int)p[3 + ch] * kx.y + (int)p[6 + ch] * kx.z + (int)p[9 + ch] * kx.w;
+                    h[ch] = __int_as_float(v + 0x4B400000) - 12582912.0f;
+                }
+            } else {
+                const uint8_t *p0 = row + o0, *p1 = row + o1, *p2 = row + o2, *p3 = row + o3;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const int v = (int)p0[ch] * kx.x + (int)p1[ch] * kx.y + (int)p2[ch] * kx.z + (int)p3[ch] * kx.w;
+                    h[ch] = __int_as_float(v + 0x4B400000) - 12582912.0f;
+                }
+            }
+        };
+        // window rows live in W[0..3] and rotate by index (the group loop is unrolled by four): no register moves
+        float W[4][3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) { W[0][ch] = w0[ch]; W[1][ch] = w1[ch]; W[2][ch] = w2[ch]; W[3][ch] = w3[ch]; }
+        auto row1 = [&](int y, const float (&r0)[3], const float (&r1)[3], const float (&r2)[3], const float (&r3)[3], const float4& b) {
             uint32_t v[3];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch)
-                v[ch] = f2u8(__fadd_rn(__fmaf_rn(w0[ch], b.x, __fmul_rn(w1[ch], b.y)), __fmaf_rn(w2[ch], b.z, __fmul_rn(w3[ch], b.w))));
-            emit(y, v);
+                v[ch] = f2u8(__fadd_rn(__fmaf_rn(r0[ch], b.x, __fmul_rn(r1[ch], b.y)), __fmaf_rn(r2[ch], b.z, __fmul_rn(r3[ch], b.w))));
+            put(y, v);
         };
         // two rows that share the window: the same four products per channel as row1, as f32x2 lanes (row A, row B)
-        auto row2 = [&](int y, const float4& ba, const float4& bb) {
+        auto row2 = [&](int y, const float (&r0)[3], const float (&r1)[3], const float (&r2)[3], const float (&r3)[3], const float4& ba, const float4& bb) {
             const unsigned long long bx = pack2(__float_as_uint(ba.x), __float_as_uint(bb.x)), by = pack2(__float_as_uint(ba.y), __float_as_uint(bb.y));
             const unsigned long long bz = pack2(__float_as_uint(ba.z), __float_as_uint(bb.z)), bw = pack2(__float_as_uint(ba.w), __float_as_uint(bb.w));
             uint32_t va[3], vb[3];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                const unsigned long long p0 = pack2(__float_as_uint(w0[ch]), __float_as_uint(w0[ch])), p1 = pack2(__float_as_uint(w1[ch]), __float_as_uint(w1[ch]));
-                const unsigned long long p2 = pack2(__float_as_uint(w2[ch]), __float_as_uint(w2[ch])), p3 = pack2(__float_as_uint(w3[ch]), __float_as_uint(w3[ch]));
+                const unsigned long long p0 = pack2(__float_as_uint(r0[ch]), __float_as_uint(r0[ch])), p1 = pack2(__float_as_uint(r1[ch]), __float_as_uint(r1[ch]));
+                const unsigned long long p2 = pack2(__float_as_uint(r2[ch]), __float_as_uint(r2[ch])), p3 = pack2(__float_as_uint(r3[ch]), __float_as_uint(r3[ch]));
                 const unsigned long long t = fadd2(ffma2(p0, bx, fmul2(p1, by)), ffma2(p2, bz, fmul2(p3, bw)));
                 float ta, tb;
                 unpack2(t, ta, tb);
                 va[ch] = f2u8(ta); vb[ch] = f2u8(tb);
             }
-            emit(y, va);
-            emit(y + 1, vb);
+            put(y, va);
+            put(y + 1, vb);
         };
         // rows before the first step (phases 0 .. S/2-1) share the initial window
-        if constexpr (S == 2) row1(0, bj[0]);
-        else row2(0, bj[0], bj[1]);
-        for (int yb = S / 2; yb < vh; yb += S) {
+        if constexpr (S == 2) row1(0, W[0], W[1], W[2], W[3], bj[0]);
+        else row2(0, W[0], W[1], W[2], W[3], bj[0], bj[1]);
+        for (int yb = S / 2; yb < vh; yb += 4 * S) {
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) { w0[ch] = w1[ch]; w1[ch] = w2[ch]; w2[ch] = w3[ch]; }
-            yo += 1;
-            hrow(yo + 3, w3);
-            if constexpr (S == 2) row2(yb, bj[1], bj[0]);
-            else { row2(yb, bj[2], bj[3]); row2(yb + 2, bj[0], bj[1]); }
+            for (int k = 0; k < 4; ++k) {                 // step k overwrites the oldest row, W[k]; the window is W[k+1 .. k+4] mod 4
+                const int y = yb + k * S;
+                yo += 1;
+                hrow_s(yo + 3, W[k]);
+                if constexpr (S == 2) row2(y, W[(k + 1) & 3], W[(k + 2) & 3], W[(k + 3) & 3], W[k], bj[1], bj[0]);
+                else {
+                    row2(y, W[(k + 1) & 3], W[(k + 2) & 3], W[(k + 3) & 3], W[k], bj[2], bj[3]);
+                    row2(y + 2, W[(k + 1) & 3], W[(k + 2) & 3], W[(k + 3) & 3], W[k], bj[0], bj[1]);
+                }
+            }
+        }
+        if (staged) {
+            fence_proxy_async();
+            __syncthreads();
+            const int vw = dxb - x0 + 1, rb = vw * 3, nb16 = rb & ~15;
+            if (tid < vh && nb16) {
+                bulk_s2g(a.dst + (size_t)(y0 + tid) * a.dpitch + (size_t)x0 * 3, s_out + tid * (BC_TW * 3), (uint32_t)nb16);
+                bulk_commit();
+            }
+            const int tb = rb - nb16;
+            for (int i = tid; i < tb * vh; i += BC_NT) {
+                const int y = i / tb, qb = nb16 + (i - y * tb);
+                a.dst[(size_t)(y0 + y) * a.dpitch + (size_t)x0 * 3 + qb] = s_out[y * (BC_TW * 3) + qb];
+            }
+            if (tid < vh && nb16) bulk_wait_read0();
         }
         return;
     }
