@@ -48,6 +48,7 @@ struct UpsharpArgs {
     uint8_t* dst; size_t dpitch; int dw, dh;        // dst may be null (mask-only)
     ResizeTables rt;
     int max_src_rows, max_src_cols;   // per-tile source window bounds in unclamped coordinates (host computed)
+    int yperiod;                      // S when dst_h == S * src_h with S = 2 or 4 (host-verified row tables), else 0
     // sharpening parameters
     float strength, edge_strength, smooth_strength;
     int preserve_tone;
@@ -95,6 +96,80 @@ __host__ __device__ inline UpsharpSmem upsharp_layout(bool resize, bool sharpen,
     L.tabs = o; o += EH * 16 + EW * 16 + 16 + EW * 4 + EH * 4 + 256 * 4 + 32;
     L.total = o;
     return L;
+}
+
+// ---- P2 for an integer vertical ratio S (2 or 4) on tiles whose ext rows need no mirroring -------------------------
+// Tile rows start at multiples of US_TH, so ext row ey has phase (ey - HALO) mod S; the vertical tap origin advances
+// exactly before a row of phase S/2.  For a run of four ext rows everything below is therefore known at compile time:
+// which source rows each output row reads (no sliding-window register moves, no branches), which of the S coefficient
+// sets it uses (registers, not shared memory), and which neighbouring rows share a window and can be filtered as one
+// packed f32x2 pair.
+__host__ __device__ constexpr int p2_phase(int S, int HALO, int j) { return (((j - HALO) % S) + S) % S; }
+__host__ __device__ constexpr int p2_off(int S, int HALO, int j) {       // source-row offset of ext row j relative to row 0 of the run
+    int o = 0;
+    for (int k = 1; k <= j; ++k) o += (p2_phase(S, HALO, k) == S / 2) ? 1 : 0;
+    return o;
+}
+
+template <bool SHARPEN>
+__device__ __forceinline__ void p2_store(uint32_t* s_up, uint8_t* s_gray, int idx_up, int idx_gray, const uint32_t (&v)[3]) {
+    s_up[idx_up] = v[0] | (v[1] << 8) | (v[2] << 16);
+    if (SHARPEN) s_gray[idx_gray] = (uint8_t)((9798 * v[2] + 19235 * v[1] + 3735 * v[0] + (1 << 14)) >> 15);
+}
+
+template <int S, int HALO, bool SHARPEN, int J, int NR>
+__device__ __forceinline__ void p2_rows(const float (&W)[NR][3], const float4 (&bj)[S], uint32_t* s_up, uint8_t* s_gray, int ey0, int ex, int eh) {
+    constexpr int EW = US_TW + 2 * HALO;
+    if constexpr (J < 4) {
+        constexpr int o = p2_off(S, HALO, J);
+        constexpr bool pair = (J + 1 < 4) && (p2_off(S, HALO, J + 1) == o);
+        const int ey = ey0 + J;
+        if constexpr (pair) {
+            const float4 ba = bj[p2_phase(S, HALO, J)], bb = bj[p2_phase(S, HALO, J + 1)];
+            const unsigned long long bx = pack2(__float_as_uint(ba.x), __float_as_uint(bb.x)), by = pack2(__float_as_uint(ba.y), __float_as_uint(bb.y));
+            const unsigned long long bz = pack2(__float_as_uint(ba.z), __float_as_uint(bb.z)), bw = pack2(__float_as_uint(ba.w), __float_as_uint(bb.w));
+            uint32_t va[3], vb[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const unsigned long long p0 = pack2(__float_as_uint(W[o][ch]), __float_as_uint(W[o][ch])), p1 = pack2(__float_as_uint(W[o + 1][ch]), __float_as_uint(W[o + 1][ch]));
+                const unsigned long long p2 = pack2(__float_as_uint(W[o + 2][ch]), __float_as_uint(W[o + 2][ch])), p3 = pack2(__float_as_uint(W[o + 3][ch]), __float_as_uint(W[o + 3][ch]));
+                const unsigned long long t = fadd2(ffma2(p0, bx, fmul2(p1, by)), ffma2(p2, bz, fmul2(p3, bw)));
+                float ta, tb;
+                unpack2(t, ta, tb);
+                va[ch] = f2u8(ta); vb[ch] = f2u8(tb);
+            }
+            if (ey < eh) p2_store<SHARPEN>(s_up, s_gray, ey * EW + ex, ey * US_GP + ex, va);
+            if (ey + 1 < eh) p2_store<SHARPEN>(s_up, s_gray, (ey + 1) * EW + ex, (ey + 1) * US_GP + ex, vb);
+            p2_rows<S, HALO, SHARPEN, J + 2, NR>(W, bj, s_up, s_gray, ey0, ex, eh);
+        } else {
+            const float4 b = bj[p2_phase(S, HALO, J)];
+            uint32_t v[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+                v[ch] = f2u8(__fadd_rn(__fmaf_rn(W[o][ch], b.x, __fmul_rn(W[o + 1][ch], b.y)), __fmaf_rn(W[o + 2][ch], b.z, __fmul_rn(W[o + 3][ch], b.w))));
+            if (ey < eh) p2_store<SHARPEN>(s_up, s_gray, ey * EW + ex, ey * US_GP + ex, v);
+            p2_rows<S, HALO, SHARPEN, J + 1, NR>(W, bj, s_up, s_gray, ey0, ex, eh);
+        }
+    }
+}
+
+template <int S, int HALO, bool SHARPEN>
+__device__ __forceinline__ void p2_fast(const float* __restrict__ s_hs, const int* __restrict__ s_yo, const float4* __restrict__ s_yc,
+                                        uint32_t* s_up, uint8_t* s_gray, int tid) {
+    constexpr int EW = US_TW + 2 * HALO, EH = US_TH + 2 * HALO, NRUN = (EH + 3) / 4;
+    constexpr int NR = 4 + p2_off(S, HALO, 3);
+    float4 bj[S];                                   // coefficient set of phase p = that of the first ext row with that phase
+#pragma unroll
+    for (int p = 0; p < S; ++p) bj[p] = s_yc[(p + HALO) % S];
+    for (int i = tid; i < NRUN * EW; i += US_NT) {
+        const int run = i / EW, ex = i - run * EW;
+        const int ey0 = run * 4;
+        const float* hp = s_hs + (s_yo[ey0] * EW + ex) * 3;
+        float W[NR][3];
+#pragma unroll
+        for (int k = 0; k < NR; ++k) { W[k][0] = hp[k * EW * 3]; W[k][1] = hp[k * EW * 3 + 1]; W[k][2] = hp[k * EW * 3 + 2]; }
+        p2_rows<S, HALO, SHARPEN, 0, NR>(W, bj, s_up, s_gray, ey0, ex, EH);
+    }
 }
 
 template <bool RESIZE, bool SHARPEN, int GK>
@@ -215,8 +290,12 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
             }
         }
         __syncthreads();
-        // ---- P2: vertical pass, float32, RNE + saturate; runs of 4 ext rows, sliding 4-row window --------
-        {
+        // ---- P2: vertical pass, float32, RNE + saturate; runs of 4 ext rows --------------------------------
+        // integer ratio and no mirrored ext rows in this tile: the statically scheduled form (p2_fast)
+        const bool rows_inside = (y0 - HALO >= 0) && (y0 + US_TH - 1 + HALO <= a.dh - 1);
+        if (rows_inside && a.yperiod == 2) p2_fast<2, HALO, SHARPEN>(s_hs, s_yo, s_yc, s_up, s_gray, tid);
+        else if (rows_inside && a.yperiod == 4) p2_fast<4, HALO, SHARPEN>(s_hs, s_yo, s_yc, s_up, s_gray, tid);
+        else {   // any ratio / edge tiles: sliding 4-row window
             constexpr int RUN = 4, NRUN = (EH + RUN - 1) / RUN;
             for (int i = tid; i < NRUN * EW; i += US_NT) {
                 const int run = i / EW, ex = i - run * EW;

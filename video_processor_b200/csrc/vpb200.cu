@@ -1280,6 +1280,7 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
         if (do_resize) {
             a.rt = ResizeTables{c->rc_chain.xofs, c->rc_chain.xcoef, c->rc_chain.yofs, c->rc_chain.ycoef};
             a.max_src_rows = c->rc_chain.max_rows[k]; a.max_src_cols = c->rc_chain.max_cols[k];
+            a.yperiod = c->rc_chain.yperiod;
         } else {
             a.max_src_rows = US_TH + 2 * halo; a.max_src_cols = US_TW + 2 * halo;
         }
