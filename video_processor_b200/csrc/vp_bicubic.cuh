@@ -59,6 +59,13 @@ __global__ void __launch_bounds__(BC_NT) k_bicubic(const BicubicArgs a) {
     const int dxb = min(a.dw - 1, x0 + BC_TW - 1), dyb = min(a.dh - 1, y0 + BC_TH - 1);
     const int ux0 = a.rt.xofs[x0], ux1 = a.rt.xofs[dxb] + 3;      // unclamped source window (inclusive)
     const int uy0 = a.rt.yofs[y0], uy1 = a.rt.yofs[dyb] + 3;
+    // the source window's bulk copies are in flight while the row tables and this column's taps are fetched
+    const int sx0 = clampi(ux0, 0, a.sw - 1), sx1 = clampi(ux1, 0, a.sw - 1);
+    const int sy0 = clampi(uy0, 0, a.sh - 1), sy1 = clampi(uy1, 0, a.sh - 1);
+    const int bx0 = (sx0 * 3) & ~15, bx1 = (sx1 + 1) * 3;
+    const int RP = L.raw_pitch;
+    const bool fast_stage = aligned16(a.src, a.spitch);
+    stage_rows_issue(s_raw, RP, a.src, a.spitch, sy0, sy1 + 1, bx0, bx1, fast_stage, bar);
     if (tid < BC_TH) {
         const int dy = min(y0 + tid, dyb);
         s_yo[tid] = a.rt.yofs[dy] - uy0;
@@ -68,12 +75,8 @@ __global__ void __launch_bounds__(BC_NT) k_bicubic(const BicubicArgs a) {
     const int dx = min(x0 + tid, dxb);
     const int cx = a.rt.xofs[dx] - ux0;
     const int4 kx = a.rt.xcoef[dx];
-
-    const int sx0 = clampi(ux0, 0, a.sw - 1), sx1 = clampi(ux1, 0, a.sw - 1);
-    const int sy0 = clampi(uy0, 0, a.sh - 1), sy1 = clampi(uy1, 0, a.sh - 1);
-    const int bx0 = (sx0 * 3) & ~15, bx1 = (sx1 + 1) * 3;
-    const int RP = L.raw_pitch;
-    stage_rows(s_raw, RP, a.src, a.spitch, 3 * a.sw, sy0, sy1 + 1, bx0, bx1, aligned16(a.src, a.spitch), bar);
+    stage_rows_wait(s_raw, RP, a.src, a.spitch, 3 * a.sw, sy0, sy1 + 1, bx0, bx1, fast_stage, bar);
+    __syncthreads();        // s_yo / s_yc
 
     // The four taps of this column as byte offsets into a staged row, replicate border applied once;
     // a source row index is clamped when it is used (only the image's first/last rows ever clamp).

@@ -281,10 +281,12 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
     const int bx0 = (vx0 * 3) & ~15, bx1 = vx1 * 3;
     const bool fast = aligned16(a.src, a.spitch);
 
+    // the halo tile's bulk copies are in flight while the tables are fetched
+    stage_rows_issue(s_raw, RP, a.src, a.spitch, vy0, vy1, bx0, bx1, fast, bar);
     for (int i = tid; i < D * D; i += BIL_NT) s_sw[i] = cand->space_w[i];
     for (int i = tid; i < 768; i += BIL_NT) s_cw[i] = cand->color_w[i];
     if (tid < D) s_xm[tid] = cand->xmax[tid];
-    stage_rows(s_raw, RP, a.src, a.spitch, 3 * a.w, vy0, vy1, bx0, bx1, fast, bar);
+    stage_rows_wait(s_raw, RP, a.src, a.spitch, 3 * a.w, vy0, vy1, bx0, bx1, fast, bar);
 
     // expand raw bytes -> BGR0 words with BORDER_REFLECT_101 resolved; warp per row, lanes along x
     const bool simple = (a.w > R) && (a.h > R);          // one mirror step suffices

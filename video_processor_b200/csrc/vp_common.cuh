@@ -95,6 +95,39 @@ __device__ __forceinline__ void stage_rows(uint8_t* s_raw, int s_pitch, const ui
     }
 }
 
+// The same staging split in two so a kernel can fill its tables while the bulk copies are in flight:
+// stage_rows_issue() starts the TMA row copies (fast path; contains one __syncthreads), stage_rows_wait() returns once
+// the rows are visible (fast path) or copies them with all threads (byte path).  Both take the same arguments.
+__device__ __forceinline__ void stage_rows_issue(uint8_t* s_raw, int s_pitch, const uint8_t* __restrict__ g, size_t gpitch,
+                                                 int y0, int y1, int bx0, int bx1, bool fast, uint64_t* bar) {
+    if (!fast) return;
+    const int tid = threadIdx.x, nrows = y1 - y0;
+    const int nb = ((bx1 + 15) & ~15) - bx0;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid < 32) {
+        if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nb * nrows));
+        __syncwarp();
+        for (int r = tid; r < nrows; r += 32)
+            bulk_g2s(s_raw + r * s_pitch, g + (size_t)(y0 + r) * gpitch + bx0, (uint32_t)nb, bar);
+    }
+}
+__device__ __forceinline__ void stage_rows_wait(uint8_t* s_raw, int s_pitch, const uint8_t* __restrict__ g, size_t gpitch,
+                                                int row_bytes, int y0, int y1, int bx0, int bx1, bool fast, uint64_t* bar) {
+    if (fast) { mbar_wait(bar, 0); return; }
+    const int tid = threadIdx.x, nt = blockDim.x, nrows = y1 - y0;
+    const int e = min(bx1, row_bytes);
+    const int nb = e - bx0;
+    for (int i = tid; i < nb * nrows; i += nt) {
+        int r = i / nb, b = i - r * nb;
+        s_raw[r * s_pitch + b] = g[(size_t)(y0 + r) * gpitch + bx0 + b];
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ bool aligned16(const void* p, size_t pitch) {
     return ((((uintptr_t)p) | pitch) & 15) == 0;
 }

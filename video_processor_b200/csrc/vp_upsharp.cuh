@@ -208,6 +208,17 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
     if (RESIZE) {
         ux0 = a.rt.xofs[dxa]; ux1 = a.rt.xofs[dxb] + 3;
         uy0 = a.rt.yofs[dya]; uy1 = a.rt.yofs[dyb] + 3;
+    } else {
+        ux0 = dxa; ux1 = dxb; uy0 = dya; uy1 = dyb;
+    }
+    // the source window's bulk copies are in flight while the per-tile tables are filled
+    const int sx0 = clampi(ux0, 0, a.sw - 1), sx1 = clampi(ux1, 0, a.sw - 1);
+    const int sy0 = clampi(uy0, 0, a.sh - 1), sy1 = clampi(uy1, 0, a.sh - 1);
+    const int bx0 = (sx0 * 3) & ~15, bx1 = (sx1 + 1) * 3;
+    const int RP = L.raw_pitch;
+    const bool fast_stage = aligned16(a.src, a.spitch);
+    stage_rows_issue(s_raw, RP, a.src, a.spitch, sy0, sy1 + 1, bx0, bx1, fast_stage, bar);
+    if (RESIZE) {
         for (int i = tid; i < EW; i += US_NT) {
             const int dx = clampi(reflect101(x0 - HALO + i, a.dw), dxa, dxb);   // clamp: unused columns of edge tiles
             s_xo[i] = a.rt.xofs[dx] - ux0; s_xc[i] = a.rt.xcoef[dx];
@@ -216,15 +227,9 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
             const int dy = clampi(reflect101(y0 - HALO + i, a.dh), dya, dyb);
             s_yo[i] = a.rt.yofs[dy] - uy0; s_yc[i] = a.rt.ycoef[dy];
         }
-    } else {
-        ux0 = dxa; ux1 = dxb; uy0 = dya; uy1 = dyb;
     }
     if (SHARPEN) s_lut[tid] = a.sig_lut[tid];   // US_NT == 256
-    const int sx0 = clampi(ux0, 0, a.sw - 1), sx1 = clampi(ux1, 0, a.sw - 1);
-    const int sy0 = clampi(uy0, 0, a.sh - 1), sy1 = clampi(uy1, 0, a.sh - 1);
-    const int bx0 = (sx0 * 3) & ~15, bx1 = (sx1 + 1) * 3;
-    const int RP = L.raw_pitch;
-    stage_rows(s_raw, RP, a.src, a.spitch, 3 * a.sw, sy0, sy1 + 1, bx0, bx1, aligned16(a.src, a.spitch), bar);
+    stage_rows_wait(s_raw, RP, a.src, a.spitch, 3 * a.sw, sy0, sy1 + 1, bx0, bx1, fast_stage, bar);
 
     if (RESIZE) {
         const int SP = L.src_pitch;
