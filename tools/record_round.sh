@@ -2,15 +2,15 @@ set -x
 for w in c4 c1 c1w c2 c3 c5; do
   extra=""; [ $w = c4 ] && extra=""; [ $w != c4 ] && extra="--cpu-frames 0"
   [ $w = c1w ] && extra="--cpu-frames 24"
-  python bench.py --workload $w $extra > gpurun_out/r01e_bench_$w.json 2> gpurun_out/r01e_bench_$w.err
+  python bench.py --workload $w $extra > gpurun_out/r01f_bench_$w.json 2> gpurun_out/r01f_bench_$w.err
 done
-python bench.py --bilateral-mode selective --frames 64 --cpu-frames 6 > gpurun_out/r01e_bench_c4_selective.json 2> gpurun_out/r01e_sel.err
-python bench.py --bilateral-mode multiscale --frames 64 --cpu-frames 6 > gpurun_out/r01e_bench_c4_multiscale.json 2> gpurun_out/r01e_ms.err
-python bench.py --adaptive-sigma --frames 64 --cpu-frames 6 > gpurun_out/r01e_bench_c4_adaptive_sigma.json 2> gpurun_out/r01e_as.err
-python bench.py --flow --frames 32 --cpu-frames 3 > gpurun_out/r01e_bench_c4_flow.json 2> gpurun_out/r01e_flow.err
-python bench.py --bilateral-mode multiscale --adaptive-sigma --flow --frames 32 --cpu-frames 3 > gpurun_out/r01e_bench_c4_reference_defaults.json 2> gpurun_out/r01e_rd.err
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r01e_bench_reference_arm.json 2> gpurun_out/r01e_ref.err
-python bench.py --steps 2 --warmup 3 --frames 16 --cpu-frames 0 --no-e2e > gpurun_out/plain_r01e.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv --log-file gpurun_out/launches_r01e.csv python bench.py --steps 2 --warmup 3 --frames 16 --cpu-frames 0 --no-e2e > gpurun_out/ncu_r01e_a.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_stats|k_bilateral|k_upsharp" -s 40 -c 4 -o gpurun_out/prof_r01e python bench.py --steps 1 --warmup 3 --frames 8 --cpu-frames 0 --no-e2e --per-frame > gpurun_out/ncu_r01e_b.log 2>&1
+python bench.py --bilateral-mode selective --frames 64 --cpu-frames 6 > gpurun_out/r01f_bench_c4_selective.json 2> gpurun_out/r01f_sel.err
+python bench.py --bilateral-mode multiscale --frames 64 --cpu-frames 6 > gpurun_out/r01f_bench_c4_multiscale.json 2> gpurun_out/r01f_ms.err
+python bench.py --adaptive-sigma --frames 64 --cpu-frames 6 > gpurun_out/r01f_bench_c4_adaptive_sigma.json 2> gpurun_out/r01f_as.err
+python bench.py --flow --frames 32 --cpu-frames 3 > gpurun_out/r01f_bench_c4_flow.json 2> gpurun_out/r01f_flow.err
+python bench.py --bilateral-mode multiscale --adaptive-sigma --flow --frames 32 --cpu-frames 3 > gpurun_out/r01f_bench_c4_reference_defaults.json 2> gpurun_out/r01f_rd.err
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r01f_bench_reference_arm.json 2> gpurun_out/r01f_ref.err
+python bench.py --steps 2 --warmup 3 --frames 16 --cpu-frames 0 --no-e2e > gpurun_out/plain_r01f.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_stats|k_bilateral|k_upsharp|k_blend|k_scene" -s 20 -c 200 --csv --log-file gpurun_out/launches_r01f.csv python bench.py --steps 2 --warmup 3 --frames 16 --cpu-frames 0 --no-e2e > gpurun_out/ncu_r01f_a.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_stats|k_bilateral|k_upsharp" -s 40 -c 4 -o gpurun_out/prof_r01f python bench.py --steps 1 --warmup 3 --frames 8 --cpu-frames 0 --no-e2e --per-frame > gpurun_out/ncu_r01f_b.log 2>&1
 ls -la gpurun_out | grep r01e
