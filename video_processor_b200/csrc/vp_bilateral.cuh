@@ -70,6 +70,23 @@ __device__ __forceinline__ uint32_t f2u8(float v) {
     return r;
 }
 
+// packed f32x2 helpers (sm_100 FFMA2 / FADD2): two float lanes per 64-bit register pair, one issue slot
+__device__ __forceinline__ unsigned long long pack2(uint32_t lo, uint32_t hi) {
+    unsigned long long r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(lo), "r"(hi)); return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b) {
+    unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+    unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+
 __device__ __forceinline__ uint32_t blend_byte(const BlendArgs& b, float cur, float p0, float p1, float p2) {
     if (b.mode == 1)               // cv::addWeighted AVX2 form: fma(cur, alpha, prev*beta)
         return f2u8(__fmaf_rn(cur, b.w[0], __fmul_rn(p0, b.w[1])));
@@ -79,10 +96,31 @@ __device__ __forceinline__ uint32_t blend_byte(const BlendArgs& b, float cur, fl
     if (b.nprev > 2) acc = __fadd_rn(acc, __fmul_rn(b.w[3], p2));
     return f2u8(__fmul_rn(acc, b.inv_wsum));
 }
+// bytes k, k+1 of a word as an exact float32 pair (PRMT magic numbers, one packed subtract of 2^23)
+__device__ __forceinline__ unsigned long long u8f_pair(uint32_t word, int k) {
+    return fadd2(pack2(__byte_perm(word, 0x4B000000u, 0x7440 + k), __byte_perm(word, 0x4B000000u, 0x7441 + k)),
+                 pack2(0xCB000000u, 0xCB000000u));
+}
+// blend_byte for two bytes at once: the same IEEE operations per lane (multiplies and adds stay separate)
+__device__ __forceinline__ unsigned long long blend_pair(const BlendArgs& b, unsigned long long cur, unsigned long long p0,
+                                                         unsigned long long p1, unsigned long long p2) {
+    const uint32_t w0 = __float_as_uint(b.w[0]), w1 = __float_as_uint(b.w[1]);
+    if (b.mode == 1) return ffma2(cur, pack2(w0, w0), fmul2(p0, pack2(w1, w1)));
+    unsigned long long acc = fmul2(pack2(w0, w0), cur);
+    acc = fadd2(acc, fmul2(pack2(w1, w1), p0));
+    if (b.nprev > 1) { const uint32_t w2 = __float_as_uint(b.w[2]); acc = fadd2(acc, fmul2(pack2(w2, w2), p1)); }
+    if (b.nprev > 2) { const uint32_t w3 = __float_as_uint(b.w[3]); acc = fadd2(acc, fmul2(pack2(w3, w3), p2)); }
+    const uint32_t iw = __float_as_uint(b.inv_wsum);
+    return fmul2(acc, pack2(iw, iw));
+}
 __device__ __forceinline__ uint32_t blend_word(const BlendArgs& b, uint32_t cur, uint32_t p0, uint32_t p1, uint32_t p2) {
     uint32_t r = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) r |= blend_byte(b, u8f(cur, k), u8f(p0, k), u8f(p1, k), u8f(p2, k)) << (8 * k);
+    for (int k = 0; k < 4; k += 2) {
+        float lo, hi;
+        unpack2(blend_pair(b, u8f_pair(cur, k), u8f_pair(p0, k), u8f_pair(p1, k), u8f_pair(p2, k)), lo, hi);
+        r |= (f2u8(lo) | (f2u8(hi) << 8)) << (8 * k);
+    }
     return r;
 }
 
@@ -114,23 +152,6 @@ template <int R> struct BilGeom {
     static constexpr int NSEG = (BIL_PX + 2 * R + 3) & ~3;    // staged neighbours per row, whole uint4s
     static constexpr int D = 2 * R + 1;
 };
-
-// packed f32x2 helpers (sm_100 FFMA2 / FADD2): two float lanes per 64-bit register pair, one issue slot
-__device__ __forceinline__ unsigned long long pack2(uint32_t lo, uint32_t hi) {
-    unsigned long long r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(lo), "r"(hi)); return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
-    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
-}
-__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b) {
-    unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
-}
-__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
-    unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
-}
 
 // one tap row of half-width XM: taps dx = -XM..XM against the PX outputs of the strip.
 // Accumulators are (sum_b, sum_g) and (sum_r, wsum) pairs: the tile's 4th byte is 1, so the pixel's
