@@ -123,6 +123,35 @@ __device__ __forceinline__ uint32_t blend_word(const BlendArgs& b, uint32_t cur,
     }
     return r;
 }
+// the same with the blend form (MODE 1 = addWeighted, 2 = blendFrames) and the frame count fixed at compile time:
+// the epilogue of k_bilateral dispatches once per strip instead of testing nprev for every byte pair
+template <int MODE, int NP>
+__device__ __forceinline__ void blend12(const BlendArgs& b, const uint32_t (&cur)[3], const uint32_t (&p0)[3], const uint32_t (&p1)[3],
+                                        const uint32_t (&p2)[3], uint32_t (&o)[3]) {
+    const uint32_t w0 = __float_as_uint(b.w[0]), w1 = __float_as_uint(b.w[1]), w2 = __float_as_uint(b.w[2]), w3 = __float_as_uint(b.w[3]);
+    const uint32_t iw = __float_as_uint(b.inv_wsum);
+    const unsigned long long W0 = pack2(w0, w0), W1 = pack2(w1, w1), W2 = pack2(w2, w2), W3 = pack2(w3, w3), IW = pack2(iw, iw);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        uint32_t r = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k += 2) {
+            unsigned long long acc;
+            if (MODE == 1) acc = ffma2(u8f_pair(cur[q], k), W0, fmul2(u8f_pair(p0[q], k), W1));
+            else {
+                acc = fmul2(W0, u8f_pair(cur[q], k));
+                acc = fadd2(acc, fmul2(W1, u8f_pair(p0[q], k)));
+                if (NP > 1) acc = fadd2(acc, fmul2(W2, u8f_pair(p1[q], k)));
+                if (NP > 2) acc = fadd2(acc, fmul2(W3, u8f_pair(p2[q], k)));
+                acc = fmul2(acc, IW);
+            }
+            float lo, hi;
+            unpack2(acc, lo, hi);
+            r |= (f2u8(lo) | (f2u8(hi) << 8)) << (8 * k);
+        }
+        o[q] = r;
+    }
+}
 
 // 12 packed bytes (4 BGR pixels) <-> memory; word accesses when the address is 4-byte aligned
 __device__ __forceinline__ void store12(uint8_t* p, const uint32_t v[3], int npx) {
@@ -456,8 +485,10 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
             // the third previous frame is fetched late: holding 9 prefetched words across the tap loop spills
             if (b.nprev > 2) load12(b.prev[2] + (size_t)gy * b.ppitch + boff, p2, npx);
             uint32_t o[3];
-#pragma unroll
-            for (int q = 0; q < 3; ++q) o[q] = blend_word(b, cur[q], p0[q], p1[q], p2[q]);
+            if (b.mode == 1) blend12<1, 1>(b, cur, p0, p1, p2, o);
+            else if (b.nprev == 1) blend12<2, 1>(b, cur, p0, p1, p2, o);
+            else if (b.nprev == 2) blend12<2, 2>(b, cur, p0, p1, p2, o);
+            else blend12<2, 3>(b, cur, p0, p1, p2, o);
             store12(dp, o, npx);
         } else {
             store12(dp, cur, npx);
