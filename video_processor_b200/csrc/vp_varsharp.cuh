@@ -10,7 +10,8 @@
 // so the stage is four kernels; the reductions are integer (sqrt and float ordering are monotonic) and the five
 // sigma-dependent Q8 Gaussian kernels are built ON THE DEVICE from the second reduction (k_sigma_levels), so the
 // host never waits:
-//   k_texture_minmax -> k_sigma_map (+ min/max of the blurred sigma map) -> k_sigma_levels -> k_varsharp
+//   k_texture_minmax (+ the u8 local-variance plane) -> k_sigma_map (+ min/max of the blurred sigma map) -> k_sigma_levels
+//   -> k_varsharp
 #pragma once
 #include "vp_bilateral.cuh"   // f2u8
 #include "vp_detail.cuh"
@@ -29,7 +30,8 @@ struct SigmaLevels {
     int q[VS_LEVELS][7];         // Q0.8 taps of cv::GaussianBlur(u8, ksize, sigma_i) per level
 };
 
-__global__ void __launch_bounds__(DT_NT) k_texture_minmax(const uint8_t* __restrict__ src, size_t pitch, int w, int h, SigmaStats* __restrict__ st) {
+__global__ void __launch_bounds__(DT_NT) k_texture_minmax(const uint8_t* __restrict__ src, size_t pitch, int w, int h, SigmaStats* __restrict__ st,
+                                                          uint8_t* __restrict__ var_out, size_t vpitch) {
     constexpr int HALO = 6, K = 7, GW = DT_TW + 2 * HALO, GH = DT_TH + 2 * HALO, MW = GW - (K - 1), MH = GH - (K - 1), VW = MW - (K - 1);
     __shared__ uint8_t s_gray[GW * GH];
     __shared__ uint16_t s_rs1[MW * GH];
@@ -47,6 +49,7 @@ __global__ void __launch_bounds__(DT_NT) k_texture_minmax(const uint8_t* __restr
         if (x0 + x < w && y0 + y < h) {
             const int v = box_at<K>(s_rs2, VW, x, y);
             lo = min(lo, v); hi = max(hi, v);
+            var_out[(size_t)(y0 + y) * vpitch + x0 + x] = (uint8_t)v;      // kept for k_sigma_map: the front end runs once
         }
     }
 #pragma unroll
@@ -60,36 +63,31 @@ __global__ void __launch_bounds__(DT_NT) k_texture_minmax(const uint8_t* __restr
 }
 
 struct SigmaMapArgs {
-    const uint8_t* src; size_t pitch; int w, h;
+    const uint8_t* var; size_t vpitch; int w, h;   // k_texture_minmax's local-variance plane
     SigmaStats* st;
     float gf[5];                 // (float)getGaussianKernel(5, 1.0) (:431)
     float* sigma; size_t spitch; // float32 plane, pitch in bytes
 };
 
+// texture = sqrt(local_var) (repaired) -> normalise by the frame's extremes -> sigma = 2.5 - 1.7 t (:423) -> 5x5 sigma 1.0
+// float Gaussian (:431, BORDER_REFLECT_101 of the sigma plane == of the variance plane) + min / max of the result
 __global__ void __launch_bounds__(DT_NT) k_sigma_map(const SigmaMapArgs a) {
-    constexpr int HALO = 8, K = 7, GW = DT_TW + 2 * HALO, GH = DT_TH + 2 * HALO, MW = GW - (K - 1), MH = GH - (K - 1);
-    constexpr int VW = MW - (K - 1), VH = MH - (K - 1);            // 68 x 36: the texture / pre-blur sigma plane
-    __shared__ uint8_t s_gray[GW * GH];
-    __shared__ uint16_t s_rs1[MW * GH];
-    __shared__ uint8_t s_dsq[MW * MH];
-    __shared__ uint16_t s_rs2[VW * MH];
+    constexpr int VW = DT_TW + 4, VH = DT_TH + 4;
     __shared__ float s_sig[VW * VH];
     __shared__ float s_row[DT_TW * VH];
     __shared__ int s_mm[2];
     const int x0 = blockIdx.x * DT_TW, y0 = blockIdx.y * DT_TH;
     if (threadIdx.x == 0) { s_mm[0] = 0x7f800000; s_mm[1] = 0; }
-    load_gray_tile<HALO>(a.src, a.pitch, a.w, a.h, x0, y0, s_gray);
     // :390-391  (t - min) / (max - min) is one MatExpr: convertTo(alpha, beta) = t * alpha + beta in float32
     const float tmin = __fsqrt_rn((float)a.st->var_min), tmax = __fsqrt_rn((float)a.st->var_max);
     const bool flat = !(tmax > tmin);
     const double inv = flat ? 0.0 : 1.0 / ((double)tmax - (double)tmin);
     const float na = (float)inv, nb = (float)(-(double)tmin * inv);
     const float smax = 2.5f, sspan = __fsub_rn(2.5f, 0.8f);                                    // :412-413
-    __syncthreads();
-    detail_variance_rows<HALO, K>(s_gray, s_rs1, s_dsq, s_rs2);
     for (int i = threadIdx.x; i < VW * VH; i += DT_NT) {
         const int y = i / VW, x = i - y * VW;
-        const float tex = __fsqrt_rn((float)box_at<K>(s_rs2, VW, x, y));                      // :383,:386 (repaired)
+        const int v = a.var[(size_t)reflect101(y0 - 2 + y, a.h) * a.vpitch + reflect101(x0 - 2 + x, a.w)];
+        const float tex = __fsqrt_rn((float)v);                                                // :386 (repaired)
         const float t = flat ? 0.f : __fmaf_rn(tex, na, nb);
         s_sig[i] = __fsub_rn(smax, __fmul_rn(t, sspan));                                       // :423
     }
@@ -197,37 +195,57 @@ __global__ void __launch_bounds__(VS_NT) k_varsharp(const VarSharpArgs a) {
     const float mn = a.lv->mn, span = a.lv->span;
     __syncthreads();
     unsigned acc6[6] = {0, 0, 0, 0, 0, 0};
-    for (int i = tid; i < VS_TW * VS_TH; i += VS_NT) {
-        const int y = i / VS_TW, x = i - y * VS_TW;
-        const int gx = x0 + x, gy = y0 + y;
-        if (gx >= a.w || gy >= a.h) continue;
-        const float sigma = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(a.sigma) + (size_t)gy * a.gpitch + (size_t)gx * 4);
-        // :476-486  level pair and interpolation factor, float32 throughout
-        int idx = 0;
-        if (span > 0.f) idx = (int)__fmul_rn(__fdiv_rn(__fsub_rn(sigma, mn), span), (float)(VS_LEVELS - 1));
-        idx = max(0, min(idx, VS_LEVELS - 2));
-        const float slo = __fadd_rn(mn, __fdiv_rn(__fmul_rn(span, (float)idx), (float)(VS_LEVELS - 1)));
-        const float shi = __fadd_rn(mn, __fdiv_rn(__fmul_rn(span, (float)(idx + 1)), (float)(VS_LEVELS - 1)));
-        const float den = __fsub_rn(shi, slo);
-        const float alpha = den > 0.f ? __fdiv_rn(__fsub_rn(sigma, slo), den) : 0.f;
-        // the two Gaussian levels at this pixel: exact Q8.16 sums, (v + 2^15) >> 16
-        unsigned long long bg_lo = 0ull, bg_hi = 0ull, r_lh = 0ull;
-        const float2* wp = s_wp[idx];
+    // a thread owns two horizontally adjacent pixels at a time: their 5x5 windows overlap in GK-1 columns, so each tile row
+    // costs GK+1 pixel loads for two outputs (the kernel is bound by shared-memory wavefronts otherwise)
+    for (int i2 = tid; i2 < (VS_TW / 2) * VS_TH; i2 += VS_NT) {
+        const int y = i2 / (VS_TW / 2), xb = 2 * (i2 - y * (VS_TW / 2));
+        const int gy = y0 + y;
+        if (x0 + xb >= a.w || gy >= a.h) continue;
+        int idx2[2]; float alpha2[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int gxk = min(x0 + xb + k, a.w - 1);
+            const float sigma = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(a.sigma) + (size_t)gy * a.gpitch + (size_t)gxk * 4);
+            // :476-486  level pair and interpolation factor, float32 throughout
+            int idx = 0;
+            if (span > 0.f) idx = (int)__fmul_rn(__fdiv_rn(__fsub_rn(sigma, mn), span), (float)(VS_LEVELS - 1));
+            idx = max(0, min(idx, VS_LEVELS - 2));
+            const float slo = __fadd_rn(mn, __fdiv_rn(__fmul_rn(span, (float)idx), (float)(VS_LEVELS - 1)));
+            const float shi = __fadd_rn(mn, __fdiv_rn(__fmul_rn(span, (float)(idx + 1)), (float)(VS_LEVELS - 1)));
+            const float den = __fsub_rn(shi, slo);
+            idx2[k] = idx;
+            alpha2[k] = den > 0.f ? __fdiv_rn(__fsub_rn(sigma, slo), den) : 0.f;
+        }
+        // the two Gaussian levels at both pixels: exact Q8.16 sums, (v + 2^15) >> 16
+        unsigned long long bg_lo2[2] = {0ull, 0ull}, bg_hi2[2] = {0ull, 0ull}, r_lh2[2] = {0ull, 0ull};
+        const float2* wp0 = s_wp[idx2[0]];
+        const float2* wp1 = s_wp[idx2[1]];
 #pragma unroll
         for (int ta = 0; ta < GK; ++ta) {
-            const float4* row = s_px + (y + ta) * EW + x;
+            const float4* row = s_px + (y + ta) * EW + xb;
+            float4 px[GK + 1];
+#pragma unroll
+            for (int tb = 0; tb <= GK; ++tb) px[tb] = row[tb];
 #pragma unroll
             for (int tb = 0; tb < GK; ++tb) {
-                const float4 px = row[tb];
-                const float2 w = wp[ta * GK + tb];
-                const unsigned long long bg = pack2(__float_as_uint(px.x), __float_as_uint(px.y));
-                bg_lo = ffma2(bg, pack2(__float_as_uint(w.x), __float_as_uint(w.x)), bg_lo);
-                bg_hi = ffma2(bg, pack2(__float_as_uint(w.y), __float_as_uint(w.y)), bg_hi);
-                r_lh = ffma2(pack2(__float_as_uint(w.x), __float_as_uint(w.y)), pack2(__float_as_uint(px.z), __float_as_uint(px.z)), r_lh);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float4 p = px[tb + k];
+                    const float2 w = (k ? wp1 : wp0)[ta * GK + tb];
+                    const unsigned long long bg = pack2(__float_as_uint(p.x), __float_as_uint(p.y));
+                    bg_lo2[k] = ffma2(bg, pack2(__float_as_uint(w.x), __float_as_uint(w.x)), bg_lo2[k]);
+                    bg_hi2[k] = ffma2(bg, pack2(__float_as_uint(w.y), __float_as_uint(w.y)), bg_hi2[k]);
+                    r_lh2[k] = ffma2(pack2(__float_as_uint(w.x), __float_as_uint(w.y)), pack2(__float_as_uint(p.z), __float_as_uint(p.z)), r_lh2[k]);
+                }
             }
         }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int x = xb + k, gx = x0 + x;
+        if (gx >= a.w) continue;
+        const float alpha = alpha2[k];
         float fl[3], fh[3];
-        unpack2(bg_lo, fl[0], fl[1]); unpack2(bg_hi, fh[0], fh[1]); unpack2(r_lh, fl[2], fh[2]);
+        unpack2(bg_lo2[k], fl[0], fl[1]); unpack2(bg_hi2[k], fh[0], fh[1]); unpack2(r_lh2[k], fl[2], fh[2]);
         unsigned lo[3], hi[3];
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) { lo[ch] = __float2uint_rz(fl[ch]) + (1u << 15); hi[ch] = __float2uint_rz(fh[ch]) + (1u << 15); }
@@ -262,6 +280,7 @@ __global__ void __launch_bounds__(VS_NT) k_varsharp(const VarSharpArgs a) {
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) { acc6[ch] += o[ch]; acc6[3 + ch] += o[ch] * o[ch]; }
         }
+      }
     }
     if (a.sums) {
         warp_partials6(acc6, s_part);

@@ -104,6 +104,7 @@ struct VsScratch {                  // AdaptiveSharpening, adaptive_sigma branch
     int w = 0, h = 0;
     float* emask = nullptr; float* sigma = nullptr; size_t fpitch = 0;   // edge mask / sigma map planes
     vp::SigmaStats* st = nullptr; vp::SigmaLevels* lv = nullptr;
+    uint8_t* var = nullptr; size_t vpitch = 0;                           // local-variance plane (k_texture_minmax -> k_sigma_map)
     uint8_t* up = nullptr; size_t upitch = 0;                            // chain only: the bicubic output
 };
 
@@ -707,7 +708,7 @@ int run_flow_temporal(vp_ctx* c, FlowTemporal& T, const vp_temporal_config& t, c
 }
 
 void free_vs_scratch(VsScratch& S) {
-    cudaFree(S.emask); cudaFree(S.sigma); cudaFree(S.st); cudaFree(S.lv); cudaFree(S.up);
+    cudaFree(S.emask); cudaFree(S.sigma); cudaFree(S.st); cudaFree(S.lv); cudaFree(S.up); cudaFree(S.var);
     S = VsScratch();
 }
 
@@ -721,6 +722,8 @@ int ensure_vs_scratch(vp_ctx* c, VsScratch& S, int w, int h, bool with_up) {
     VP_CUDA(c, cudaMalloc(&S.sigma, S.fpitch * h));
     VP_CUDA(c, cudaMalloc(&S.st, sizeof(SigmaStats)));
     VP_CUDA(c, cudaMalloc(&S.lv, sizeof(SigmaLevels)));
+    S.vpitch = align_up((size_t)w, 256);
+    VP_CUDA(c, cudaMalloc(&S.var, S.vpitch * h));
     if (with_up) {
         S.upitch = align_up((size_t)w * 3, 256);
         VP_CUDA(c, cudaMalloc(&S.up, S.upitch * h));
@@ -730,14 +733,15 @@ int ensure_vs_scratch(vp_ctx* c, VsScratch& S, int w, int h, bool with_up) {
 
 // calculateTextureMap + calculateAdaptiveSigma (src/adaptive_sharpening.cpp:357-440) -> sigma plane, and the extremes of
 // that plane in S.st for k_sigma_levels
-int launch_sigma_map(vp_ctx* c, SigmaStats* st_dev, const uint8_t* src, size_t pitch, int w, int h, float* sigma, size_t spitch, cudaStream_t st) {
+int launch_sigma_map(vp_ctx* c, SigmaStats* st_dev, uint8_t* var, size_t vpitch, const uint8_t* src, size_t pitch, int w, int h,
+                     float* sigma, size_t spitch, cudaStream_t st) {
     static const SigmaStats init{0x7fffffff, 0, 0x7f800000, 0};
     ProfScope ps(c, K_UPSHARP, st);
     VP_CUDA(c, cudaMemcpyAsync(st_dev, &init, sizeof(init), cudaMemcpyHostToDevice, st));
     const dim3 grid((w + DT_TW - 1) / DT_TW, (h + DT_TH - 1) / DT_TH);
-    k_texture_minmax<<<grid, DT_NT, 0, st>>>(src, pitch, w, h, st_dev);
+    k_texture_minmax<<<grid, DT_NT, 0, st>>>(src, pitch, w, h, st_dev, var, vpitch);
     SigmaMapArgs a{};
-    a.src = src; a.pitch = pitch; a.w = w; a.h = h; a.st = st_dev;
+    a.var = var; a.vpitch = vpitch; a.w = w; a.h = h; a.st = st_dev;
     const std::vector<double> g = vp_host::gaussian_kernel_f64(5, 1.0);   // literal Size(5,5), 1.0 at :431
     for (int i = 0; i < 5; ++i) a.gf[i] = (float)g[i];
     a.sigma = sigma; a.spitch = spitch;
@@ -762,7 +766,7 @@ int run_varsharp(vp_ctx* c, VsScratch& S, const vp_sharpen_config& cfg, const fl
     m.max_src_rows = US_TH + 2 * US_HALO; m.max_src_cols = US_TW + 2 * US_HALO;
     m.mask_out = S.emask; m.mask_out_pitch = S.fpitch;
     rc = launch_upsharp(c, m, false, true, st); if (rc) return rc;
-    rc = launch_sigma_map(c, S.st, src, spitch, w, h, S.sigma, S.fpitch, st); if (rc) return rc;
+    rc = launch_sigma_map(c, S.st, S.var, S.vpitch, src, spitch, w, h, S.sigma, S.fpitch, st); if (rc) return rc;
     ProfScope ps(c, K_UPSHARP, st);
     k_sigma_levels<<<1, 32, 0, st>>>(S.st, cfg.kernel_size, S.lv);
     VarSharpArgs a{};
@@ -1721,8 +1725,8 @@ int vp_sigma_map(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, float* d_sig
     if (sigma_pitch < (size_t)w * 4) return fail(c, VP_ERR_INVALID_ARG, "vp_sigma_map: sigma pitch < 4*width");
     VP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
-    if (!c->vs_tmp.st) VP_CUDA(c, cudaMalloc(&c->vs_tmp.st, sizeof(SigmaStats)));
-    return launch_sigma_map(c, c->vs_tmp.st, d_src, src_pitch, w, h, d_sigma, sigma_pitch, st);
+    rc = ensure_vs_scratch(c, c->vs_tmp, w, h, false); if (rc) return rc;
+    return launch_sigma_map(c, c->vs_tmp.st, c->vs_tmp.var, c->vs_tmp.vpitch, d_src, src_pitch, w, h, d_sigma, sigma_pitch, st);
 }
 
 int vp_optical_flow(vp_ctx* c, const vp_temporal_config* cfg, const uint8_t* d_prev, const uint8_t* d_cur, size_t pitch,
