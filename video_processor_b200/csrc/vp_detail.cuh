@@ -7,8 +7,8 @@
 // instead of NaN, and everything else is as written (including the saturating u8 subtract / multiply at :268-269).
 //
 // createDetailMask needs two whole-frame maxima (cv::minMaxLoc :281,:284) before any pixel can be normalised, so it
-// is two kernels: k_detail_max (integer: max gx^2+gy^2 and max local_var - sqrt is monotonic) and k_detail_mask,
-// which recomputes the cheap integer stages per tile instead of spilling four planes to HBM.  Every stencil border
+// is two kernels: k_detail_max (integer: max gx^2+gy^2 and max local_var - sqrt is monotonic; it also stores both integers
+// per pixel in one 32-bit plane) and k_detail_mask, which normalises that plane, applies the sigmoid and the final blur.  Every stencil border
 // is BORDER_REFLECT_101 of its own input; all the kernels involved are mirror symmetric (box, Gaussian, |Sobel|),
 // so evaluating them on the reflect-padded gray tile reproduces OpenCV's per-stage padding.
 #pragma once
@@ -84,7 +84,9 @@ __device__ __forceinline__ int sobel_g2(const uint8_t* __restrict__ g, int gw) {
     return gx * gx + gy * gy;
 }
 
-__global__ void __launch_bounds__(DT_NT) k_detail_max(const uint8_t* __restrict__ src, size_t pitch, int w, int h, DetailMax* __restrict__ out) {
+// also stores (gx^2+gy^2) << 8 | local_var per pixel: k_detail_mask reads that plane instead of redoing the front end
+__global__ void __launch_bounds__(DT_NT) k_detail_max(const uint8_t* __restrict__ src, size_t pitch, int w, int h, DetailMax* __restrict__ out,
+                                                      uint32_t* __restrict__ dv, int dvp) {
     constexpr int HALO = 4, GW = DT_TW + 2 * HALO, GH = DT_TH + 2 * HALO, MW = GW - 4, MH = GH - 4, VW = MW - 4;
     __shared__ uint8_t s_gray[GW * GH];
     __shared__ uint16_t s_rs1[MW * GH];
@@ -100,8 +102,10 @@ __global__ void __launch_bounds__(DT_NT) k_detail_max(const uint8_t* __restrict_
     for (int i = threadIdx.x; i < DT_TW * DT_TH; i += DT_NT) {
         const int y = i / DT_TW, x = i - y * DT_TW;
         if (x0 + x < w && y0 + y < h) {
-            var = max(var, box_at<5>(s_rs2, VW, x, y));                          // :272 local_var
-            g2 = max(g2, sobel_g2(s_gray + (y + HALO) * GW + x + HALO, GW));   // :251-256
+            const int v = box_at<5>(s_rs2, VW, x, y);                           // :272 local_var
+            const int q = sobel_g2(s_gray + (y + HALO) * GW + x + HALO, GW);    // :251-256, < 2^22
+            var = max(var, v); g2 = max(g2, q);
+            dv[(size_t)(y0 + y) * dvp + x0 + x] = ((uint32_t)q << 8) | (uint32_t)v;
         }
     }
 #pragma unroll
@@ -115,7 +119,7 @@ __global__ void __launch_bounds__(DT_NT) k_detail_max(const uint8_t* __restrict_
 }
 
 struct DetailMaskArgs {
-    const uint8_t* src; size_t pitch; int w, h;
+    const uint32_t* dv; int dvp; int w, h;   // k_detail_max's plane: (gx^2+gy^2) << 8 | local_var
     const DetailMax* mx;
     double thr;                  // detail_threshold / 255.0 (:291)
     float gf[5];                 // (float)getGaussianKernel(5, 1.0) (:306)
@@ -123,25 +127,20 @@ struct DetailMaskArgs {
 };
 
 __global__ void __launch_bounds__(DT_NT) k_detail_mask(const DetailMaskArgs a) {
-    constexpr int HALO = 6, GW = DT_TW + 2 * HALO, GH = DT_TH + 2 * HALO, MW = GW - 4, MH = GH - 4, VW = MW - 4, VH = MH - 4;
-    __shared__ uint8_t s_gray[GW * GH];
-    __shared__ uint16_t s_rs1[MW * GH];
-    __shared__ uint8_t s_dsq[MW * MH];
-    __shared__ uint16_t s_rs2[VW * MH];
+    constexpr int VW = DT_TW + 4, VH = DT_TH + 4;
     __shared__ float s_sig[VW * VH];
     __shared__ float s_row[DT_TW * VH];
     const int x0 = blockIdx.x * DT_TW, y0 = blockIdx.y * DT_TH;
-    load_gray_tile<HALO>(a.src, a.pitch, a.w, a.h, x0, y0, s_gray);
     // :281-285  Mat / max  ==  convertTo(alpha = 1/max): one float32 multiply by (float)(1.0 / max)
     const float magmax = __fsqrt_rn((float)a.mx->g2), texmax = __fsqrt_rn((float)a.mx->var);
     const float inv_mag = magmax > 0.f ? (float)(1.0 / (double)magmax) : 0.f;
     const float inv_tex = texmax > 0.f ? (float)(1.0 / (double)texmax) : 0.f;
-    __syncthreads();
-    detail_variance_rows<HALO, 5>(s_gray, s_rs1, s_dsq, s_rs2);
     for (int i = threadIdx.x; i < VW * VH; i += DT_NT) {
         const int y = i / VW, x = i - y * VW;
-        const float tex = __fsqrt_rn((float)box_at<5>(s_rs2, VW, x, y));                          // :272,:276 (repaired)
-        const float mag = __fsqrt_rn((float)sobel_g2(s_gray + (y + 4) * GW + x + 4, GW));       // :251-256
+        // BORDER_REFLECT_101 of the sigmoid plane (:306) == of the per-pixel inputs it is a function of
+        const uint32_t q = a.dv[(size_t)reflect101(y0 - 2 + y, a.h) * a.dvp + reflect101(x0 - 2 + x, a.w)];
+        const float tex = __fsqrt_rn((float)(q & 0xffu));                                       // :272,:276 (repaired)
+        const float mag = __fsqrt_rn((float)(q >> 8));                                          // :251-256
         const float nm = __fmul_rn(mag, inv_mag), nt = __fmul_rn(tex, inv_tex);
         const float detail = (float)((double)nm * 0.7 + (double)nt * 0.3);                      // :288
         s_sig[i] = (float)(1.0 / (1.0 + exp(-((double)detail - a.thr) * 10.0)));                // :296-300 (double, float store)

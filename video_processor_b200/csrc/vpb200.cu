@@ -71,6 +71,7 @@ struct MsScratch {                  // SelectiveBilateral's selective / multi-sc
     int lw[5] = {0, 0, 0, 0, 0}, lh[5] = {0, 0, 0, 0, 0};
     float* mask = nullptr; size_t mpitch = 0;
     vp::DetailMax* mx = nullptr;
+    uint32_t* dv = nullptr; int dvp = 0;   // k_detail_max's per-pixel plane (level-0 size; smaller levels reuse it)
 };
 
 struct FlowLevel {                  // one pyramid level of the Farneback engine
@@ -349,7 +350,7 @@ inline int bil_num_scales(const vp_bilateral_config& b) { return std::max(1, std
 
 void free_ms_scratch(MsScratch& S) {
     for (int i = 0; i < 5; ++i) { cudaFree(S.lvl[i]); cudaFree(S.proc[i]); }
-    cudaFree(S.mask); cudaFree(S.mx);
+    cudaFree(S.mask); cudaFree(S.mx); cudaFree(S.dv);
     S = MsScratch();
 }
 
@@ -368,6 +369,8 @@ int ensure_ms_scratch(vp_ctx* c, MsScratch& S, int w, int h, int n, bool p0) {
     S.mpitch = align_up((size_t)w * 4, 256);
     VP_CUDA(c, cudaMalloc(&S.mask, S.mpitch * h));
     VP_CUDA(c, cudaMalloc(&S.mx, sizeof(DetailMax)));
+    S.dvp = (int)align_up((size_t)w, 64);
+    VP_CUDA(c, cudaMalloc(&S.dv, (size_t)S.dvp * h * sizeof(uint32_t)));
     return VP_OK;
 }
 
@@ -388,13 +391,13 @@ int build_multiscale_cands(vp_ctx* c, const vp_bilateral_config& cfg, BilCand** 
 }
 
 int launch_detail_mask(vp_ctx* c, const uint8_t* src, size_t pitch, int w, int h, double detail_threshold,
-                       DetailMax* mx, float* mask, size_t mpitch, cudaStream_t st) {
+                       DetailMax* mx, uint32_t* dv, int dvp, float* mask, size_t mpitch, cudaStream_t st) {
     ProfScope ps(c, K_BIL_OTHER, st);
     VP_CUDA(c, cudaMemsetAsync(mx, 0, sizeof(DetailMax), st));
     const dim3 grid((w + DT_TW - 1) / DT_TW, (h + DT_TH - 1) / DT_TH);
-    k_detail_max<<<grid, DT_NT, 0, st>>>(src, pitch, w, h, mx);
+    k_detail_max<<<grid, DT_NT, 0, st>>>(src, pitch, w, h, mx, dv, dvp);
     DetailMaskArgs a{};
-    a.src = src; a.pitch = pitch; a.w = w; a.h = h; a.mx = mx;
+    a.dv = dv; a.dvp = dvp; a.w = w; a.h = h; a.mx = mx;
     a.thr = detail_threshold / 255.0;
     const std::vector<double> g = vp_host::gaussian_kernel_f64(5, 1.0);   // literal Size(5,5), 1.0 at :306
     for (int i = 0; i < 5; ++i) a.gf[i] = (float)g[i];
@@ -435,7 +438,7 @@ int run_bilateral_modes(vp_ctx* c, MsScratch& S, const vp_bilateral_config& cfg,
             rc = launch_bilateral(c, a, rad, st, i == 0 ? kind : K_BIL_OTHER); if (rc) return rc;
         }
         for (int i = n - 1; i > 0; --i) {                                        // :185-230
-            rc = launch_detail_mask(c, proc[i - 1], pp[i - 1], S.lw[i - 1], S.lh[i - 1], cfg.detail_threshold, S.mx, S.mask, S.mpitch, st);
+            rc = launch_detail_mask(c, proc[i - 1], pp[i - 1], S.lw[i - 1], S.lh[i - 1], cfg.detail_threshold, S.mx, S.dv, S.dvp, S.mask, S.mpitch, st);
             if (rc) return rc;
             MsBlendArgs b{proc[i - 1], pp[i - 1], S.lw[i - 1], S.lh[i - 1], proc[i], pp[i], S.lw[i], S.lh[i], S.mask, S.mpitch};
             ProfScope ps(c, K_BIL_OTHER, st);
@@ -448,7 +451,7 @@ int run_bilateral_modes(vp_ctx* c, MsScratch& S, const vp_bilateral_config& cfg,
     }
     // selective: detail mask of the input, the plain (adaptive) filter, the joint blend (:121-136, :373-439)
     rc = ensure_ms_scratch(c, S, w, h, 1, true); if (rc) return rc;
-    rc = launch_detail_mask(c, src, spitch, w, h, cfg.detail_threshold, S.mx, S.mask, S.mpitch, st); if (rc) return rc;
+    rc = launch_detail_mask(c, src, spitch, w, h, cfg.detail_threshold, S.mx, S.dv, S.dvp, S.mask, S.mpitch, st); if (rc) return rc;
     if (cfg.adaptive_params) {
         VP_CUDA(c, cudaMemsetAsync(sr.sums, 0, 6 * sizeof(unsigned long long), st));
         rc = launch_stats(c, src, spitch, w, h, sr.sums, SelOut{sr.counter, sr.sel, (double)w * h}, st); if (rc) return rc;
@@ -1633,8 +1636,8 @@ int vp_detail_mask(vp_ctx* c, double detail_threshold, const uint8_t* d_src, siz
     if (mask_pitch < (size_t)w * 4) return fail(c, VP_ERR_INVALID_ARG, "vp_detail_mask: mask pitch < 4*width");
     VP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
-    if (!c->ms_tmp.mx) VP_CUDA(c, cudaMalloc(&c->ms_tmp.mx, sizeof(DetailMax)));
-    return launch_detail_mask(c, d_src, src_pitch, w, h, detail_threshold, c->ms_tmp.mx, d_mask, mask_pitch, st);
+    rc = ensure_ms_scratch(c, c->ms_tmp, w, h, 1, true); if (rc) return rc;
+    return launch_detail_mask(c, d_src, src_pitch, w, h, detail_threshold, c->ms_tmp.mx, c->ms_tmp.dv, c->ms_tmp.dvp, d_mask, mask_pitch, st);
 }
 
 int vp_pyr_down(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, int src_w, int src_h, uint8_t* d_dst, size_t dst_pitch, void* stream) {
