@@ -256,3 +256,37 @@ def test_against_frozen_opencv_vectors(vp, ctx):
     assert np.array_equal(down.cpu().numpy(), g["pyr_down"]) and np.array_equal(up.cpu().numpy(), g["pyr_up"])
     assert np.abs(mask.cpu().numpy() - g["detail_mask"]).max() <= 5e-6
     assert np.abs(sig.cpu().numpy() - g["sigma_map"]).max() <= 5e-6
+
+
+def test_full_size_1080p_against_opencv(vp, ctx):
+    """BASELINE's frame size: Farneback, the temporal stage and the repaired branches against the real OpenCV kernels"""
+    import cv2
+    w, h = 1920, 1080
+    f0, f1, f2 = synth.clip("scene", w, h, 3)
+    t = RC.TemporalConfig(use_flow=True, scene_detect=True)
+    flow = gpu_flow(vp, ctx, f0, f1, t)
+    g0, g1 = cv2.cvtColor(f0, cv2.COLOR_BGR2GRAY), cv2.cvtColor(f1, cv2.COLOR_BGR2GRAY)
+    ref = cv2.calcOpticalFlowFarneback(g0, g1, None, t.pyr_scale, t.levels, t.winsize, t.iterations, t.poly_n, t.poly_sigma, 0)
+    assert np.abs(flow - ref).max() <= 5e-3, np.abs(flow - ref).max()
+    outs = run_tc(vp, [f0, f1, f2], t, w, h)
+    oracle = RC.TemporalConsistencyFull(t, RC.Cv2Ops())
+    for i, (o, f) in enumerate(zip(outs, (f0, f1, f2))):
+        r = oracle.process(f)
+        mx, n = G.diff_stats(o, r)
+        assert mx <= 1 and n <= o.size * 0.01, (i, mx, n)
+    # SelectiveBilateral multi-scale and AdaptiveSharpening adaptive_sigma at the same size
+    ops = RC.Cv2Ops()
+    src = G.to_dev(f0)
+    dst = G.dev_empty(h, w)
+    bcfg = RC.BilateralConfig(use_multiscale=True, num_scales=3)
+    ctx.call("vp_selective_bilateral", G.bilateral_cfg(vp, bcfg), src.data_ptr(), G.pitch(src), dst.data_ptr(), G.pitch(dst), w, h, None)
+    G.sync()
+    r = RC.selective_bilateral_process(ops, f0, bcfg)
+    mx, _ = G.diff_stats(dst.cpu().numpy(), r)
+    assert mx <= 4 and RC.psnr(dst.cpu().numpy(), r) >= 50.0
+    scfg = RC.SharpenConfig(adaptive_sigma=True)
+    ctx.call("vp_sharpen", G.sharpen_cfg(vp, scfg), src.data_ptr(), G.pitch(src), dst.data_ptr(), G.pitch(dst), w, h, None)
+    G.sync()
+    r = RC.sharpen_variable_sigma(ops, f0, scfg)
+    mx, n = G.diff_stats(dst.cpu().numpy(), r)
+    assert mx <= 2 and n <= r.size * 0.02, (mx, n)
