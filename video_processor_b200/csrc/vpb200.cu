@@ -336,7 +336,7 @@ int launch_bilateral(vp_ctx* c, BilArgs& a, const int radius[3], cudaStream_t st
     ProfScope ps(c, kind, st);
     int rmax = 0;
     for (int i = 0; i < 3; ++i) { a.radius[i] = radius[i]; rmax = std::max(rmax, radius[i]); }
-    a.ns = rmax <= 3 ? 2 : 1;     // small windows: taller tiles amortise the per-CTA table/halo cost
+    a.ns = rmax <= 2 ? 4 : (rmax <= 3 ? 2 : 1);     // small windows: taller tiles amortise the per-CTA table/halo cost
     const dim3 grid((a.w + BIL_TW - 1) / BIL_TW, (a.h + BIL_TH * a.ns - 1) / (BIL_TH * a.ns));
     k_bilateral<<<grid, BIL_NT, bil_smem_bytes(rmax, a.ns), st>>>(a);
     VP_CUDA(c, cudaGetLastError());
@@ -976,7 +976,7 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
     VP_CUDA(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     VP_CUDA(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
     VP_CUDA(c, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
-    VP_CUDA(c, cudaFuncSetAttribute(k_bilateral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(bil_smem_bytes(BIL_RMAX, 1), bil_smem_bytes(3, 2))));
+    VP_CUDA(c, cudaFuncSetAttribute(k_bilateral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(bil_smem_bytes(BIL_RMAX, 1), std::max(bil_smem_bytes(3, 2), bil_smem_bytes(2, 4)))));
     VP_CUDA(c, cudaFuncSetAttribute(k_bicubic<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_bicubic<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_bicubic<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
