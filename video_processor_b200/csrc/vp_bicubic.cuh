@@ -120,20 +120,36 @@ __global__ void __launch_bounds__(BC_NT) k_bicubic(const BicubicArgs a) {
             o[0] = (uint8_t)v[0]; o[1] = (uint8_t)v[1]; o[2] = (uint8_t)v[2];
         }
     };
+    // 16-byte aligned frames: pixels are staged in shared memory and each tile row leaves as one TMA bulk store;
+    // otherwise the quad-shuffle path
+    uint8_t* s_out = smem + L.out;
+    const bool staged = aligned16(a.dst, a.dpitch);
+    auto put = [&](int y, const uint32_t (&v)[3]) {
+        if (staged) {
+            if (y < vh) { uint8_t* o = s_out + y * (BC_TW * 3) + tid * 3; o[0] = (uint8_t)v[0]; o[1] = (uint8_t)v[1]; o[2] = (uint8_t)v[2]; }
+        } else emit(y, v);
+    };
+    auto flush_staged = [&]() {
+        if (!staged) return;
+        fence_proxy_async();
+        __syncthreads();
+        const int vw = dxb - x0 + 1, rb = vw * 3, nb16 = rb & ~15;
+        if (tid < vh && nb16) {
+            bulk_s2g(a.dst + (size_t)(y0 + tid) * a.dpitch + (size_t)x0 * 3, s_out + tid * (BC_TW * 3), (uint32_t)nb16);
+            bulk_commit();
+        }
+        const int tb = rb - nb16;
+        for (int i = tid; i < tb * vh; i += BC_NT) {
+            const int y = i / tb, qb = nb16 + (i - y * tb);
+            a.dst[(size_t)(y0 + y) * a.dpitch + (size_t)x0 * 3 + qb] = s_out[y * (BC_TW * 3) + qb];
+        }
+        if (tid < vh && nb16) bulk_wait_read0();
+    };
     if constexpr (S > 0) {
         // rows y0 + y with y % S == j use coefficient set j (y0 is a multiple of BC_TH, hence of S)
         float4 bj[S];
 #pragma unroll
         for (int j = 0; j < S; ++j) bj[j] = s_yc[j];
-        // 16-byte aligned frames: pixels are staged in shared memory and each tile row leaves as one TMA bulk store;
-        // otherwise the quad-shuffle path of the generic kernel
-        uint8_t* s_out = smem + L.out;
-        const bool staged = aligned16(a.dst, a.dpitch);
-        auto put = [&](int y, const uint32_t (&v)[3]) {
-            if (staged) {
-                if (y < vh) { uint8_t* o = s_out + y * (BC_TW * 3) + tid * 3; o[0] = (uint8_t)v[0]; o[1] = (uint8_t)v[1]; o[2] = (uint8_t)v[2]; }
-            } else emit(y, v);
-        };
         // the four taps are 12 consecutive bytes unless the column touches the replicate border
         const bool contig = (o1 == o0 + 3) && (o2 == o0 + 6) && (o3 == o0 + 9);
         auto hrow_s = [&](int rr, float (&h)[3]) {
@@ -198,21 +214,7 @@ __global__ void __launch_bounds__(BC_NT) k_bicubic(const BicubicArgs a) {
                 }
             }
         }
-        if (staged) {
-            fence_proxy_async();
-            __syncthreads();
-            const int vw = dxb - x0 + 1, rb = vw * 3, nb16 = rb & ~15;
-            if (tid < vh && nb16) {
-                bulk_s2g(a.dst + (size_t)(y0 + tid) * a.dpitch + (size_t)x0 * 3, s_out + tid * (BC_TW * 3), (uint32_t)nb16);
-                bulk_commit();
-            }
-            const int tb = rb - nb16;
-            for (int i = tid; i < tb * vh; i += BC_NT) {
-                const int y = i / tb, qb = nb16 + (i - y * tb);
-                a.dst[(size_t)(y0 + y) * a.dpitch + (size_t)x0 * 3 + qb] = s_out[y * (BC_TW * 3) + qb];
-            }
-            if (tid < vh && nb16) bulk_wait_read0();
-        }
+        flush_staged();
         return;
     }
     for (int y = 0; y < vh; ++y) {
@@ -232,8 +234,9 @@ __global__ void __launch_bounds__(BC_NT) k_bicubic(const BicubicArgs a) {
         for (int ch = 0; ch < 3; ++ch)
             v[ch] = f2u8(__fadd_rn(__fmaf_rn(w0[ch], b.x, __fmul_rn(w1[ch], b.y)),
                                    __fmaf_rn(w2[ch], b.z, __fmul_rn(w3[ch], b.w))));
-        emit(y, v);
+        put(y, v);
     }
+    flush_staged();
 }
 
 }  // namespace vp
