@@ -168,7 +168,7 @@ int vp_process_device(vp_ctx* ctx, const uint8_t* d_src, size_t src_pitch,
  * lane forks from it and joins it again, so work queued on `stream` before / after the call is ordered
  * before / after the whole batch.  d_dst[i] == NULL marks a warm-up frame; d_dst[i] and d_dst[i+1]
  * must not alias. */
-int vp_set_batch_lanes(vp_ctx* ctx, int lanes);     /* 1..4 stream lanes for the batch call (default 3; 4 for bicubic-only) */
+int vp_set_batch_lanes(vp_ctx* ctx, int lanes);     /* 1..4 stream lanes for the batch call (default 4) */
 int vp_process_batch_device(vp_ctx* ctx, int n, const uint8_t* const* d_src, size_t src_pitch,
                             uint8_t* const* d_dst, size_t dst_pitch, void* stream);
 /* Host frames, synchronous (pinned staging inside when the buffers are not pinned). */

@@ -1065,7 +1065,7 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
         rc = ensure_siglut(c, &c->d_siglut, &c->siglut_thr, &c->siglut_valid, g.sharpen.edge_threshold, c->s_compute);
         if (rc) return rc;
     }
-    c->nlanes = (!g.bicubic_enhance && !g.use_pre && !g.use_sharpen && !g.use_post) ? 4 : 3;
+    c->nlanes = 4;
     c->has_chain = true;
     return VP_OK;
 }
