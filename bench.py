@@ -540,7 +540,7 @@ def main():
                        "sharding": "contiguous frame segments, no collective",
                        "l2": f"inputs ({F}x{inb >> 20} MiB) and output ring ({NOUT}x{outb >> 20} MiB) exceed the 126 MB L2",
                        "roofline_pass": "per-kernel CUDA events in a separate pass of one step, one stream, one frame at a time",
-                       "api": "vp_process_device per frame" if args.per_frame else "vp_process_batch_device (two stream lanes)"},
+                       "api": "vp_process_device per frame" if args.per_frame else "vp_process_batch_device (four stream lanes)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(tl.item()), "roofline": roof, "cpu_baseline": cpu, "latency": latency,
         }
         print(json.dumps(line), flush=True)
