@@ -61,43 +61,12 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Stage image rows [y0,y1) x bytes [bx0,bx1) (bx0 a multiple of 16) into shared memory,
-// row r at s_raw + (r-y0)*s_pitch, byte b at offset b-bx0.  `fast` (base and pitch 16-byte
-// aligned) uses one TMA bulk copy per row issued by warp 0 and completes on `bar` (parity 0);
-// otherwise all threads copy bytes.  Every thread must call it; returns after the data is visible.
-__device__ __forceinline__ void stage_rows(uint8_t* s_raw, int s_pitch, const uint8_t* __restrict__ g, size_t gpitch,
-                                           int row_bytes, int y0, int y1, int bx0, int bx1, bool fast, uint64_t* bar) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int nrows = y1 - y0;
-    if (fast) {
-        // over-fetch to the next 16-byte boundary stays inside the row's pitch span (pitch % 16 == 0)
-        const int nb = ((bx1 + 15) & ~15) - bx0;
-        if (tid == 0) {
-            mbar_init(bar, 1);
-            mbar_fence_init();
-        }
-        __syncthreads();
-        if (tid < 32) {
-            if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nb * nrows));
-            __syncwarp();
-            for (int r = tid; r < nrows; r += 32)
-                bulk_g2s(s_raw + r * s_pitch, g + (size_t)(y0 + r) * gpitch + bx0, (uint32_t)nb, bar);
-        }
-        mbar_wait(bar, 0);
-    } else {
-        const int e = min(bx1, row_bytes);
-        const int nb = e - bx0;
-        for (int i = tid; i < nb * nrows; i += nt) {
-            int r = i / nb, b = i - r * nb;
-            s_raw[r * s_pitch + b] = g[(size_t)(y0 + r) * gpitch + bx0 + b];
-        }
-        __syncthreads();
-    }
-}
-
-// The same staging split in two so a kernel can fill its tables while the bulk copies are in flight:
-// stage_rows_issue() starts the TMA row copies (fast path; contains one __syncthreads), stage_rows_wait() returns once
-// the rows are visible (fast path) or copies them with all threads (byte path).  Both take the same arguments.
+// Stage image rows [y0,y1) x bytes [bx0,bx1) (bx0 a multiple of 16) into shared memory, row r at
+// s_raw + (r-y0)*s_pitch, byte b at offset b-bx0.  `fast` (base and pitch 16-byte aligned) uses one TMA bulk copy
+// per row issued by warp 0 and completing on `bar` (parity 0); otherwise all threads copy bytes.  The staging is split
+// in two so a kernel can fill its tables while the bulk copies are in flight: stage_rows_issue() starts the copies
+// (fast path; contains one __syncthreads), stage_rows_wait() returns once the rows are visible.  Every thread must
+// call both, with the same arguments.
 __device__ __forceinline__ void stage_rows_issue(uint8_t* s_raw, int s_pitch, const uint8_t* __restrict__ g, size_t gpitch,
                                                  int y0, int y1, int bx0, int bx1, bool fast, uint64_t* bar) {
     if (!fast) return;
