@@ -274,3 +274,26 @@ def test_chain_adaptive_sigma_plain_bilateral(vp):
         out = dst.cpu().numpy()
         mx, _ = G.diff_stats(out, ref)
         assert RC.psnr(out, ref) >= 50.0 and mx <= 4, (RC.psnr(out, ref), mx)
+
+
+def test_widened_rows_with_odd_pitches(vp, ctx):
+    """rows that are neither 4- nor 16-byte aligned take the byte paths: same results"""
+    w, h = 150, 70
+    img = synth.frame("scene", w, h, 3)
+    src = G.padded_dev(img, 7)
+    dst = torch.zeros((h, w * 3 + 5), dtype=torch.uint8, device="cuda")
+
+    def out():
+        G.sync()
+        o = dst.cpu().numpy()
+        assert not o[:, w * 3:].any()
+        return o[:, :w * 3].reshape(h, w, 3)
+
+    for ocfg in (RC.BilateralConfig(selective=True, use_multiscale=False), RC.BilateralConfig(use_multiscale=True, num_scales=3)):
+        ctx.call("vp_selective_bilateral", G.bilateral_cfg(vp, ocfg), src.data_ptr(), G.pitch(src), dst.data_ptr(), G.pitch(dst), w, h, None)
+        a = out().copy()
+        b = run_selective(vp, ctx, img, ocfg)
+        assert np.array_equal(a, b)
+    scfg = RC.SharpenConfig(adaptive_sigma=True)
+    ctx.call("vp_sharpen", G.sharpen_cfg(vp, scfg), src.data_ptr(), G.pitch(src), dst.data_ptr(), G.pitch(dst), w, h, None)
+    assert np.array_equal(out(), run_sharpen(vp, ctx, img, scfg))
