@@ -143,7 +143,10 @@ def traffic_for(kernel):
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
         entries = t[sorted(t)[-1]]
-        bil = sorted((k for k in entries if "k_bilateral" in k), key=lambda k: int(k.split("@grid")[1]))
+        # PRE is the first k_bilateral launch of a frame, POST the last ("#n" = order in the capture; older captures
+        # only carry the grid size, where PRE had the smaller grid)
+        bil = sorted((k for k in entries if "k_bilateral" in k),
+                     key=lambda k: (int(k.split("#")[1]) if "#" in k else 0, int(k.split("@grid")[1].split("#")[0])))
         pick = {"stats": [k for k in entries if "k_stats" in k],
                 "upsharp": [k for k in entries if "k_upsharp" in k or "k_bicubic" in k],
                 "bilateral_pre": bil[:1], "bilateral_post": bil[-1:]}.get(kernel, [])

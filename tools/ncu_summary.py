@@ -48,6 +48,7 @@ keys = ["Kernel Name", "launch__grid_size", "gpu__time_duration.sum", "dram__byt
 keys = [k for k in keys if k in h]
 units = rr[1]
 traffic = {}
+seen = collections.Counter()      # launches of the same kernel are told apart by their order in the captured frame
 with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.csv"), "w") as f:
     w = csv.writer(f)
     w.writerow([f"{k} [{units[h.index(k)]}]" if units[h.index(k)] else k for k in keys])
@@ -57,7 +58,9 @@ with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.csv"), "w") as f:
         ur, uw = units[h.index("dram__bytes_read.sum")], units[h.index("dram__bytes_write.sum")]
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         b = float(r[h.index("dram__bytes_read.sum")]) * scale.get(ur, 1) + float(r[h.index("dram__bytes_write.sum")]) * scale.get(uw, 1)
-        traffic.setdefault(name.split("(")[0] + f"@grid{grid}", []).append(int(b))
+        base = name.split("(")[0]
+        traffic.setdefault(base + f"@grid{grid}#{seen[base]}", []).append(int(b))
+        seen[base] += 1
 tj = os.path.join(ROOT, "profiles", "traffic.json")
 old = json.load(open(tj)) if os.path.exists(tj) else {}
 old[tag] = {k: int(sum(v) / len(v)) for k, v in traffic.items()}
