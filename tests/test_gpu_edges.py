@@ -120,3 +120,34 @@ def test_full_size_invariants(vp, ctx):
     G.sync()
     x = img.reshape(-1, 3).astype(np.int64)
     assert sums.cpu().tolist() == x.sum(0).tolist() + (x * x).sum(0).tolist()
+
+
+def test_context_lifecycle_does_not_leak(vp):
+    """create / run / destroy every kind of chain context repeatedly: device memory returns to where it started"""
+    import torch
+    sw, sh = 96, 64
+    variants = []
+    for ms, asg, flow in [(False, False, False), (True, True, True), (False, True, False), (True, False, True)]:
+        t = RC.TemporalConfig(use_flow=flow, scene_detect=flow)
+        o = RC.ChainConfig(dst_w=2 * sw, dst_h=2 * sh, temporal=RC.TEMPORAL_BLEND_FRAMES, temporal_cfg=t,
+                           pre=RC.BilateralConfig(RC.PRE_PROCESSING, True, True, 7, 30.0, 30.0, ms, 30.0, 1.5, 2.0, ms, 3),
+                           sharpen=RC.SharpenConfig(0.8, 1.2, 0.4, 30.0, 1.5, 5, True, True, asg),
+                           post=RC.BilateralConfig(RC.POST_PROCESSING, True, True, 5, 20.0, 20.0, ms, 30.0, 1.2, 1.5, ms, 2))
+        variants.append(o)
+    frames = [G.to_dev(f) for f in synth.clip("scene", sw, sh, 3)]
+    dst = G.dev_empty(2 * sh, 2 * sw)
+
+    def cycle():
+        for o in variants:
+            with vp.Context(G.chain_cfg(vp, o, sw, sh)) as ctx:
+                for f in frames:
+                    ctx.call("vp_process_device", f.data_ptr(), sw * 3, dst.data_ptr(), G.pitch(dst), None)
+                ctx.call("vp_synchronize")
+    cycle()
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(5):
+        cycle()
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < (8 << 20), (free0, free1)
