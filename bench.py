@@ -343,9 +343,19 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints a banner)
-        dist.init_process_group("nccl", device_id=dev)
-        dist.barrier()
+        # NCCL prints its version banner on file descriptor 1 when the first communicator is built: keep stdout to the
+        # one JSON line by pointing fd 1 at stderr until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     from video_processor_b200 import capi
 
     wl = args.workload
