@@ -245,12 +245,36 @@ __global__ void __launch_bounds__(256) k_box_solve(const float* __restrict__ M, 
     const int x0 = blockIdx.x * BOX_T, y0 = blockIdx.y * BOX_T;
     const int lx = threadIdx.x & 31, r0 = (threadIdx.x >> 5) * 4;
     double acc[4][5];
+    // staging addresses are the same for the five planes: with the window known at compile time a warp owns tile rows
+    // wrp, wrp+8, ... and a lane the columns lane and lane+32, all clamped once (rows / columns replicate)
+    constexpr int NRW = MT > 0 ? (BOX_T + 2 * MT + 7) / 8 : 1;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    size_t roff[NRW];
+    int cx0 = 0, cx1 = 0;
+    if (MT > 0) {
+        static_assert(MT == 0 || BOX_T + 2 * MT <= 64, "two columns per lane");
+        cx0 = min(max(x0 - m + lane, 0), w - 1);
+        cx1 = min(max(x0 - m + lane + 32, 0), w - 1);
+#pragma unroll
+        for (int k = 0; k < NRW; ++k) roff[k] = (size_t)min(max(y0 - m + wrp + 8 * k, 0), h - 1) * mp;
+    }
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
         const float* p = M + c * mps;
-        for (int i = threadIdx.x; i < ch * ch; i += 256) {
-            const int ty = i / ch, tx = i - ty * ch;
-            s_m[ty * cp + tx] = p[(size_t)min(max(y0 - m + ty, 0), h - 1) * mp + min(max(x0 - m + tx, 0), w - 1)];
+        if (MT > 0) {
+#pragma unroll
+            for (int k = 0; k < NRW; ++k) {
+                const int ty = wrp + 8 * k;
+                if (ty < ch) {
+                    s_m[ty * cp + lane] = p[roff[k] + cx0];
+                    if (lane + 32 < ch) s_m[ty * cp + lane + 32] = p[roff[k] + cx1];
+                }
+            }
+        } else {
+            for (int i = threadIdx.x; i < ch * ch; i += 256) {
+                const int ty = i / ch, tx = i - ty * ch;
+                s_m[ty * cp + tx] = p[(size_t)min(max(y0 - m + ty, 0), h - 1) * mp + min(max(x0 - m + tx, 0), w - 1)];
+            }
         }
         __syncthreads();
         for (int task = threadIdx.x; task < ch * (BOX_T / BOX_SEG); task += 256) {
