@@ -41,9 +41,14 @@ __device__ __forceinline__ void linear_tap(int d, double scale, int sn, int& s0,
 }
 
 // separable float32 Gaussian, BORDER_REFLECT_101, accumulation left to right without FMA (cv::GaussianBlur on CV_32F)
+// `varies` (optional): a device flag that is zero when the input plane is known to be the constant 1.0f everywhere (the
+// reliability mask of a frame without fast motion); the result is then `const_out`, the value the very same float
+// sequence produces on a constant plane (computed by the host), and the taps are skipped.
 template <bool ROWS>
-__global__ void __launch_bounds__(256) k_gauss_f32(const float* __restrict__ src, int sp, float* __restrict__ dst, int dp, int w, int h, const GaussTaps t) {
+__global__ void __launch_bounds__(256) k_gauss_f32(const float* __restrict__ src, int sp, float* __restrict__ dst, int dp, int w, int h, const GaussTaps t,
+                                                   const int* __restrict__ varies = nullptr, float const_out = 0.f) {
     VP_FLOW_XY;
+    if (varies && *varies == 0) { dst[(size_t)y * dp + x] = const_out; return; }
     const int r = t.ksize >> 1;
     float acc = 0.f;
     const int c = ROWS ? x : y, n = ROWS ? w : h;
@@ -340,13 +345,14 @@ __global__ void __launch_bounds__(256) k_warp(const uint8_t* __restrict__ src, s
 
 // calculateFlowReliabilityMask before its blur (:331-344): 1 where |f| <= threshold, else clamp(expf(-(|f| - thr) / 10), 0, 1)
 __global__ void __launch_bounds__(256) k_reliability(const float* __restrict__ flow_x, const float* __restrict__ flow_y, int fp,
-                                                     float* __restrict__ mask, int mp, int w, int h, float thr) {
+                                                     float* __restrict__ mask, int mp, int w, int h, float thr, int* __restrict__ varies) {
     VP_FLOW_XY;
     const float fx = flow_x[(size_t)y * fp + x], fy = flow_y[(size_t)y * fp + x];
     const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)));
     float r = 1.f;
     if (mag > thr) r = fminf(fmaxf(expf(__fdiv_rn(-__fsub_rn(mag, thr), 10.0f)), 0.f), 1.f);
     mask[(size_t)y * mp + x] = r;
+    if (r != 1.f) *varies = 1;          // benign race: every writer stores the same value
 }
 
 // blendFrames with reliability masks (:380-436): weight_i = e^{-i/2} * mask_i * blend_factor_i in float32, accumulation

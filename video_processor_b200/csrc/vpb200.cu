@@ -158,6 +158,7 @@ struct vp_ctx {
     FlowTemporal ftc;               // temporal.use_flow
     FlowEngine flow_tmp;            // stage-wise vp_optical_flow
     float* flow_tmp_mask = nullptr; size_t flow_tmp_mask_n = 0;
+    int* d_mask_varies = nullptr;   // reliability mask: set when any raw value differs from 1.0f
     MsScratch ms_tmp;               // stage-wise scratch
     VsScratch vs_tmp;
     ResizeCache rc_chain, rc_tmp;
@@ -637,9 +638,16 @@ int flow_solve(vp_ctx* c, FlowEngine& E, int prev, int cur, cudaStream_t st) {
 int launch_reliability(vp_ctx* c, const float* fx, const float* fy, int fp, float thr, float* mask, int mp, float* tmp, int w, int h, cudaStream_t st) {
     ProfScope ps(c, K_BLEND, st);
     const GaussTaps t = gauss_taps(15, 5.0);
-    k_reliability<<<grid2d(w, h), 256, 0, st>>>(fx, fy, fp, mask, mp, w, h, thr);
-    k_gauss_f32<true><<<grid2d(w, h), 256, 0, st>>>(mask, mp, tmp, mp, w, h, t);
-    k_gauss_f32<false><<<grid2d(w, h), 256, 0, st>>>(tmp, mp, mask, mp, w, h, t);
+    // a frame without motion above the threshold has a mask of exactly 1.0f everywhere; its blur is then a constant - the
+    // value the same float32 tap sequence gives on a constant plane - and k_gauss_f32 only stores it (flag set by k_reliability)
+    if (!c->d_mask_varies) VP_CUDA(c, cudaMalloc(&c->d_mask_varies, sizeof(int)));
+    VP_CUDA(c, cudaMemsetAsync(c->d_mask_varies, 0, sizeof(int), st));
+    volatile float c1 = 0.f, c2 = 0.f;
+    for (int i = 0; i < t.ksize; ++i) { volatile float p = 1.0f * t.k[i]; c1 = i == 0 ? p : c1 + p; }
+    for (int i = 0; i < t.ksize; ++i) { volatile float p = c1 * t.k[i]; c2 = i == 0 ? p : c2 + p; }
+    k_reliability<<<grid2d(w, h), 256, 0, st>>>(fx, fy, fp, mask, mp, w, h, thr, c->d_mask_varies);
+    k_gauss_f32<true><<<grid2d(w, h), 256, 0, st>>>(mask, mp, tmp, mp, w, h, t, c->d_mask_varies, c1);
+    k_gauss_f32<false><<<grid2d(w, h), 256, 0, st>>>(tmp, mp, mask, mp, w, h, t, c->d_mask_varies, c2);
     VP_CUDA(c, cudaGetLastError());
     c->launches += 3;
     return VP_OK;
@@ -959,7 +967,7 @@ void vp_destroy(vp_ctx* c) {
     cudaFree(c->d_cand_be); cudaFree(c->d_scene_acc); cudaFree(c->d_scene_state); cudaFree(c->d_use);
     cudaFree(c->d_cand_pre); cudaFree(c->d_cand_post); cudaFree(c->d_cand_tmp); cudaFree(c->d_cand_sel);
     cudaFree(c->d_cand_ms_pre); cudaFree(c->d_cand_ms_post); cudaFree(c->d_cand_ms_tmp);
-    free_flow_temporal(c->ftc); free_flow_engine(c->flow_tmp); cudaFree(c->flow_tmp_mask);
+    free_flow_temporal(c->ftc); free_flow_engine(c->flow_tmp); cudaFree(c->flow_tmp_mask); cudaFree(c->d_mask_varies);
     free_ms_scratch(c->ms_tmp); free_vs_scratch(c->vs_tmp);
     free_resize(c->rc_chain); free_resize(c->rc_tmp);
     cudaFree(c->d_siglut); cudaFree(c->d_siglut_tmp);
