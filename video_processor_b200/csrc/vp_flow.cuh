@@ -44,11 +44,33 @@ __device__ __forceinline__ void linear_tap(int d, double scale, int sn, int& s0,
 // `varies` (optional): a device flag that is zero when the input plane is known to be the constant 1.0f everywhere (the
 // reliability mask of a frame without fast motion); the result is then `const_out`, the value the very same float
 // sequence produces on a constant plane (computed by the host), and the taps are skipped.
-template <bool ROWS>
+// KS > 0: kernel size known at compile time (3 = full-resolution pyramid level, 15 = reliability mask), taps unrolled
+template <bool ROWS, int KS = 0>
 __global__ void __launch_bounds__(256) k_gauss_f32(const float* __restrict__ src, int sp, float* __restrict__ dst, int dp, int w, int h, const GaussTaps t,
                                                    const int* __restrict__ varies = nullptr, float const_out = 0.f) {
     VP_FLOW_XY;
     if (varies && *varies == 0) { dst[(size_t)y * dp + x] = const_out; return; }
+    if constexpr (KS > 0) {
+        constexpr int R = KS / 2;
+        const int c = ROWS ? x : y, n = ROWS ? w : h;
+        float acc = 0.f;
+        if (c >= R && c + R < n) {
+            const float* p = ROWS ? src + (size_t)y * sp + (x - R) : src + (size_t)(y - R) * sp + x;
+#pragma unroll
+            for (int i = 0; i < KS; ++i) {
+                const float v = ROWS ? p[i] : p[(size_t)i * sp];
+                acc = i == 0 ? __fmul_rn(v, t.k[0]) : __fadd_rn(acc, __fmul_rn(v, t.k[i]));
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < KS; ++i) {
+                const float v = ROWS ? src[(size_t)y * sp + reflect101(x + i - R, w)] : src[(size_t)reflect101(y + i - R, h) * sp + x];
+                acc = i == 0 ? __fmul_rn(v, t.k[0]) : __fadd_rn(acc, __fmul_rn(v, t.k[i]));
+            }
+        }
+        dst[(size_t)y * dp + x] = acc;
+        return;
+    }
     const int r = t.ksize >> 1;
     float acc = 0.f;
     const int c = ROWS ? x : y, n = ROWS ? w : h;

@@ -588,8 +588,13 @@ int flow_expand(vp_ctx* c, FlowEngine& E, const uint8_t* bgr, size_t pitch, int 
         const GaussTaps t = gauss_taps(L.ksize, L.sigma);
         const float* img = L.I;
         if (L.w == E.w && L.h == E.h) {        // full resolution: the resize is the identity
-            k_gauss_f32<true><<<grid2d(E.w, E.h), 256, 0, st>>>(E.gray, L0.p, E.blur_a, L0.p, E.w, E.h, t);
-            k_gauss_f32<false><<<grid2d(E.w, E.h), 256, 0, st>>>(E.blur_a, L0.p, E.blur_b, L0.p, E.w, E.h, t);
+            if (t.ksize == 3) {
+                k_gauss_f32<true, 3><<<grid2d(E.w, E.h), 256, 0, st>>>(E.gray, L0.p, E.blur_a, L0.p, E.w, E.h, t);
+                k_gauss_f32<false, 3><<<grid2d(E.w, E.h), 256, 0, st>>>(E.blur_a, L0.p, E.blur_b, L0.p, E.w, E.h, t);
+            } else {
+                k_gauss_f32<true><<<grid2d(E.w, E.h), 256, 0, st>>>(E.gray, L0.p, E.blur_a, L0.p, E.w, E.h, t);
+                k_gauss_f32<false><<<grid2d(E.w, E.h), 256, 0, st>>>(E.blur_a, L0.p, E.blur_b, L0.p, E.w, E.h, t);
+            }
             img = E.blur_b;
         } else {                               // blur only where the resize samples: row pass at 2 columns per output column ...
             k_gauss_rows_at<<<grid2d(2 * L.w, E.h), 256, 0, st>>>(E.gray, L0.p, E.w, E.h, E.blur_a, L0.p, L.w, t);
@@ -646,8 +651,8 @@ int launch_reliability(vp_ctx* c, const float* fx, const float* fy, int fp, floa
     for (int i = 0; i < t.ksize; ++i) { volatile float p = 1.0f * t.k[i]; c1 = i == 0 ? p : c1 + p; }
     for (int i = 0; i < t.ksize; ++i) { volatile float p = c1 * t.k[i]; c2 = i == 0 ? p : c2 + p; }
     k_reliability<<<grid2d(w, h), 256, 0, st>>>(fx, fy, fp, mask, mp, w, h, thr, c->d_mask_varies);
-    k_gauss_f32<true><<<grid2d(w, h), 256, 0, st>>>(mask, mp, tmp, mp, w, h, t, c->d_mask_varies, c1);
-    k_gauss_f32<false><<<grid2d(w, h), 256, 0, st>>>(tmp, mp, mask, mp, w, h, t, c->d_mask_varies, c2);
+    k_gauss_f32<true, 15><<<grid2d(w, h), 256, 0, st>>>(mask, mp, tmp, mp, w, h, t, c->d_mask_varies, c1);
+    k_gauss_f32<false, 15><<<grid2d(w, h), 256, 0, st>>>(tmp, mp, mask, mp, w, h, t, c->d_mask_varies, c2);
     VP_CUDA(c, cudaGetLastError());
     c->launches += 3;
     return VP_OK;
