@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(256) k_gauss_f32(const float* __restrict__ src
 // columns and two source rows per output pixel.  k_gauss_rows_at runs the row pass at those columns only (compact plane
 // of 2*w' columns), k_gauss_cols_resize runs the column pass at the four taps and interpolates - the same arithmetic per
 // sample as the full blur followed by the resize, on a fraction of the samples.
+template <int KS = 0>
 __global__ void __launch_bounds__(256) k_gauss_rows_at(const float* __restrict__ src, int sp, int sw, int sh, float* __restrict__ dst, int dp,
                                                        int dw, const GaussTaps t) {
     const int w = 2 * dw, h = sh;
@@ -101,15 +102,23 @@ __global__ void __launch_bounds__(256) k_gauss_rows_at(const float* __restrict__
     int x0; float fx;
     linear_tap(x >> 1, (double)sw / (double)dw, sw, x0, fx);
     const int sx = (x & 1) ? min(x0 + 1, sw - 1) : x0;
-    const int r = t.ksize >> 1;
+    const int ks = KS > 0 ? KS : t.ksize, r = ks >> 1;
     const float* row = src + (size_t)y * sp;
     float acc = 0.f;
-    for (int i = 0; i < t.ksize; ++i) {
-        const float v = row[reflect101(sx + i - r, sw)];
-        acc = i == 0 ? __fmul_rn(v, t.k[0]) : __fadd_rn(acc, __fmul_rn(v, t.k[i]));
+    if (sx >= r && sx + r < sw) {
+        const float* p = row + sx - r;
+#pragma unroll
+        for (int i = 0; i < ks; ++i) acc = i == 0 ? __fmul_rn(p[0], t.k[0]) : __fadd_rn(acc, __fmul_rn(p[i], t.k[i]));
+    } else {
+#pragma unroll
+        for (int i = 0; i < ks; ++i) {
+            const float v = row[reflect101(sx + i - r, sw)];
+            acc = i == 0 ? __fmul_rn(v, t.k[0]) : __fadd_rn(acc, __fmul_rn(v, t.k[i]));
+        }
     }
     dst[(size_t)y * dp + x] = acc;
 }
+template <int KS = 0>
 __global__ void __launch_bounds__(256) k_gauss_cols_resize(const float* __restrict__ src, int sp, int sw, int sh, float* __restrict__ dst, int dp,
                                                            int w, int h, const GaussTaps t) {
     VP_FLOW_XY;
@@ -117,13 +126,14 @@ __global__ void __launch_bounds__(256) k_gauss_cols_resize(const float* __restri
     linear_tap(x, (double)sw / (double)w, sw, x0, fx);
     linear_tap(y, (double)sh / (double)h, sh, y0, fy);
     const int y1 = min(y0 + 1, sh - 1);
-    const int r = t.ksize >> 1;
+    const int ks = KS > 0 ? KS : t.ksize, r = ks >> 1;
     float v[2][2];
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
         const int yy = a ? y1 : y0;
         float acc0 = 0.f, acc1 = 0.f;
-        for (int i = 0; i < t.ksize; ++i) {
+#pragma unroll
+        for (int i = 0; i < ks; ++i) {
             const float* p = src + (size_t)reflect101(yy + i - r, sh) * sp + 2 * x;
             const float2 q = *reinterpret_cast<const float2*>(p);
             acc0 = i == 0 ? __fmul_rn(q.x, t.k[0]) : __fadd_rn(acc0, __fmul_rn(q.x, t.k[i]));
@@ -159,11 +169,14 @@ __global__ void __launch_bounds__(256) k_resize_linear_f32(const float* __restri
 struct PolyTaps { int n; float g[8], xg[8], xxg[8]; double ig11, ig03, ig33, ig55; };   // FarnebackPrepareGaussian, taps 0..n
 
 // FarnebackPolyExp, vertical part: three float32 moment rows per pixel (rows clamp at the border)
+template <int N = 0>
 __global__ void __launch_bounds__(256) k_polyexp_v(const float* __restrict__ src, int sp, float* __restrict__ tmp, int tp, size_t tps, int w, int h, const PolyTaps t) {
     VP_FLOW_XY;
+    const int n = N > 0 ? N : t.n;
     const float s0 = src[(size_t)y * sp + x];
     float r0 = __fmul_rn(s0, t.g[0]), r1 = 0.f, r2 = 0.f;
-    for (int k = 1; k <= t.n; ++k) {
+#pragma unroll
+    for (int k = 1; k <= n; ++k) {
         const float a = src[(size_t)max(y - k, 0) * sp + x], b = src[(size_t)min(y + k, h - 1) * sp + x];
         const float p = __fadd_rn(a, b);
         r0 = __fadd_rn(r0, __fmul_rn(t.g[k], p));
@@ -174,13 +187,16 @@ __global__ void __launch_bounds__(256) k_polyexp_v(const float* __restrict__ src
     tmp[o] = r0; tmp[tps + o] = r1; tmp[2 * tps + o] = r2;
 }
 // horizontal part: double accumulators over float32 partial products exactly as the C++ mixes them; columns replicate
+template <int N = 0>
 __global__ void __launch_bounds__(256) k_polyexp_h(const float* __restrict__ tmp, int tp, size_t tps, float* __restrict__ R, int rp, size_t rps, int w, int h, const PolyTaps t) {
     VP_FLOW_XY;
+    const int n = N > 0 ? N : t.n;
     const float* r0 = tmp + (size_t)y * tp;
     const float* r1 = r0 + tps;
     const float* r2 = r0 + 2 * tps;
     double b1 = (double)__fmul_rn(r0[x], t.g[0]), b2 = 0, b3 = (double)__fmul_rn(r1[x], t.g[0]), b4 = 0, b5 = (double)__fmul_rn(r2[x], t.g[0]), b6 = 0;
-    for (int k = 1; k <= t.n; ++k) {
+#pragma unroll
+    for (int k = 1; k <= n; ++k) {
         const int xp = min(x + k, w - 1), xm = max(x - k, 0);
         const double tg = (double)__fadd_rn(r0[xp], r0[xm]);
         b1 += tg * (double)t.g[k];

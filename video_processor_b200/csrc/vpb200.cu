@@ -597,11 +597,23 @@ int flow_expand(vp_ctx* c, FlowEngine& E, const uint8_t* bgr, size_t pitch, int 
             }
             img = E.blur_b;
         } else {                               // blur only where the resize samples: row pass at 2 columns per output column ...
-            k_gauss_rows_at<<<grid2d(2 * L.w, E.h), 256, 0, st>>>(E.gray, L0.p, E.w, E.h, E.blur_a, L0.p, L.w, t);
-            k_gauss_cols_resize<<<grid2d(L.w, L.h), 256, 0, st>>>(E.blur_a, L0.p, E.w, E.h, L.I, L.p, L.w, L.h, t);   // ... column pass at 2 rows
+            const dim3 gr = grid2d(2 * L.w, E.h), gc = grid2d(L.w, L.h);      // ... column pass at 2 rows
+#define VP_PYR(KS)                                                                                                  \
+            do {                                                                                                    \
+                k_gauss_rows_at<KS><<<gr, 256, 0, st>>>(E.gray, L0.p, E.w, E.h, E.blur_a, L0.p, L.w, t);            \
+                k_gauss_cols_resize<KS><<<gc, 256, 0, st>>>(E.blur_a, L0.p, E.w, E.h, L.I, L.p, L.w, L.h, t);       \
+            } while (0)
+            if (t.ksize == 3) VP_PYR(3); else if (t.ksize == 9) VP_PYR(9); else if (t.ksize == 19) VP_PYR(19); else VP_PYR(0);
+#undef VP_PYR
         }
-        k_polyexp_v<<<grid2d(L.w, L.h), 256, 0, st>>>(img, img == L.I ? L.p : L0.p, E.tmp, L.p, L.ps, L.w, L.h, E.poly);
-        k_polyexp_h<<<grid2d(L.w, L.h), 256, 0, st>>>(E.tmp, L.p, L.ps, L.R[which], L.p, L.ps, L.w, L.h, E.poly);
+        const int ip = img == L.I ? L.p : L0.p;
+        if (E.poly.n == 5) {
+            k_polyexp_v<5><<<grid2d(L.w, L.h), 256, 0, st>>>(img, ip, E.tmp, L.p, L.ps, L.w, L.h, E.poly);
+            k_polyexp_h<5><<<grid2d(L.w, L.h), 256, 0, st>>>(E.tmp, L.p, L.ps, L.R[which], L.p, L.ps, L.w, L.h, E.poly);
+        } else {
+            k_polyexp_v<0><<<grid2d(L.w, L.h), 256, 0, st>>>(img, ip, E.tmp, L.p, L.ps, L.w, L.h, E.poly);
+            k_polyexp_h<0><<<grid2d(L.w, L.h), 256, 0, st>>>(E.tmp, L.p, L.ps, L.R[which], L.p, L.ps, L.w, L.h, E.poly);
+        }
         c->launches += 4;
     }
     VP_CUDA(c, cudaGetLastError());
