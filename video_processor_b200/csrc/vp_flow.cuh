@@ -96,11 +96,11 @@ __global__ void __launch_bounds__(256) k_gauss_f32(const float* __restrict__ src
 // sample as the full blur followed by the resize, on a fraction of the samples.
 template <int KS = 0>
 __global__ void __launch_bounds__(256) k_gauss_rows_at(const float* __restrict__ src, int sp, int sw, int sh, float* __restrict__ dst, int dp,
-                                                       int dw, const GaussTaps t) {
+                                                       int dw, const GaussTaps t, double xscale) {
     const int w = 2 * dw, h = sh;
     VP_FLOW_XY;
     int x0; float fx;
-    linear_tap(x >> 1, (double)sw / (double)dw, sw, x0, fx);
+    linear_tap(x >> 1, xscale, sw, x0, fx);
     const int sx = (x & 1) ? min(x0 + 1, sw - 1) : x0;
     const int ks = KS > 0 ? KS : t.ksize, r = ks >> 1;
     const float* row = src + (size_t)y * sp;
@@ -120,11 +120,11 @@ __global__ void __launch_bounds__(256) k_gauss_rows_at(const float* __restrict__
 }
 template <int KS = 0>
 __global__ void __launch_bounds__(256) k_gauss_cols_resize(const float* __restrict__ src, int sp, int sw, int sh, float* __restrict__ dst, int dp,
-                                                           int w, int h, const GaussTaps t) {
+                                                           int w, int h, const GaussTaps t, double xscale, double yscale) {
     VP_FLOW_XY;
     int x0, y0; float fx, fy;
-    linear_tap(x, (double)sw / (double)w, sw, x0, fx);
-    linear_tap(y, (double)sh / (double)h, sh, y0, fy);
+    linear_tap(x, xscale, sw, x0, fx);
+    linear_tap(y, yscale, sh, y0, fy);
     const int y1 = min(y0 + 1, sh - 1);
     const int ks = KS > 0 ? KS : t.ksize, r = ks >> 1;
     float v[2][2];
@@ -150,11 +150,12 @@ __global__ void __launch_bounds__(256) k_gauss_cols_resize(const float* __restri
 // cv::resize(INTER_LINEAR) on CV_32F planes (nch planes, plane strides sps / dps), optional scale of the result
 // (`flow *= 1 / pyr_scale`).  Horizontal interpolation of both rows first, then vertical, all float32 without FMA.
 __global__ void __launch_bounds__(256) k_resize_linear_f32(const float* __restrict__ src, int sp, size_t sps, int sw, int sh,
-                                                           float* __restrict__ dst, int dp, size_t dps, int w, int h, int nch, float mul) {
+                                                           float* __restrict__ dst, int dp, size_t dps, int w, int h, int nch, float mul,
+                                                           double xscale, double yscale) {
     VP_FLOW_XY;
     int x0, y0; float fx, fy;
-    linear_tap(x, (double)sw / (double)w, sw, x0, fx);
-    linear_tap(y, (double)sh / (double)h, sh, y0, fy);
+    linear_tap(x, xscale, sw, x0, fx);
+    linear_tap(y, yscale, sh, y0, fy);
     const int x1 = min(x0 + 1, sw - 1), y1 = min(y0 + 1, sh - 1);
     const float a0 = __fsub_rn(1.f, fx), b0 = __fsub_rn(1.f, fy);
     for (int c = 0; c < nch; ++c) {

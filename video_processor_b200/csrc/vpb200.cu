@@ -597,11 +597,12 @@ int flow_expand(vp_ctx* c, FlowEngine& E, const uint8_t* bgr, size_t pitch, int 
             }
             img = E.blur_b;
         } else {                               // blur only where the resize samples: row pass at 2 columns per output column ...
+            const double xs = (double)E.w / (double)L.w, ys = (double)E.h / (double)L.h;   // cv::resize scale_x / scale_y
             const dim3 gr = grid2d(2 * L.w, E.h), gc = grid2d(L.w, L.h);      // ... column pass at 2 rows
 #define VP_PYR(KS)                                                                                                  \
             do {                                                                                                    \
-                k_gauss_rows_at<KS><<<gr, 256, 0, st>>>(E.gray, L0.p, E.w, E.h, E.blur_a, L0.p, L.w, t);            \
-                k_gauss_cols_resize<KS><<<gc, 256, 0, st>>>(E.blur_a, L0.p, E.w, E.h, L.I, L.p, L.w, L.h, t);       \
+                k_gauss_rows_at<KS><<<gr, 256, 0, st>>>(E.gray, L0.p, E.w, E.h, E.blur_a, L0.p, L.w, t, xs);        \
+                k_gauss_cols_resize<KS><<<gc, 256, 0, st>>>(E.blur_a, L0.p, E.w, E.h, L.I, L.p, L.w, L.h, t, xs, ys);\
             } while (0)
             if (t.ksize == 3) VP_PYR(3); else if (t.ksize == 9) VP_PYR(9); else if (t.ksize == 19) VP_PYR(19); else VP_PYR(0);
 #undef VP_PYR
@@ -631,7 +632,8 @@ int flow_solve(vp_ctx* c, FlowEngine& E, int prev, int cur, cudaStream_t st) {
         if (k == E.nlev - 1) VP_CUDA(c, cudaMemsetAsync(L.flow, 0, 2 * L.ps * sizeof(float), st));
         else {
             const FlowLevel& U = E.lv[k + 1];
-            k_resize_linear_f32<<<g, 256, 0, st>>>(U.flow, U.p, U.ps, U.w, U.h, L.flow, L.p, L.ps, L.w, L.h, 2, (float)(1.0 / E.prm.pyr_scale));
+            k_resize_linear_f32<<<g, 256, 0, st>>>(U.flow, U.p, U.ps, U.w, U.h, L.flow, L.p, L.ps, L.w, L.h, 2, (float)(1.0 / E.prm.pyr_scale),
+                                                    (double)U.w / (double)L.w, (double)U.h / (double)L.h);
             c->launches++;
         }
         k_update_matrices<<<g, 256, 0, st>>>(L.R[prev], L.R[cur], L.p, L.ps, L.flow, L.p, L.ps, E.M, L.p, L.ps, L.w, L.h);
