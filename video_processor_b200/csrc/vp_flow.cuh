@@ -274,10 +274,15 @@ __global__ void __launch_bounds__(256) k_update_matrices(const float* __restrict
 // the column window over the row sums.  ~10 shared-memory accesses per pixel and plane instead of 2 x (2m+1); the five sums
 // stay in registers, M is read ~2x, nothing is spilled to HBM.  Shared pitches are odd so lanes walking rows hit distinct banks.
 constexpr int BOX_T = 32, BOX_SEG = 8;
-__host__ __device__ inline size_t box_smem_bytes(int m) {
+__host__ __device__ inline size_t box_smem_bytes(int m, bool two_tiles = false) {
     const int ch = BOX_T + 2 * m;
-    return (size_t)ch * (BOX_T + 1) * sizeof(double) + (size_t)ch * (ch | 1) * sizeof(float);
+    return (size_t)ch * (BOX_T + 1) * sizeof(double) + (size_t)(two_tiles ? 2 : 1) * ch * (ch | 1) * sizeof(float);
 }
+__device__ __forceinline__ void cp_async_f32(float* smem, const float* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // MT > 0: window half-width known at compile time (the reference's winsize 15 -> MT = 7), loops unrolled, constant divisors
 template <int MT>
 __global__ void __launch_bounds__(256) k_box_solve(const float* __restrict__ M, int mp, size_t mps, float* __restrict__ flow, int fp, size_t fps,
@@ -302,18 +307,27 @@ __global__ void __launch_bounds__(256) k_box_solve(const float* __restrict__ M, 
 #pragma unroll
         for (int k = 0; k < NRW; ++k) roff[k] = (size_t)min(max(y0 - m + wrp + 8 * k, 0), h - 1) * mp;
     }
+    // MT > 0: two halo tiles; plane c + 1 streams in (cp.async, no registers) while plane c is summed
+    auto stage_async = [&](int c) {
+        const float* p = M + c * mps;
+        float* d = s_m + (c & 1) * ch * cp;
+#pragma unroll
+        for (int k = 0; k < NRW; ++k) {
+            const int ty = wrp + 8 * k;
+            if (ty < ch) {
+                cp_async_f32(d + ty * cp + lane, p + roff[k] + cx0);
+                if (lane + 32 < ch) cp_async_f32(d + ty * cp + lane + 32, p + roff[k] + cx1);
+            }
+        }
+        cp_async_commit();
+    };
+    if (MT > 0) stage_async(0);
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
         const float* p = M + c * mps;
+        const float* tile = s_m + (MT > 0 ? (c & 1) * ch * cp : 0);
         if (MT > 0) {
-#pragma unroll
-            for (int k = 0; k < NRW; ++k) {
-                const int ty = wrp + 8 * k;
-                if (ty < ch) {
-                    s_m[ty * cp + lane] = p[roff[k] + cx0];
-                    if (lane + 32 < ch) s_m[ty * cp + lane + 32] = p[roff[k] + cx1];
-                }
-            }
+            if (c + 1 < 5) { stage_async(c + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
         } else {
             for (int i = threadIdx.x; i < ch * ch; i += 256) {
                 const int ty = i / ch, tx = i - ty * ch;
@@ -323,7 +337,7 @@ __global__ void __launch_bounds__(256) k_box_solve(const float* __restrict__ M, 
         __syncthreads();
         for (int task = threadIdx.x; task < ch * (BOX_T / BOX_SEG); task += 256) {
             const int seg = task / ch, row = task - seg * ch;
-            const float* q = s_m + row * cp + seg * BOX_SEG;           // first column of the first window
+            const float* q = tile + row * cp + seg * BOX_SEG;          // first column of the first window
             double s = 0.0;
 #pragma unroll
             for (int k = 0; k <= win; ++k) s += (double)q[k];

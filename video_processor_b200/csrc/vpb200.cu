@@ -535,7 +535,7 @@ int ensure_flow_engine(vp_ctx* c, FlowEngine& E, int w, int h, const vp_temporal
     if (prm.flags != 0) return fail(c, VP_ERR_UNSUPPORTED, "Farneback flags other than 0 are not built");
     if (prm.winsize < 1 || !(prm.winsize & 1) || prm.winsize > 63) return fail(c, VP_ERR_UNSUPPORTED, "Farneback winsize must be odd, 1..63");
     VP_CUDA(c, cudaFuncSetAttribute(k_box_solve<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)box_smem_bytes(31)));
-    VP_CUDA(c, cudaFuncSetAttribute(k_box_solve<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)box_smem_bytes(7)));
+    VP_CUDA(c, cudaFuncSetAttribute(k_box_solve<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)box_smem_bytes(7, true)));
     if (prm.iterations < 1 || prm.levels < 0 || prm.levels > 7 || !(prm.pyr_scale > 0.0 && prm.pyr_scale < 1.0))
         return fail(c, VP_ERR_INVALID_ARG, "Farneback: iterations >= 1, levels 0..7, 0 < pyr_scale < 1");
     VP_CUDA(c, cudaDeviceSynchronize());
@@ -640,7 +640,7 @@ int flow_solve(vp_ctx* c, FlowEngine& E, int prev, int cur, cudaStream_t st) {
         c->launches++;
         for (int i = 0; i < E.prm.iterations; ++i) {
             const dim3 gb((L.w + BOX_T - 1) / BOX_T, (L.h + BOX_T - 1) / BOX_T);
-            if (m == 7) k_box_solve<7><<<gb, 256, box_smem_bytes(m), st>>>(E.M, L.p, L.ps, L.flow, L.p, L.ps, L.w, L.h, m, scale);
+            if (m == 7) k_box_solve<7><<<gb, 256, box_smem_bytes(m, true), st>>>(E.M, L.p, L.ps, L.flow, L.p, L.ps, L.w, L.h, m, scale);
             else k_box_solve<0><<<gb, 256, box_smem_bytes(m), st>>>(E.M, L.p, L.ps, L.flow, L.p, L.ps, L.w, L.h, m, scale);
             c->launches++;
             if (i < E.prm.iterations - 1) {
