@@ -339,27 +339,36 @@ __global__ void __launch_bounds__(256) k_box_solve(const float* __restrict__ M, 
             const int seg = task / ch, row = task - seg * ch;
             const float* q = tile + row * cp + seg * BOX_SEG;          // first column of the first window
             double s = 0.0;
+            float head[BOX_SEG - 1];                                   // the values the window drops again: read once
 #pragma unroll
-            for (int k = 0; k <= win; ++k) s += (double)q[k];
+            for (int k = 0; k <= win; ++k) {
+                const float v = q[k];
+                if (k < BOX_SEG - 1) head[k] = v;
+                s += (double)v;
+            }
             double* o = s_r + row * rp + seg * BOX_SEG;
             o[0] = s;
 #pragma unroll
             for (int t = 1; t < BOX_SEG; ++t) {
                 s += (double)q[t + win];
-                s -= (double)q[t - 1];
+                s -= (double)(MT > 0 && MT * 2 + 1 >= BOX_SEG - 1 ? head[t - 1] : q[t - 1]);
                 o[t] = s;
             }
         }
         __syncthreads();
         const double* v = s_r + r0 * rp + lx;                          // window rows r0 .. r0 + 2m of the tile's halo rows
-        double a = 0.0;
+        double a = 0.0, top[3];
 #pragma unroll
-        for (int k = 0; k <= win; ++k) a += v[k * rp];
+        for (int k = 0; k <= win; ++k) {
+            const double u = v[k * rp];
+            if (k < 3) top[k] = u;
+            a += u;
+        }
         acc[0][c] = a * scale;
 #pragma unroll
         for (int t = 1; t < 4; ++t) {
             a += v[(t + win) * rp];
-            a -= v[(t - 1) * rp];
+            a -= (MT > 0 ? top[t - 1] : v[(t - 1) * rp]);
             acc[t][c] = a * scale;
         }
     }
