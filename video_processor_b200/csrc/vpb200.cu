@@ -726,7 +726,10 @@ int run_flow_temporal(vp_ctx* c, FlowTemporal& T, const vp_temporal_config& t, c
             a.blend_strength = t.blend_strength;
             a.dst = dst; a.dpitch = dst_pitch; a.w = w; a.h = h;
             ProfScope ps(c, K_BLEND, st);
-            k_blend_masked<<<grid2d(w, h), 256, 0, st>>>(a);
+            const bool words = w % 4 == 0 && ((uintptr_t)cur | cur_pitch | (uintptr_t)dst | dst_pitch | T.rpitch) % 4 == 0 &&
+                               ((uintptr_t)T.mask[0] | (uintptr_t)T.mask[1] | (uintptr_t)T.mask[2]) % 16 == 0 && L0.p % 4 == 0;
+            if (words) k_blend_masked4<<<grid2d(w / 4, h), 256, 0, st>>>(a);
+            else k_blend_masked<<<grid2d(w, h), 256, 0, st>>>(a);
             VP_CUDA(c, cudaGetLastError());
             c->launches++;
         }
