@@ -78,7 +78,7 @@ struct FlowLevel {                  // one pyramid level of the Farneback engine
     int w = 0, h = 0, p = 0; size_t ps = 0;      // size, row pitch and plane stride in floats
     int ksize = 3; double sigma = 0;             // pre-smoothing of the full-resolution image for this level
     float* I = nullptr;                          // level image
-    float* R[2] = {nullptr, nullptr};            // polynomial expansions (5 planes), ping-pong previous / current frame
+    float* R[3] = {nullptr, nullptr, nullptr};   // polynomial expansions (5 planes) of the last 2 (stand-alone) / 3 (chain) frames
     float* flow = nullptr;                       // 2 planes
 };
 struct FlowEngine {                 // cv::calcOpticalFlowFarneback for one frame size and parameter set
@@ -92,7 +92,10 @@ struct FlowEngine {                 // cv::calcOpticalFlowFarneback for one fram
 };
 struct FlowTemporal {               // TemporalConsistency::process with the flow front end: device state
     FlowEngine eng;
-    int cur = 0;                    // which R[] holds the newest frame's expansions
+    int cur = 0;                    // which R[] holds the newest frame's expansions (ring of three: frame t+1 is expanded
+                                    // on its own lane while the iterations between t-1 and t still read the other two)
+    cudaEvent_t ev_expand = nullptr;                         // last flow_expand done (its scratch planes are shared)
+    cudaEvent_t ev_solve[3] = {nullptr, nullptr, nullptr};   // [s]: the iterations whose newer frame sits in R[s] are done
     bool have_prev = false;
     uint8_t* raw_prev = nullptr; size_t rpitch = 0;          // the previous unblended input (:158)
     uint8_t* warped[3] = {nullptr, nullptr, nullptr};        // remap(frame t-1-i, its flow): fixed once computed
@@ -472,14 +475,15 @@ int run_bilateral_modes(vp_ctx* c, MsScratch& S, const vp_bilateral_config& cfg,
 
 // ---- Farneback engine (vp_flow.cuh) ---------------------------------------------------------------------------
 void free_flow_engine(FlowEngine& E) {
-    for (FlowLevel& L : E.lv) { cudaFree(L.I); cudaFree(L.R[0]); cudaFree(L.R[1]); cudaFree(L.flow); }
+    for (FlowLevel& L : E.lv) { cudaFree(L.I); cudaFree(L.R[0]); cudaFree(L.R[1]); cudaFree(L.R[2]); cudaFree(L.flow); }
     cudaFree(E.gray); cudaFree(E.blur_a); cudaFree(E.blur_b); cudaFree(E.tmp); cudaFree(E.M);
     E = FlowEngine();
 }
 void free_flow_temporal(FlowTemporal& T) {
     free_flow_engine(T.eng);
     cudaFree(T.raw_prev); cudaFree(T.mtmp);
-    for (int i = 0; i < 3; ++i) { cudaFree(T.warped[i]); cudaFree(T.mask[i]); }
+    for (int i = 0; i < 3; ++i) { cudaFree(T.warped[i]); cudaFree(T.mask[i]); if (T.ev_solve[i]) cudaEventDestroy(T.ev_solve[i]); }
+    if (T.ev_expand) cudaEventDestroy(T.ev_expand);
     T = FlowTemporal();
 }
 
@@ -530,7 +534,7 @@ bool same_flow_params(const vp_temporal_config& a, const vp_temporal_config& b) 
            a.iterations == b.iterations && a.poly_n == b.poly_n && a.flags == b.flags;
 }
 
-int ensure_flow_engine(vp_ctx* c, FlowEngine& E, int w, int h, const vp_temporal_config& prm) {
+int ensure_flow_engine(vp_ctx* c, FlowEngine& E, int w, int h, const vp_temporal_config& prm, int nR = 2) {
     if (E.w == w && E.h == h && E.gray && same_flow_params(E.prm, prm)) return VP_OK;
     if (prm.flags != 0) return fail(c, VP_ERR_UNSUPPORTED, "Farneback flags other than 0 are not built");
     if (prm.winsize < 1 || !(prm.winsize & 1) || prm.winsize > 63) return fail(c, VP_ERR_UNSUPPORTED, "Farneback winsize must be odd, 1..63");
@@ -559,7 +563,8 @@ int ensure_flow_engine(vp_ctx* c, FlowEngine& E, int w, int h, const vp_temporal
         if (L.ksize > 19) return fail(c, VP_ERR_UNSUPPORTED, "Farneback: pyramid pre-smoothing kernel > 19 (pyr_scale^levels too small)");
         L.w = (int)std::lrint(w * scale); L.h = (int)std::lrint(h * scale);
         L.p = (int)align_up((size_t)L.w, 64); L.ps = (size_t)L.p * L.h;
-        VP_CUDA(c, planes(&L.I, 1, L)); VP_CUDA(c, planes(&L.R[0], 5, L)); VP_CUDA(c, planes(&L.R[1], 5, L)); VP_CUDA(c, planes(&L.flow, 2, L));
+        VP_CUDA(c, planes(&L.I, 1, L)); VP_CUDA(c, planes(&L.flow, 2, L));
+        for (int r = 0; r < nR; ++r) VP_CUDA(c, planes(&L.R[r], 5, L));
     }
     const FlowLevel& L0 = E.lv[0];
     VP_CUDA(c, planes(&E.gray, 1, L0)); VP_CUDA(c, planes(&E.blur_a, 1, L0)); VP_CUDA(c, planes(&E.blur_b, 1, L0));
@@ -676,7 +681,9 @@ int ensure_flow_temporal(vp_ctx* c, FlowTemporal& T, int w, int h, const vp_temp
     if (T.raw_prev && T.eng.w == w && T.eng.h == h && same_flow_params(T.eng.prm, prm)) return VP_OK;
     VP_CUDA(c, cudaDeviceSynchronize());
     free_flow_temporal(T);
-    int rc = ensure_flow_engine(c, T.eng, w, h, prm); if (rc) return rc;
+    int rc = ensure_flow_engine(c, T.eng, w, h, prm, 3); if (rc) return rc;
+    VP_CUDA(c, cudaEventCreateWithFlags(&T.ev_expand, cudaEventDisableTiming));
+    for (int i = 0; i < 3; ++i) VP_CUDA(c, cudaEventCreateWithFlags(&T.ev_solve[i], cudaEventDisableTiming));
     T.rpitch = align_up((size_t)w * 3, 256);
     VP_CUDA(c, cudaMalloc(&T.raw_prev, T.rpitch * h));
     const FlowLevel& L0 = T.eng.lv[0];
@@ -692,15 +699,28 @@ int ensure_flow_temporal(vp_ctx* c, FlowTemporal& T, int w, int h, const vp_temp
 // The warped copy of a buffered frame and its reliability mask depend only on that frame and on the flow computed when
 // its successor arrived (:127-138), so both are computed once and kept in a ring instead of being redone every frame.
 // `use_dev` is k_scene_decide's verdict for this frame (how many buffered frames may be used; 0 = pass through).
+// Part 1, independent of the previous frame's blend: the new frame's pyramid and polynomial expansion.  It may run (on this
+// frame's lane) while the previous frame's iterations are still going: it waits only for the previous expansion (shared
+// scratch planes) and for the iterations that last read the R slot it overwrites.
+int flow_temporal_expand(vp_ctx* c, FlowTemporal& T, const uint8_t* cur, size_t cur_pitch, cudaStream_t st) {
+    const int nxt = (T.cur + 1) % 3;
+    VP_CUDA(c, cudaStreamWaitEvent(st, T.ev_expand, 0));
+    VP_CUDA(c, cudaStreamWaitEvent(st, T.ev_solve[(nxt + 1) % 3], 0));
+    int rc = flow_expand(c, T.eng, cur, cur_pitch, nxt, st); if (rc) return rc;
+    VP_CUDA(c, cudaEventRecord(T.ev_expand, st));
+    return VP_OK;
+}
+// Part 2, in temporal order (after the previous frame is complete): iterations, warp, mask, blend.
 int run_flow_temporal(vp_ctx* c, FlowTemporal& T, const vp_temporal_config& t, const uint8_t* cur, size_t cur_pitch,
                       uint8_t* dst, size_t dst_pitch, const int* use_dev, cudaStream_t st) {
     FlowEngine& E = T.eng;
     const int w = E.w, h = E.h;
     const FlowLevel& L0 = E.lv[0];
-    const int nxt = T.cur ^ 1;
-    int rc = flow_expand(c, E, cur, cur_pitch, nxt, st); if (rc) return rc;
+    const int nxt = (T.cur + 1) % 3;
+    int rc = VP_OK;
     if (T.have_prev) {
         rc = flow_solve(c, E, T.cur, nxt, st); if (rc) return rc;                       // :95 flow prev -> cur
+        VP_CUDA(c, cudaEventRecord(T.ev_solve[nxt], st));
         const int slot = T.head;
         {
             ProfScope ps(c, K_BLEND, st);
@@ -1349,6 +1369,7 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
             rc = launch_bilateral(c, a, c->cand_post_rad, st, K_BIL_POST); if (rc) return rc;
             cur = L.d_post; cur_pitch = c->frame_pitch;
         }
+        rc = flow_temporal_expand(c, c->ftc, cur, cur_pitch, st); if (rc) return rc;
         if (temporal_dep) VP_CUDA(c, cudaStreamWaitEvent(st, temporal_dep, 0));
         {
             SceneAccumArgs sa{cur, cur_pitch, c->ftc.have_prev ? c->ftc.raw_prev : nullptr, c->ftc.rpitch, g.dst_w, g.dst_h, c->d_scene_acc};
