@@ -40,6 +40,16 @@ __device__ __forceinline__ void linear_tap(int d, double scale, int sn, int& s0,
     s0 = sx; f = fx;
 }
 
+// the taps of a whole axis, tabulated once per engine (the double arithmetic above costs more than the resize itself)
+struct LinTap { int s0; float f; };
+__global__ void k_linear_taps(int n, double scale, int sn, LinTap* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    LinTap t;
+    linear_tap(i, scale, sn, t.s0, t.f);
+    out[i] = t;
+}
+
 // separable float32 Gaussian, BORDER_REFLECT_101, accumulation left to right without FMA (cv::GaussianBlur on CV_32F)
 // `varies` (optional): a device flag that is zero when the input plane is known to be the constant 1.0f everywhere (the
 // reliability mask of a frame without fast motion); the result is then `const_out`, the value the very same float
@@ -96,11 +106,10 @@ __global__ void __launch_bounds__(256) k_gauss_f32(const float* __restrict__ src
 // sample as the full blur followed by the resize, on a fraction of the samples.
 template <int KS = 0>
 __global__ void __launch_bounds__(256) k_gauss_rows_at(const float* __restrict__ src, int sp, int sw, int sh, float* __restrict__ dst, int dp,
-                                                       int dw, const GaussTaps t, double xscale) {
+                                                       int dw, const GaussTaps t, const LinTap* __restrict__ tx) {
     const int w = 2 * dw, h = sh;
     VP_FLOW_XY;
-    int x0; float fx;
-    linear_tap(x >> 1, xscale, sw, x0, fx);
+    const int x0 = __ldg(&tx[x >> 1].s0);
     const int sx = (x & 1) ? min(x0 + 1, sw - 1) : x0;
     const int ks = KS > 0 ? KS : t.ksize, r = ks >> 1;
     const float* row = src + (size_t)y * sp;
@@ -120,11 +129,11 @@ __global__ void __launch_bounds__(256) k_gauss_rows_at(const float* __restrict__
 }
 template <int KS = 0>
 __global__ void __launch_bounds__(256) k_gauss_cols_resize(const float* __restrict__ src, int sp, int sw, int sh, float* __restrict__ dst, int dp,
-                                                           int w, int h, const GaussTaps t, double xscale, double yscale) {
+                                                           int w, int h, const GaussTaps t, const LinTap* __restrict__ tx, const LinTap* __restrict__ ty) {
     VP_FLOW_XY;
-    int x0, y0; float fx, fy;
-    linear_tap(x, xscale, sw, x0, fx);
-    linear_tap(y, yscale, sh, y0, fy);
+    const float fx = __ldg(&tx[x].f);
+    const int y0 = __ldg(&ty[y].s0);
+    const float fy = __ldg(&ty[y].f);
     const int y1 = min(y0 + 1, sh - 1);
     const int ks = KS > 0 ? KS : t.ksize, r = ks >> 1;
     float v[2][2];
@@ -151,11 +160,10 @@ __global__ void __launch_bounds__(256) k_gauss_cols_resize(const float* __restri
 // (`flow *= 1 / pyr_scale`).  Horizontal interpolation of both rows first, then vertical, all float32 without FMA.
 __global__ void __launch_bounds__(256) k_resize_linear_f32(const float* __restrict__ src, int sp, size_t sps, int sw, int sh,
                                                            float* __restrict__ dst, int dp, size_t dps, int w, int h, int nch, float mul,
-                                                           double xscale, double yscale) {
+                                                           const LinTap* __restrict__ tx, const LinTap* __restrict__ ty) {
     VP_FLOW_XY;
-    int x0, y0; float fx, fy;
-    linear_tap(x, xscale, sw, x0, fx);
-    linear_tap(y, yscale, sh, y0, fy);
+    const int x0 = __ldg(&tx[x].s0), y0 = __ldg(&ty[y].s0);
+    const float fx = __ldg(&tx[x].f), fy = __ldg(&ty[y].f);
     const int x1 = min(x0 + 1, sw - 1), y1 = min(y0 + 1, sh - 1);
     const float a0 = __fsub_rn(1.f, fx), b0 = __fsub_rn(1.f, fy);
     for (int c = 0; c < nch; ++c) {

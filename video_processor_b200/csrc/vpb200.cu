@@ -80,6 +80,8 @@ struct FlowLevel {                  // one pyramid level of the Farneback engine
     float* I = nullptr;                          // level image
     float* R[3] = {nullptr, nullptr, nullptr};   // polynomial expansions (5 planes) of the last 2 (stand-alone) / 3 (chain) frames
     float* flow = nullptr;                       // 2 planes
+    vp::LinTap* px = nullptr; vp::LinTap* py = nullptr;   // cv::resize(INTER_LINEAR) taps, full resolution -> this level
+    vp::LinTap* ux = nullptr; vp::LinTap* uy = nullptr;   // ... and the next coarser level's flow -> this level
 };
 struct FlowEngine {                 // cv::calcOpticalFlowFarneback for one frame size and parameter set
     int w = 0, h = 0, nlev = 0;     // nlev = levels + 1 pyramid entries, [0] = full resolution
@@ -475,7 +477,7 @@ int run_bilateral_modes(vp_ctx* c, MsScratch& S, const vp_bilateral_config& cfg,
 
 // ---- Farneback engine (vp_flow.cuh) ---------------------------------------------------------------------------
 void free_flow_engine(FlowEngine& E) {
-    for (FlowLevel& L : E.lv) { cudaFree(L.I); cudaFree(L.R[0]); cudaFree(L.R[1]); cudaFree(L.R[2]); cudaFree(L.flow); }
+    for (FlowLevel& L : E.lv) { cudaFree(L.I); cudaFree(L.R[0]); cudaFree(L.R[1]); cudaFree(L.R[2]); cudaFree(L.flow); cudaFree(L.px); cudaFree(L.py); cudaFree(L.ux); cudaFree(L.uy); }
     cudaFree(E.gray); cudaFree(E.blur_a); cudaFree(E.blur_b); cudaFree(E.tmp); cudaFree(E.M);
     E = FlowEngine();
 }
@@ -566,6 +568,18 @@ int ensure_flow_engine(vp_ctx* c, FlowEngine& E, int w, int h, const vp_temporal
         VP_CUDA(c, planes(&L.I, 1, L)); VP_CUDA(c, planes(&L.flow, 2, L));
         for (int r = 0; r < nR; ++r) VP_CUDA(c, planes(&L.R[r], 5, L));
     }
+    auto taps = [&](LinTap** t, int n, int sn) {          // tabulated on the device: the very arithmetic the kernels used inline
+        cudaError_t e = cudaMalloc(t, (size_t)n * sizeof(LinTap));
+        if (e != cudaSuccess) return e;
+        k_linear_taps<<<(n + 255) / 256, 256>>>(n, (double)sn / (double)n, sn, *t);
+        return cudaGetLastError();
+    };
+    for (int k = 0; k < E.nlev; ++k) {
+        FlowLevel& L = E.lv[k];
+        VP_CUDA(c, taps(&L.px, L.w, w)); VP_CUDA(c, taps(&L.py, L.h, h));
+        if (k + 1 < E.nlev) { VP_CUDA(c, taps(&L.ux, L.w, E.lv[k + 1].w)); VP_CUDA(c, taps(&L.uy, L.h, E.lv[k + 1].h)); }
+    }
+    VP_CUDA(c, cudaDeviceSynchronize());
     const FlowLevel& L0 = E.lv[0];
     VP_CUDA(c, planes(&E.gray, 1, L0)); VP_CUDA(c, planes(&E.blur_a, 1, L0)); VP_CUDA(c, planes(&E.blur_b, 1, L0));
     VP_CUDA(c, planes(&E.tmp, 3, L0)); VP_CUDA(c, planes(&E.M, 5, L0));
@@ -602,12 +616,11 @@ int flow_expand(vp_ctx* c, FlowEngine& E, const uint8_t* bgr, size_t pitch, int 
             }
             img = E.blur_b;
         } else {                               // blur only where the resize samples: row pass at 2 columns per output column ...
-            const double xs = (double)E.w / (double)L.w, ys = (double)E.h / (double)L.h;   // cv::resize scale_x / scale_y
             const dim3 gr = grid2d(2 * L.w, E.h), gc = grid2d(L.w, L.h);      // ... column pass at 2 rows
 #define VP_PYR(KS)                                                                                                  \
             do {                                                                                                    \
-                k_gauss_rows_at<KS><<<gr, 256, 0, st>>>(E.gray, L0.p, E.w, E.h, E.blur_a, L0.p, L.w, t, xs);        \
-                k_gauss_cols_resize<KS><<<gc, 256, 0, st>>>(E.blur_a, L0.p, E.w, E.h, L.I, L.p, L.w, L.h, t, xs, ys);\
+                k_gauss_rows_at<KS><<<gr, 256, 0, st>>>(E.gray, L0.p, E.w, E.h, E.blur_a, L0.p, L.w, t, L.px);      \
+                k_gauss_cols_resize<KS><<<gc, 256, 0, st>>>(E.blur_a, L0.p, E.w, E.h, L.I, L.p, L.w, L.h, t, L.px, L.py);\
             } while (0)
             if (t.ksize == 3) VP_PYR(3); else if (t.ksize == 9) VP_PYR(9); else if (t.ksize == 19) VP_PYR(19); else VP_PYR(0);
 #undef VP_PYR
@@ -637,8 +650,7 @@ int flow_solve(vp_ctx* c, FlowEngine& E, int prev, int cur, cudaStream_t st) {
         if (k == E.nlev - 1) VP_CUDA(c, cudaMemsetAsync(L.flow, 0, 2 * L.ps * sizeof(float), st));
         else {
             const FlowLevel& U = E.lv[k + 1];
-            k_resize_linear_f32<<<g, 256, 0, st>>>(U.flow, U.p, U.ps, U.w, U.h, L.flow, L.p, L.ps, L.w, L.h, 2, (float)(1.0 / E.prm.pyr_scale),
-                                                    (double)U.w / (double)L.w, (double)U.h / (double)L.h);
+            k_resize_linear_f32<<<g, 256, 0, st>>>(U.flow, U.p, U.ps, U.w, U.h, L.flow, L.p, L.ps, L.w, L.h, 2, (float)(1.0 / E.prm.pyr_scale), L.ux, L.uy);
             c->launches++;
         }
         k_update_matrices<<<g, 256, 0, st>>>(L.R[prev], L.R[cur], L.p, L.ps, L.flow, L.p, L.ps, E.M, L.p, L.ps, L.w, L.h);
