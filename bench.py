@@ -12,7 +12,7 @@ A "step" is one contiguous segment of --frames frames per GPU (weak scaling: N G
 of one clip; rank k>0 first runs the temporal warm-up frames of its segment, inside the timed region).
 `value` = frames of all ranks / max-over-ranks device time (CUDA events), inputs resident in HBM.
 `e2e`   = the same through vp_submit_host/vp_wait with pinned HOST frames (H2D + D2H inside the timed
-region, three streams).  The roofline object describes the kernel that takes the most device time.
+region, H2D / compute-lane / D2H streams).  The roofline object describes the kernel that takes the most device time.
 torch is plumbing only (device buffers, stream, events, process group); every kernel is libvpb200's.
 """
 import argparse
@@ -504,7 +504,7 @@ def main():
         e2e = {"value": world * F * nsteps / float(tdt.item()), "unit": "frames/s",
                "h2d_bytes_per_step": (world * F + int(twarm.item())) * inb, "d2h_bytes_per_step": world * F * outb,
                "timing": "host wall clock around submit/wait of whole steps, synchronised both sides, max over ranks",
-               "api": "vp_submit_host/vp_wait (pinned host frames, 3 streams, depth %d)" % depth}
+               "api": "vp_submit_host/vp_wait (pinned host frames, H2D + compute lanes + D2H streams, depth %d)" % depth}
 
     # ---- single-frame latency (BASELINE config C5): one frame in flight, synchronise after each ---------
     latency = None

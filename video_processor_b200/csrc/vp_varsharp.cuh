@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(VS_NT) k_varsharp(const VarSharpArgs a) {
         unsigned long long bg_lo2[2] = {0ull, 0ull}, bg_hi2[2] = {0ull, 0ull}, r_lh2[2] = {0ull, 0ull};
         const float2* wp0 = s_wp[idx2[0]];
         const float2* wp1 = s_wp[idx2[1]];
+        const bool same = idx2[0] == idx2[1];
 #pragma unroll
         for (int ta = 0; ta < GK; ++ta) {
             const float4* row = s_px + (y + ta) * EW + xb;
@@ -228,10 +229,13 @@ __global__ void __launch_bounds__(VS_NT) k_varsharp(const VarSharpArgs a) {
             for (int tb = 0; tb <= GK; ++tb) px[tb] = row[tb];
 #pragma unroll
             for (int tb = 0; tb < GK; ++tb) {
+                // neighbours mostly share their level pair (the sigma map is a 5x5-blurred field): one weight load then
+                const float2 wa = wp0[ta * GK + tb];
+                const float2 wb = same ? wa : wp1[ta * GK + tb];
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     const float4 p = px[tb + k];
-                    const float2 w = (k ? wp1 : wp0)[ta * GK + tb];
+                    const float2 w = k ? wb : wa;
                     const unsigned long long bg = pack2(__float_as_uint(p.x), __float_as_uint(p.y));
                     bg_lo2[k] = ffma2(bg, pack2(__float_as_uint(w.x), __float_as_uint(w.x)), bg_lo2[k]);
                     bg_hi2[k] = ffma2(bg, pack2(__float_as_uint(w.y), __float_as_uint(w.y)), bg_hi2[k]);

@@ -135,6 +135,9 @@ struct vp_ctx {
     int nlanes = 2;                 // lanes vp_process_batch_device cycles through (vp_set_batch_lanes)
     cudaEvent_t ev_batch = nullptr;
     int last_lane = 0;
+    // vp_submit_host cycles through the lanes as well: frames in flight overlap on the device, the temporal stages stay in
+    // order through host_prev_done; the device entry points join the lanes before they touch the temporal state again
+    int host_lane = 0; cudaEvent_t host_prev_done = nullptr;
     size_t map_pitch = 0; int hy_tiles_x = 0, hy_tiles_y = 0, hy_grid = 0; size_t dirty_bytes = 0;
     BilCand* d_cand_be = nullptr; int cand_be_rad[3] = {0, 0, 0};
     // scene-change detection (temporal.scene_detect)
@@ -1454,9 +1457,19 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
     return VP_OK;
 }
 
+// after pipelined host frames: order `st0` behind every lane they used
+static int join_host_lanes(vp_ctx* c, cudaStream_t st0) {
+    if (!c->host_prev_done) return VP_OK;
+    for (int l = 0; l < 4; ++l)
+        if (c->lanes[l].ev_done && (l == 0 || c->lanes[l].st)) VP_CUDA(c, cudaStreamWaitEvent(st0, c->lanes[l].ev_done, 0));
+    c->host_prev_done = nullptr; c->host_lane = 0;
+    return VP_OK;
+}
+
 int vp_process_device(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t* d_dst, size_t dst_pitch, void* stream) {
     if (!c) return VP_ERR_INVALID_ARG;
     VP_CUDA(c, cudaSetDevice(c->device));
+    { int rc = join_host_lanes(c, stream ? (cudaStream_t)stream : c->s_compute); if (rc) return rc; }
     return process_frame(c, 0, stream ? (cudaStream_t)stream : c->s_compute, nullptr, d_src, src_pitch, d_dst, dst_pitch);
 }
 
@@ -1499,6 +1512,7 @@ int vp_process_batch_device(vp_ctx* c, int n, const uint8_t* const* d_src, size_
     for (int l = 1; l < NL; ++l) { rc = ensure_lane(c, l); if (rc) return rc; }
     if (NL == 1 && !c->lanes[0].ev_done) VP_CUDA(c, cudaEventCreateWithFlags(&c->lanes[0].ev_done, cudaEventDisableTiming));
     cudaStream_t st0 = stream ? (cudaStream_t)stream : c->s_compute;
+    rc = join_host_lanes(c, st0); if (rc) return rc;
     // lane 1 forks from, and later joins, the caller's stream: everything is ordered after what is already
     // queued there, and events the caller records on it bracket the whole batch
     if (NL > 1) {
@@ -1584,10 +1598,26 @@ int vp_submit_host(vp_ctx* c, const uint8_t* src, size_t src_step, uint8_t* dst,
     }
     VP_CUDA(c, cudaMemcpy2DAsync(s.d_in, c->pre_pitch, hsrc, hstep, in_row, g.src_h, cudaMemcpyHostToDevice, c->s_h2d));
     VP_CUDA(c, cudaEventRecord(s.ev_h2d, c->s_h2d));
-    VP_CUDA(c, cudaStreamWaitEvent(c->s_compute, s.ev_h2d, 0));
-    rc = vp_process_device(c, s.d_in, c->pre_pitch, dst ? s.d_out : nullptr, c->frame_pitch, c->s_compute);
+    // one lane per frame in flight: the next frame's PRE / upscale / POST (and flow expansion) overlap this frame's tail;
+    // process_frame orders the temporal stage behind the previous frame through host_prev_done
+    const int NL = std::min(c->nlanes, PIPE_DEPTH);
+    for (int l = 1; l < NL; ++l) { rc = ensure_lane(c, l); if (rc) return rc; }
+    if (!c->lanes[0].ev_done) VP_CUDA(c, cudaEventCreateWithFlags(&c->lanes[0].ev_done, cudaEventDisableTiming));
+    const int ln = c->host_lane % NL;
+    cudaStream_t st = ln == 0 ? c->s_compute : c->lanes[ln].st;
+    if (!c->host_prev_done && ln != 0) return fail(c, VP_ERR_STATE, "vp_submit_host: lane order lost");
+    if (!c->host_prev_done && NL > 1) {            // first pipelined frame: the other lanes start behind what s_compute holds
+        if (!c->ev_batch) VP_CUDA(c, cudaEventCreateWithFlags(&c->ev_batch, cudaEventDisableTiming));
+        VP_CUDA(c, cudaEventRecord(c->ev_batch, c->s_compute));
+        for (int l = 1; l < NL; ++l) VP_CUDA(c, cudaStreamWaitEvent(c->lanes[l].st, c->ev_batch, 0));
+    }
+    VP_CUDA(c, cudaStreamWaitEvent(st, s.ev_h2d, 0));
+    rc = process_frame(c, ln, st, c->host_prev_done, s.d_in, c->pre_pitch, dst ? s.d_out : nullptr, c->frame_pitch);
     if (rc) return rc;
-    VP_CUDA(c, cudaEventRecord(s.ev_comp, c->s_compute));
+    VP_CUDA(c, cudaEventRecord(c->lanes[ln].ev_done, st));
+    c->host_prev_done = c->lanes[ln].ev_done;
+    c->host_lane = (ln + 1) % NL;
+    VP_CUDA(c, cudaEventRecord(s.ev_comp, st));
     s.user_dst = dst; s.user_dst_step = dst_step; s.staged_out = false;
     if (dst) {
         VP_CUDA(c, cudaStreamWaitEvent(c->s_d2h, s.ev_comp, 0));
