@@ -225,6 +225,49 @@ def test_host_paths_match_device_path(vp):
             assert np.array_equal(o.numpy(), d)
 
 
+@pytest.mark.parametrize("flow", [False, True])
+def test_host_pipeline_lanes_mixed_with_device_calls(vp, flow):
+    """vp_submit_host runs consecutive frames on different compute lanes; device entry points issued while host frames
+    are still in flight (no vp_wait in between) must see the temporal state those frames leave, and the other way round."""
+    sw, sh, n = 640, 360, 13
+    ocfg = RC.ChainConfig(dst_w=2 * sw, dst_h=2 * sh, temporal=RC.TEMPORAL_BLEND_FRAMES)
+    if flow:
+        ocfg.temporal_cfg = RC.TemporalConfig(use_flow=True, scene_detect=True)
+    frames = synth.clip("scene", sw, sh, n)
+    dev, _ = run_chain_device(vp, ocfg, frames, sw, sh)
+    cfg = G.chain_cfg(vp, ocfg, sw, sh)
+    dw, dh = ocfg.dst_w, ocfg.dst_h
+    with vp.Context(cfg) as ctx:
+        pin_in = [torch.from_numpy(f).pin_memory() for f in frames]
+        pin_out = [torch.zeros((dh, dw, 3), dtype=torch.uint8).pin_memory() for _ in frames]
+        d_in = [G.to_dev(f) for f in frames]
+        d_out = [G.dev_empty(dh, dw) for _ in frames]
+        inflight = 0
+
+        def submit(i):
+            nonlocal inflight
+            if inflight == vp.lib.vp_pipeline_depth(ctx.handle):
+                ctx.call("vp_wait"); inflight -= 1
+            ctx.call("vp_submit_host", pin_in[i].data_ptr(), sw * 3, pin_out[i].data_ptr(), dw * 3)
+            inflight += 1
+
+        for i in range(0, 4):
+            submit(i)
+        for i in range(4, 6):                                    # device calls right behind the frames in flight
+            ctx.call("vp_process_device", d_in[i].data_ptr(), G.pitch(d_in[i]), d_out[i].data_ptr(), G.pitch(d_out[i]), None)
+        for i in range(6, 9):
+            submit(i)
+        sp = (C.c_void_p * 4)(*[t.data_ptr() for t in d_in[9:13]])
+        dp = (C.c_void_p * 4)(*[t.data_ptr() for t in d_out[9:13]])
+        ctx.call("vp_process_batch_device", 4, sp, sw * 3, dp, dw * 3, None)
+        while inflight:
+            ctx.call("vp_wait"); inflight -= 1
+        ctx.call("vp_synchronize")
+        for i in range(n):
+            got = d_out[i].cpu().numpy() if i in (4, 5) or i >= 9 else pin_out[i].numpy()
+            assert np.array_equal(got, dev[i]), i
+
+
 def test_full_size_c2_against_cv2(vp):
     """BASELINE config C2 at full size against the real OpenCV kernels (cv2) on one scene frame pair."""
     sw, sh = 1920, 1080

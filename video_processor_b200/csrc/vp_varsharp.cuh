@@ -172,15 +172,65 @@ constexpr int VS_TW = 64, VS_TH = 32, VS_NT = 256;   // tile, threads
 
 // The two Gaussian levels of a pixel are exact integer sums sum(p * q_a * q_b) < 2^24, so they are accumulated in float32
 // (FFMA is full rate, IMAD is not) as packed pairs: (b, g) x w_low, (b, g) x w_high and r x (w_low, w_high) - three FFMA2 per
-// tap, fed by one 128-bit pixel load and one 64-bit weight-pair load.
+// tap, fed by 128-bit pixel loads and 64-bit weight-pair loads.  The kernel is bound by shared-memory wavefronts, so a thread
+// owns four VERTICALLY adjacent pixels (lanes stay adjacent in x: conflict-free 128-bit loads; two or four horizontally
+// adjacent pixels per thread put the lanes 32 / 64 bytes apart and cost 2x / 4x the wavefronts): a tile column costs GK+3
+// pixel loads and - when the four pixels share their level pair, the usual case on the 5x5-blurred sigma map - GK weight
+// loads for four outputs.  The sums are exact, so the tap order (column-major here) does not matter.
+constexpr int VS_PX = 4;
+template <int GK, bool SAME>
+__device__ __forceinline__ void varsharp_cols(const float4* __restrict__ tile, int EW, const float2* const (&wp)[VS_PX],
+                                              unsigned long long (&bg_lo)[VS_PX], unsigned long long (&bg_hi)[VS_PX],
+                                              unsigned long long (&r_lh)[VS_PX]) {
+#pragma unroll
+    for (int tb = 0; tb < GK; ++tb) {
+        unsigned long long bg[GK + VS_PX - 1], rr[GK + VS_PX - 1];
+#pragma unroll
+        for (int r = 0; r < GK + VS_PX - 1; ++r) {
+            const float4 p = tile[r * EW + tb];
+            bg[r] = pack2(__float_as_uint(p.x), __float_as_uint(p.y));
+            rr[r] = pack2(__float_as_uint(p.z), __float_as_uint(p.z));
+        }
+#pragma unroll
+        for (int ta = 0; ta < GK; ++ta) {
+#pragma unroll
+            for (int k = 0; k < VS_PX; ++k) {
+                const float2 w = wp[SAME ? 0 : k][ta * GK + tb];          // SAME: one load, hoisted out of the k loop
+                bg_lo[k] = ffma2(bg[ta + k], pack2(__float_as_uint(w.x), __float_as_uint(w.x)), bg_lo[k]);
+                bg_hi[k] = ffma2(bg[ta + k], pack2(__float_as_uint(w.y), __float_as_uint(w.y)), bg_hi[k]);
+                r_lh[k] = ffma2(pack2(__float_as_uint(w.x), __float_as_uint(w.y)), rr[ta + k], r_lh[k]);
+            }
+        }
+    }
+}
+
 template <int GK>
-__global__ void __launch_bounds__(VS_NT) k_varsharp(const VarSharpArgs a) {
+__global__ void __launch_bounds__(VS_NT, 3) k_varsharp(const VarSharpArgs a) {
     constexpr int GR = GK / 2, EW = VS_TW + 2 * GR, EH = VS_TH + 2 * GR;
+    static_assert(VS_TH % VS_PX == 0, "pixel groups tile the column");
     __shared__ float4 s_px[EW * EH];                     // (b, g, r, packed BGR0 bits), reflect-101 padded
     __shared__ float2 s_wp[VS_LEVELS - 1][GK * GK];      // (q[l][a] q[l][b], q[l+1][a] q[l+1][b]) for adjacent levels
     __shared__ unsigned long long s_part[(VS_NT / 32) * 6];
+    __shared__ float s_lev[VS_LEVELS];                   // the sigma of each level, :470-473
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * VS_TW, y0 = blockIdx.y * VS_TH;
+    // the per-pixel sigma and edge-mask values of this thread's pixel groups: requested first, so their latency hides behind
+    // the tile staging instead of stalling the first use after the barrier
+    constexpr int NG = VS_TW * (VS_TH / VS_PX) / VS_NT;
+    static_assert(VS_TW * (VS_TH / VS_PX) % VS_NT == 0, "whole pixel groups per thread");
+    float sg[VS_PX], em[VS_PX];
+    auto fetch = [&](int g, float (&s4)[VS_PX], float (&e4)[VS_PX]) {
+        const int i4 = tid + g * VS_NT;
+        const int gx = min(x0 + i4 % VS_TW, a.w - 1), yb = y0 + VS_PX * (i4 / VS_TW);
+#pragma unroll
+        for (int k = 0; k < VS_PX; ++k) {
+            const int gyk = min(yb + k, a.h - 1);
+            s4[k] = __ldg(reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(a.sigma) + (size_t)gyk * a.gpitch + (size_t)gx * 4));
+            e4[k] = __ldg(reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(a.emask) + (size_t)gyk * a.epitch + (size_t)gx * 4));
+        }
+    };
+    fetch(0, sg, em);
+#pragma unroll 4
     for (int i = tid; i < EW * EH; i += VS_NT) {
         const int ty = i / EW, tx = i - ty * EW;
         const int sx = reflect101(x0 - GR + tx, a.w), sy = reflect101(y0 - GR + ty, a.h);
@@ -193,60 +243,48 @@ __global__ void __launch_bounds__(VS_NT) k_varsharp(const VarSharpArgs a) {
         s_wp[l][t] = make_float2((float)(a.lv->q[l][ta] * a.lv->q[l][tb]), (float)(a.lv->q[l + 1][ta] * a.lv->q[l + 1][tb]));
     }
     const float mn = a.lv->mn, span = a.lv->span;
+    if (tid < VS_LEVELS) s_lev[tid] = __fadd_rn(mn, __fdiv_rn(__fmul_rn(span, (float)tid), (float)(VS_LEVELS - 1)));
     __syncthreads();
     unsigned acc6[6] = {0, 0, 0, 0, 0, 0};
-    // a thread owns two horizontally adjacent pixels at a time: their 5x5 windows overlap in GK-1 columns, so each tile row
-    // costs GK+1 pixel loads for two outputs (the kernel is bound by shared-memory wavefronts otherwise)
-    for (int i2 = tid; i2 < (VS_TW / 2) * VS_TH; i2 += VS_NT) {
-        const int y = i2 / (VS_TW / 2), xb = 2 * (i2 - y * (VS_TW / 2));
-        const int gy = y0 + y;
-        if (x0 + xb >= a.w || gy >= a.h) continue;
-        int idx2[2]; float alpha2[2];
+#pragma unroll 1
+    for (int g = 0; g < NG; ++g) {              // not unrolled: the body is several thousand instructions (instruction cache)
+        const int i4 = tid + g * VS_NT;
+        const int yb = VS_PX * (i4 / VS_TW), x = i4 % VS_TW;
+        const int gx = x0 + x;
+        float sg_cur[VS_PX], em_cur[VS_PX];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int gxk = min(x0 + xb + k, a.w - 1);
-            const float sigma = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(a.sigma) + (size_t)gy * a.gpitch + (size_t)gxk * 4);
+        for (int k = 0; k < VS_PX; ++k) { sg_cur[k] = sg[k]; em_cur[k] = em[k]; }
+        if (g + 1 < NG) fetch(g + 1, sg, em);   // the next group's values travel while this one is computed
+        if (gx >= a.w || y0 + yb >= a.h) continue;
+        int idx2[VS_PX]; float alpha2[VS_PX];
+#pragma unroll
+        for (int k = 0; k < VS_PX; ++k) {
+            const float sigma = sg_cur[k];
             // :476-486  level pair and interpolation factor, float32 throughout
             int idx = 0;
             if (span > 0.f) idx = (int)__fmul_rn(__fdiv_rn(__fsub_rn(sigma, mn), span), (float)(VS_LEVELS - 1));
             idx = max(0, min(idx, VS_LEVELS - 2));
-            const float slo = __fadd_rn(mn, __fdiv_rn(__fmul_rn(span, (float)idx), (float)(VS_LEVELS - 1)));
-            const float shi = __fadd_rn(mn, __fdiv_rn(__fmul_rn(span, (float)(idx + 1)), (float)(VS_LEVELS - 1)));
+            const float slo = s_lev[idx], shi = s_lev[idx + 1];
             const float den = __fsub_rn(shi, slo);
             idx2[k] = idx;
             alpha2[k] = den > 0.f ? __fdiv_rn(__fsub_rn(sigma, slo), den) : 0.f;
         }
-        // the two Gaussian levels at both pixels: exact Q8.16 sums, (v + 2^15) >> 16
-        unsigned long long bg_lo2[2] = {0ull, 0ull}, bg_hi2[2] = {0ull, 0ull}, r_lh2[2] = {0ull, 0ull};
-        const float2* wp0 = s_wp[idx2[0]];
-        const float2* wp1 = s_wp[idx2[1]];
-        const bool same = idx2[0] == idx2[1];
+        // the two Gaussian levels at the four pixels: exact Q8.16 sums, (v + 2^15) >> 16
+        unsigned long long bg_lo2[VS_PX], bg_hi2[VS_PX], r_lh2[VS_PX];
+        const float2* wp[VS_PX];
+        bool same = true;
 #pragma unroll
-        for (int ta = 0; ta < GK; ++ta) {
-            const float4* row = s_px + (y + ta) * EW + xb;
-            float4 px[GK + 1];
-#pragma unroll
-            for (int tb = 0; tb <= GK; ++tb) px[tb] = row[tb];
-#pragma unroll
-            for (int tb = 0; tb < GK; ++tb) {
-                // neighbours mostly share their level pair (the sigma map is a 5x5-blurred field): one weight load then
-                const float2 wa = wp0[ta * GK + tb];
-                const float2 wb = same ? wa : wp1[ta * GK + tb];
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const float4 p = px[tb + k];
-                    const float2 w = k ? wb : wa;
-                    const unsigned long long bg = pack2(__float_as_uint(p.x), __float_as_uint(p.y));
-                    bg_lo2[k] = ffma2(bg, pack2(__float_as_uint(w.x), __float_as_uint(w.x)), bg_lo2[k]);
-                    bg_hi2[k] = ffma2(bg, pack2(__float_as_uint(w.y), __float_as_uint(w.y)), bg_hi2[k]);
-                    r_lh2[k] = ffma2(pack2(__float_as_uint(w.x), __float_as_uint(w.y)), pack2(__float_as_uint(p.z), __float_as_uint(p.z)), r_lh2[k]);
-                }
-            }
+        for (int k = 0; k < VS_PX; ++k) {
+            bg_lo2[k] = bg_hi2[k] = r_lh2[k] = 0ull;
+            wp[k] = s_wp[idx2[k]];
+            same = same && idx2[k] == idx2[0];
         }
+        if (same) varsharp_cols<GK, true>(s_px + yb * EW + x, EW, wp, bg_lo2, bg_hi2, r_lh2);
+        else varsharp_cols<GK, false>(s_px + yb * EW + x, EW, wp, bg_lo2, bg_hi2, r_lh2);
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int x = xb + k, gx = x0 + x;
-        if (gx >= a.w) continue;
+      for (int k = 0; k < VS_PX; ++k) {
+        const int y = yb + k, gy = y0 + y;
+        if (gy >= a.h) continue;
         const float alpha = alpha2[k];
         float fl[3], fh[3];
         unpack2(bg_lo2[k], fl[0], fl[1]); unpack2(bg_hi2[k], fh[0], fh[1]); unpack2(r_lh2[k], fl[2], fh[2]);
@@ -255,7 +293,7 @@ __global__ void __launch_bounds__(VS_NT) k_varsharp(const VarSharpArgs a) {
         for (int ch = 0; ch < 3; ++ch) { lo[ch] = __float2uint_rz(fl[ch]) + (1u << 15); hi[ch] = __float2uint_rz(fh[ch]) + (1u << 15); }
         const uint32_t cpx = __float_as_uint(s_px[(y + GR) * EW + x + GR].w);
         const int u[3] = {(int)(cpx & 0xff), (int)((cpx >> 8) & 0xff), (int)((cpx >> 16) & 0xff)};
-        const float e = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(a.emask) + (size_t)gy * a.epitch + (size_t)gx * 4);
+        const float e = em_cur[k];
         const float t1 = __fmul_rn(e, a.edge_strength);
         const float t2 = __fmul_rn(__fsub_rn(1.0f, e), a.smooth_strength);
         const float st = __fmul_rn(a.strength, __fadd_rn(t1, t2));                              // :538-541
