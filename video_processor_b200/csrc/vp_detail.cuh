@@ -238,17 +238,64 @@ struct MsBlendArgs {
     const uint8_t* coarse; size_t cpitch; int cw, ch;
     const float* mask; size_t mpitch;
 };
+// A thread owns the 2x2 block of fine pixels behind one coarse cell: the four pyrUp values share one 3x3 coarse
+// neighbourhood (27 byte loads for four pixels instead of 108, the row sums formed once), the integer sums are the very
+// ones of pyr_up_pixel.  A2: rows of `fine` are 2-byte aligned and rows of `mask` 8-byte aligned (pixel pairs move as
+// three 16-bit words and one float2); otherwise bytes and single floats.
+template <bool A2>
 __global__ void __launch_bounds__(256) k_ms_blend(const MsBlendArgs a) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31), j = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int x = 2 * i, y = 2 * j;
     if (x >= a.fw || y >= a.fh) return;
-    int up[3];
-    pyr_up_pixel(a.coarse, a.cpitch, a.cw, a.ch, x, y, up);
-    const float d = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(a.mask) + (size_t)y * a.mpitch + (size_t)x * 4);
-    const float cwt = __fsub_rn(1.0f, d);
-    uint8_t* f = a.fine + (size_t)y * a.fpitch + (size_t)x * 3;
+    const int ci = min(i, a.cw - 1), cj = min(j, a.ch - 1);
+    const int xs[3] = {ci > 0 ? ci - 1 : (a.cw > 1 ? 1 : 0), ci, min(ci + 1, a.cw - 1)};
+    const int ys[3] = {cj > 0 ? cj - 1 : (a.ch > 1 ? 1 : 0), cj, min(cj + 1, a.ch - 1)};
+    int he[3][3], ho[3][3];                                      // [coarse row][channel]: even / odd fine column
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        f[c] = (uint8_t)rne_sat_u8(__fadd_rn(__fmul_rn((float)f[c], d), __fmul_rn((float)up[c], cwt)));
+    for (int r = 0; r < 3; ++r) {
+        const uint8_t* row = a.coarse + (size_t)ys[r] * a.cpitch;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int lo = __ldg(row + 3 * xs[0] + c), mid = __ldg(row + 3 * xs[1] + c), hi = __ldg(row + 3 * xs[2] + c);
+            he[r][c] = lo + 6 * mid + hi;
+            ho[r][c] = 4 * (mid + hi);
+        }
+    }
+    const bool x1 = x + 1 < a.fw;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+        if (y + dy >= a.fh) break;
+        int up[2][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            up[0][c] = ((dy ? 4 * (he[1][c] + he[2][c]) : he[0][c] + 6 * he[1][c] + he[2][c]) + 32) >> 6;
+            up[1][c] = ((dy ? 4 * (ho[1][c] + ho[2][c]) : ho[0][c] + 6 * ho[1][c] + ho[2][c]) + 32) >> 6;
+        }
+        uint8_t* f = a.fine + (size_t)(y + dy) * a.fpitch + (size_t)x * 3;
+        const float* mrow = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(a.mask) + (size_t)(y + dy) * a.mpitch) + x;
+        if (A2 && x1) {
+            const float2 d2 = *reinterpret_cast<const float2*>(mrow);
+            uint16_t* f16 = reinterpret_cast<uint16_t*>(f);
+            const uint32_t w0 = f16[0], w1 = f16[1], w2 = f16[2];
+            const int fin[6] = {(int)(w0 & 0xff), (int)(w0 >> 8), (int)(w1 & 0xff), (int)(w1 >> 8), (int)(w2 & 0xff), (int)(w2 >> 8)};
+            int o[6];
+#pragma unroll
+            for (int b = 0; b < 6; ++b) {
+                const float d = b < 3 ? d2.x : d2.y;
+                o[b] = rne_sat_u8(__fadd_rn(__fmul_rn((float)fin[b], d), __fmul_rn((float)up[b / 3][b % 3], __fsub_rn(1.0f, d))));
+            }
+            f16[0] = (uint16_t)(o[0] | (o[1] << 8)); f16[1] = (uint16_t)(o[2] | (o[3] << 8)); f16[2] = (uint16_t)(o[4] | (o[5] << 8));
+        } else {
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                if (dx && !x1) break;
+                const float d = mrow[dx];
+                const float cwt = __fsub_rn(1.0f, d);
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    f[3 * dx + c] = (uint8_t)rne_sat_u8(__fadd_rn(__fmul_rn((float)f[3 * dx + c], d), __fmul_rn((float)up[dx][c], cwt)));
+            }
+        }
     }
 }
 

@@ -451,8 +451,10 @@ int run_bilateral_modes(vp_ctx* c, MsScratch& S, const vp_bilateral_config& cfg,
             if (rc) return rc;
             MsBlendArgs b{proc[i - 1], pp[i - 1], S.lw[i - 1], S.lh[i - 1], proc[i], pp[i], S.lw[i], S.lh[i], S.mask, S.mpitch};
             ProfScope ps(c, K_BIL_OTHER, st);
-            const dim3 grid((S.lw[i - 1] + 31) / 32, (S.lh[i - 1] + 7) / 8);
-            k_ms_blend<<<grid, eb, 0, st>>>(b);
+            const dim3 grid(((S.lw[i - 1] + 1) / 2 + 31) / 32, ((S.lh[i - 1] + 1) / 2 + 7) / 8);    // a thread per 2x2 block
+            const bool a2 = ((uintptr_t)b.fine | b.fpitch) % 2 == 0 && ((uintptr_t)b.mask | b.mpitch) % 8 == 0;
+            if (a2) k_ms_blend<true><<<grid, eb, 0, st>>>(b);
+            else k_ms_blend<false><<<grid, eb, 0, st>>>(b);
             VP_CUDA(c, cudaGetLastError());
             c->launches++;
         }
