@@ -167,28 +167,47 @@ __global__ void __launch_bounds__(DT_NT) k_detail_mask(const DetailMaskArgs a) {
 }
 
 // cv::pyrDown on CV_8UC3 (:148-150): [1 4 6 4 1] x [1 4 6 4 1], BORDER_REFLECT_101, (v + 128) >> 8 at even (y, x)
+// A thread owns a 2x2 block of outputs: their 5x5 windows overlap in a 7x7 source window (49 pixel loads for four outputs
+// instead of 100) and the two horizontal sums of a source row feed both output rows.  Integer sums, so the result is the
+// one of the plain per-output evaluation.
 __global__ void __launch_bounds__(256) k_pyr_down(const uint8_t* __restrict__ src, size_t spitch, int sw, int sh,
                                                   uint8_t* __restrict__ dst, size_t dpitch, int dw, int dh) {
-    const int ox = blockIdx.x * 32 + (threadIdx.x & 31), oy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int ox = 2 * (blockIdx.x * 32 + (threadIdx.x & 31)), oy = 2 * (blockIdx.y * 8 + (threadIdx.x >> 5));
     if (ox >= dw || oy >= dh) return;
-    const int kw[5] = {1, 4, 6, 4, 1};
-    int xs[5];
+    int xs[7];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) xs[k] = 3 * reflect101(2 * ox + k - 2, sw);
-    int acc[3] = {0, 0, 0};
+    for (int k = 0; k < 7; ++k) xs[k] = 3 * reflect101(2 * ox + k - 2, sw);
+    int acc[2][2][3] = {};                                        // [output row][output column][channel]
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
+    for (int j = 0; j < 7; ++j) {
         const uint8_t* row = src + (size_t)reflect101(2 * oy + j - 2, sh) * spitch;
-        int r[3] = {0, 0, 0};
+        int r0[3], r1[3];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const uint8_t* p = row + xs[k];
-            r[0] += kw[k] * __ldg(p); r[1] += kw[k] * __ldg(p + 1); r[2] += kw[k] * __ldg(p + 2);
+        for (int c = 0; c < 3; ++c) {
+            int v[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) v[k] = __ldg(row + xs[k] + c);
+            r0[c] = v[0] + v[4] + 4 * (v[1] + v[3]) + 6 * v[2];
+            r1[c] = v[2] + v[6] + 4 * (v[3] + v[5]) + 6 * v[4];
         }
-        acc[0] += kw[j] * r[0]; acc[1] += kw[j] * r[1]; acc[2] += kw[j] * r[2];
+        const int kw[5] = {1, 4, 6, 4, 1};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (j < 5) { acc[0][0][c] += kw[j] * r0[c]; acc[0][1][c] += kw[j] * r1[c]; }
+            if (j >= 2) { acc[1][0][c] += kw[j - 2] * r0[c]; acc[1][1][c] += kw[j - 2] * r1[c]; }
+        }
     }
-    uint8_t* o = dst + (size_t)oy * dpitch + (size_t)ox * 3;
-    o[0] = (uint8_t)((acc[0] + 128) >> 8); o[1] = (uint8_t)((acc[1] + 128) >> 8); o[2] = (uint8_t)((acc[2] + 128) >> 8);
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+        if (oy + dy >= dh) break;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            if (ox + dx >= dw) break;
+            uint8_t* o = dst + (size_t)(oy + dy) * dpitch + (size_t)(ox + dx) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) o[c] = (uint8_t)((acc[dy][dx][c] + 128) >> 8);
+        }
+    }
 }
 
 // one axis of cv::pyrUp: the (at most three) coarse indices and integer weights behind fine index x.

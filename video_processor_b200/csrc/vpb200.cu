@@ -434,7 +434,7 @@ int run_bilateral_modes(vp_ctx* c, MsScratch& S, const vp_bilateral_config& cfg,
         for (int i = 1; i < n; ++i) { lvl[i] = S.lvl[i]; lp[i] = S.pitch[i]; proc[i] = S.proc[i]; pp[i] = S.pitch[i]; }
         for (int i = 1; i < n; ++i) {                                            // :146-151
             ProfScope ps(c, K_BIL_OTHER, st);
-            const dim3 grid((S.lw[i] + 31) / 32, (S.lh[i] + 7) / 8);
+            const dim3 grid(((S.lw[i] + 1) / 2 + 31) / 32, ((S.lh[i] + 1) / 2 + 7) / 8);           // a thread per 2x2 outputs
             k_pyr_down<<<grid, eb, 0, st>>>(lvl[i - 1], lp[i - 1], S.lw[i - 1], S.lh[i - 1], S.lvl[i], S.pitch[i], S.lw[i], S.lh[i]);
             VP_CUDA(c, cudaGetLastError());
             c->launches++;
@@ -1743,7 +1743,7 @@ int vp_pyr_down(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, int src_w, in
     VP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
     ProfScope ps(c, K_BIL_OTHER, st);
-    k_pyr_down<<<dim3((dw + 31) / 32, (dh + 7) / 8), 256, 0, st>>>(d_src, src_pitch, src_w, src_h, d_dst, dst_pitch, dw, dh);
+    k_pyr_down<<<dim3(((dw + 1) / 2 + 31) / 32, ((dh + 1) / 2 + 7) / 8), 256, 0, st>>>(d_src, src_pitch, src_w, src_h, d_dst, dst_pitch, dw, dh);
     VP_CUDA(c, cudaGetLastError());
     c->launches++;
     return VP_OK;
