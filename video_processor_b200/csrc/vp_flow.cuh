@@ -158,20 +158,29 @@ __global__ void __launch_bounds__(256) k_gauss_cols_resize(const float* __restri
 
 // cv::resize(INTER_LINEAR) on CV_32F planes (nch planes, plane strides sps / dps), optional scale of the result
 // (`flow *= 1 / pyr_scale`).  Horizontal interpolation of both rows first, then vertical, all float32 without FMA.
+template <int NCH>
 __global__ void __launch_bounds__(256) k_resize_linear_f32(const float* __restrict__ src, int sp, size_t sps, int sw, int sh,
-                                                           float* __restrict__ dst, int dp, size_t dps, int w, int h, int nch, float mul,
+                                                           float* __restrict__ dst, int dp, size_t dps, int w, int h, float mul,
                                                            const LinTap* __restrict__ tx, const LinTap* __restrict__ ty) {
     VP_FLOW_XY;
-    const int x0 = __ldg(&tx[x].s0), y0 = __ldg(&ty[y].s0);
-    const float fx = __ldg(&tx[x].f), fy = __ldg(&ty[y].f);
+    const LinTap ax = tx[x], ay = ty[y];
+    const int x0 = ax.s0, y0 = ay.s0;
+    const float fx = ax.f, fy = ay.f;
     const int x1 = min(x0 + 1, sw - 1), y1 = min(y0 + 1, sh - 1);
     const float a0 = __fsub_rn(1.f, fx), b0 = __fsub_rn(1.f, fy);
-    for (int c = 0; c < nch; ++c) {
+    const int r0 = y0 * sp, r1 = y1 * sp, o = y * dp + x;          // planes are far below 2^31 elements
+    float v00[NCH], v01[NCH], v10[NCH], v11[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
         const float* s = src + c * sps;
-        const float h0 = __fadd_rn(__fmul_rn(s[(size_t)y0 * sp + x0], a0), __fmul_rn(s[(size_t)y0 * sp + x1], fx));
-        const float h1 = __fadd_rn(__fmul_rn(s[(size_t)y1 * sp + x0], a0), __fmul_rn(s[(size_t)y1 * sp + x1], fx));
+        v00[c] = __ldg(s + r0 + x0); v01[c] = __ldg(s + r0 + x1); v10[c] = __ldg(s + r1 + x0); v11[c] = __ldg(s + r1 + x1);
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const float h0 = __fadd_rn(__fmul_rn(v00[c], a0), __fmul_rn(v01[c], fx));
+        const float h1 = __fadd_rn(__fmul_rn(v10[c], a0), __fmul_rn(v11[c], fx));
         const float v = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, fy));
-        dst[c * dps + (size_t)y * dp + x] = mul == 1.f ? v : __fmul_rn(v, mul);
+        dst[c * dps + o] = mul == 1.f ? v : __fmul_rn(v, mul);
     }
 }
 

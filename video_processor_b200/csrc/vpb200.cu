@@ -655,7 +655,7 @@ int flow_solve(vp_ctx* c, FlowEngine& E, int prev, int cur, cudaStream_t st) {
         if (k == E.nlev - 1) VP_CUDA(c, cudaMemsetAsync(L.flow, 0, 2 * L.ps * sizeof(float), st));
         else {
             const FlowLevel& U = E.lv[k + 1];
-            k_resize_linear_f32<<<g, 256, 0, st>>>(U.flow, U.p, U.ps, U.w, U.h, L.flow, L.p, L.ps, L.w, L.h, 2, (float)(1.0 / E.prm.pyr_scale), L.ux, L.uy);
+            k_resize_linear_f32<2><<<g, 256, 0, st>>>(U.flow, U.p, U.ps, U.w, U.h, L.flow, L.p, L.ps, L.w, L.h, (float)(1.0 / E.prm.pyr_scale), L.ux, L.uy);
             c->launches++;
         }
         k_update_matrices<<<g, 256, 0, st>>>(L.R[prev], L.R[cur], L.p, L.ps, L.flow, L.p, L.ps, E.M, L.p, L.ps, L.w, L.h);
