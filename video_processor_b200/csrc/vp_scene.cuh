@@ -78,6 +78,8 @@ struct SceneAccumArgs {
     SceneAccum* acc;
 };
 
+// A CTA walks whole rows (no per-pixel division), a thread takes four pixels as three words when the rows are word aligned,
+// and a warp issues one shared-memory atomic per distinct bin (neighbouring pixels mostly share their bin).
 __global__ void __launch_bounds__(256) k_scene_accum(const SceneAccumArgs a) {
     __shared__ unsigned s_hist[64];
     __shared__ unsigned long long s_mad;
@@ -85,18 +87,40 @@ __global__ void __launch_bounds__(256) k_scene_accum(const SceneAccumArgs a) {
     if (threadIdx.x == 0) s_mad = 0ull;
     __syncthreads();
     unsigned mad = 0;
-    const long long total = (long long)a.w * a.h;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int y = (int)(i / a.w), x = (int)(i - (long long)y * a.w);
-        const uint8_t* p = a.cur + (size_t)y * a.cpitch + (size_t)x * 3;
-        const int g = gray_of((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16));
-        atomicAdd(&s_hist[g >> 2], 1u);
-        if (a.prev) {
-            const uint8_t* q = a.prev + (size_t)y * a.ppitch + (size_t)x * 3;
-            mad += abs(g - gray_of((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16)));
+    const bool words = ((uintptr_t)a.cur | a.cpitch) % 4 == 0 && (!a.prev || ((uintptr_t)a.prev | a.ppitch) % 4 == 0);
+    const int ngroups = (a.w + 3) / 4;
+    auto load4 = [&](const uint8_t* row, int gx, int npx, uint32_t (&px)[4]) {
+        if (words && npx == 4) {
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(row) + 3 * gx;
+            const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+            px[0] = w0 & 0xffffffu; px[1] = (w0 >> 24) | ((w1 & 0xffffu) << 8); px[2] = (w1 >> 16) | ((w2 & 0xffu) << 16); px[3] = w2 >> 8;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint8_t* p = row + (size_t)(4 * gx + min(j, npx - 1)) * 3;
+                px[j] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+            }
+        }
+    };
+    for (int y = blockIdx.x; y < a.h; y += gridDim.x) {
+        const uint8_t* crow = a.cur + (size_t)y * a.cpitch;
+        const uint8_t* prow = a.prev ? a.prev + (size_t)y * a.ppitch : nullptr;
+        for (int gx = threadIdx.x; gx < ngroups; gx += blockDim.x) {
+            const int npx = min(4, a.w - 4 * gx);
+            uint32_t c[4], q[4] = {0, 0, 0, 0};
+            load4(crow, gx, npx, c);
+            if (prow) load4(prow, gx, npx, q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int g = gray_of(c[j]);
+                const int bin = j < npx ? g >> 2 : -1;
+                const unsigned same = __match_any_sync(__activemask(), bin);
+                if (bin >= 0 && (int)(__ffs(same) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&s_hist[bin], (unsigned)__popc(same));
+                if (prow && j < npx) mad += abs(g - gray_of(q[j]));
+            }
         }
     }
-    {   // per-thread sums fit 32 bits only for short strides: widen before the warp reduction
+    {   // widen before the warp reduction
         unsigned long long m = mad;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
