@@ -162,10 +162,10 @@ int vp_profile_read(vp_ctx* ctx, double* total_ms, uint64_t* launches, int nkind
 int vp_process_device(vp_ctx* ctx, const uint8_t* d_src, size_t src_pitch,
                       uint8_t* d_dst, size_t dst_pitch, void* stream);
 /* file / --fast mode: n device frames known ahead (src/main.cpp:627-629 `simulate_realtime=false`).
- * Consecutive frames alternate between two internal streams with their own intermediates, so one
- * frame's reduction / prologue latency overlaps the other's kernels; the temporal stage still sees frames
- * in order (an event orders frame i's blend after frame i-1's).  Asynchronous on `stream`: the second
- * lane forks from it and joins it again, so work queued on `stream` before / after the call is ordered
+ * Consecutive frames cycle through up to four internal stream lanes with their own intermediates, so one
+ * frame's reduction / prologue latency overlaps the others' kernels; the temporal stage still sees frames
+ * in order (an event orders frame i's blend after frame i-1's).  Asynchronous on `stream`: the other
+ * lanes fork from it and join it again, so work queued on `stream` before / after the call is ordered
  * before / after the whole batch.  d_dst[i] == NULL marks a warm-up frame; d_dst[i] and d_dst[i+1]
  * must not alias. */
 int vp_set_batch_lanes(vp_ctx* ctx, int lanes);     /* 1..4 stream lanes for the batch call (default 4) */
@@ -173,10 +173,13 @@ int vp_process_batch_device(vp_ctx* ctx, int n, const uint8_t* const* d_src, siz
                             uint8_t* const* d_dst, size_t dst_pitch, void* stream);
 /* Host frames, synchronous (pinned staging inside when the buffers are not pinned). */
 int vp_process_host(vp_ctx* ctx, const uint8_t* src, size_t src_step, uint8_t* dst, size_t dst_step);
-/* Host frames, pipelined: up to vp_pipeline_depth() frames in flight; H2D, kernels and D2H run on
- * three streams so copy overlaps compute (replaces FrameBuffer's deep copy, src/frame_buffer.cpp:
- * 31-37, and the per-op upload/download of src/processor.cpp:98-124).  vp_wait returns the oldest
- * submitted frame.  dst == NULL at submit = warm-up frame (no output; vp_wait still pairs with it). */
+/* Host frames, pipelined: up to vp_pipeline_depth() frames in flight; H2D and D2H have a stream each
+ * and the frames in flight cycle through the compute lanes of the batch call, so copies overlap
+ * compute and consecutive frames overlap each other while the temporal stage still sees them in
+ * order (replaces FrameBuffer's deep copy, src/frame_buffer.cpp:31-37, and the per-op upload /
+ * download of src/processor.cpp:98-124).  Device entry points called while host frames are in flight
+ * are ordered behind them.  vp_wait returns the oldest submitted frame.  dst == NULL at submit =
+ * warm-up frame (no output; vp_wait still pairs with it). */
 int vp_pipeline_depth(const vp_ctx* ctx);
 int vp_submit_host(vp_ctx* ctx, const uint8_t* src, size_t src_step, uint8_t* dst, size_t dst_step);
 int vp_wait(vp_ctx* ctx);
