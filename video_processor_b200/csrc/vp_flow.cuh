@@ -100,6 +100,27 @@ __global__ void __launch_bounds__(256) k_gauss_f32(const float* __restrict__ src
     dst[(size_t)y * dp + x] = acc;
 }
 
+// The 3x3 blur of the full-resolution level as one kernel: a thread owns four vertically adjacent pixels, forms the six row
+// results they need in registers (the very float sequence of the row pass: left to right, no FMA, reflect-101) and runs the
+// column pass over them - no intermediate plane, 18 loads for four outputs.
+__global__ void __launch_bounds__(256) k_gauss3x3_f32(const float* __restrict__ src, int sp, float* __restrict__ dst, int dp, int w, int h,
+                                                      const GaussTaps t) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y0 = (blockIdx.y * 8 + (threadIdx.x >> 5)) * 4;
+    if (x >= w || y0 >= h) return;
+    const int xl = reflect101(x - 1, w), xr = reflect101(x + 1, w);
+    float r[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        const float* p = src + (size_t)reflect101(min(y0 + j - 1, h), h) * sp;     // rows beyond h feed outputs that are not stored
+        r[j] = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(p + xl), t.k[0]), __fmul_rn(__ldg(p + x), t.k[1])), __fmul_rn(__ldg(p + xr), t.k[2]));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (y0 + k >= h) break;
+        dst[(size_t)(y0 + k) * dp + x] = __fadd_rn(__fadd_rn(__fmul_rn(r[k], t.k[0]), __fmul_rn(r[k + 1], t.k[1])), __fmul_rn(r[k + 2], t.k[2]));
+    }
+}
+
 // Pyramid levels below full resolution only need the blurred image where cv::resize(INTER_LINEAR) samples it: two source
 // columns and two source rows per output pixel.  k_gauss_rows_at runs the row pass at those columns only (compact plane
 // of 2*w' columns), k_gauss_cols_resize runs the column pass at the four taps and interpolates - the same arithmetic per

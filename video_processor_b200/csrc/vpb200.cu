@@ -613,8 +613,7 @@ int flow_expand(vp_ctx* c, FlowEngine& E, const uint8_t* bgr, size_t pitch, int 
         const float* img = L.I;
         if (L.w == E.w && L.h == E.h) {        // full resolution: the resize is the identity
             if (t.ksize == 3) {
-                k_gauss_f32<true, 3><<<grid2d(E.w, E.h), 256, 0, st>>>(E.gray, L0.p, E.blur_a, L0.p, E.w, E.h, t);
-                k_gauss_f32<false, 3><<<grid2d(E.w, E.h), 256, 0, st>>>(E.blur_a, L0.p, E.blur_b, L0.p, E.w, E.h, t);
+                k_gauss3x3_f32<<<dim3((E.w + 31) / 32, (E.h + 31) / 32), 256, 0, st>>>(E.gray, L0.p, E.blur_b, L0.p, E.w, E.h, t);
             } else {
                 k_gauss_f32<true><<<grid2d(E.w, E.h), 256, 0, st>>>(E.gray, L0.p, E.blur_a, L0.p, E.w, E.h, t);
                 k_gauss_f32<false><<<grid2d(E.w, E.h), 256, 0, st>>>(E.blur_a, L0.p, E.blur_b, L0.p, E.w, E.h, t);
@@ -638,7 +637,7 @@ int flow_expand(vp_ctx* c, FlowEngine& E, const uint8_t* bgr, size_t pitch, int 
             k_polyexp_v<0><<<grid2d(L.w, L.h), 256, 0, st>>>(img, ip, E.tmp, L.p, L.ps, L.w, L.h, E.poly);
             k_polyexp_h<0><<<grid2d(L.w, L.h), 256, 0, st>>>(E.tmp, L.p, L.ps, L.R[which], L.p, L.ps, L.w, L.h, E.poly);
         }
-        c->launches += 4;
+        c->launches += (img == E.blur_b && t.ksize == 3) ? 3 : 4;
     }
     VP_CUDA(c, cudaGetLastError());
     return VP_OK;
