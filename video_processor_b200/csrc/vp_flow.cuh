@@ -59,7 +59,10 @@ template <bool ROWS, int KS = 0>
 __global__ void __launch_bounds__(256) k_gauss_f32(const float* __restrict__ src, int sp, float* __restrict__ dst, int dp, int w, int h, const GaussTaps t,
                                                    const int* __restrict__ varies = nullptr, float const_out = 0.f) {
     VP_FLOW_XY;
-    if (varies && *varies == 0) { dst[(size_t)y * dp + x] = const_out; return; }
+    if (varies && *varies == 0) {          // constant plane: the row pass's output is never read, the column pass stores the constant
+        if (!ROWS) dst[(size_t)y * dp + x] = const_out;
+        return;
+    }
     if constexpr (KS > 0) {
         constexpr int R = KS / 2;
         const int c = ROWS ? x : y, n = ROWS ? w : h;
