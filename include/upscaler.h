@@ -51,7 +51,7 @@ public:
 
     // --- additions for file/--fast mode (not in the reference) ---------------------------------
     // Pipelined form of upscale(): up to pipelineDepth() frames in flight, H2D / kernels / D2H on
-    // three streams.  `output` must stay alive until the matching wait() returns.
+    // an H2D stream, the compute lanes and a D2H stream.  `output` must stay alive until the matching wait() returns.
     int pipelineDepth() const;
     bool submit(const cv::Mat& input, cv::Mat& output);
     bool wait();

@@ -114,8 +114,8 @@ struct VsScratch {                  // AdaptiveSharpening, adaptive_sigma branch
     uint8_t* up = nullptr; size_t upitch = 0;                            // chain only: the bicubic output
 };
 
-struct Lane {                       // per-frame intermediates; two lanes let consecutive frames overlap
-    cudaStream_t st = nullptr;      // lane 1's own stream (lane 0 runs on the caller's / the compute stream)
+struct Lane {                       // per-frame intermediates; the lanes let consecutive frames overlap
+    cudaStream_t st = nullptr;      // lanes 1..3: their own stream (lane 0 runs on the caller's / the compute stream)
     uint8_t* d_pre = nullptr;       // PRE-filtered frame, src resolution
     uint8_t* d_sharp = nullptr;     // bicubic+sharpen output, dst resolution
     unsigned long long* d_sums = nullptr;   // [0..5] PRE input, [6..11] POST input, [12..17] stage-wise scratch
