@@ -1451,8 +1451,10 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
         a.cur = cur; a.cpitch = cur_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.row_bytes = g.dst_w * 3; a.h = g.dst_h;
         a.blend = bl;
         rc = launch_blend(c, a, st); if (rc) return rc;
-    } else if (cur == d_src) {
-        VP_CUDA(c, cudaMemcpy2DAsync(d_dst, dst_pitch, d_src, src_pitch, (size_t)g.src_w * 3, g.src_h, cudaMemcpyDeviceToDevice, st));
+    } else if (d_dst && cur != d_dst) {
+        // no kernel has written the caller's frame: every stage is off (cur == d_src) or the PRE filter was the last one
+        // (cur == the lane's d_pre; sizes are equal here, a resize always writes d_dst or feeds a later stage)
+        VP_CUDA(c, cudaMemcpy2DAsync(d_dst, dst_pitch, cur, cur_pitch, (size_t)g.dst_w * 3, g.dst_h, cudaMemcpyDeviceToDevice, st));
     }
     temporal_advance(c, temporal);
     return VP_OK;
