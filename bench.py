@@ -155,6 +155,67 @@ def traffic_for(kernel):
         return None
 
 
+def warp_inst_per_frame():
+    """smsp__inst_executed.sum per frame of the C4 chain from the newest committed ncu --set full capture
+    (profiles/kernel_counters.json, written by tools/ncu_summary.py): {kernel: warp instructions}, tag."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "kernel_counters.json")) as f:
+            t = json.load(f)
+        tag = sorted(t)[-1]
+        return {k: v["warp_inst"] for k, v in t[tag].items()}, tag
+    except Exception:
+        return None, None
+
+
+def copy_ceiling(dev, barrier, world, dist, inb, outb, depth, seconds=0.6):
+    """tools/copy_peak.py's `both` leg (plain pinned cudaMemcpyAsync loops of this workload's per-frame transfers) on
+    every rank at once: the box's host<->device ceiling at this N, measured in the same process group as `e2e`."""
+    import importlib.util
+    import torch
+    spec = importlib.util.spec_from_file_location("copy_peak", os.path.join(ROOT, "tools", "copy_peak.py"))
+    cp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cp)
+    d, u, sec = cp.measure(dev, "both", seconds, barrier, d2h_bytes=outb, h2d_bytes=inb, depth=depth)
+    tb = torch.tensor([d, u], dtype=torch.float64, device=dev)
+    tt = torch.tensor([sec], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    d, u, sec = float(tb[0].item()), float(tb[1].item()), float(tt.item())
+    return {"d2h_gbs": d / sec / 1e9, "h2d_gbs": u / sec / 1e9, "total_gbs": (d + u) / sec / 1e9, "frames_per_s": d / outb / sec}
+
+
+def single_frame_latency(capi, torch, h, process, frames, outs, sw, dw, dh, stream, nlat):
+    """BASELINE config C5's figure: one frame in flight, synchronise after each (device time from CUDA events, wall time
+    launch-to-done, and the synchronous pinned-host call)."""
+    def pct(v, q):
+        v = sorted(v)
+        return v[min(len(v) - 1, int(q * len(v)))]
+    capi.lib.vp_reset_temporal(h)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nlat)]
+    wall = []
+    for i in range(nlat):
+        t0 = time.perf_counter()
+        evs[i][0].record()
+        capi.check(process(h, frames[i % len(frames)].data_ptr(), sw * 3, outs[i % len(outs)].data_ptr(), dw * 3, stream), h)
+        evs[i][1].record()
+        evs[i][1].synchronize()
+        wall.append((time.perf_counter() - t0) * 1e6)
+    dev_us = [a.elapsed_time(b) * 1e3 for a, b in evs]
+    hin1 = frames[0].cpu().pin_memory()
+    hout1 = torch.empty((dh, dw, 3), dtype=torch.uint8).pin_memory()
+    host = []
+    for i in range(min(nlat, 300)):
+        t0 = time.perf_counter()
+        capi.check(capi.lib.vp_process_host(h, hin1.data_ptr(), sw * 3, hout1.data_ptr(), dw * 3), h)
+        host.append((time.perf_counter() - t0) * 1e6)
+    return {"frames": nlat, "unit": "us",
+            "device": {"p50": round(pct(dev_us, .5), 2), "p99": round(pct(dev_us, .99), 2)},
+            "launch_to_done_wall": {"p50": round(pct(wall, .5), 2), "p99": round(pct(wall, .99), 2)},
+            "host_frame_sync_api": {"p50": round(pct(host, .5), 2), "p99": round(pct(host, .99), 2),
+                                    "note": "vp_process_host: pinned H2D + kernels + pinned D2H, one frame in flight"}}
+
+
 USE_FLOW = False             # --flow
 ADAPTIVE_SIGMA = False       # --adaptive-sigma: AdaptiveSharpening's variable-sigma branch (SURVEY 8(f)4, repaired semantics)
 BILATERAL_MODE = "plain"     # --bilateral-mode: plain (north-star chain) | selective | multiscale (SURVEY 8(f)2, repaired semantics)
@@ -307,6 +368,7 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=4, help="frames per step of the reference arm")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-c5-latency", action="store_true", help="skip the C5 single-frame latency sample of the default line")
     ap.add_argument("--scene-detect", action="store_true", help="enable TemporalConsistency::detectSceneChange (blend becomes its own kernel)")
     ap.add_argument("--lanes", type=int, default=0, help="stream lanes of the batch API (0 = library default)")
     ap.add_argument("--per-frame", action="store_true", help="one vp_process_device call per frame on one stream (no batch API)")
@@ -429,6 +491,9 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     launches = ctx.launches - l0
+    # parity_check (rank 0): the frames the timed batch call left in the output ring, to be compared below with what
+    # one vp_process_device call per frame writes there
+    timed_tail = [o.clone() for o in outs] if rank == 0 and not args.per_frame else None
     barrier()
     clocks = sampler.stop() if sampler else None
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -442,12 +507,19 @@ def main():
     # ---- per-kernel device times (second pass, events around every launch) -> roofline ---------------
     roof = None
     kernels = {}
+    parity = {}
     if rank == 0:
         capi.lib.vp_profile_enable(h, 1)
         step_per_frame()
         torch.cuda.synchronize()
         prof = ctx.profile_read()
         capi.lib.vp_profile_enable(h, 0)
+        if timed_tail is not None:
+            import hashlib
+            same = all(torch.equal(a, b) for a, b in zip(timed_tail, outs))
+            parity["batch_api_vs_per_frame"] = {"result": "ok" if same else "MISMATCH", "frames_compared": min(NOUT, F),
+                                                "sha256_last_frame": hashlib.sha256(outs[(F - 1) % NOUT].cpu().numpy().tobytes()).hexdigest()[:16]}
+            del timed_tail
         peak, peak_src = peaks()
         tot = sum(v[0] for v in prof.values()) or 1.0
         for k, (tms_k, n) in prof.items():
@@ -458,11 +530,30 @@ def main():
         dom = max((k for k in kernels if kernels[k]["achieved_gbs"] is not None), key=lambda k: kernels[k]["share"])
         traffic = traffic_for(dom)
         ach = kernels[dom]["achieved_gbs"]
+        per_gpu_fps = fps / world
+        chain = {"alg_bytes_per_frame": chain_bytes, "achieved": round(chain_bytes * per_gpu_fps / 1e9, 1),
+                 "frac": round(chain_bytes * per_gpu_fps / 1e9 / peak, 4),
+                 "counting": "in + out + state reads + state write as the code moves them (blendFrames reads buffer_size previous frames)"}
+        if temporal == "frames":
+            # SURVEY 8(d) counted one state read (its a7 row says "<= 2 previous"); the code blends buffer_size = 3
+            # previous frames, hence two figures for the same run
+            b8d = inb + outb + 2 * outb
+            chain["survey_8d"] = {"alg_bytes_per_frame": b8d, "achieved": round(b8d * per_gpu_fps / 1e9, 1),
+                                  "frac": round(b8d * per_gpu_fps / 1e9 / peak, 4)}
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
                 "traffic": traffic, "peak_source": peak_src, "avg_us": kernels[dom]["avg_us"], "share_of_step": kernels[dom]["share"],
-                "chain": {"alg_bytes_per_frame": chain_bytes, "achieved": round(chain_bytes * fps / world / 1e9, 1),
-                          "frac": round(chain_bytes * fps / world / 1e9 / peak, 4)},
-                "kernels": kernels}
+                "chain": chain, "kernels": kernels}
+        # the bound that binds these stencils: warp-instruction issue (one per SM sub-partition and clock)
+        winst, wtag = warp_inst_per_frame()
+        if winst and wl in ("c4", "c2") and BILATERAL_MODE == "plain" and not ADAPTIVE_SIGMA and not USE_FLOW:
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            per_frame = sum(winst.values())
+            ipeak = sms * 4 * mhz * 1e6
+            roof["secondary"] = {"bound": "issue", "unit": "warp-inst/s", "warp_inst_per_frame": per_frame, "per_kernel": winst,
+                                 "source": f"smsp__inst_executed.sum, profiles/kernel_counters.json [{wtag}]",
+                                 "achieved": per_frame * per_gpu_fps, "peak": ipeak, "peak_def": f"{sms} SMs x 4 schedulers x {mhz:.0f} MHz",
+                                 "frac": round(per_frame * per_gpu_fps / ipeak, 4)}
 
     # ---- e2e: pinned host frames through vp_submit_host / vp_wait -----------------------------------
     e2e = None
@@ -501,41 +592,69 @@ def main():
         twarm = torch.tensor([warm], dtype=torch.int64, device=dev)
         if world > 1:
             dist.all_reduce(twarm, op=dist.ReduceOp.SUM)
-        e2e = {"value": world * F * nsteps / float(tdt.item()), "unit": "frames/s",
-               "h2d_bytes_per_step": (world * F + int(twarm.item())) * inb, "d2h_bytes_per_step": world * F * outb,
+        e2e_fps = world * F * nsteps / float(tdt.item())
+        h2d_step, d2h_step = (world * F + int(twarm.item())) * inb, world * F * outb
+        e2e = {"value": e2e_fps, "unit": "frames/s",
+               "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
                "timing": "host wall clock around submit/wait of whole steps, synchronised both sides, max over ranks",
                "api": "vp_submit_host/vp_wait (pinned host frames, H2D + compute lanes + D2H streams, depth %d)" % depth}
+        # the same transfers as plain pinned copy loops on every rank at once: what the box's PCIe / host fabric allows
+        # at this N (tools/copy_peak.py); e2e is bound by it, not by a kernel
+        try:
+            ceil = copy_ceiling(dev, barrier, world, dist, inb, outb, depth)
+            ach = (h2d_step + d2h_step) * nsteps / float(tdt.item()) / 1e9
+            e2e["roofline"] = {"bound": "host<->device copies (PCIe / host fabric)", "unit": "GB/s",
+                               "achieved_gbs": round(ach, 2), "peak_gbs": round(ceil["total_gbs"], 2),
+                               "frac": round(ach / ceil["total_gbs"], 4),
+                               "peak_d2h_gbs": round(ceil["d2h_gbs"], 2), "peak_h2d_gbs": round(ceil["h2d_gbs"], 2),
+                               "frames_per_s_ceiling": round(ceil["frames_per_s"], 1),
+                               "peak_source": f"measured in this run at N={world}: concurrent pinned cudaMemcpyAsync loops, "
+                                              f"{outb} B d2h + {inb} B h2d per frame, depth {depth} (tools/copy_peak.py)"}
+        except Exception as ex:   # the ceiling is a report, never a reason to lose the line
+            e2e["roofline"] = {"error": repr(ex)}
+        # parity_check of the host path (rank 0): the first frames of the segment through submit/wait against one
+        # vp_process_device call per frame
+        if rank == 0:
+            npar = min(8, F)
+            capi.lib.vp_reset_temporal(h)
+            ref_out = [torch.empty((dh, dw, 3), dtype=torch.uint8, device=dev) for _ in range(npar)]
+            for i in range(warm + npar):
+                capi.check(process(h, seg[i].data_ptr(), sw * 3, ref_out[i - warm].data_ptr() if i >= warm else None, dw * 3, stream), h)
+            torch.cuda.synchronize()
+            capi.lib.vp_reset_temporal(h)
+            pin_in = [seg[i].cpu().pin_memory() for i in range(warm + npar)]
+            pin_out = [torch.zeros((dh, dw, 3), dtype=torch.uint8).pin_memory() for _ in range(npar)]
+            inflight = 0
+            for i in range(warm + npar):
+                if inflight == depth:
+                    capi.check(wait(h), h)
+                    inflight -= 1
+                capi.check(submit(h, pin_in[i].data_ptr(), sw * 3, pin_out[i - warm].data_ptr() if i >= warm else None, dw * 3), h)
+                inflight += 1
+            while inflight:
+                capi.check(wait(h), h)
+                inflight -= 1
+            same = all(torch.equal(a.cpu(), b) for a, b in zip(ref_out, pin_out))
+            parity["host_api_vs_per_frame"] = {"result": "ok" if same else "MISMATCH", "frames_compared": npar}
+            del ref_out, pin_in, pin_out
 
     # ---- single-frame latency (BASELINE config C5): one frame in flight, synchronise after each ---------
     latency = None
     nlat = args.latency_frames if args.latency_frames is not None else (1000 if wl == "c5" else 0)
     if rank == 0 and nlat > 0:
-        def pct(v, q):
-            v = sorted(v)
-            return v[min(len(v) - 1, int(q * len(v)))]
-        capi.lib.vp_reset_temporal(h)
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nlat)]
-        wall = []
-        for i in range(nlat):
-            t0 = time.perf_counter()
-            evs[i][0].record()
-            capi.check(process(h, seg[i % len(seg)].data_ptr(), sw * 3, outs[i % NOUT].data_ptr(), dw * 3, stream), h)
-            evs[i][1].record()
-            evs[i][1].synchronize()
-            wall.append((time.perf_counter() - t0) * 1e6)
-        dev_us = [a.elapsed_time(b) * 1e3 for a, b in evs]
-        hin1 = seg[0].cpu().pin_memory()
-        hout1 = torch.empty((dh, dw, 3), dtype=torch.uint8).pin_memory()
-        host = []
-        for i in range(min(nlat, 300)):
-            t0 = time.perf_counter()
-            capi.check(capi.lib.vp_process_host(h, hin1.data_ptr(), sw * 3, hout1.data_ptr(), dw * 3), h)
-            host.append((time.perf_counter() - t0) * 1e6)
-        latency = {"frames": nlat, "unit": "us",
-                   "device": {"p50": round(pct(dev_us, .5), 2), "p99": round(pct(dev_us, .99), 2)},
-                   "launch_to_done_wall": {"p50": round(pct(wall, .5), 2), "p99": round(pct(wall, .99), 2)},
-                   "host_frame_sync_api": {"p50": round(pct(host, .5), 2), "p99": round(pct(host, .99), 2),
-                                           "note": "vp_process_host: pinned H2D + kernels + pinned D2H, one frame in flight"}}
+        latency = single_frame_latency(capi, torch, h, process, seg, outs, sw, dw, dh, stream, nlat)
+    # BASELINE config C5 (bare INTER_CUBIC x4 960x540 -> 3840x2160, single-frame latency) rides along with the default
+    # line so the driver-run record carries it: its own small context, 1000 single frames
+    latency_c5 = None
+    if rank == 0 and wl == "c4" and not args.no_c5_latency and BILATERAL_MODE == "plain" and not ADAPTIVE_SIGMA and not USE_FLOW:
+        cfg5, _ = build_cfg(capi, "c5", None)
+        w5, h5, dw5, dh5 = WORKLOADS["c5"][:4]
+        ctx5 = capi.Context(cfg5, device=local_rank)
+        fr5 = [torch_frame(args.kind, w5, h5, i, SEED + 5, dev) for i in range(32)]
+        out5 = outs if (dw5, dh5) == (dw, dh) else [torch.empty((dh5, dw5, 3), dtype=torch.uint8, device=dev) for _ in range(4)]
+        latency_c5 = single_frame_latency(capi, torch, ctx5.handle, process, fr5, out5, w5, dw5, dh5, stream, 1000)
+        latency_c5["workload"] = workload_name("c5", "none")
+        ctx5.close()
 
     cpu = None
     if rank == 0 and world == 1 and args.cpu_frames > 0:
@@ -554,7 +673,9 @@ def main():
                        "l2": f"inputs ({F}x{inb >> 20} MiB) and output ring ({NOUT}x{outb >> 20} MiB) exceed the 126 MB L2",
                        "roofline_pass": "per-kernel CUDA events in a separate pass of one step, one stream, one frame at a time",
                        "api": "vp_process_device per frame" if args.per_frame else "vp_process_batch_device (four stream lanes)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(tl.item()), "roofline": roof, "cpu_baseline": cpu, "latency": latency,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(tl.item()), "roofline": roof, "cpu_baseline": cpu, "latency": latency, "latency_c5": latency_c5,
+            "parity_check": ("ok" if parity and all(v["result"] == "ok" for v in parity.values()) else ("FAILED" if parity else None)),
+            "parity_detail": parity or None,
         }
         print(json.dumps(line), flush=True)
     ctx.close()

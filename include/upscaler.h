@@ -13,7 +13,10 @@
 #pragma once
 #include <memory>
 #include <string>
+#include <vector>
 #include "vp/mat.h"
+
+struct vp_chain_config;
 
 class SelectiveBilateral;
 class AdaptiveSharpening;
@@ -51,13 +54,19 @@ public:
 
     // --- additions for file/--fast mode (not in the reference) ---------------------------------
     // Pipelined form of upscale(): up to pipelineDepth() frames in flight, H2D / kernels / D2H on
-    // an H2D stream, the compute lanes and a D2H stream.  `output` must stay alive until the matching wait() returns.
+    // an H2D stream, the compute lanes and a D2H stream.  `input` AND `output` must stay alive and untouched until the
+    // matching wait() returns (a pinned input Mat is read by DMA after submit() returns - do not reuse the capture Mat).
     int pipelineDepth() const;
     bool submit(const cv::Mat& input, cv::Mat& output);
     bool wait();
     // Runs a frame through the chain for its temporal side effects only (multi-GPU segment warm-up).
     bool warmup(const cv::Mat& input);
     void setDevice(int device) { m_device = device; }
+    // file/--fast mode over several B200s (the loop of src/main.cpp:222-355 with the whole clip known ahead): the frames are
+    // cut into contiguous segments, one per device, each preceded by its temporal warm-up frames; outputs come back in clip
+    // order and are bit-identical to calling upscale() frame by frame on one device.  `devices` empty = every visible B200.
+    // A thin wrapper over vp_run_segments (include/vpb200.h); this object's own temporal state is not touched.
+    bool upscaleSegments(const std::vector<cv::Mat>& inputs, std::vector<cv::Mat>& outputs, const std::vector<int>& devices = {});
 
 private:
     struct Chain;
@@ -72,6 +81,7 @@ private:
     bool initializeImpl();
     bool initializeEnhancements();
     bool ensureChain(int src_w, int src_h);
+    bool buildChainConfig(int src_w, int src_h, vp_chain_config* out) const;
 
     std::unique_ptr<SelectiveBilateral> m_bilateral_pre;
     std::unique_ptr<AdaptiveSharpening> m_sharpening;

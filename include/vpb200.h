@@ -15,7 +15,10 @@
  *     reference's "processing thread", src/pipeline.cpp:351-383, src/main.cpp:222-259);
  *   - device-pointer entry points are asynchronous on `stream` (a cudaStream_t passed as void*,
  *     NULL = the context's own compute stream); host-pointer entry points are synchronous unless
- *     named submit/wait;
+ *     named submit/wait.  The stage-wise entry points keep their parameter tables and scratch planes per
+ *     context, not per stream: use ONE stream per vp_ctx for them (a call with new parameters on a second
+ *     stream may rewrite tables a kernel still running on the first one reads); contexts are cheap, take one
+ *     per stream;
  *   - there is NO CPU fallback: without a usable sm_100 device vp_create() fails.
  */
 #ifndef VPB200_H
@@ -28,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VPB200_ABI_VERSION 3
+#define VPB200_ABI_VERSION 4
 
 typedef enum vp_status {
     VP_OK = 0,
@@ -179,10 +182,44 @@ int vp_process_host(vp_ctx* ctx, const uint8_t* src, size_t src_step, uint8_t* d
  * order (replaces FrameBuffer's deep copy, src/frame_buffer.cpp:31-37, and the per-op upload /
  * download of src/processor.cpp:98-124).  Device entry points called while host frames are in flight
  * are ordered behind them.  vp_wait returns the oldest submitted frame.  dst == NULL at submit =
- * warm-up frame (no output; vp_wait still pairs with it). */
+ * warm-up frame (no output; vp_wait still pairs with it).  BOTH buffers belong to the library from
+ * vp_submit_host until the matching vp_wait returns: a pinned `src` is read by DMA after the call returns
+ * (do not overwrite, release or recycle it - e.g. the capture Mat - before vp_wait), `dst` is written until then.
+ * A failed vp_wait leaves the frame in flight (call again or destroy the context); a failed vp_submit_host
+ * queues nothing and clears the temporal history. */
 int vp_pipeline_depth(const vp_ctx* ctx);
 int vp_submit_host(vp_ctx* ctx, const uint8_t* src, size_t src_step, uint8_t* dst, size_t dst_step);
 int vp_wait(vp_ctx* ctx);
+/* ---- file / --fast mode over several devices (src/main.cpp:222-355 processing loop with simulate_realtime = false,
+ * :627-629) ----------------------------------------------------------------------------------------------------
+ * The clip's nframes frames are cut into ndev contiguous segments [floor(k n / G), floor((k+1) n / G)); device
+ * devices[k] runs segment k on its own host thread and vp_ctx, frames pipelined through vp_submit_host / vp_wait,
+ * after first feeding the temporal warm-up frames its first output depends on (0 without a temporal stage, 1 for
+ * VP_TEMPORAL_MAIN_BLEND, buffer_size for VP_TEMPORAL_BLEND_FRAMES) with no output.  No data moves between devices.
+ * Outputs are bit-identical to a one-device run of the same clip.  Returns the first failing segment's status;
+ * vp_segments_last_error() describes it (per calling thread).  `report` (ndev entries) may be NULL. */
+typedef struct vp_segment_report {
+    int32_t device;
+    int32_t first_frame;       /* frames [first_frame, start) are warm-up frames (no output)                       */
+    int32_t start, stop;       /* frames [start, stop) are this segment's output                                   */
+    int32_t status;            /* vp_status of the segment                                                         */
+    int32_t reserved_;
+    double seconds;            /* host wall time of the segment's frame loop (context creation excluded)           */
+} vp_segment_report;
+/* the partition itself (what vp_run_segments uses): frames [*first, *start) warm-up, [*start, *stop) output */
+int vp_plan_segment(int nframes, int nsegments, int k, const vp_temporal_config* temporal, int* first, int* start, int* stop);
+/* host frames given as pointer arrays (pinned memory makes the copies true DMA; pageable memory is staged) */
+int vp_run_segments(const vp_chain_config* cfg, const int* devices, int ndev, int nframes,
+                    const uint8_t* const* src, size_t src_step, uint8_t* const* dst, size_t dst_step,
+                    vp_segment_report* report);
+/* the same with a decoder / encoder on either side: `source` fills a pinned buffer with frame `frame`, `sink` receives
+ * each output frame.  Both are called from the segment's own thread - concurrently across segments, in increasing frame
+ * order within one - and return 0 on success (anything else aborts the run).  sink may be NULL. */
+typedef int (*vp_frame_source)(void* user, int frame, uint8_t* buf, size_t step);
+typedef int (*vp_frame_sink)(void* user, int frame, const uint8_t* buf, size_t step);
+int vp_run_segments_cb(const vp_chain_config* cfg, const int* devices, int ndev, int nframes,
+                       vp_frame_source source, vp_frame_sink sink, void* user, vp_segment_report* report);
+const char* vp_segments_last_error(void);
 /* TemporalConsistency::reset (src/temporal_consistency.cpp:52-59); also main.cpp's history clear */
 int vp_reset_temporal(vp_ctx* ctx);
 /* (d, sigma_color, sigma_space) calculateAdaptiveParams selected for the LAST processed frame;

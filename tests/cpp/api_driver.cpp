@@ -99,6 +99,15 @@ int main(int argc, char** argv) {
             ++inflight;
         }
         while (inflight--) if (!up.wait()) return fail("wait (drain)");
+    } else if (mode == "segments") {
+        // file/--fast mode over several devices: VP_SEGMENT_DEVICES = "0,0,0" or "0,1" (default: every visible device)
+        Upscaler up(Upscaler::REAL_ESRGAN, true);
+        if (!up.initialize(tw, th)) return fail("Upscaler::initialize");
+        std::vector<int> devs;
+        if (const char* e = std::getenv("VP_SEGMENT_DEVICES"))
+            for (const char* p = e; *p; ++p) if (*p >= '0' && *p <= '9') devs.push_back(*p - '0');
+        if (!up.upscaleSegments(frames, outs, devs)) return fail("upscaleSegments");
+        if ((int)outs.size() != n) return fail("upscaleSegments output count");
     } else if (mode == "toggles") {
         // keys 1-4 of test_enhancements.cpp: stages switched off one by one between frames
         Upscaler up(Upscaler::REAL_ESRGAN, true);

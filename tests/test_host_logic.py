@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(vp):
     assert declared == set(vp.PROTOTYPES), declared ^ set(vp.PROTOTYPES)
     for name in declared:
         assert hasattr(vp.lib, name)
-    assert vp.lib.vp_abi_version() == 3
+    assert vp.lib.vp_abi_version() == 4
 
 
 def test_struct_layout_matches_header(vp):
@@ -59,6 +59,39 @@ def test_no_cpu_fallback(vp):
         vp.Context(vp.default_chain_config(64, 64, 128, 128))
     assert e.value.code == vp.VP_ERR_NO_DEVICE
     assert vp.lib.vp_process_device(None, None, 0, None, 0, None) == vp.VP_ERR_INVALID_ARG
+
+
+def test_plan_segment_matches_sharding_py(vp):
+    """vp_plan_segment (the partition vp_run_segments uses, csrc/host/segments.cpp) == video_processor_b200/sharding.py
+    (what bench.py's ranks use): same segments, same warm-up frames, for every temporal mode."""
+    import ctypes as C
+    from video_processor_b200 import sharding
+    for mode, name, bs in [(vp.VP_TEMPORAL_NONE, "none", 3), (vp.VP_TEMPORAL_MAIN_BLEND, "main", 3),
+                           (vp.VP_TEMPORAL_BLEND_FRAMES, "frames", 3), (vp.VP_TEMPORAL_BLEND_FRAMES, "frames", 2)]:
+        t = vp.TemporalConfig()
+        t.mode, t.buffer_size = mode, bs
+        for n, g in [(300, 8), (7, 3), (5, 8), (0, 2), (100, 1), (2, 2)]:
+            covered = []
+            for k in range(g):
+                f, a, b = C.c_int(), C.c_int(), C.c_int()
+                assert vp.lib.vp_plan_segment(n, g, k, C.byref(t), C.byref(f), C.byref(a), C.byref(b)) == 0
+                first, warm, start, stop = sharding.plan(n, g, k, name, bs)
+                assert (f.value, a.value, b.value) == (first, start, stop)
+                covered += list(range(a.value, b.value))
+            assert covered == list(range(n))
+    assert vp.lib.vp_plan_segment(10, 0, 0, C.byref(t), None, None, None) == vp.VP_ERR_INVALID_ARG
+    assert vp.lib.vp_plan_segment(10, 2, 2, C.byref(t), None, None, None) == vp.VP_ERR_INVALID_ARG
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device behaviour")
+def test_run_segments_refuses_without_gpu(vp):
+    import ctypes as C
+    cfg = vp.default_chain_config(64, 64, 128, 128)
+    a = np.zeros((64, 64, 3), np.uint8)
+    o = np.zeros((128, 128, 3), np.uint8)
+    rc = vp.lib.vp_run_segments(C.byref(cfg), (C.c_int * 1)(0), 1, 1, (C.c_void_p * 1)(a.ctypes.data), 192,
+                                (C.c_void_p * 1)(o.ctypes.data), 384, None)
+    assert rc == vp.VP_ERR_NO_DEVICE and b"no CPU fallback" in vp.lib.vp_segments_last_error()
 
 
 # ---- host tables ----------------------------------------------------------------------------------

@@ -3,6 +3,8 @@
  - profiles/<tag>_launches.csv   : per-kernel launch count / average duration / share of the captured step
  - profiles/<tag>_ncu_summary.csv: one row per captured launch (duration, DRAM bytes, issue/pipe utilisation, stalls)
  - profiles/traffic.json         : dram__bytes_read.sum + dram__bytes_write.sum per launch, keyed like bench.py's kernels
+ - profiles/kernel_counters.json : per kernel of ONE C4 frame (stats, bilateral_pre, upsharp, bilateral_post): warp instructions
+                                   (smsp__inst_executed.sum), DRAM bytes, duration - bench.py's issue roofline reads it
 """
 import collections
 import csv
@@ -48,6 +50,7 @@ keys = ["Kernel Name", "launch__grid_size", "gpu__time_duration.sum", "dram__byt
 keys = [k for k in keys if k in h]
 units = rr[1]
 traffic = {}
+counters = collections.OrderedDict()
 seen = collections.Counter()      # launches of the same kernel are told apart by their order in the captured frame
 with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.csv"), "w") as f:
     w = csv.writer(f)
@@ -60,7 +63,18 @@ with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.csv"), "w") as f:
         b = float(r[h.index("dram__bytes_read.sum")]) * scale.get(ur, 1) + float(r[h.index("dram__bytes_write.sum")]) * scale.get(uw, 1)
         base = name.split("(")[0]
         traffic.setdefault(base + f"@grid{grid}#{seen[base]}", []).append(int(b))
+        kind = {"k_stats": "stats", "k_bilateral": "bilateral_pre" if seen[base] == 0 else "bilateral_post"}.get(base)
+        if kind is None and "k_upsharp" in base:
+            kind = "upsharp"
+        if kind and "smsp__inst_executed.sum" in h:
+            counters[kind] = {"warp_inst": int(float(r[h.index("smsp__inst_executed.sum")])), "dram_bytes": int(b),
+                              "us": round(float(r[h.index("gpu__time_duration.sum")]), 2), "grid": grid}
         seen[base] += 1
+kj = os.path.join(ROOT, "profiles", "kernel_counters.json")
+oldk = json.load(open(kj)) if os.path.exists(kj) else {}
+if counters:
+    oldk[tag] = counters
+    json.dump(oldk, open(kj, "w"), indent=1, sort_keys=True)
 tj = os.path.join(ROOT, "profiles", "traffic.json")
 old = json.load(open(tj)) if os.path.exists(tj) else {}
 old[tag] = {k: int(sum(v) / len(v)) for k, v in traffic.items()}

@@ -37,6 +37,15 @@ class TemporalConfig(C.Structure):
                 ("poly_n", C.c_int32), ("flags", C.c_int32), ("reserved3_", C.c_int32)]
 
 
+class SegmentReport(C.Structure):
+    _fields_ = [("device", C.c_int32), ("first_frame", C.c_int32), ("start", C.c_int32), ("stop", C.c_int32),
+                ("status", C.c_int32), ("reserved_", C.c_int32), ("seconds", C.c_double)]
+
+
+FRAME_SOURCE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t)
+FRAME_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t)
+
+
 class ChainConfig(C.Structure):
     _fields_ = [("src_w", C.c_int32), ("src_h", C.c_int32), ("dst_w", C.c_int32), ("dst_h", C.c_int32),
                 ("use_pre", C.c_int32), ("use_sharpen", C.c_int32), ("use_post", C.c_int32), ("bicubic_enhance", C.c_int32),
@@ -67,6 +76,12 @@ PROTOTYPES = {
     "vp_pipeline_depth": (C.c_int, [_vp]),
     "vp_submit_host": (C.c_int, [_vp, _u8p, _sz, _u8p, _sz]),
     "vp_wait": (C.c_int, [_vp]),
+    "vp_plan_segment": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(TemporalConfig), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vp_run_segments": (C.c_int, [C.POINTER(ChainConfig), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_void_p), _sz,
+                                  C.POINTER(C.c_void_p), _sz, C.POINTER(SegmentReport)]),
+    "vp_run_segments_cb": (C.c_int, [C.POINTER(ChainConfig), C.POINTER(C.c_int), C.c_int, C.c_int, FRAME_SOURCE, FRAME_SINK,
+                                     C.c_void_p, C.POINTER(SegmentReport)]),
+    "vp_segments_last_error": (C.c_char_p, []),
     "vp_reset_temporal": (C.c_int, [_vp]),
     "vp_get_stage_params": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "vp_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), _sz]),

@@ -93,9 +93,10 @@ bool Upscaler::initializeEnhancements() {
     return true;
 }
 
-bool Upscaler::ensureChain(int src_w, int src_h) {
-    vp_chain_config c{};
-    vp_default_chain_config(&c, src_w, src_h, m_target_width, m_target_height);
+bool Upscaler::buildChainConfig(int src_w, int src_h, vp_chain_config* out) const {
+    vp_chain_config& c = *out;
+    c = vp_chain_config{};
+    if (vp_default_chain_config(&c, src_w, src_h, m_target_width, m_target_height) != VP_OK) return false;
     if (m_algorithm == BICUBIC) {
         // CPUImpl::upscale for BICUBIC (src/upscaler.cpp:75-84): pre-blur, cv::resize(INTER_CUBIC),
         // enhanceBicubicResult; the temporal smoothing of main.cpp:269-292 stays with the caller
@@ -127,6 +128,12 @@ bool Upscaler::ensureChain(int src_w, int src_h) {
         c.temporal.levels = tc.levels; c.temporal.winsize = tc.winsize; c.temporal.iterations = tc.iterations;
         c.temporal.poly_n = tc.poly_n; c.temporal.flags = tc.flags;
     }
+    return true;
+}
+
+bool Upscaler::ensureChain(int src_w, int src_h) {
+    vp_chain_config c{};
+    if (!buildChainConfig(src_w, src_h, &c)) return false;
     if (m_chain && m_chain->device == m_device && std::memcmp(&m_chain->cfg, &c, sizeof(c)) == 0) return true;
     if (m_chain && m_chain->ctx) {          // drain frames in flight before the context is replaced
         while (vp_wait(m_chain->ctx) == VP_OK) {}

@@ -1616,7 +1616,15 @@ int vp_submit_host(vp_ctx* c, const uint8_t* src, size_t src_step, uint8_t* dst,
     }
     VP_CUDA(c, cudaStreamWaitEvent(st, s.ev_h2d, 0));
     rc = process_frame(c, ln, st, c->host_prev_done, s.d_in, c->pre_pitch, dst ? s.d_out : nullptr, c->frame_pitch);
-    if (rc) return rc;
+    if (rc) {
+        // the slot is not queued, so nothing would wait for its upload before the next submit reuses d_in / h_in: drain the
+        // copy stream and the lane here, and drop the temporal history (the failed frame may have advanced it half way)
+        cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(st); cudaGetLastError();
+        const std::string keep = c->err;
+        vp_reset_temporal(c);
+        c->err = keep;
+        return rc;
+    }
     VP_CUDA(c, cudaEventRecord(c->lanes[ln].ev_done, st));
     c->host_prev_done = c->lanes[ln].ev_done;
     c->host_lane = (ln + 1) % NL;
@@ -1642,8 +1650,9 @@ int vp_wait(vp_ctx* c) {
     if (c->inflight.empty()) return fail(c, VP_ERR_STATE, "vp_wait: nothing submitted");
     VP_CUDA(c, cudaSetDevice(c->device));
     HostSlot& s = c->slots[c->inflight.front()];
-    c->inflight.pop_front();
+    // the frame leaves the queue only once it is known to be complete: a CUDA error here keeps it (and its slot) in flight
     VP_CUDA(c, cudaEventSynchronize(s.user_dst ? s.ev_d2h : s.ev_comp));
+    c->inflight.pop_front();
     if (s.user_dst && s.staged_out) {
         const size_t out_row = (size_t)c->cfg.dst_w * 3;
         for (int y = 0; y < c->cfg.dst_h; ++y)
