@@ -78,17 +78,48 @@ def measure(dev, mode, seconds, barrier, d2h_bytes=D2H_BYTES, h2d_bytes=H2D_BYTE
     return (n * d2h_bytes if do_d else 0), (n * h2d_bytes if do_u else 0), ms / 1e3
 
 
-def _worker(rank, world, mode, seconds, bar, q):
+def gpu_locality(index):
+    """(numa_node, local_cpulist) of GPU `index` from sysfs, or (None, None)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(index), "pci_domain_id", 0)
+        dev = torch.cuda.get_device_properties(index).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0" % (dom, bus, dev)
+        return int(open(path + "/numa_node").read()), open(path + "/local_cpulist").read().strip()
+    except Exception:
+        return None, None
+
+
+def bind_local(index):
+    """Pin this process to the CPUs next to GPU `index` BEFORE any pinned allocation (first touch then places the
+    pages on that node).  Returns the cpu list used, or None when sysfs offers nothing narrower than all CPUs."""
+    node, cpus = gpu_locality(index)
+    if not cpus:
+        return None
+    ids = set()
+    for part in cpus.split(","):
+        a, _, b = part.partition("-")
+        ids.update(range(int(a), int(b or a) + 1))
+    ids &= os.sched_getaffinity(0)
+    if not ids:
+        return None
+    os.sched_setaffinity(0, ids)
+    return cpus
+
+
+def _worker(rank, world, mode, seconds, bar, q, bind=False):
     import torch
+    where = bind_local(rank) if bind else None
     d, u, s = measure(torch.device("cuda", rank), mode, seconds, bar.wait)
-    q.put((rank, d, u, s))
+    q.put((rank, d, u, s, where))
 
 
-def run(world, mode, seconds):
+def run(world, mode, seconds, bind=False):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     bar, q = ctx.Barrier(world), ctx.Queue()
-    ps = [ctx.Process(target=_worker, args=(r, world, mode, seconds, bar, q)) for r in range(world)]
+    ps = [ctx.Process(target=_worker, args=(r, world, mode, seconds, bar, q, bind)) for r in range(world)]
     for p in ps:
         p.start()
     res = sorted(q.get(timeout=300) for _ in ps)
@@ -100,6 +131,8 @@ def run(world, mode, seconds):
            "d2h_gbs": round(d2h / tmax / 1e9, 2), "h2d_gbs": round(h2d / tmax / 1e9, 2),
            "total_gbs": round((d2h + h2d) / tmax / 1e9, 2),
            "per_rank_gbs": [round((r[1] + r[2]) / r[3] / 1e9, 2) for r in res]}
+    if bind:
+        out["bound_to_cpus"] = [r[4] for r in res]
     if mode == "both":
         out["frames_per_s_ceiling"] = round(d2h / D2H_BYTES / tmax, 1)
     return out
@@ -110,6 +143,7 @@ def main():
     ap.add_argument("--gpus", default="1")
     ap.add_argument("--seconds", type=float, default=1.0)
     ap.add_argument("--modes", default="d2h,h2d,both")
+    ap.add_argument("--bind", action="store_true", help="pin every rank to its GPU's local CPUs before allocating pinned memory")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     import torch
@@ -120,12 +154,13 @@ def main():
             print(f"skip N={n}: only {have} device(s)", file=sys.stderr)
             continue
         for mode in a.modes.split(","):
-            r = run(n, mode, a.seconds)
+            r = run(n, mode, a.seconds, a.bind)
             print(json.dumps(r), flush=True)
             rows.append(r)
     doc = {"what": "concurrent pinned-memory copy ceiling, one process per GPU, one cudaMemcpyAsync per copy "
                    "(24,883,200 B d2h / 6,220,800 B h2d per frame of the C4 chain)",
-           "gpu": torch.cuda.get_device_name(0), "devices_on_box": have, "host_cpus": os.cpu_count(), "rows": rows}
+           "gpu": torch.cuda.get_device_name(0), "devices_on_box": have, "host_cpus": os.cpu_count(),
+           "gpu_locality": [gpu_locality(i) for i in range(have)], "rows": rows}
     if a.out:
         with open(a.out, "w") as f:
             json.dump(doc, f, indent=1)

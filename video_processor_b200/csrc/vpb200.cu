@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "vp_bicubic.cuh"
+#include "vp_bicubic_int.cuh"
 #include "vp_bilateral.cuh"
 #include "vp_blend.cuh"
 #include "vp_canny.cuh"
@@ -51,6 +52,9 @@ struct ResizeCache {
     int max_rows[2] = {0, 0}, max_cols[2] = {0, 0};   // [0] halo 0, [1] halo US_HALO (k_upsharp tiles)
     int bc_rows = 0, bc_cols = 0;                     // k_bicubic tiles
     int yperiod = 0;                                  // 2 / 4 when the row tables are periodic with an integer ratio (k_bicubic<S>)
+    int int_ratio = 0;                                // 2 / 4 when BOTH axes have that integer ratio and the tables are the
+                                                      // periodic ones k_bicubic_int<S> assumes (verified entry by entry)
+    float xk[4][4] = {}, yk[4][4] = {};               // its per-phase taps
 };
 
 struct HostSlot {
@@ -311,6 +315,23 @@ int ensure_resize(vp_ctx* c, ResizeCache& rc, int sw, int sh, int dw, int dh, cu
             if (y >= S && std::memcmp(&yb[(size_t)y * 4], &yb[(size_t)(y - S) * 4], 4 * sizeof(float)) != 0) ok = false;
         }
         if (ok) rc.yperiod = S;
+    }
+    // integer ratio S on both axes: tap origin of output x is x/S - 2 + (x % S >= S/2) and the taps repeat with period S
+    rc.int_ratio = 0;
+    for (int S : {2, 4}) {
+        if (dw != S * sw || dh != S * sh || rc.yperiod != S) continue;
+        bool ok = true;
+        for (int x = 0; x < dw && ok; ++x) {
+            if (tx.ofs[x] != x / S - 2 + ((x % S) >= S / 2 ? 1 : 0)) ok = false;
+            if (x >= S && std::memcmp(&xc[(size_t)x * 4], &xc[(size_t)(x - S) * 4], 4 * sizeof(int)) != 0) ok = false;
+            for (int t = 0; t < 4; ++t) if (std::abs(xc[(size_t)x * 4 + t]) > 4096) ok = false;     // exact in the float32 pass
+        }
+        for (int y = 0; y < dh && ok; ++y)
+            if (ty.ofs[y] != y / S - 2 + ((y % S) >= S / 2 ? 1 : 0)) ok = false;
+        if (!ok) continue;
+        rc.int_ratio = S;
+        for (int p = 0; p < S; ++p)
+            for (int t = 0; t < 4; ++t) { rc.xk[p][t] = (float)xc[(size_t)p * 4 + t]; rc.yk[p][t] = yb[(size_t)p * 4 + t]; }
     }
     rc.sw = sw; rc.sh = sh; rc.dw = dw; rc.dh = dh;
     return VP_OK;
@@ -890,6 +911,20 @@ int launch_upsharp(vp_ctx* c, UpsharpArgs& a, bool do_resize, bool do_sharpen, c
 
 int launch_bicubic(vp_ctx* c, const uint8_t* src, size_t spitch, int sw, int sh, uint8_t* dst, size_t dpitch, int dw, int dh,
                    const ResizeCache& rcache, cudaStream_t st) {
+    if (rcache.int_ratio) {
+        // integer ratio on both axes (BASELINE C1 / C5): the float4-window kernel, half the instructions per pixel
+        BicubicIntArgs b{};
+        b.src = src; b.spitch = spitch; b.sw = sw; b.sh = sh; b.dst = dst; b.dpitch = dpitch; b.dw = dw; b.dh = dh;
+        for (int p = 0; p < 4; ++p)
+            for (int t = 0; t < 4; ++t) { b.xk[p][t] = make_float2(rcache.xk[p][t], rcache.xk[p][t]); b.yk[p][t] = make_float2(rcache.yk[p][t], rcache.yk[p][t]); }
+        const dim3 grid((dw + BI_TW - 1) / BI_TW, (dh + BI_TH - 1) / BI_TH);
+        ProfScope ps(c, K_UPSHARP, st);
+        if (rcache.int_ratio == 2) k_bicubic_int<2><<<grid, BI_NT, BicubicIntGeom<2>::TOTAL, st>>>(b);
+        else k_bicubic_int<4><<<grid, BI_NT, BicubicIntGeom<4>::TOTAL, st>>>(b);
+        VP_CUDA(c, cudaGetLastError());
+        c->launches++;
+        return VP_OK;
+    }
     BicubicArgs a{};
     a.src = src; a.spitch = spitch; a.sw = sw; a.sh = sh; a.dst = dst; a.dpitch = dpitch; a.dw = dw; a.dh = dh;
     a.rt = ResizeTables{rcache.xofs, rcache.xcoef, rcache.yofs, rcache.ycoef};
@@ -1046,6 +1081,8 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
     VP_CUDA(c, cudaFuncSetAttribute(k_bicubic<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_bicubic<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_bicubic<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VP_CUDA(c, cudaFuncSetAttribute(k_bicubic_int<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BicubicIntGeom<2>::TOTAL));
+    VP_CUDA(c, cudaFuncSetAttribute(k_bicubic_int<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BicubicIntGeom<4>::TOTAL));
     VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
