@@ -49,23 +49,27 @@ def needs_build():
     return any(os.path.getmtime(p) > t for p in _deps())
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant/defines: a development build `libvpb200_<variant>.so` with extra -D flags, for A/B timing on the GPU box
+    (`VPB200_LIB=<path> python bench.py ...`); the product library is the plain build."""
+    lib = LIB if not variant else os.path.join(HERE, f"libvpb200_{variant}.so")
+    if not variant and not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB] + _sources()
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", lib] + _sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
-    with open(os.path.join(HERE, "build.log"), "w") as f:
+    with open(os.path.join(HERE, "build.log" if not variant else f"build_{variant}.log"), "w") as f:
         f.write(" ".join(cmd) + "\n" + log)
     if res.returncode != 0:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building libvpb200.so")
     if verbose:
         print(log)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
-    print(LIB)
+    var = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    defs = [a[2:] for a in sys.argv if a.startswith("-D")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=var, defines=defs))

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvpb200.so")
+# VPB200_LIB: a development build of the same library (video_processor_b200/build.py --variant) for A/B timing
+LIB_PATH = os.environ.get("VPB200_LIB") or os.path.join(_HERE, "libvpb200.so")
 
 VP_OK = 0
 VP_ERR_INVALID_ARG, VP_ERR_UNSUPPORTED, VP_ERR_CUDA, VP_ERR_NO_DEVICE, VP_ERR_STATE, VP_ERR_NOMEM = -1, -2, -3, -4, -5, -6

@@ -23,13 +23,28 @@ namespace vp {
 
 constexpr int BIL_TW = 64, BIL_TH = 16, BIL_PX = 4, BIL_NT = 256, BIL_RMAX = 7;
 
-struct BilCand {                   // one (d, sigma) parameter set, device memory
+// Weight classes of a small window: taps at the same squared distance share their space weight, so for radius <= 3
+// the host folds it into the colour LUT - class_w[c][n] = fl(space_w(d2) * color_w[n]), the very product the filter
+// would form - and the tap loop drops its multiply.  d2 -> class index; the centre (d2 = 0) needs no table.
+constexpr int BIL_CLS_RMAX = 3, BIL_NCLS = 6;          // radius 3: d2 in {1, 2, 4, 5, 8, 9}
+__host__ __device__ constexpr int bil_class_of(int d2) {
+    return d2 == 1 ? 0 : d2 == 2 ? 1 : d2 == 4 ? 2 : d2 == 5 ? 3 : d2 == 8 ? 4 : d2 == 9 ? 5 : -1;
+}
+__host__ __device__ constexpr int bil_nclasses(int r) { return r == 1 ? 1 : r == 2 ? 3 : r == 3 ? 6 : 0; }
+
+struct __align__(16) BilHead {     // what every radius needs; a CTA fetches it into static shared memory with one bulk copy
+    float color_w[768];
+    float space_w[228];            // [(i+r)*(2r+1) + (j+r)], (2*7+1)^2 = 225 used
+    int xmax[16];                  // half-width of tap row i (index i + r): floor(sqrt(r^2 - i^2))
     int radius;
     int d;
-    int xmax[2 * BIL_RMAX + 1];    // half-width of tap row i (index i + r): floor(sqrt(r^2 - i^2))
-    float space_w[(2 * BIL_RMAX + 1) * (2 * BIL_RMAX + 1)];  // [(i+r)*(2r+1) + (j+r)]
-    float color_w[768];
+    int pad_[2];
 };
+struct __align__(16) BilCand {     // one (d, sigma) parameter set, device memory
+    BilHead head;
+    float class_w[BIL_NCLS][768];  // radius <= BIL_CLS_RMAX only; the first bil_nclasses(r) tables go to dynamic shared memory
+};
+static_assert(sizeof(BilHead) % 16 == 0, "bulk copies move whole 16-byte units");
 
 struct BlendArgs {
     int mode;                      // VP_TEMPORAL_*
@@ -185,11 +200,19 @@ template <int R> struct BilGeom {
 // one tap row of half-width XM: taps dx = -XM..XM against the PX outputs of the strip.
 // Accumulators are (sum_b, sum_g) and (sum_r, wsum) pairs: the tile's 4th byte is 1, so the pixel's
 // (r, 1.0) pair turns wsum += w into the second half of one FFMA2 (fma(1, w, wsum) == wsum + w).
-template <int R, int XM>
-__device__ __forceinline__ void bil_row(const uint32_t (&seg)[BilGeom<R>::NSEG], const float* __restrict__ sw_row,
-                                        const float* __restrict__ s_cw, const uint32_t (&ctr)[BIL_PX],
+// DY is the row's offset from the window centre when the caller knows it at compile time (small windows), else
+// BIL_DY_ANY.  Two kinds of tap skip the per-pixel colour-distance lookup:
+//   * the centre tap (colour distance 0 by construction): its weight space_w(0) * color_w[0] is formed once per row call;
+//   * with class tables (R <= BIL_CLS_RMAX, DY known) the weight is class_w[class(DY^2 + dx^2)][n], the host-made product.
+constexpr int BIL_DY_ANY = 99;
+template <int R, int XM, int DY>
+__device__ __forceinline__ void bil_row(const uint32_t (&seg)[BilGeom<R>::NSEG], const BilHead& T, const float* __restrict__ s_cls, int row,
+                                        const uint32_t (&ctr)[BIL_PX],
                                         unsigned long long (&abg)[BIL_PX], unsigned long long (&arw)[BIL_PX]) {
     constexpr int N = BIL_PX + 2 * XM;                        // neighbours this row touches
+    constexpr bool CENTER_ROW = (DY == 0) || (DY == BIL_DY_ANY && XM == R);      // only row 0 is R taps wide
+    constexpr bool CLS = (R <= BIL_CLS_RMAX) && (DY != BIL_DY_ANY);
+    const float* __restrict__ sw_row = T.space_w + row * BilGeom<R>::D;
     unsigned long long pbg[N], pra[N];
     const unsigned long long bias = pack2(0xCB000000u, 0xCB000000u);   // (-2^23, -2^23)
 #pragma unroll
@@ -200,12 +223,23 @@ __device__ __forceinline__ void bil_row(const uint32_t (&seg)[BilGeom<R>::NSEG],
     }
 #pragma unroll
     for (int dx = -XM; dx <= XM; ++dx) {
-        const float sw = sw_row[dx + R];
+        if (CENTER_ROW && dx == 0) {
+            const uint32_t wgt = __float_as_uint(__fmul_rn(sw_row[R], T.color_w[0]));
+            const unsigned long long w2 = pack2(wgt, wgt);
+#pragma unroll
+            for (int j = 0; j < BIL_PX; ++j) {
+                abg[j] = ffma2(pbg[j + XM], w2, abg[j]);
+                arw[j] = ffma2(pra[j + XM], w2, arw[j]);
+            }
+            continue;
+        }
+        const float sw = CLS ? 0.f : sw_row[dx + R];
+        const float* __restrict__ lut = CLS ? s_cls + 768 * bil_class_of(CLS ? DY * DY + dx * dx : 1) : T.color_w;
 #pragma unroll
         for (int j = 0; j < BIL_PX; ++j) {
             const int i = j + dx + XM;
             const unsigned n = __vsadu4(seg[i + R - XM], ctr[j]);   // VABSDIFF4.ACC: |db|+|dg|+|dr| (+|1-1|)
-            const uint32_t wgt = __float_as_uint(__fmul_rn(sw, s_cw[n]));
+            const uint32_t wgt = __float_as_uint(CLS ? lut[n] : __fmul_rn(sw, lut[n]));
             const unsigned long long w2 = pack2(wgt, wgt);
             abg[j] = ffma2(pbg[i], w2, abg[j]);
             arw[j] = ffma2(pra[i], w2, arw[j]);
@@ -215,16 +249,16 @@ __device__ __forceinline__ void bil_row(const uint32_t (&seg)[BilGeom<R>::NSEG],
 
 template <int R, int XM>
 struct BilRowSwitch {
-    __device__ __forceinline__ static void run(int xm, const uint32_t (&seg)[BilGeom<R>::NSEG], const float* sw_row, const float* s_cw,
+    __device__ __forceinline__ static void run(int xm, const uint32_t (&seg)[BilGeom<R>::NSEG], const BilHead& T, int row,
                                                const uint32_t (&ctr)[BIL_PX], unsigned long long (&abg)[BIL_PX],
                                                unsigned long long (&arw)[BIL_PX]) {
-        if (xm == XM) bil_row<R, XM>(seg, sw_row, s_cw, ctr, abg, arw);
-        else BilRowSwitch<R, XM - 1>::run(xm, seg, sw_row, s_cw, ctr, abg, arw);
+        if (xm == XM) bil_row<R, XM, BIL_DY_ANY>(seg, T, nullptr, row, ctr, abg, arw);
+        else BilRowSwitch<R, XM - 1>::run(xm, seg, T, row, ctr, abg, arw);
     }
 };
 template <int R>
 struct BilRowSwitch<R, -1> {
-    __device__ __forceinline__ static void run(int, const uint32_t (&)[BilGeom<R>::NSEG], const float*, const float*,
+    __device__ __forceinline__ static void run(int, const uint32_t (&)[BilGeom<R>::NSEG], const BilHead&, int,
                                                const uint32_t (&)[BIL_PX], unsigned long long (&)[BIL_PX],
                                                unsigned long long (&)[BIL_PX]) {}
 };
@@ -238,11 +272,11 @@ __host__ __device__ constexpr int bil_xmax(int R, int i) {
 
 // small windows: every tap row unrolled with its compile-time half-width (no row switch, no xmax loads)
 template <int R, int ROW>
-__device__ __forceinline__ void bil_rows_unrolled(const uint32_t* __restrict__ s_tile, const float* __restrict__ s_sw,
-                                                  const float* __restrict__ s_cw, int lx, int ly, const uint32_t (&ctr)[BIL_PX],
+__device__ __forceinline__ void bil_rows_unrolled(const uint32_t* __restrict__ s_tile, const BilHead& T, const float* __restrict__ s_cls, int lx, int ly,
+                                                  const uint32_t (&ctr)[BIL_PX],
                                                   unsigned long long (&abg)[BIL_PX], unsigned long long (&arw)[BIL_PX]) {
     if constexpr (ROW <= 2 * R) {
-        constexpr int TP = BilGeom<R>::TP, NSEG = BilGeom<R>::NSEG, D = BilGeom<R>::D;
+        constexpr int TP = BilGeom<R>::TP, NSEG = BilGeom<R>::NSEG;
         const uint4* rowp = reinterpret_cast<const uint4*>(s_tile + (ly + ROW) * TP + lx);
         uint32_t seg[NSEG];
 #pragma unroll
@@ -250,17 +284,17 @@ __device__ __forceinline__ void bil_rows_unrolled(const uint32_t* __restrict__ s
             const uint4 v = rowp[q];
             seg[4 * q] = v.x; seg[4 * q + 1] = v.y; seg[4 * q + 2] = v.z; seg[4 * q + 3] = v.w;
         }
-        bil_row<R, bil_xmax(R, ROW - R)>(seg, s_sw + ROW * D, s_cw, ctr, abg, arw);
-        bil_rows_unrolled<R, ROW + 1>(s_tile, s_sw, s_cw, lx, ly, ctr, abg, arw);
+        bil_row<R, bil_xmax(R, ROW - R), ROW - R>(seg, T, s_cls, ROW, ctr, abg, arw);
+        bil_rows_unrolled<R, ROW + 1>(s_tile, T, s_cls, lx, ly, ctr, abg, arw);
     }
 }
 
 constexpr int BIL_UNROLL_RMAX = 3;
+static_assert(BIL_CLS_RMAX <= BIL_UNROLL_RMAX, "class tables need compile-time tap rows");
 
 template <int R>
-__device__ __forceinline__ void bil_strip(const uint32_t* __restrict__ s_tile, const float* __restrict__ s_sw,
-                                       const float* __restrict__ s_cw, const int* __restrict__ s_xm,
-                                       int lx, int ly, uint32_t out[BIL_PX]) {
+__device__ __forceinline__ void bil_strip(const uint32_t* __restrict__ s_tile, const BilHead& T, const float* __restrict__ s_cls, int lx, int ly,
+                                          uint32_t out[BIL_PX]) {
     constexpr int TP = BilGeom<R>::TP, NSEG = BilGeom<R>::NSEG, D = BilGeom<R>::D;
     uint32_t ctr[BIL_PX];
     unsigned long long abg[BIL_PX], arw[BIL_PX];
@@ -270,7 +304,7 @@ __device__ __forceinline__ void bil_strip(const uint32_t* __restrict__ s_tile, c
         abg[j] = arw[j] = 0ull;
     }
     if constexpr (R <= BIL_UNROLL_RMAX) {
-        bil_rows_unrolled<R, 0>(s_tile, s_sw, s_cw, lx, ly, ctr, abg, arw);
+        bil_rows_unrolled<R, 0>(s_tile, T, s_cls, lx, ly, ctr, abg, arw);
     } else {
 #pragma unroll 1
         for (int row = 0; row < D; ++row) {
@@ -281,7 +315,7 @@ __device__ __forceinline__ void bil_strip(const uint32_t* __restrict__ s_tile, c
                 const uint4 v = rowp[q];
                 seg[4 * q] = v.x; seg[4 * q + 1] = v.y; seg[4 * q + 2] = v.z; seg[4 * q + 3] = v.w;
             }
-            BilRowSwitch<R, R>::run(s_xm[row], seg, s_sw + row * D, s_cw, ctr, abg, arw);
+            BilRowSwitch<R, R>::run(T.xmax[row], seg, T, row, ctr, abg, arw);
         }
     }
 #pragma unroll
@@ -294,35 +328,33 @@ __device__ __forceinline__ void bil_strip(const uint32_t* __restrict__ s_tile, c
     }
 }
 
-// dynamic shared memory: [ tile words | space_w | xmax | raw bytes | mbarrier ]; the colour LUT is static
-// shared memory so its base folds into the LDS immediate
+// dynamic shared memory: [ tile words | raw bytes | mbarrier | class tables (radius <= BIL_CLS_RMAX) ]; the head of the
+// parameter set (colour LUT, space weights, row half-widths) is static shared memory so its base folds into the LDS immediates
 __host__ __device__ inline int bil_tile_pitch(int r) { return (BIL_TW + 2 * r + 3) & ~3; }
 __host__ __device__ inline int bil_raw_pitch(int r) { return (((BIL_TW + 2 * r) * 3 + 15 + 15) & ~15) + 16; }
-__host__ __device__ inline int bil_sw_words(int r) { return ((2 * r + 1) * (2 * r + 1) + 3) & ~3; }
+__host__ __device__ inline int bil_class_bytes(int r) { return r <= BIL_CLS_RMAX ? bil_nclasses(r) * 768 * 4 : 0; }
 __host__ inline size_t bil_smem_bytes(int r, int ns) {
     size_t tile = (size_t)bil_tile_pitch(r) * (BIL_TH * ns + 2 * r) * 4;
     size_t raw = (size_t)bil_raw_pitch(r) * (BIL_TH * ns + 2 * r);
-    return tile + bil_sw_words(r) * 4 + 16 * 4 + raw + 16;
+    return tile + raw + 16 + bil_class_bytes(r);
 }
 
 __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ float s_cw[768];
+    __shared__ BilHead s_cand;
     const int tid = threadIdx.x;
     const int sel = a.sel ? *a.sel : 0;
     const BilCand* __restrict__ cand = a.cand + sel;
     const int R = a.radius[sel];
-    const int D = 2 * R + 1;
     const int TP = bil_tile_pitch(R);
     const int TH = BIL_TH * a.ns;
     const int TROWS = TH + 2 * R;
     const int RP = bil_raw_pitch(R);
 
     uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem);
-    float* s_sw = reinterpret_cast<float*>(smem + (size_t)TP * TROWS * 4);
-    int* s_xm = reinterpret_cast<int*>(s_sw + bil_sw_words(R));
-    uint8_t* s_raw = reinterpret_cast<uint8_t*>(s_xm + 16);
+    uint8_t* s_raw = smem + (size_t)TP * TROWS * 4;
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_raw + (size_t)RP * TROWS);
+    float* s_cls = reinterpret_cast<float*>(bar + 2);
 
     const int x0 = blockIdx.x * BIL_TW, y0 = blockIdx.y * TH;
     // valid source window (image coordinates) the halo tile touches
@@ -331,11 +363,9 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
     const int bx0 = (vx0 * 3) & ~15, bx1 = vx1 * 3;
     const bool fast = aligned16(a.src, a.spitch);
 
-    // the halo tile's bulk copies are in flight while the tables are fetched
-    stage_rows_issue(s_raw, RP, a.src, a.spitch, vy0, vy1, bx0, bx1, fast, bar);
-    for (int i = tid; i < D * D; i += BIL_NT) s_sw[i] = cand->space_w[i];
-    for (int i = tid; i < 768; i += BIL_NT) s_cw[i] = cand->color_w[i];
-    if (tid < D) s_xm[tid] = cand->xmax[tid];
+    // the halo tile and the parameter set arrive by bulk copies on one mbarrier
+    stage_rows_issue(s_raw, RP, a.src, a.spitch, vy0, vy1, bx0, bx1, fast, bar, &s_cand, &cand->head, (uint32_t)sizeof(BilHead),
+                     s_cls, cand->class_w, (uint32_t)bil_class_bytes(R));
     stage_rows_wait(s_raw, RP, a.src, a.spitch, 3 * a.w, vy0, vy1, bx0, bx1, fast, bar);
 
     // expand raw bytes -> BGR0 words with BORDER_REFLECT_101 resolved; warp per row, lanes along x
@@ -345,15 +375,16 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
         // BGR1 words with funnel shifts and byte permutes and stores them as one 128-bit word
         const int c0 = 3 * vx0 - bx0;                    // byte offset of tile column 0 inside a raw row, 0..15
         const int sh = 8 * (c0 & 3);
+        // the (row, 4-pixel group) items are spread over all threads, not a warp per row: TP/4 is 17-20 groups
         const int ng = TP >> 2;
-        const int lane = tid & 31, wrp = tid >> 5;
-        for (int ty = wrp; ty < TROWS; ty += BIL_NT / 32) {
+        const int dty = BIL_NT / ng, dg = BIL_NT - dty * ng;
+        int ty = tid / ng, g = tid - ty * ng;
+        for (; ty < TROWS; ty += dty) {
             int sy = y0 - R + ty;
             sy = sy < 0 ? -sy : sy; sy = sy >= a.h ? 2 * a.h - 2 - sy : sy;
-            if (lane >= ng) continue;
             uint4 o = make_uint4(0x01000000u, 0x01000000u, 0x01000000u, 0x01000000u);
             if (sy >= vy0 && sy < vy1) {                 // false only for unused rows of bottom-edge tiles
-                const uint32_t* q = reinterpret_cast<const uint32_t*>(s_raw + (sy - vy0) * RP + (c0 & ~3)) + 3 * lane;
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(s_raw + (sy - vy0) * RP + (c0 & ~3)) + 3 * g;
                 const uint32_t r0 = q[0], r1 = q[1], r2 = q[2], r3 = q[3];
                 const uint32_t w0 = __funnelshift_r(r0, r1, sh), w1 = __funnelshift_r(r1, r2, sh), w2 = __funnelshift_r(r2, r3, sh);
                 o.x = __byte_perm(w0, 0x01010101u, 0x4210);
@@ -361,7 +392,9 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
                 o.z = (__byte_perm(w1, w2, 0x3432) & 0x00ffffffu) | 0x01000000u;
                 o.w = __byte_perm(w2, 0x01010101u, 0x4321);
             }
-            *reinterpret_cast<uint4*>(s_tile + ty * TP + 4 * lane) = o;
+            *reinterpret_cast<uint4*>(s_tile + ty * TP + 4 * g) = o;
+            g += dg;
+            if (g >= ng) { g -= ng; ++ty; }
         }
     } else {
         const int TWH = BIL_TW + 2 * R;
@@ -414,13 +447,13 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
         }
         uint32_t out[BIL_PX];
         switch (R) {
-            case 1: bil_strip<1>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
-            case 2: bil_strip<2>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
-            case 3: bil_strip<3>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
-            case 4: bil_strip<4>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
-            case 5: bil_strip<5>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
-            case 6: bil_strip<6>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
-            default: bil_strip<7>(s_tile, s_sw, s_cw, s_xm, lx, ly, out); break;
+            case 1: bil_strip<1>(s_tile, s_cand, s_cls, lx, ly, out); break;
+            case 2: bil_strip<2>(s_tile, s_cand, s_cls, lx, ly, out); break;
+            case 3: bil_strip<3>(s_tile, s_cand, s_cls, lx, ly, out); break;
+            case 4: bil_strip<4>(s_tile, s_cand, s_cls, lx, ly, out); break;
+            case 5: bil_strip<5>(s_tile, s_cand, s_cls, lx, ly, out); break;
+            case 6: bil_strip<6>(s_tile, s_cand, s_cls, lx, ly, out); break;
+            default: bil_strip<7>(s_tile, s_cand, s_cls, lx, ly, out); break;
         }
         if (a.emap) {
             // 2x2 dilate (anchor (1,1)): pixel x is an edge if map[y-1..y][x-1..x] holds a 2.  The strip's four

@@ -39,13 +39,15 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // try_wait suspends the thread in hardware for up to the hint (ns) before it returns false, so the loop body is
+    // issued a handful of times, not once per scheduler slot
     uint32_t done;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
     } while (!done);
 }
 // 16-byte aligned src, dst; bytes a multiple of 16
@@ -65,20 +67,33 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // s_raw + (r-y0)*s_pitch, byte b at offset b-bx0.  `fast` (base and pitch 16-byte aligned) uses one TMA bulk copy
 // per row issued by warp 0 and completing on `bar` (parity 0); otherwise all threads copy bytes.  The staging is split
 // in two so a kernel can fill its tables while the bulk copies are in flight: stage_rows_issue() starts the copies
-// (fast path; contains one __syncthreads), stage_rows_wait() returns once the rows are visible.  Every thread must
-// call both, with the same arguments.
+// (fast path: warp 0 only, no CTA barrier), stage_rows_wait() returns once the rows are visible to every thread.
+// Only warp 0 polls the mbarrier - the other warps sleep in the CTA barrier behind it instead of spending issue slots
+// on a spin loop (ncu: the all-warps spin was 3-8 % of the executed instructions of the tiled kernels).  Every thread
+// must call both, with the same arguments.  `tab_*` / `tab2_*`: optional table blocks (16-byte aligned, a multiple of
+// 16 bytes) fetched by one more bulk copy each on the same mbarrier; on the slow path the threads copy them word by word.
 __device__ __forceinline__ void stage_rows_issue(uint8_t* s_raw, int s_pitch, const uint8_t* __restrict__ g, size_t gpitch,
-                                                 int y0, int y1, int bx0, int bx1, bool fast, uint64_t* bar) {
-    if (!fast) return;
-    const int tid = threadIdx.x, nrows = y1 - y0;
-    const int nb = ((bx1 + 15) & ~15) - bx0;
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        mbar_fence_init();
+                                                 int y0, int y1, int bx0, int bx1, bool fast, uint64_t* bar,
+                                                 void* tab_dst = nullptr, const void* tab_src = nullptr, uint32_t tab_bytes = 0,
+                                                 void* tab2_dst = nullptr, const void* tab2_src = nullptr, uint32_t tab2_bytes = 0) {
+    const int tid = threadIdx.x;
+    if (!fast) {
+        for (uint32_t i = tid; i < tab_bytes / 4; i += blockDim.x)
+            reinterpret_cast<uint32_t*>(tab_dst)[i] = reinterpret_cast<const uint32_t*>(tab_src)[i];
+        for (uint32_t i = tid; i < tab2_bytes / 4; i += blockDim.x)
+            reinterpret_cast<uint32_t*>(tab2_dst)[i] = reinterpret_cast<const uint32_t*>(tab2_src)[i];
+        return;
     }
-    __syncthreads();
     if (tid < 32) {
-        if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nb * nrows));
+        const int nrows = y1 - y0;
+        const int nb = ((bx1 + 15) & ~15) - bx0;
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            mbar_fence_init();
+            mbar_arrive_expect_tx(bar, (uint32_t)(nb * nrows) + tab_bytes + tab2_bytes);
+            if (tab_bytes) bulk_g2s(tab_dst, tab_src, tab_bytes, bar);
+            if (tab2_bytes) bulk_g2s(tab2_dst, tab2_src, tab2_bytes, bar);
+        }
         __syncwarp();
         for (int r = tid; r < nrows; r += 32)
             bulk_g2s(s_raw + r * s_pitch, g + (size_t)(y0 + r) * gpitch + bx0, (uint32_t)nb, bar);
@@ -86,7 +101,11 @@ __device__ __forceinline__ void stage_rows_issue(uint8_t* s_raw, int s_pitch, co
 }
 __device__ __forceinline__ void stage_rows_wait(uint8_t* s_raw, int s_pitch, const uint8_t* __restrict__ g, size_t gpitch,
                                                 int row_bytes, int y0, int y1, int bx0, int bx1, bool fast, uint64_t* bar) {
-    if (fast) { mbar_wait(bar, 0); return; }
+    if (fast) {
+        if (threadIdx.x < 32) mbar_wait(bar, 0);
+        __syncthreads();
+        return;
+    }
     const int tid = threadIdx.x, nt = blockDim.x, nrows = y1 - y0;
     const int e = min(bx1, row_bytes);
     const int nb = e - bx0;

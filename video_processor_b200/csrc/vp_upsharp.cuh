@@ -241,10 +241,12 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
             // BGR0 words with funnel shifts and byte permutes and stores them as one 128-bit word
             const int c0 = 3 * ux0 - bx0;               // byte offset of window column 0 inside a raw row, 0..15
             const int sh = 8 * (c0 & 3);
+            // the (row, 4-pixel group) items are spread over all threads, not a warp per row: a row is ~10 groups
             const int ng = (ncols + 3) >> 2;
-            for (int rr = wrp; rr < nrows; rr += US_NT / 32) {
-                if (lane >= ng) continue;
-                const uint32_t* q = reinterpret_cast<const uint32_t*>(s_raw + (clampi(uy0 + rr, 0, a.sh - 1) - sy0) * RP + (c0 & ~3)) + 3 * lane;
+            const int drr = US_NT / ng, dg = US_NT - drr * ng;
+            int rr = tid / ng, g = tid - rr * ng;
+            for (; rr < nrows; rr += drr) {
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(s_raw + (clampi(uy0 + rr, 0, a.sh - 1) - sy0) * RP + (c0 & ~3)) + 3 * g;
                 const uint32_t r0 = q[0], r1 = q[1], r2 = q[2], r3 = q[3];
                 const uint32_t w0 = __funnelshift_r(r0, r1, sh), w1 = __funnelshift_r(r1, r2, sh), w2 = __funnelshift_r(r2, r3, sh);
                 uint4 o;
@@ -252,7 +254,9 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
                 o.y = __byte_perm(w0, w1, 0x7543) & 0x00ffffffu;
                 o.z = __byte_perm(w1, w2, 0x7432) & 0x00ffffffu;
                 o.w = w2 >> 8;
-                *reinterpret_cast<uint4*>(s_src + rr * SP + 4 * lane) = o;
+                *reinterpret_cast<uint4*>(s_src + rr * SP + 4 * g) = o;
+                g += dg;
+                if (g >= ng) { g -= ng; ++rr; }
             }
         } else {
             for (int rr = wrp; rr < nrows; rr += US_NT / 32) {

@@ -234,15 +234,28 @@ int check_frame(vp_ctx* c, const void* p, size_t pitch, int w, int h, const char
 // ---- table uploads ------------------------------------------------------------------------------
 void fill_cand(BilCand& bc, const vp_host::BilateralTables& t) {
     std::memset(&bc, 0, sizeof(bc));
-    bc.radius = t.radius;
-    bc.d = t.d;
+    bc.head.radius = t.radius;
+    bc.head.d = t.d;
     for (int i = -t.radius; i <= t.radius; ++i) {
         int xm = 0;
         while ((xm + 1) * (xm + 1) + i * i <= t.radius * t.radius) ++xm;
-        bc.xmax[i + t.radius] = xm;
+        bc.head.xmax[i + t.radius] = xm;
     }
-    std::memcpy(bc.space_w, t.space_w.data(), t.space_w.size() * sizeof(float));
-    std::memcpy(bc.color_w, t.color_w.data(), 768 * sizeof(float));
+    std::memcpy(bc.head.space_w, t.space_w.data(), t.space_w.size() * sizeof(float));
+    std::memcpy(bc.head.color_w, t.color_w.data(), 768 * sizeof(float));
+    if (t.radius <= BIL_CLS_RMAX) {            // class tables: the tap weight space_w * color_w[n] formed here, once
+        const int D = 2 * t.radius + 1;
+        for (int i = -t.radius; i <= t.radius; ++i)
+            for (int j = -t.radius; j <= t.radius; ++j) {
+                const int cls = bil_class_of(i * i + j * j);
+                if (i * i + j * j > t.radius * t.radius || cls < 0) continue;
+                const volatile float sw = t.space_w[(size_t)(i + t.radius) * D + (j + t.radius)];
+                for (int n = 0; n < 768; ++n) {
+                    const volatile float prod = sw * bc.head.color_w[n];      // one IEEE single multiply, as the kernel's FMUL
+                    bc.class_w[cls][n] = prod;
+                }
+            }
+    }
 }
 
 int build_selective_cands(vp_ctx* c, const vp_bilateral_config& cfg, BilCand* d_cand, int radius[3], cudaStream_t st) {
@@ -368,7 +381,9 @@ int launch_bilateral(vp_ctx* c, BilArgs& a, const int radius[3], cudaStream_t st
     for (int i = 0; i < 3; ++i) { a.radius[i] = radius[i]; rmax = std::max(rmax, radius[i]); }
     a.ns = rmax <= 2 ? 4 : (rmax <= 3 ? 2 : 1);     // small windows: taller tiles amortise the per-CTA table/halo cost
     const dim3 grid((a.w + BIL_TW - 1) / BIL_TW, (a.h + BIL_TH * a.ns - 1) / (BIL_TH * a.ns));
-    k_bilateral<<<grid, BIL_NT, bil_smem_bytes(rmax, a.ns), st>>>(a);
+    size_t smem = 0;                                // the device picks one of the candidates: size for the largest layout
+    for (int i = 0; i < 3; ++i) smem = std::max(smem, bil_smem_bytes(radius[i], a.ns));
+    k_bilateral<<<grid, BIL_NT, smem, st>>>(a);
     VP_CUDA(c, cudaGetLastError());
     c->launches++;
     return VP_OK;
@@ -1077,7 +1092,12 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
     VP_CUDA(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     VP_CUDA(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
     VP_CUDA(c, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
-    VP_CUDA(c, cudaFuncSetAttribute(k_bilateral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(bil_smem_bytes(BIL_RMAX, 1), std::max(bil_smem_bytes(3, 2), bil_smem_bytes(2, 4)))));
+    {
+        size_t bil_max = 0;                         // every (candidate radius, strips per thread) pair launch_bilateral can pick
+        for (int rmax = 1; rmax <= BIL_RMAX; ++rmax)
+            for (int r = 1; r <= rmax; ++r) bil_max = std::max(bil_max, bil_smem_bytes(r, rmax <= 2 ? 4 : (rmax <= 3 ? 2 : 1)));
+        VP_CUDA(c, cudaFuncSetAttribute(k_bilateral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bil_max));
+    }
     VP_CUDA(c, cudaFuncSetAttribute(k_bicubic<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_bicubic<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_bicubic<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
