@@ -72,6 +72,10 @@ struct BilArgs {
     // sum |gray(out) - gray(previous unblended frame = blend.prev[0])|; null = off
     SceneAccum* scene;
     BlendArgs blend;
+    // 16-byte aligned frames: the halo tile of candidate i arrives as one tensor-map box (bil_raw_pitch(r_i) - 16 bytes wide,
+    // BIL_TH * ns + 2 r_i rows) instead of one bulk copy per row
+    int use_tm;
+    alignas(64) CUtensorMap tm[3];
 };
 
 // exact u8 -> f32: bytes [b,0,0,0x4B] are the float 2^23 + b
@@ -205,6 +209,9 @@ template <int R> struct BilGeom {
 //   * the centre tap (colour distance 0 by construction): its weight space_w(0) * color_w[0] is formed once per row call;
 //   * with class tables (R <= BIL_CLS_RMAX, DY known) the weight is class_w[class(DY^2 + dx^2)][n], the host-made product.
 constexpr int BIL_DY_ANY = 99;
+#ifndef VP_BIL_I2F
+#define VP_BIL_I2F 1
+#endif
 template <int R, int XM, int DY>
 __device__ __forceinline__ void bil_row(const uint32_t (&seg)[BilGeom<R>::NSEG], const BilHead& T, const float* __restrict__ s_cls, int row,
                                         const uint32_t (&ctr)[BIL_PX],
@@ -218,8 +225,18 @@ __device__ __forceinline__ void bil_row(const uint32_t (&seg)[BilGeom<R>::NSEG],
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const uint32_t p = seg[i + R - XM];
+#if VP_BIL_I2F >= 1
+        // (b, g) through the conversion unit (I2F.U8 with a byte selector, one instruction per value on the otherwise
+        // idle XU pipe) instead of two PRMTs and half a FADD2 on the ALU / FMA pipes
+        pbg[i] = pack2(__float_as_uint((float)(p & 0xffu)), __float_as_uint((float)((p >> 8) & 0xffu)));
+#else
         pbg[i] = fadd2(pack2(__byte_perm(p, 0x4B000000u, 0x7440), __byte_perm(p, 0x4B000000u, 0x7441)), bias);
+#endif
+#if VP_BIL_I2F >= 2
+        pra[i] = pack2(__float_as_uint((float)((p >> 16) & 0xffu)), 0x3f800000u);
+#else
         pra[i] = fadd2(pack2(__byte_perm(p, 0x4B000000u, 0x7442), __byte_perm(p, 0x4B000000u, 0x7443)), bias);
+#endif
     }
 #pragma unroll
     for (int dx = -XM; dx <= XM; ++dx) {
@@ -333,13 +350,14 @@ __device__ __forceinline__ void bil_strip(const uint32_t* __restrict__ s_tile, c
 __host__ __device__ inline int bil_tile_pitch(int r) { return (BIL_TW + 2 * r + 3) & ~3; }
 __host__ __device__ inline int bil_raw_pitch(int r) { return (((BIL_TW + 2 * r) * 3 + 15 + 15) & ~15) + 16; }
 __host__ __device__ inline int bil_class_bytes(int r) { return r <= BIL_CLS_RMAX ? bil_nclasses(r) * 768 * 4 : 0; }
+__host__ __device__ inline size_t bil_tile_bytes(int r, int trows) { return ((size_t)bil_tile_pitch(r) * trows * 4 + 127) & ~(size_t)127; }
 __host__ inline size_t bil_smem_bytes(int r, int ns) {
-    size_t tile = (size_t)bil_tile_pitch(r) * (BIL_TH * ns + 2 * r) * 4;
+    size_t tile = bil_tile_bytes(r, BIL_TH * ns + 2 * r);
     size_t raw = (size_t)bil_raw_pitch(r) * (BIL_TH * ns + 2 * r);
     return tile + raw + 16 + bil_class_bytes(r);
 }
 
-__global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
+__global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const __grid_constant__ BilArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ BilHead s_cand;
     const int tid = threadIdx.x;
@@ -349,11 +367,12 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
     const int TP = bil_tile_pitch(R);
     const int TH = BIL_TH * a.ns;
     const int TROWS = TH + 2 * R;
-    const int RP = bil_raw_pitch(R);
+    const bool tm = a.use_tm != 0;                          // implies 16-byte aligned frames
+    const int RP = bil_raw_pitch(R) - (tm ? 16 : 0);        // a TMA box is dense
 
     uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem);
-    uint8_t* s_raw = smem + (size_t)TP * TROWS * 4;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_raw + (size_t)RP * TROWS);
+    uint8_t* s_raw = smem + bil_tile_bytes(R, TROWS);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_raw + (size_t)bil_raw_pitch(R) * TROWS);
     float* s_cls = reinterpret_cast<float*>(bar + 2);
 
     const int x0 = blockIdx.x * BIL_TW, y0 = blockIdx.y * TH;
@@ -364,8 +383,10 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const BilArgs a) {
     const bool fast = aligned16(a.src, a.spitch);
 
     // the halo tile and the parameter set arrive by bulk copies on one mbarrier
-    stage_rows_issue(s_raw, RP, a.src, a.spitch, vy0, vy1, bx0, bx1, fast, bar, &s_cand, &cand->head, (uint32_t)sizeof(BilHead),
-                     s_cls, cand->class_w, (uint32_t)bil_class_bytes(R));
+    if (tm) stage_box_issue(s_raw, &a.tm[sel], bx0, vy0, (uint32_t)(RP * TROWS), bar, &s_cand, &cand->head, (uint32_t)sizeof(BilHead),
+                            s_cls, cand->class_w, (uint32_t)bil_class_bytes(R));
+    else stage_rows_issue(s_raw, RP, a.src, a.spitch, vy0, vy1, bx0, bx1, fast, bar, &s_cand, &cand->head, (uint32_t)sizeof(BilHead),
+                          s_cls, cand->class_w, (uint32_t)bil_class_bytes(R));
     stage_rows_wait(s_raw, RP, a.src, a.spitch, 3 * a.w, vy0, vy1, bx0, bx1, fast, bar);
 
     // expand raw bytes -> BGR0 words with BORDER_REFLECT_101 resolved; warp per row, lanes along x

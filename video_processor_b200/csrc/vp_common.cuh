@@ -1,6 +1,7 @@
 // vp_common.cuh - device helpers shared by the sm_100a kernels of libvpb200.
 // Border maps, TMA (bulk async copy) row staging with an mbarrier, saturating casts.
 #pragma once
+#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -63,6 +64,20 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// 2-D tensor-map TMA (SASS UTMALDG / UTMASTG): one instruction moves a whole box; rows outside the tensor are
+// zero-filled on loads and clipped on stores.  Shared-memory side 128-byte aligned, dense rows of the box width.
+__device__ __forceinline__ void tma_load_2d(void* sdst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(sdst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, const void* ssrc) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(ssrc)) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+
 // Stage image rows [y0,y1) x bytes [bx0,bx1) (bx0 a multiple of 16) into shared memory, row r at
 // s_raw + (r-y0)*s_pitch, byte b at offset b-bx0.  `fast` (base and pitch 16-byte aligned) uses one TMA bulk copy
 // per row issued by warp 0 and completing on `bar` (parity 0); otherwise all threads copy bytes.  The staging is split
@@ -114,6 +129,22 @@ __device__ __forceinline__ void stage_rows_wait(uint8_t* s_raw, int s_pitch, con
         s_raw[r * s_pitch + b] = g[(size_t)(y0 + r) * gpitch + bx0 + b];
     }
     __syncthreads();
+}
+
+// The same staging as ONE tensor-map box (SASS UTMALDG): box rows are dense in shared memory (pitch = box width), the
+// part of the box outside the image is zero-filled and still counted, so the expected byte count is the whole box.
+// Thread 0 issues; pair with stage_rows_wait(..., fast = true, ...).  s_raw 128-byte aligned.
+__device__ __forceinline__ void stage_box_issue(uint8_t* s_raw, const CUtensorMap* tm, int c0, int c1, uint32_t box_bytes, uint64_t* bar,
+                                                void* tab_dst = nullptr, const void* tab_src = nullptr, uint32_t tab_bytes = 0,
+                                                void* tab2_dst = nullptr, const void* tab2_src = nullptr, uint32_t tab2_bytes = 0) {
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        mbar_arrive_expect_tx(bar, box_bytes + tab_bytes + tab2_bytes);
+        tma_load_2d(s_raw, tm, c0, c1, bar);
+        if (tab_bytes) bulk_g2s(tab_dst, tab_src, tab_bytes, bar);
+        if (tab2_bytes) bulk_g2s(tab2_dst, tab2_src, tab2_bytes, bar);
+    }
 }
 
 __device__ __forceinline__ bool aligned16(const void* p, size_t pitch) {

@@ -60,6 +60,11 @@ struct UpsharpArgs {
     const float* mask_in; size_t mask_in_pitch;      // optional: use this mask instead of computing it
     unsigned long long* sums;    // optional: accumulate sum x / sum x^2 of the output (6 x u64)
     SelOut fin;                  // optional: last CTA turns the sums into the POST noise class
+    // 16-byte aligned frames: the source window arrives (box raw_pitch - 16 bytes x max_src_rows) and the finished tile
+    // leaves (box US_TW * 3 bytes x US_TH) as one tensor-map TMA box each
+    int use_tm_src, use_tm_dst;
+    alignas(64) CUtensorMap tm_src;
+    alignas(64) CUtensorMap tm_dst;
 };
 
 struct UpsharpSmem {             // byte offsets into dynamic shared memory
@@ -173,7 +178,7 @@ __device__ __forceinline__ void p2_fast(const float* __restrict__ s_hs, const in
 }
 
 template <bool RESIZE, bool SHARPEN, int GK>
-__global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
+__global__ void __launch_bounds__(US_NT) k_upsharp(const __grid_constant__ UpsharpArgs a) {
     constexpr int HALO = SHARPEN ? US_HALO : 0;
     constexpr int EW = US_TW + 2 * HALO, EH = US_TH + 2 * HALO;
     constexpr int GR = GK / 2;
@@ -215,9 +220,11 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
     const int sx0 = clampi(ux0, 0, a.sw - 1), sx1 = clampi(ux1, 0, a.sw - 1);
     const int sy0 = clampi(uy0, 0, a.sh - 1), sy1 = clampi(uy1, 0, a.sh - 1);
     const int bx0 = (sx0 * 3) & ~15, bx1 = (sx1 + 1) * 3;
-    const int RP = L.raw_pitch;
+    const bool tm_src = a.use_tm_src != 0;                    // implies fast_stage
+    const int RP = L.raw_pitch - (tm_src ? 16 : 0);           // a TMA box is dense
     const bool fast_stage = aligned16(a.src, a.spitch);
-    stage_rows_issue(s_raw, RP, a.src, a.spitch, sy0, sy1 + 1, bx0, bx1, fast_stage, bar);
+    if (tm_src) stage_box_issue(s_raw, &a.tm_src, bx0, sy0, (uint32_t)(RP * a.max_src_rows), bar);
+    else stage_rows_issue(s_raw, RP, a.src, a.spitch, sy0, sy1 + 1, bx0, bx1, fast_stage, bar);
     if (RESIZE) {
         for (int i = tid; i < EW; i += US_NT) {
             const int dx = clampi(reflect101(x0 - HALO + i, a.dw), dxa, dxb);   // clamp: unused columns of edge tiles
@@ -542,7 +549,10 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const UpsharpArgs a) {
     if (a.sums && (tid >> 5) == 1) warp_flush_and_finalize(s_part, US_NT / 32, a.sums, a.fin, gridDim.x * gridDim.y);
 
     // ---- P6: staged tile -> HBM: one TMA bulk store per row (16-byte aligned frames), else bytes ----
-    if (a.dst) {
+    if (a.dst && a.use_tm_dst) {
+        // one box store; the part of an edge tile outside the frame is clipped by the TMA unit
+        if (tid == 0) { tma_store_2d(&a.tm_dst, x0 * 3, y0, s_out); bulk_commit(); bulk_wait_read0(); }
+    } else if (a.dst) {
         const int rb = vw * 3;                               // valid bytes per tile row
         const bool al = aligned16(a.dst, a.dpitch);          // x0*3 = 192*blockIdx.x is a multiple of 16
         const int nb16 = al ? (rb & ~15) : 0;

@@ -361,6 +361,33 @@ int ensure_siglut(vp_ctx* c, float** d_lut, float* cached_thr, bool* valid, floa
     return VP_OK;
 }
 
+// ---- tensor maps (2-D TMA boxes) -------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled is a host-side pure function of the driver; it is fetched through the runtime so the library
+// carries no link-time dependency on libcuda (it must still load, and refuse, on a machine without a driver).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+// rows of `w_elems` elements (1 or 2 bytes each), `h` rows `pitch` bytes apart (a multiple of 16, base 16-byte aligned)
+bool make_tmap_2d(CUtensorMap* tm, int elem_bytes, const void* base, uint64_t w_elems, uint64_t h, uint64_t pitch, uint32_t box_w, uint32_t box_h) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || ((uintptr_t)base & 15) || (pitch & 15) || box_w > 256 || box_h > 256) return false;
+    const cuuint64_t gdim[2] = {w_elems, h}, gstride[1] = {pitch};
+    const cuuint32_t box[2] = {box_w, box_h}, estr[2] = {1, 1};
+    return fn(tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride,
+              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // ---- launches -----------------------------------------------------------------------------------
 int launch_stats(vp_ctx* c, const uint8_t* src, size_t pitch, int w, int h, unsigned long long* sums, const SelOut& fin, cudaStream_t st) {
     ProfScope ps(c, K_STATS, st);
@@ -383,6 +410,12 @@ int launch_bilateral(vp_ctx* c, BilArgs& a, const int radius[3], cudaStream_t st
     const dim3 grid((a.w + BIL_TW - 1) / BIL_TW, (a.h + BIL_TH * a.ns - 1) / (BIL_TH * a.ns));
     size_t smem = 0;                                // the device picks one of the candidates: size for the largest layout
     for (int i = 0; i < 3; ++i) smem = std::max(smem, bil_smem_bytes(radius[i], a.ns));
+    a.use_tm = 1;                                   // one box per candidate radius
+    for (int i = 0; i < 3 && a.use_tm; ++i) {
+        if (i > 0 && radius[i] == radius[i - 1]) { a.tm[i] = a.tm[i - 1]; continue; }
+        a.use_tm = make_tmap_2d(&a.tm[i], 1, a.src, (uint64_t)a.w * 3, a.h, a.spitch, (uint32_t)bil_raw_pitch(radius[i]) - 16,
+                                (uint32_t)(BIL_TH * a.ns + 2 * radius[i]));
+    }
     k_bilateral<<<grid, BIL_NT, smem, st>>>(a);
     VP_CUDA(c, cudaGetLastError());
     c->launches++;
@@ -908,6 +941,8 @@ int launch_upsharp(vp_ctx* c, UpsharpArgs& a, bool do_resize, bool do_sharpen, c
     const UpsharpSmem L = upsharp_layout(do_resize, do_sharpen, a.max_src_rows, a.max_src_cols);
     if (L.total > 200 * 1024) return fail(c, VP_ERR_UNSUPPORTED, "resize ratio needs more shared memory than a CTA has");
     const dim3 grid((a.dw + US_TW - 1) / US_TW, (a.dh + US_TH - 1) / US_TH);
+    a.use_tm_src = make_tmap_2d(&a.tm_src, 1, a.src, (uint64_t)a.sw * 3, a.sh, a.spitch, (uint32_t)L.raw_pitch - 16, (uint32_t)a.max_src_rows);
+    a.use_tm_dst = a.dst && make_tmap_2d(&a.tm_dst, 1, a.dst, (uint64_t)a.dw * 3, a.dh, a.dpitch, US_TW * 3, US_TH);
     ProfScope ps(c, K_UPSHARP, st);
     if (!do_sharpen) k_upsharp<true, false, 5><<<grid, US_NT, L.total, st>>>(a);
     else if (do_resize) {
@@ -932,10 +967,17 @@ int launch_bicubic(vp_ctx* c, const uint8_t* src, size_t spitch, int sw, int sh,
         b.src = src; b.spitch = spitch; b.sw = sw; b.sh = sh; b.dst = dst; b.dpitch = dpitch; b.dw = dw; b.dh = dh;
         for (int p = 0; p < 4; ++p)
             for (int t = 0; t < 4; ++t) { b.xk[p][t] = make_float2(rcache.xk[p][t], rcache.xk[p][t]); b.yk[p][t] = make_float2(rcache.yk[p][t], rcache.yk[p][t]); }
-        const dim3 grid((dw + BI_TW - 1) / BI_TW, (dh + BI_TH - 1) / BI_TH);
+        if (rcache.int_ratio == 2)
+            b.use_tm = make_tmap_2d(&b.tm_src, 1, src, (uint64_t)sw * 3, sh, spitch, BicubicIntGeom<2>::WB, BicubicIntGeom<2>::WR) &&
+                       make_tmap_2d(&b.tm_dst, 2, dst, (uint64_t)dw * 3 / 2, dh, dpitch, BI_TW * 3 / 2, BI_TH);
+        else
+            b.use_tm = make_tmap_2d(&b.tm_src, 1, src, (uint64_t)sw * 3, sh, spitch, BicubicIntGeom<4>::WB, BicubicIntGeom<4>::WR) &&
+                       make_tmap_2d(&b.tm_dst, 2, dst, (uint64_t)dw * 3 / 2, dh, dpitch, BI_TW * 3 / 2, BI_TH);
+        const int ntx = (dw + BI_TW - 1) / BI_TW, ntiles = ntx * ((dh + BI_TH - 1) / BI_TH);
+        const int grid = (ntiles + BI_K - 1) / BI_K;
         ProfScope ps(c, K_UPSHARP, st);
-        if (rcache.int_ratio == 2) k_bicubic_int<2><<<grid, BI_NT, BicubicIntGeom<2>::TOTAL, st>>>(b);
-        else k_bicubic_int<4><<<grid, BI_NT, BicubicIntGeom<4>::TOTAL, st>>>(b);
+        if (rcache.int_ratio == 2) k_bicubic_int<2><<<grid, BI_NT, BicubicIntGeom<2>::TOTAL, st>>>(b, ntx, ntiles);
+        else k_bicubic_int<4><<<grid, BI_NT, BicubicIntGeom<4>::TOTAL, st>>>(b, ntx, ntiles);
         VP_CUDA(c, cudaGetLastError());
         c->launches++;
         return VP_OK;
