@@ -673,7 +673,7 @@ def main():
                        "l2": f"inputs ({F}x{inb >> 20} MiB) and output ring ({NOUT}x{outb >> 20} MiB) exceed the 126 MB L2",
                        "roofline_pass": "per-kernel CUDA events in a separate pass of one step, one stream, one frame at a time",
                        "api": "vp_process_device per frame" if args.per_frame else "vp_process_batch_device (four stream lanes)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(tl.item()), "roofline": roof, "cpu_baseline": cpu, "latency": latency, "latency_c5": latency_c5,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(tl.item()), "batch_graph_replays": int(capi.lib.vp_batch_graph_replays(h)), "roofline": roof, "cpu_baseline": cpu, "latency": latency, "latency_c5": latency_c5,
             "parity_check": ("ok" if parity and all(v["result"] == "ok" for v in parity.values()) else ("FAILED" if parity else None)),
             "parity_detail": parity or None,
         }

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VPB200_ABI_VERSION 4
+#define VPB200_ABI_VERSION 5
 
 typedef enum vp_status {
     VP_OK = 0,
@@ -172,6 +172,13 @@ int vp_process_device(vp_ctx* ctx, const uint8_t* d_src, size_t src_pitch,
  * before / after the whole batch.  d_dst[i] == NULL marks a warm-up frame; d_dst[i] and d_dst[i+1]
  * must not alias. */
 int vp_set_batch_lanes(vp_ctx* ctx, int lanes);     /* 1..4 stream lanes for the batch call (default 4) */
+/* CUDA-graph replay (default on): a batch of >= 8 frames whose arguments - frame pointers, pitches, stream, temporal ring
+ * position - repeat is captured on its second sighting and afterwards launched as ONE instantiated graph (file mode cycles
+ * through a fixed ring of frame buffers; src/main.cpp:222-355).  Only chains whose frames are plain kernel launches are
+ * captured (the north-star chain and its bicubic-only / no-temporal forms); results are bit-identical either way.
+ * vp_batch_graph_replays counts the batches that went out as a graph. */
+int vp_set_batch_graphs(vp_ctx* ctx, int on);
+uint64_t vp_batch_graph_replays(const vp_ctx* ctx);
 int vp_process_batch_device(vp_ctx* ctx, int n, const uint8_t* const* d_src, size_t src_pitch,
                             uint8_t* const* d_dst, size_t dst_pitch, void* stream);
 /* Host frames, synchronous (pinned staging inside when the buffers are not pinned). */

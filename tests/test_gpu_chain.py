@@ -161,6 +161,52 @@ def test_batch_api_is_bit_identical_to_per_frame(vp, temporal):
                 assert np.array_equal(dsts[i].cpu().numpy(), ref[i]), i
 
 
+@pytest.mark.parametrize("temporal", [RC.TEMPORAL_NONE, RC.TEMPORAL_MAIN_BLEND, RC.TEMPORAL_BLEND_FRAMES])
+def test_batch_graph_replay_is_bit_identical(vp, temporal):
+    """The CUDA-graph form of vp_process_batch_device: the same batch (same frame buffers, same ring position) runs
+    eagerly, is captured on its second sighting and replayed afterwards; every pass must equal one vp_process_device call
+    per frame - also after the input buffers' CONTENTS changed (the graph bakes pointers, not pixels) and with graphs
+    switched off again."""
+    sw, sh, n = 128, 72, 12
+    ocfg = RC.ChainConfig(dst_w=2 * sw, dst_h=2 * sh, temporal=temporal)
+    clips = [synth.clip("scene", sw, sh, n), synth.clip("noise", sw, sh, n)]
+    flags = [False] * 3 + [True] * (n - 3)
+    refs = [run_chain_device(vp, ocfg, fr, sw, sh, outputs=flags)[0] for fr in clips]
+    cfg = G.chain_cfg(vp, ocfg, sw, sh)
+    with vp.Context(cfg) as ctx:
+        srcs = [G.to_dev(f) for f in clips[0]]
+        dsts = [G.dev_empty(ocfg.dst_h, ocfg.dst_w) if fl else None for fl in flags]
+        sp = (C.c_void_p * n)(*[t.data_ptr() for t in srcs])
+        dp = (C.c_void_p * n)(*[d.data_ptr() if d is not None else None for d in dsts])
+
+        def run_and_check(ref):
+            ctx.call("vp_reset_temporal")
+            for d in dsts:
+                if d is not None:
+                    d.zero_()
+            ctx.call("vp_process_batch_device", n, sp, sw * 3, dp, ocfg.dst_w * 3, None)
+            ctx.call("vp_synchronize")
+            for i in range(n):
+                if flags[i]:
+                    assert np.array_equal(dsts[i].cpu().numpy(), ref[i]), i
+
+        for _ in range(4):                    # eager, capture + launch, replay, replay
+            run_and_check(refs[0])
+        assert vp.lib.vp_batch_graph_replays(ctx.handle) == 3
+        for t, f in zip(srcs, clips[1]):      # new pixels behind the same pointers
+            t.copy_(G.to_dev(f))
+        run_and_check(refs[1])
+        assert vp.lib.vp_batch_graph_replays(ctx.handle) == 4
+        ctx.call("vp_set_batch_graphs", 0)
+        run_and_check(refs[1])
+        assert vp.lib.vp_batch_graph_replays(ctx.handle) == 4
+        # switched on again: the cache was dropped, so one eager pass, then a fresh capture
+        ctx.call("vp_set_batch_graphs", 1)
+        run_and_check(refs[1])
+        run_and_check(refs[1])
+        assert vp.lib.vp_batch_graph_replays(ctx.handle) == 5
+
+
 @pytest.mark.parametrize("kind", ["scene", "noise", "flat"])
 @pytest.mark.parametrize("size,scale", [((160, 96), 2), ((131, 67), 2), ((96, 54), 4)])
 def test_bicubic_wrapper_chain(vp, kind, size, scale):

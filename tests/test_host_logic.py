@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(vp):
     assert declared == set(vp.PROTOTYPES), declared ^ set(vp.PROTOTYPES)
     for name in declared:
         assert hasattr(vp.lib, name)
-    assert vp.lib.vp_abi_version() == 4
+    assert vp.lib.vp_abi_version() == 5
 
 
 def test_struct_layout_matches_header(vp):

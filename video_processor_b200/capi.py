@@ -72,6 +72,8 @@ PROTOTYPES = {
     "vp_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
     "vp_process_device": (C.c_int, [_vp, _u8p, _sz, _u8p, _sz, C.c_void_p]),
     "vp_set_batch_lanes": (C.c_int, [_vp, C.c_int]),
+    "vp_set_batch_graphs": (C.c_int, [_vp, C.c_int]),
+    "vp_batch_graph_replays": (C.c_uint64, [_vp]),
     "vp_process_batch_device": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_void_p), _sz, C.POINTER(C.c_void_p), _sz, C.c_void_p]),
     "vp_process_host": (C.c_int, [_vp, _u8p, _sz, _u8p, _sz]),
     "vp_pipeline_depth": (C.c_int, [_vp]),

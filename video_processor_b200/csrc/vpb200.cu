@@ -136,6 +136,14 @@ struct Lane {                       // per-frame intermediates; the lanes let co
 struct vp_ctx {
     int device = 0;
     Lane lanes[4];
+    // CUDA-graph replay of vp_process_batch_device: a batch whose arguments (frame pointers, pitches, temporal ring
+    // position) were seen before is launched as one instantiated graph instead of 1-4 kernel launches per frame from the
+    // host - file mode cycles through a fixed ring of frame buffers, and the bicubic-only chains are launch-bound otherwise
+    struct BatchGraph { uint64_t key = 0; cudaGraphExec_t exec = nullptr; int head = 0, nvalid = 0, last_lane = 0; uint64_t launches = 0, used = 0; };
+    std::vector<BatchGraph> graphs;
+    std::vector<uint64_t> graph_seen;               // keys run eagerly once (tables warmed); the next sighting is captured
+    bool graph_ok = true; uint64_t graph_clock = 0, graph_replays = 0;
+    cudaEvent_t ev_cap_batch = nullptr, ev_cap_done[4] = {nullptr, nullptr, nullptr, nullptr};
     int nlanes = 2;                 // lanes vp_process_batch_device cycles through (vp_set_batch_lanes)
     cudaEvent_t ev_batch = nullptr;
     int last_lane = 0;
@@ -1113,6 +1121,9 @@ void vp_destroy(vp_ctx* c) {
         if (L.st) cudaStreamDestroy(L.st);
     }
     if (c->ev_batch) cudaEventDestroy(c->ev_batch);
+    for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
+    if (c->ev_cap_batch) cudaEventDestroy(c->ev_cap_batch);
+    for (auto& e : c->ev_cap_done) if (e) cudaEventDestroy(e);
     for (auto& p : c->d_state) cudaFree(p);
     cudaFree(c->d_cand_be); cudaFree(c->d_scene_acc); cudaFree(c->d_scene_state); cudaFree(c->d_use);
     cudaFree(c->d_cand_pre); cudaFree(c->d_cand_post); cudaFree(c->d_cand_tmp); cudaFree(c->d_cand_sel);
@@ -1603,22 +1614,26 @@ int vp_set_batch_lanes(vp_ctx* c, int lanes) {
     return VP_OK;
 }
 
-int vp_process_batch_device(vp_ctx* c, int n, const uint8_t* const* d_src, size_t src_pitch, uint8_t* const* d_dst, size_t dst_pitch,
-                            void* stream) {
-    if (!c || n < 0 || (n && (!d_src || !d_dst))) return VP_ERR_INVALID_ARG;
-    if (!c->has_chain) return fail(c, VP_ERR_STATE, "vp_process_batch_device: context was created without a chain config");
-    if (n == 0) return VP_OK;
+static void drop_batch_graphs(vp_ctx* c) {
+    for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
+    c->graphs.clear(); c->graph_seen.clear();
+}
+int vp_set_batch_graphs(vp_ctx* c, int on) {
+    if (!c) return VP_ERR_INVALID_ARG;
     VP_CUDA(c, cudaSetDevice(c->device));
+    c->graph_ok = on != 0;
+    if (!on) drop_batch_graphs(c);
+    return VP_OK;
+}
+uint64_t vp_batch_graph_replays(const vp_ctx* c) { return c ? c->graph_replays : 0; }
+
+// the frames of one batch over the stream lanes (eagerly, or while `st0` is being captured into a graph)
+static int batch_enqueue(vp_ctx* c, int n, int NL, cudaStream_t st0, const uint8_t* const* d_src, size_t src_pitch, uint8_t* const* d_dst,
+                         size_t dst_pitch) {
     int rc = VP_OK;
-    const int NL = std::min(c->nlanes, n);
-    for (int l = 1; l < NL; ++l) { rc = ensure_lane(c, l); if (rc) return rc; }
-    if (NL == 1 && !c->lanes[0].ev_done) VP_CUDA(c, cudaEventCreateWithFlags(&c->lanes[0].ev_done, cudaEventDisableTiming));
-    cudaStream_t st0 = stream ? (cudaStream_t)stream : c->s_compute;
-    rc = join_host_lanes(c, st0); if (rc) return rc;
     // lane 1 forks from, and later joins, the caller's stream: everything is ordered after what is already
     // queued there, and events the caller records on it bracket the whole batch
     if (NL > 1) {
-        if (!c->ev_batch) VP_CUDA(c, cudaEventCreateWithFlags(&c->ev_batch, cudaEventDisableTiming));
         VP_CUDA(c, cudaEventRecord(c->ev_batch, st0));
         for (int l = 1; l < NL; ++l) VP_CUDA(c, cudaStreamWaitEvent(c->lanes[l].st, c->ev_batch, 0));
     }
@@ -1633,6 +1648,96 @@ int vp_process_batch_device(vp_ctx* c, int n, const uint8_t* const* d_src, size_
     }
     for (int l = 1; l < NL; ++l) VP_CUDA(c, cudaStreamWaitEvent(st0, c->lanes[l].ev_done, 0));   // join
     return VP_OK;
+}
+
+// chains whose frames are nothing but kernel launches on the lane streams (no lazily built tables, no host
+// synchronisation, no cooperative launch): the north-star chain and its bicubic-only / no-temporal forms
+static bool batch_graphable(const vp_ctx* c) {
+    const vp_chain_config& g = c->cfg;
+    if (!c->graph_ok || c->prof_on || g.bicubic_enhance || c->d_scene_acc) return false;
+    if (g.temporal.mode != VP_TEMPORAL_NONE && g.temporal.use_flow) return false;
+    if (g.use_pre && (g.pre.selective || g.pre.use_multiscale)) return false;
+    if (g.use_post && (g.post.selective || g.post.use_multiscale)) return false;
+    if (g.use_sharpen && g.sharpen.adaptive_sigma) return false;
+    return true;
+}
+
+int vp_process_batch_device(vp_ctx* c, int n, const uint8_t* const* d_src, size_t src_pitch, uint8_t* const* d_dst, size_t dst_pitch,
+                            void* stream) {
+    if (!c || n < 0 || (n && (!d_src || !d_dst))) return VP_ERR_INVALID_ARG;
+    if (!c->has_chain) return fail(c, VP_ERR_STATE, "vp_process_batch_device: context was created without a chain config");
+    if (n == 0) return VP_OK;
+    VP_CUDA(c, cudaSetDevice(c->device));
+    int rc = VP_OK;
+    const int NL = std::min(c->nlanes, n);
+    for (int l = 1; l < NL; ++l) { rc = ensure_lane(c, l); if (rc) return rc; }
+    if (NL == 1 && !c->lanes[0].ev_done) VP_CUDA(c, cudaEventCreateWithFlags(&c->lanes[0].ev_done, cudaEventDisableTiming));
+    cudaStream_t st0 = stream ? (cudaStream_t)stream : c->s_compute;
+    rc = join_host_lanes(c, st0); if (rc) return rc;
+    if (NL > 1 && !c->ev_batch) VP_CUDA(c, cudaEventCreateWithFlags(&c->ev_batch, cudaEventDisableTiming));
+
+    if (n >= 8 && batch_graphable(c)) {
+        // FNV-1a over everything a frame's launches depend on besides the (fixed) configuration and lane buffers
+        uint64_t key = 1469598103934665603ull;
+        auto mix = [&](uint64_t v) { for (int b = 0; b < 8; ++b) { key ^= (v >> (8 * b)) & 0xff; key *= 1099511628211ull; } };
+        mix((uint64_t)n); mix((uint64_t)NL); mix(src_pitch); mix(dst_pitch); mix((uint64_t)c->head); mix((uint64_t)c->nvalid);
+        mix((uint64_t)(uintptr_t)st0);
+        for (int i = 0; i < n; ++i) { mix((uint64_t)(uintptr_t)d_src[i]); mix((uint64_t)(uintptr_t)d_dst[i]); }
+        for (auto& g : c->graphs)
+            if (g.key == key) {
+                VP_CUDA(c, cudaGraphLaunch(g.exec, st0));
+                c->head = g.head; c->nvalid = g.nvalid; c->last_lane = g.last_lane; c->launches += g.launches;
+                g.used = ++c->graph_clock; c->graph_replays++;
+                return VP_OK;
+            }
+        const bool seen = std::find(c->graph_seen.begin(), c->graph_seen.end(), key) != c->graph_seen.end();
+        if (!seen) {
+            if (c->graph_seen.size() >= 64) c->graph_seen.erase(c->graph_seen.begin());
+            c->graph_seen.push_back(key);
+        } else {
+            // second sighting: capture the batch (capture-only events: an event recorded inside a capture cannot be waited
+            // on by later eager work), instantiate, replay from now on
+            cudaEvent_t saved_batch = c->ev_batch, saved_done[4];
+            if (!c->ev_cap_batch) VP_CUDA(c, cudaEventCreateWithFlags(&c->ev_cap_batch, cudaEventDisableTiming));
+            for (int l = 0; l < NL; ++l) {
+                saved_done[l] = c->lanes[l].ev_done;
+                if (!c->ev_cap_done[l]) VP_CUDA(c, cudaEventCreateWithFlags(&c->ev_cap_done[l], cudaEventDisableTiming));
+            }
+            const int head0 = c->head, nvalid0 = c->nvalid, lane0 = c->last_lane; const uint64_t launches0 = c->launches;
+            cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+            bool ok = cudaStreamBeginCapture(st0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                c->ev_batch = c->ev_cap_batch;
+                for (int l = 0; l < NL; ++l) c->lanes[l].ev_done = c->ev_cap_done[l];
+                const int crc = batch_enqueue(c, n, NL, st0, d_src, src_pitch, d_dst, dst_pitch);
+                c->ev_batch = saved_batch;
+                for (int l = 0; l < NL; ++l) c->lanes[l].ev_done = saved_done[l];
+                ok = cudaStreamEndCapture(st0, &graph) == cudaSuccess && crc == VP_OK && graph != nullptr;
+                if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+                if (graph) cudaGraphDestroy(graph);
+            }
+            if (ok) {
+                vp_ctx::BatchGraph g;
+                g.key = key; g.exec = exec; g.head = c->head; g.nvalid = c->nvalid; g.last_lane = c->last_lane;
+                g.launches = c->launches - launches0; g.used = ++c->graph_clock;
+                if (c->graphs.size() >= 4) {         // least recently used out
+                    size_t lru = 0;
+                    for (size_t i = 1; i < c->graphs.size(); ++i) if (c->graphs[i].used < c->graphs[lru].used) lru = i;
+                    cudaGraphExecDestroy(c->graphs[lru].exec);
+                    c->graphs.erase(c->graphs.begin() + lru);
+                }
+                c->graphs.push_back(g);
+                VP_CUDA(c, cudaGraphLaunch(exec, st0));
+                c->graph_replays++;
+                return VP_OK;
+            }
+            // capture refused (e.g. the caller's stream is itself being captured): stay eager from now on
+            cudaGetLastError();
+            c->graph_ok = false;
+            c->head = head0; c->nvalid = nvalid0; c->last_lane = lane0; c->launches = launches0;
+        }
+    }
+    return batch_enqueue(c, n, NL, st0, d_src, src_pitch, d_dst, dst_pitch);
 }
 
 int vp_get_stage_params(vp_ctx* c, int which, int* d, double* sigma_color, double* sigma_space) {
