@@ -1,11 +1,12 @@
 // temporal_consistency.h - TemporalConsistency with the reference's interface
 // (reference include/temporal_consistency.h:16-141).
 //
-// Built: the frame-buffer policy of process() (src/temporal_consistency.cpp:61-172) and blendFrames
-// (:355-444, with the float32 accumulator the code evidently intends; the literal code writes Vec3f
-// into a CV_8UC3 Mat, :367 vs :408).  The optical-flow / warp / scene-change front end is outside the
-// hot path: previous frames enter the blend unwarped with reliability 1, the
-// flow fields of Config are carried but unused.
+// Built: process() as the reference writes it (src/temporal_consistency.cpp:61-172) - the frame-buffer policy, the
+// scene-change reset (detectSceneChange :283-323), cv::calcOpticalFlowFarneback with the Config's parameters (:174-224),
+// the cv::remap warp of every buffered frame with its own stored flow (:127-135), the reliability masks (:325-353) and
+// blendFrames (:355-444, with the float32 accumulator the code evidently intends; the literal code writes Vec3f into a
+// CV_8UC3 Mat, :367 vs :408).  All of it runs on the device.  Limits: buffer_size <= 3, Farneback
+// `flags` must be 0 (the reference passes 0; OPTFLOW_USE_INITIAL_FLOW / OPTFLOW_FARNEBACK_GAUSSIAN are not built).
 #pragma once
 #include <memory>
 #include <mutex>

@@ -12,6 +12,17 @@
 #if __has_include(<opencv2/core.hpp>) && !defined(VP_FORCE_MAT_SHIM)
 #include <opencv2/core.hpp>
 #define VP_HAVE_OPENCV 1
+namespace vp {
+// page-locked storage for the Mats the library creates (csrc/host/mat_alloc.cpp): what keeps FrameBuffer slots and
+// output frames on the asynchronous-DMA path when the build uses real OpenCV (reference: src/frame_buffer.cpp:31-37)
+cv::MatAllocator* pinnedMatAllocator();
+inline void createPinned(cv::Mat& m, int rows, int cols, int type) {
+    if (!m.empty() && m.rows == rows && m.cols == cols && m.type() == type && m.allocator == pinnedMatAllocator()) return;
+    m.release();
+    m.allocator = pinnedMatAllocator();
+    m.create(rows, cols, type);
+}
+}  // namespace vp
 #else
 #define VP_HAVE_OPENCV 0
 #include <cstddef>
@@ -96,4 +107,8 @@ private:
 };
 
 }  // namespace cv
+namespace vp {
+// the shim pins every frame-sized Mat (detail::allocate), so this is plain create()
+inline void createPinned(cv::Mat& m, int rows, int cols, int type) { m.create(rows, cols, type); }
+}  // namespace vp
 #endif

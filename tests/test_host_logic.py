@@ -236,3 +236,20 @@ def test_bench_synthetic_clip_matches_oracle_synth():
     for kind in ("noise", "scene", "flat"):
         a = bench.torch_frame(kind, 96, 40, 3, bench.SEED, torch.device("cpu")).numpy()
         assert np.array_equal(a, synth.frame(kind, 96, 40, 3, bench.SEED))
+
+
+def test_opencv_pinned_allocator_branch_compiles():
+    """The drop-in build against real OpenCV keeps FrameBuffer slots and output frames page-locked through a
+    cv::MatAllocator (csrc/host/mat_alloc.cpp, VP_HAVE_OPENCV branch; reference src/frame_buffer.cpp:31-37).  This image has
+    no OpenCV, so the branch is at least held to the compiler against a stand-in header with OpenCV 4.x's declarations
+    (tests/mock_opencv) - a syntax / interface check, not a run."""
+    import shutil
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("no g++")
+    cuda_inc = "/usr/local/cuda/include"
+    cmd = [gxx, "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "tests", "mock_opencv"), "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(ROOT, "video_processor_b200", "csrc"), "-I", cuda_inc,
+           os.path.join(ROOT, "video_processor_b200", "csrc", "host", "mat_alloc.cpp")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr

@@ -54,7 +54,7 @@ public:
     }
     bool download(cv::Mat& output, int w, int h, int type, size_t elem) {
         cudaSetDevice(device_);
-        output.create(h, w, type);
+        vp::createPinned(output, h, w, type);
         if (cudaMemcpy2DAsync(output.data, output.step, d_out_, out_pitch_, (size_t)w * elem, h,
                               cudaMemcpyDeviceToHost, stream_) != cudaSuccess) return false;
         return cudaStreamSynchronize(stream_) == cudaSuccess;

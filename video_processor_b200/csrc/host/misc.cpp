@@ -153,7 +153,7 @@ bool VideoEnhancer::enhance(const cv::Mat& input, cv::Mat& output) {
         }
         m_impl->cfg = c;
     }
-    output.create(input.rows, input.cols, CV_8UC3);
+    vp::createPinned(output, input.rows, input.cols, CV_8UC3);
     if (vp_process_host(m_impl->ctx, input.data, input.step, output.data, output.step) != VP_OK) {
         std::cerr << "VideoEnhancer: " << vp_last_error(m_impl->ctx) << std::endl;
         input.copyTo(output);
@@ -185,7 +185,9 @@ bool FrameBuffer::pushFrame(const cv::Mat& frame, bool blocking) {
         if (!blocking) return false;
         m_not_full.wait(lock, [this]() { return !full(); });
     }
-    // deep copy into the slot; Mat::create reuses the slot's pinned storage when the geometry matches
+    // deep copy into the slot (src/frame_buffer.cpp:31-37): the slot is page-locked - with the Mat shim and, through the
+    // pinned cv::MatAllocator, with real OpenCV - and copyTo's create() keeps that storage while the geometry matches
+    vp::createPinned(m_frames[m_head], frame.rows, frame.cols, frame.type());
     frame.copyTo(m_frames[m_head]);
     m_head = nextIndex(m_head);
     m_size++;

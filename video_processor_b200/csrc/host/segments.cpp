@@ -200,7 +200,7 @@ bool Upscaler::upscaleSegments(const std::vector<cv::Mat>& inputs, std::vector<c
     std::vector<const uint8_t*> src(inputs.size());
     std::vector<uint8_t*> dst(inputs.size());
     for (size_t i = 0; i < inputs.size(); ++i) {
-        outputs[i].create(m_target_height, m_target_width, CV_8UC3);
+        vp::createPinned(outputs[i], m_target_height, m_target_width, CV_8UC3);
         src[i] = inputs[i].data; dst[i] = outputs[i].data;
     }
     const int rc = vp_run_segments(&c, dev.data(), (int)dev.size(), (int)inputs.size(), src.data(), f0.step, dst.data(), outputs[0].step, nullptr);

@@ -197,7 +197,7 @@ bool TemporalConsistency::process(const cv::Mat& input, cv::Mat& output) {
         }
         s.cfg = c;
     }
-    output.create(input.rows, input.cols, CV_8UC3);
+    vp::createPinned(output, input.rows, input.cols, CV_8UC3);
     if (!vp_host_api::is_bgr8(input) ||
         vp_process_host(s.ctx, input.data, input.step, output.data, output.step) != VP_OK) {
         std::cerr << "Error in temporal consistency: " << vp_last_error(s.ctx) << std::endl;

@@ -163,7 +163,7 @@ bool Upscaler::upscale(const cv::Mat& input, cv::Mat& output) {
         return false;
     }
     if (!ensureChain(input.cols, input.rows)) return false;
-    output.create(m_target_height, m_target_width, CV_8UC3);
+    vp::createPinned(output, m_target_height, m_target_width, CV_8UC3);
     const int rc = vp_process_host(m_chain->ctx, input.data, input.step, output.data, output.step);
     if (rc != VP_OK) {
         std::cerr << "Error in enhanced upscaling: " << vp_last_error(m_chain->ctx) << std::endl;
@@ -177,7 +177,7 @@ int Upscaler::pipelineDepth() const { return m_chain && m_chain->ctx ? vp_pipeli
 bool Upscaler::submit(const cv::Mat& input, cv::Mat& output) {
     if (!m_initialized || input.empty() || !vp_host_api::is_bgr8(input)) return false;
     if (!ensureChain(input.cols, input.rows)) return false;
-    output.create(m_target_height, m_target_width, CV_8UC3);
+    vp::createPinned(output, m_target_height, m_target_width, CV_8UC3);
     return vp_submit_host(m_chain->ctx, input.data, input.step, output.data, output.step) == VP_OK;
 }
 

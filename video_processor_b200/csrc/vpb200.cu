@@ -144,6 +144,7 @@ struct vp_ctx {
     std::vector<uint64_t> graph_seen;               // keys run eagerly once (tables warmed); the next sighting is captured
     bool graph_ok = true; uint64_t graph_clock = 0, graph_replays = 0;
     cudaEvent_t ev_cap_batch = nullptr, ev_cap_done[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t stage_ev = nullptr; cudaStream_t stage_last = nullptr; bool stage_any = false;   // StageOrder
     int nlanes = 2;                 // lanes vp_process_batch_device cycles through (vp_set_batch_lanes)
     cudaEvent_t ev_batch = nullptr;
     int last_lane = 0;
@@ -206,6 +207,17 @@ int fail(vp_ctx* c, int code, const std::string& msg) {
 
 enum { K_STATS = 0, K_BIL_PRE = 1, K_UPSHARP = 2, K_BIL_POST = 3, K_BLEND = 4, K_BIL_OTHER = 5, K_NKINDS = 6 };
 
+// The stage-wise entry points take a stream per call but share per-context tables and scratch (candidate tables, resize
+// tables, the sigmoid LUT, mask / pyramid / flow scratch).  Successive stage-wise calls on DIFFERENT streams of one context
+// are therefore ordered on the device: a call first makes its stream wait for the previous call's last kernel, so a table
+// re-upload or a scratch reuse can never overtake a kernel that still reads the old contents.  (Frees synchronise the
+// device by themselves.)  Calls on one stream cost nothing extra.
+struct StageOrder {
+    vp_ctx* c; cudaStream_t st;
+    StageOrder(vp_ctx* c_, cudaStream_t s);
+    ~StageOrder();
+};
+
 struct ProfScope {   // brackets one launch with CUDA events on its stream when profiling is on
     vp_ctx* c; int kind; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr;
     static cudaEvent_t get(vp_ctx* c) {
@@ -221,6 +233,14 @@ struct ProfScope {   // brackets one launch with CUDA events on its stream when 
         if (e0) { cudaEventRecord(e1, st); c->prof_recs.push_back({kind, e0, e1}); }
     }
 };
+
+StageOrder::StageOrder(vp_ctx* c_, cudaStream_t s) : c(c_), st(s) {
+    if (c->stage_any && c->stage_last != st) cudaStreamWaitEvent(st, c->stage_ev, 0);
+}
+StageOrder::~StageOrder() {
+    if (!c->stage_ev && cudaEventCreateWithFlags(&c->stage_ev, cudaEventDisableTiming) != cudaSuccess) { c->stage_ev = nullptr; return; }
+    if (cudaEventRecord(c->stage_ev, st) == cudaSuccess) { c->stage_last = st; c->stage_any = true; }
+}
 
 #define VP_CUDA(ctx, call)                                                                          \
     do {                                                                                            \
@@ -1121,6 +1141,7 @@ void vp_destroy(vp_ctx* c) {
         if (L.st) cudaStreamDestroy(L.st);
     }
     if (c->ev_batch) cudaEventDestroy(c->ev_batch);
+    if (c->stage_ev) cudaEventDestroy(c->stage_ev);
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
     if (c->ev_cap_batch) cudaEventDestroy(c->ev_cap_batch);
     for (auto& e : c->ev_cap_done) if (e) cudaEventDestroy(e);
@@ -1882,6 +1903,7 @@ int vp_bicubic(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, int src_w, int
     if (dst_w < src_w || dst_h < src_h) return fail(c, VP_ERR_UNSUPPORTED, "vp_bicubic: downscaling is not built");
     VP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    StageOrder stage_order(c, st);
     ResizeCache& rcache = (c->has_chain && c->rc_chain.sw == src_w && c->rc_chain.sh == src_h &&
                            c->rc_chain.dw == dst_w && c->rc_chain.dh == dst_h && c->rc_chain.xofs) ? c->rc_chain : c->rc_tmp;
     rc = ensure_resize(c, rcache, src_w, src_h, dst_w, dst_h, st); if (rc) return rc;
@@ -1895,6 +1917,7 @@ int vp_bilateral(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, uint8_t* d_d
     rc = check_frame(c, d_dst, dst_pitch, w, h, "vp_bilateral(dst)"); if (rc) return rc;
     VP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    StageOrder stage_order(c, st);
     if (!(c->tmp_d == d && c->tmp_sc == sigma_color && c->tmp_ss == sigma_space)) {
         vp_host::BilateralTables t = vp_host::bilateral_tables(d, sigma_color, sigma_space);
         if (t.radius > BIL_RMAX) return fail(c, VP_ERR_UNSUPPORTED, "vp_bilateral: radius > 7 (diameter > 15) is not built");
@@ -1917,6 +1940,7 @@ int vp_selective_bilateral(vp_ctx* c, const vp_bilateral_config* cfg, const uint
     rc = check_frame(c, d_dst, dst_pitch, w, h, "vp_selective_bilateral(dst)"); if (rc) return rc;
     VP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    StageOrder stage_order(c, st);
     if (!c->tmp_sel_valid || std::memcmp(&c->tmp_sel_cfg, cfg, sizeof(*cfg)) != 0) {
         VP_CUDA(c, cudaStreamSynchronize(st));
         c->tmp_sel_valid = false;
@@ -1945,6 +1969,7 @@ int vp_detail_mask(vp_ctx* c, double detail_threshold, const uint8_t* d_src, siz
     if (mask_pitch < (size_t)w * 4) return fail(c, VP_ERR_INVALID_ARG, "vp_detail_mask: mask pitch < 4*width");
     VP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    StageOrder stage_order(c, st);
     rc = ensure_ms_scratch(c, c->ms_tmp, w, h, 1, true); if (rc) return rc;
     return launch_detail_mask(c, d_src, src_pitch, w, h, detail_threshold, c->ms_tmp.mx, c->ms_tmp.dv, c->ms_tmp.dvp, d_mask, mask_pitch, st);
 }
@@ -1956,6 +1981,7 @@ int vp_pyr_down(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, int src_w, in
     rc = check_frame(c, d_dst, dst_pitch, dw, dh, "vp_pyr_down(dst)"); if (rc) return rc;
     VP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    StageOrder stage_order(c, st);
     ProfScope ps(c, K_BIL_OTHER, st);
     k_pyr_down<<<dim3(((dw + 1) / 2 + 31) / 32, ((dh + 1) / 2 + 7) / 8), 256, 0, st>>>(d_src, src_pitch, src_w, src_h, d_dst, dst_pitch, dw, dh);
     VP_CUDA(c, cudaGetLastError());
@@ -1972,6 +1998,7 @@ int vp_pyr_up(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, int src_w, int 
         return fail(c, VP_ERR_UNSUPPORTED, "vp_pyr_up: dst must be 2*src or 2*src-1 per axis");
     VP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    StageOrder stage_order(c, st);
     ProfScope ps(c, K_BIL_OTHER, st);
     k_pyr_up<<<dim3((dst_w + 31) / 32, (dst_h + 7) / 8), 256, 0, st>>>(d_src, src_pitch, src_w, src_h, d_dst, dst_pitch, dst_w, dst_h);
     VP_CUDA(c, cudaGetLastError());
@@ -1984,6 +2011,7 @@ int vp_mean_stddev_sums(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, int w
     int rc = check_frame(c, d_src, src_pitch, w, h, "vp_mean_stddev_sums(src)"); if (rc) return rc;
     VP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    StageOrder stage_order(c, st);
     VP_CUDA(c, cudaMemsetAsync(d_sums, 0, 6 * sizeof(uint64_t), st));
     return launch_stats(c, d_src, src_pitch, w, h, reinterpret_cast<unsigned long long*>(d_sums), SelOut{nullptr, nullptr, 0.0}, st);
 }
@@ -1998,6 +2026,7 @@ static int sharpen_common(vp_ctx* c, const vp_sharpen_config* cfg, const uint8_t
         return fail(c, VP_ERR_INVALID_ARG, std::string(who) + ": mask pitch < 4*width");
     VP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    StageOrder stage_order(c, st);
     UpsharpArgs a{};
     rc = fill_sharpen_args(c, a, *cfg); if (rc) return rc;
     rc = ensure_siglut(c, &c->d_siglut_tmp, &c->siglut_tmp_thr, &c->siglut_tmp_valid, cfg->edge_threshold, st); if (rc) return rc;
@@ -2037,6 +2066,7 @@ int vp_sigma_map(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, float* d_sig
     if (sigma_pitch < (size_t)w * 4) return fail(c, VP_ERR_INVALID_ARG, "vp_sigma_map: sigma pitch < 4*width");
     VP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    StageOrder stage_order(c, st);
     rc = ensure_vs_scratch(c, c->vs_tmp, w, h, false); if (rc) return rc;
     return launch_sigma_map(c, c->vs_tmp.st, c->vs_tmp.var, c->vs_tmp.vpitch, d_src, src_pitch, w, h, d_sigma, sigma_pitch, st);
 }
@@ -2049,6 +2079,7 @@ int vp_optical_flow(vp_ctx* c, const vp_temporal_config* cfg, const uint8_t* d_p
     if (flow_pitch < (size_t)w * 4) return fail(c, VP_ERR_INVALID_ARG, "vp_optical_flow: flow pitch < 4*width");
     VP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    StageOrder stage_order(c, st);
     FlowEngine& E = c->flow_tmp;
     rc = ensure_flow_engine(c, E, w, h, *cfg); if (rc) return rc;
     rc = flow_expand(c, E, d_prev, pitch, 0, st); if (rc) return rc;
@@ -2068,6 +2099,7 @@ int vp_warp_flow(vp_ctx* c, const uint8_t* d_src, size_t src_pitch, const float*
     if (flow_pitch < (size_t)w * 4 || (flow_pitch & 3)) return fail(c, VP_ERR_INVALID_ARG, "vp_warp_flow: flow pitch");
     VP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    StageOrder stage_order(c, st);
     ProfScope ps(c, K_BLEND, st);
     k_warp<<<grid2d(w, h), 256, 0, st>>>(d_src, src_pitch, d_flow_x, d_flow_y, (int)(flow_pitch / 4), d_dst, dst_pitch, w, h);
     VP_CUDA(c, cudaGetLastError());
@@ -2082,6 +2114,7 @@ int vp_flow_reliability(vp_ctx* c, const float* d_flow_x, const float* d_flow_y,
         return fail(c, VP_ERR_INVALID_ARG, "vp_flow_reliability: pitch");
     VP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    StageOrder stage_order(c, st);
     const size_t need = mask_pitch / 4 * (size_t)h;
     if (c->flow_tmp_mask_n < need) {
         VP_CUDA(c, cudaStreamSynchronize(st));
@@ -2101,6 +2134,7 @@ int vp_add_weighted(vp_ctx* c, const uint8_t* d_a, size_t a_pitch, double alpha,
     rc = check_frame(c, d_dst, dst_pitch, w, h, "vp_add_weighted(dst)"); if (rc) return rc;
     VP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    StageOrder stage_order(c, st);
     BlendKArgs a{};
     a.cur = d_a; a.cpitch = a_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.row_bytes = 3 * w; a.h = h;
     a.blend.mode = VP_TEMPORAL_MAIN_BLEND; a.blend.nprev = 1; a.blend.prev[0] = d_b; a.blend.ppitch = b_pitch;
@@ -2117,6 +2151,7 @@ int vp_temporal_blend(vp_ctx* c, const uint8_t* const* d_frames, int nframes, si
     rc = check_frame(c, d_dst, dst_pitch, w, h, "vp_temporal_blend(dst)"); if (rc) return rc;
     VP_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    StageOrder stage_order(c, st);
     BlendKArgs a{};
     a.cur = d_frames[0]; a.cpitch = pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.row_bytes = 3 * w; a.h = h;
     vp_temporal_config t{VP_TEMPORAL_BLEND_FRAMES, 3, blend_strength, 0.6f, 0, 100.0f};
