@@ -1,9 +1,11 @@
-# A/B timing of library variants on the C4 chain: bash tools/ab.sh tag variant1 variant2 ...   ("base" = the product build)
+# A/B timing of library variants on the C4 chain: bash tools/ab.sh tag variant1 variant2 ...
+#   "base" = the product build, "env:NAME=VALUE" = the product build under that environment, else libvpb200_<variant>.so
 T=$1; shift
 mkdir -p gpurun_out
 for v in "$@"; do
-  lib=video_processor_b200/libvpb200.so; [ "$v" != base ] && lib=video_processor_b200/libvpb200_$v.so
-  VPB200_LIB=$PWD/$lib python bench.py --cpu-frames 0 --no-c5-latency --no-e2e ${AB_ARGS} > gpurun_out/${T}_$v.json 2> gpurun_out/${T}_$v.err
+  lib=video_processor_b200/libvpb200.so; envs=""
+  case "$v" in base) ;; env:*) envs="${v#env:}"; v=$(echo "$v" | tr -c 'A-Za-z0-9_\n' '_') ;; *) lib=video_processor_b200/libvpb200_$v.so ;; esac
+  env $envs VPB200_LIB=$PWD/$lib python bench.py --cpu-frames 0 --no-c5-latency --no-e2e ${AB_ARGS} > gpurun_out/${T}_$v.json 2> gpurun_out/${T}_$v.err
   python - <<PY
 import json
 d=json.load(open("gpurun_out/${T}_$v.json"))

@@ -75,6 +75,10 @@ struct BilArgs {
     // 16-byte aligned frames: the halo tile of candidate i arrives as one tensor-map box (bil_raw_pitch(r_i) - 16 bytes wide,
     // BIL_TH * ns + 2 r_i rows) instead of one bulk copy per row
     int use_tm;
+    // src_bgrx: `src` holds one 32-bit word per pixel (B, G, R, 1) - k_upsharp's out_bgrx form.  The halo tile then arrives by
+    // TMA directly as the tile words (box TP x TROWS of 32-bit units at (x0 - r, y0 - r), zero-filled outside the image);
+    // only tiles on the image border run a pass that mirrors the outside positions.  Requires use_tm.
+    int src_bgrx;
     alignas(64) CUtensorMap tm[3];
 };
 
@@ -195,9 +199,14 @@ __device__ __forceinline__ void load12(const uint8_t* p, uint32_t v[3], int npx)
     }
 }
 
-template <int R> struct BilGeom {
-    static constexpr int TP = (BIL_TW + 2 * R + 3) & ~3;      // tile pitch in pixels (16-byte rows)
-    static constexpr int NSEG = (BIL_PX + 2 * R + 3) & ~3;    // staged neighbours per row, whole uint4s
+// XO: physical column of the tile's first logical column (x0 - R).  0 when the kernel builds the tile itself; in the
+// 32-bit-source form the tile arrives by TMA, whose box must start on a 16-byte boundary of the source row: the box starts
+// PAD = (R + 3) & ~3 pixels left of x0 and the logical columns sit XO = PAD - R words into each tile row.
+__host__ __device__ constexpr int bil_pad(int r) { return (r + 3) & ~3; }
+__host__ __device__ constexpr int bil_xo(int r) { return bil_pad(r) - r; }
+template <int R, int XO = 0> struct BilGeom {
+    static constexpr int TP = XO ? BIL_TW + 2 * (R + XO) : (BIL_TW + 2 * R + 3) & ~3;   // tile pitch in pixels (16-byte rows)
+    static constexpr int NSEG = (BIL_PX + 2 * R + XO + 3) & ~3;                         // staged words per row, whole uint4s
     static constexpr int D = 2 * R + 1;
 };
 
@@ -212,19 +221,25 @@ constexpr int BIL_DY_ANY = 99;
 #ifndef VP_BIL_I2F
 #define VP_BIL_I2F 1
 #endif
-template <int R, int XM, int DY>
-__device__ __forceinline__ void bil_row(const uint32_t (&seg)[BilGeom<R>::NSEG], const BilHead& T, const float* __restrict__ s_cls, int row,
+#ifndef VP_BIL_PREFETCH
+#define VP_BIL_PREFETCH 2      // previous frames of the temporal blend requested before the tap loop (0, 1 or 2 of them)
+#endif
+#ifndef VP_BIL_MINB
+#define VP_BIL_MINB 4          // resident CTAs per SM the register allocation is held to (256 threads each: 64 registers)
+#endif
+template <int R, int XM, int DY, int XO>
+__device__ __forceinline__ void bil_row(const uint32_t (&seg)[BilGeom<R, XO>::NSEG], const BilHead& T, const float* __restrict__ s_cls, int row,
                                         const uint32_t (&ctr)[BIL_PX],
                                         unsigned long long (&abg)[BIL_PX], unsigned long long (&arw)[BIL_PX]) {
     constexpr int N = BIL_PX + 2 * XM;                        // neighbours this row touches
     constexpr bool CENTER_ROW = (DY == 0) || (DY == BIL_DY_ANY && XM == R);      // only row 0 is R taps wide
     constexpr bool CLS = (R <= BIL_CLS_RMAX) && (DY != BIL_DY_ANY);
-    const float* __restrict__ sw_row = T.space_w + row * BilGeom<R>::D;
+    const float* __restrict__ sw_row = T.space_w + row * BilGeom<R, XO>::D;
     unsigned long long pbg[N], pra[N];
     const unsigned long long bias = pack2(0xCB000000u, 0xCB000000u);   // (-2^23, -2^23)
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        const uint32_t p = seg[i + R - XM];
+        const uint32_t p = seg[i + R - XM + XO];
 #if VP_BIL_I2F >= 1
         // (b, g) through the conversion unit (I2F.U8 with a byte selector, one instruction per value on the otherwise
         // idle XU pipe) instead of two PRMTs and half a FADD2 on the ALU / FMA pipes
@@ -255,7 +270,7 @@ __device__ __forceinline__ void bil_row(const uint32_t (&seg)[BilGeom<R>::NSEG],
 #pragma unroll
         for (int j = 0; j < BIL_PX; ++j) {
             const int i = j + dx + XM;
-            const unsigned n = __vsadu4(seg[i + R - XM], ctr[j]);   // VABSDIFF4.ACC: |db|+|dg|+|dr| (+|1-1|)
+            const unsigned n = __vsadu4(seg[i + R - XM + XO], ctr[j]);   // VABSDIFF4.ACC: |db|+|dg|+|dr| (+|1-1|)
             const uint32_t wgt = __float_as_uint(CLS ? lut[n] : __fmul_rn(sw, lut[n]));
             const unsigned long long w2 = pack2(wgt, wgt);
             abg[j] = ffma2(pbg[i], w2, abg[j]);
@@ -264,18 +279,18 @@ __device__ __forceinline__ void bil_row(const uint32_t (&seg)[BilGeom<R>::NSEG],
     }
 }
 
-template <int R, int XM>
+template <int R, int XM, int XO>
 struct BilRowSwitch {
-    __device__ __forceinline__ static void run(int xm, const uint32_t (&seg)[BilGeom<R>::NSEG], const BilHead& T, int row,
+    __device__ __forceinline__ static void run(int xm, const uint32_t (&seg)[BilGeom<R, XO>::NSEG], const BilHead& T, int row,
                                                const uint32_t (&ctr)[BIL_PX], unsigned long long (&abg)[BIL_PX],
                                                unsigned long long (&arw)[BIL_PX]) {
-        if (xm == XM) bil_row<R, XM, BIL_DY_ANY>(seg, T, nullptr, row, ctr, abg, arw);
-        else BilRowSwitch<R, XM - 1>::run(xm, seg, T, row, ctr, abg, arw);
+        if (xm == XM) bil_row<R, XM, BIL_DY_ANY, XO>(seg, T, nullptr, row, ctr, abg, arw);
+        else BilRowSwitch<R, XM - 1, XO>::run(xm, seg, T, row, ctr, abg, arw);
     }
 };
-template <int R>
-struct BilRowSwitch<R, -1> {
-    __device__ __forceinline__ static void run(int, const uint32_t (&)[BilGeom<R>::NSEG], const BilHead&, int,
+template <int R, int XO>
+struct BilRowSwitch<R, -1, XO> {
+    __device__ __forceinline__ static void run(int, const uint32_t (&)[BilGeom<R, XO>::NSEG], const BilHead&, int,
                                                const uint32_t (&)[BIL_PX], unsigned long long (&)[BIL_PX],
                                                unsigned long long (&)[BIL_PX]) {}
 };
@@ -288,12 +303,12 @@ __host__ __device__ constexpr int bil_xmax(int R, int i) {
 }
 
 // small windows: every tap row unrolled with its compile-time half-width (no row switch, no xmax loads)
-template <int R, int ROW>
+template <int R, int ROW, int XO>
 __device__ __forceinline__ void bil_rows_unrolled(const uint32_t* __restrict__ s_tile, const BilHead& T, const float* __restrict__ s_cls, int lx, int ly,
                                                   const uint32_t (&ctr)[BIL_PX],
                                                   unsigned long long (&abg)[BIL_PX], unsigned long long (&arw)[BIL_PX]) {
     if constexpr (ROW <= 2 * R) {
-        constexpr int TP = BilGeom<R>::TP, NSEG = BilGeom<R>::NSEG;
+        constexpr int TP = BilGeom<R, XO>::TP, NSEG = BilGeom<R, XO>::NSEG;
         const uint4* rowp = reinterpret_cast<const uint4*>(s_tile + (ly + ROW) * TP + lx);
         uint32_t seg[NSEG];
 #pragma unroll
@@ -301,27 +316,27 @@ __device__ __forceinline__ void bil_rows_unrolled(const uint32_t* __restrict__ s
             const uint4 v = rowp[q];
             seg[4 * q] = v.x; seg[4 * q + 1] = v.y; seg[4 * q + 2] = v.z; seg[4 * q + 3] = v.w;
         }
-        bil_row<R, bil_xmax(R, ROW - R), ROW - R>(seg, T, s_cls, ROW, ctr, abg, arw);
-        bil_rows_unrolled<R, ROW + 1>(s_tile, T, s_cls, lx, ly, ctr, abg, arw);
+        bil_row<R, bil_xmax(R, ROW - R), ROW - R, XO>(seg, T, s_cls, ROW, ctr, abg, arw);
+        bil_rows_unrolled<R, ROW + 1, XO>(s_tile, T, s_cls, lx, ly, ctr, abg, arw);
     }
 }
 
 constexpr int BIL_UNROLL_RMAX = 3;
 static_assert(BIL_CLS_RMAX <= BIL_UNROLL_RMAX, "class tables need compile-time tap rows");
 
-template <int R>
+template <int R, int XO>
 __device__ __forceinline__ void bil_strip(const uint32_t* __restrict__ s_tile, const BilHead& T, const float* __restrict__ s_cls, int lx, int ly,
                                           uint32_t out[BIL_PX]) {
-    constexpr int TP = BilGeom<R>::TP, NSEG = BilGeom<R>::NSEG, D = BilGeom<R>::D;
+    constexpr int TP = BilGeom<R, XO>::TP, NSEG = BilGeom<R, XO>::NSEG, D = BilGeom<R, XO>::D;
     uint32_t ctr[BIL_PX];
     unsigned long long abg[BIL_PX], arw[BIL_PX];
 #pragma unroll
     for (int j = 0; j < BIL_PX; ++j) {
-        ctr[j] = s_tile[(ly + R) * TP + lx + R + j];
+        ctr[j] = s_tile[(ly + R) * TP + lx + R + XO + j];
         abg[j] = arw[j] = 0ull;
     }
     if constexpr (R <= BIL_UNROLL_RMAX) {
-        bil_rows_unrolled<R, 0>(s_tile, T, s_cls, lx, ly, ctr, abg, arw);
+        bil_rows_unrolled<R, 0, XO>(s_tile, T, s_cls, lx, ly, ctr, abg, arw);
     } else {
 #pragma unroll 1
         for (int row = 0; row < D; ++row) {
@@ -332,7 +347,7 @@ __device__ __forceinline__ void bil_strip(const uint32_t* __restrict__ s_tile, c
                 const uint4 v = rowp[q];
                 seg[4 * q] = v.x; seg[4 * q + 1] = v.y; seg[4 * q + 2] = v.z; seg[4 * q + 3] = v.w;
             }
-            BilRowSwitch<R, R>::run(T.xmax[row], seg, T, row, ctr, abg, arw);
+            BilRowSwitch<R, R, XO>::run(T.xmax[row], seg, T, row, ctr, abg, arw);
         }
     }
 #pragma unroll
@@ -348,23 +363,27 @@ __device__ __forceinline__ void bil_strip(const uint32_t* __restrict__ s_tile, c
 // dynamic shared memory: [ tile words | raw bytes | mbarrier | class tables (radius <= BIL_CLS_RMAX) ]; the head of the
 // parameter set (colour LUT, space weights, row half-widths) is static shared memory so its base folds into the LDS immediates
 __host__ __device__ inline int bil_tile_pitch(int r) { return (BIL_TW + 2 * r + 3) & ~3; }
+__host__ __device__ inline int bil_tile_pitch_x(int r) { return BIL_TW + 2 * bil_pad(r); }       // 32-bit-source form (>= bil_tile_pitch)
 __host__ __device__ inline int bil_raw_pitch(int r) { return (((BIL_TW + 2 * r) * 3 + 15 + 15) & ~15) + 16; }
 __host__ __device__ inline int bil_class_bytes(int r) { return r <= BIL_CLS_RMAX ? bil_nclasses(r) * 768 * 4 : 0; }
-__host__ __device__ inline size_t bil_tile_bytes(int r, int trows) { return ((size_t)bil_tile_pitch(r) * trows * 4 + 127) & ~(size_t)127; }
+__host__ __device__ inline size_t bil_tile_bytes(int r, int trows) { return ((size_t)bil_tile_pitch_x(r) * trows * 4 + 127) & ~(size_t)127; }
 __host__ inline size_t bil_smem_bytes(int r, int ns) {
     size_t tile = bil_tile_bytes(r, BIL_TH * ns + 2 * r);
     size_t raw = (size_t)bil_raw_pitch(r) * (BIL_TH * ns + 2 * r);
     return tile + raw + 16 + bil_class_bytes(r);
 }
 
-__global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const __grid_constant__ BilArgs a) {
+// BGRX: the source holds 32-bit (B, G, R, 1) pixels (BilArgs::src_bgrx) - compiled as its own kernel so neither form carries
+// the other's registers
+template <bool BGRX>
+__global__ void __launch_bounds__(BIL_NT, VP_BIL_MINB) k_bilateral(const __grid_constant__ BilArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ BilHead s_cand;
     const int tid = threadIdx.x;
     const int sel = a.sel ? *a.sel : 0;
     const BilCand* __restrict__ cand = a.cand + sel;
     const int R = a.radius[sel];
-    const int TP = bil_tile_pitch(R);
+    const int TP = BGRX ? bil_tile_pitch_x(R) : bil_tile_pitch(R);
     const int TH = BIL_TH * a.ns;
     const int TROWS = TH + 2 * R;
     const bool tm = a.use_tm != 0;                          // implies 16-byte aligned frames
@@ -383,7 +402,9 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const __grid_constant__
     const bool fast = aligned16(a.src, a.spitch);
 
     // the halo tile and the parameter set arrive by bulk copies on one mbarrier
-    if (tm) stage_box_issue(s_raw, &a.tm[sel], bx0, vy0, (uint32_t)(RP * TROWS), bar, &s_cand, &cand->head, (uint32_t)sizeof(BilHead),
+    if (BGRX) stage_box_issue(reinterpret_cast<uint8_t*>(s_tile), &a.tm[sel], x0 - bil_pad(R), y0 - R, (uint32_t)(TP * TROWS * 4), bar,
+                              &s_cand, &cand->head, (uint32_t)sizeof(BilHead), s_cls, cand->class_w, (uint32_t)bil_class_bytes(R));
+    else if (tm) stage_box_issue(s_raw, &a.tm[sel], bx0, vy0, (uint32_t)(RP * TROWS), bar, &s_cand, &cand->head, (uint32_t)sizeof(BilHead),
                             s_cls, cand->class_w, (uint32_t)bil_class_bytes(R));
     else stage_rows_issue(s_raw, RP, a.src, a.spitch, vy0, vy1, bx0, bx1, fast, bar, &s_cand, &cand->head, (uint32_t)sizeof(BilHead),
                           s_cls, cand->class_w, (uint32_t)bil_class_bytes(R));
@@ -391,7 +412,23 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const __grid_constant__
 
     // expand raw bytes -> BGR0 words with BORDER_REFLECT_101 resolved; warp per row, lanes along x
     const bool simple = (a.w > R) && (a.h > R);          // one mirror step suffices
-    if (fast && simple && x0 >= R && x0 + BIL_TW + R <= a.w) {
+    if (BGRX) {
+        // the tile words are already in place; positions outside the image (zero-filled by the TMA unit) take their
+        // BORDER_REFLECT_101 mirror, which lies inside the image and inside this tile (host: w, h > 2 r)
+        if (x0 < R || y0 < R || x0 + BIL_TW + R > a.w || y0 + TH + R > a.h) {
+            const int ox = x0 - bil_pad(R), oy = y0 - R;       // image position of tile word (0, 0)
+            for (int i = tid; i < TROWS * TP; i += BIL_NT) {
+                const int ty = i / TP, tx = i - ty * TP;
+                const int sx = ox + tx, sy = oy + ty;
+                if ((unsigned)sx < (unsigned)a.w && (unsigned)sy < (unsigned)a.h) continue;
+                int mx = sx < 0 ? -sx : sx; mx = mx >= a.w ? 2 * a.w - 2 - mx : mx;
+                int my = sy < 0 ? -sy : sy; my = my >= a.h ? 2 * a.h - 2 - my : my;
+                const int qx = mx - ox, qy = my - oy;
+                if ((unsigned)qx < (unsigned)TP && (unsigned)qy < (unsigned)TROWS && mx >= 0 && my >= 0)
+                    s_tile[i] = s_tile[qy * TP + qx];       // sources are in-image positions: never rewritten by this pass
+            }
+        }
+    } else if (fast && simple && x0 >= R && x0 + BIL_TW + R <= a.w) {
         // no horizontal mirroring in this tile: a lane turns 12 raw bytes (4 pixels, any byte phase) into four
         // BGR1 words with funnel shifts and byte permutes and stores them as one 128-bit word
         const int c0 = 3 * vx0 - bx0;                    // byte offset of tile column 0 inside a raw row, 0..15
@@ -462,21 +499,26 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const __grid_constant__
         if (gy >= a.h) break;
         // previous frames of the temporal blend: issue the loads before the tap loop hides their latency
         uint32_t p0[3] = {0, 0, 0}, p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0};
+#if VP_BIL_PREFETCH
         if (doblend || scene_prev) {
             load12(b.prev[0] + (size_t)gy * b.ppitch + boff, p0, npx);
-            if (doblend && b.nprev > 1) load12(b.prev[1] + (size_t)gy * b.ppitch + boff, p1, npx);
+            if (VP_BIL_PREFETCH > 1 && doblend && b.nprev > 1) load12(b.prev[1] + (size_t)gy * b.ppitch + boff, p1, npx);
         }
+#endif
         uint32_t out[BIL_PX];
+#if VP_BIL_PREFETCH < 2
+        const bool late_p1 = doblend && b.nprev > 1;
+#endif
         switch (R) {
-            case 1: bil_strip<1>(s_tile, s_cand, s_cls, lx, ly, out); break;
-            case 2: bil_strip<2>(s_tile, s_cand, s_cls, lx, ly, out); break;
-            case 3: bil_strip<3>(s_tile, s_cand, s_cls, lx, ly, out); break;
-            case 4: bil_strip<4>(s_tile, s_cand, s_cls, lx, ly, out); break;
-            case 5: bil_strip<5>(s_tile, s_cand, s_cls, lx, ly, out); break;
-            case 6: bil_strip<6>(s_tile, s_cand, s_cls, lx, ly, out); break;
-            default: bil_strip<7>(s_tile, s_cand, s_cls, lx, ly, out); break;
+            case 1: bil_strip<1, BGRX ? bil_xo(1) : 0>(s_tile, s_cand, s_cls, lx, ly, out); break;
+            case 2: bil_strip<2, BGRX ? bil_xo(2) : 0>(s_tile, s_cand, s_cls, lx, ly, out); break;
+            case 3: bil_strip<3, BGRX ? bil_xo(3) : 0>(s_tile, s_cand, s_cls, lx, ly, out); break;
+            case 4: bil_strip<4, BGRX ? bil_xo(4) : 0>(s_tile, s_cand, s_cls, lx, ly, out); break;
+            case 5: bil_strip<5, BGRX ? bil_xo(5) : 0>(s_tile, s_cand, s_cls, lx, ly, out); break;
+            case 6: bil_strip<6, BGRX ? bil_xo(6) : 0>(s_tile, s_cand, s_cls, lx, ly, out); break;
+            default: bil_strip<7, BGRX ? bil_xo(7) : 0>(s_tile, s_cand, s_cls, lx, ly, out); break;
         }
-        if (a.emap) {
+        if (!BGRX && a.emap) {
             // 2x2 dilate (anchor (1,1)): pixel x is an edge if map[y-1..y][x-1..x] holds a 2.  The strip's four
             // map bytes of a row arrive as one aligned word (gx % 4 == 0, pitch % 4 == 0) plus the byte left of it.
             uint32_t m = 0;
@@ -513,6 +555,12 @@ __global__ void __launch_bounds__(BIL_NT, 4) k_bilateral(const __grid_constant__
                 }
             }
         }
+#if VP_BIL_PREFETCH < 1
+        if (doblend || scene_prev) load12(b.prev[0] + (size_t)gy * b.ppitch + boff, p0, npx);
+#endif
+#if VP_BIL_PREFETCH < 2
+        if (late_p1) load12(b.prev[1] + (size_t)gy * b.ppitch + boff, p1, npx);
+#endif
         // epilogue: optional temporal blend, state store, output store (12 contiguous bytes per strip)
         uint32_t cur[3];   // 12 packed bytes B G R B | G R B G | R B G R
         cur[0] = (out[0] & 0xffffffu) | (out[1] << 24);

@@ -63,6 +63,10 @@ struct UpsharpArgs {
     // 16-byte aligned frames: the source window arrives (box raw_pitch - 16 bytes x max_src_rows) and the finished tile
     // leaves (box US_TW * 3 bytes x US_TH) as one tensor-map TMA box each
     int use_tm_src, use_tm_dst;
+    // out_bgrx: the tile leaves as one 32-bit word per pixel (B, G, R, 1) - the lane buffer between this kernel and the POST
+    // bilateral, whose halo tile then arrives by TMA already in the form its tap loop reads (no expansion pass there);
+    // tm_dst is then a tensor of 32-bit units and use_tm_dst is set
+    int out_bgrx;
     alignas(64) CUtensorMap tm_src;
     alignas(64) CUtensorMap tm_dst;
 };
@@ -85,7 +89,7 @@ __host__ __device__ inline UpsharpSmem upsharp_layout(bool resize, bool sharpen,
     const int rawb = L.raw_pitch * max_src_rows;
     const int srcb = resize ? ((L.src_pitch * max_src_rows * 4 + 15) & ~15) : 0;
     const int sig = sharpen ? (US_TW + 4) * (US_TH + 4) * 4 : 0;
-    const int outb = US_TH * US_TW * 3;
+    const int outb = US_TH * US_TW * 4;         // staged output tile: 3 bytes per pixel, or one word (out_bgrx)
     const int sigout = ((sig > outb ? sig : outb) + 15) & ~15;
     L.raw = o; L.src = o + rawb; L.sig = o;
     o += (rawb + srcb > sigout ? rawb + srcb : sigout);
@@ -177,7 +181,8 @@ __device__ __forceinline__ void p2_fast(const float* __restrict__ s_hs, const in
     }
 }
 
-template <bool RESIZE, bool SHARPEN, int GK>
+// OUTX: UpsharpArgs::out_bgrx as a compile-time flag (its own kernel: the three-byte form carries none of its code)
+template <bool RESIZE, bool SHARPEN, int GK, bool OUTX = false>
 __global__ void __launch_bounds__(US_NT) k_upsharp(const __grid_constant__ UpsharpArgs a) {
     constexpr int HALO = SHARPEN ? US_HALO : 0;
     constexpr int EW = US_TW + 2 * HALO, EH = US_TH + 2 * HALO;
@@ -383,7 +388,8 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const __grid_constant__ Upsha
             const uint32_t px = s_up[y * EW + x];
             uint8_t* o = s_out + y * (US_TW * 3) + x * 3;
             const unsigned v0 = px & 0xff, v1 = (px >> 8) & 0xff, v2 = (px >> 16) & 0xff;
-            o[0] = v0; o[1] = v1; o[2] = v2;
+            if (OUTX) reinterpret_cast<uint32_t*>(s_out)[y * US_TW + x] = (px & 0xffffffu) | 0x01000000u;
+            else { o[0] = v0; o[1] = v1; o[2] = v2; }
             if (a.sums && x < vw && y < vh) {
                 acc6[0] += v0; acc6[1] += v1; acc6[2] += v2;
                 acc6[3] += v0 * v0; acc6[4] += v1 * v1; acc6[5] += v2 * v2;
@@ -533,8 +539,12 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const __grid_constant__ Upsha
                     o[1] = sat_u8(yo + ((cb * -5636 + cr * -11698 + (1 << 13)) >> 14));
                     o[2] = sat_u8(yo + ((cr * 22987 + (1 << 13)) >> 14));
                 }
-                uint8_t* ob = s_out + y * (US_TW * 3) + x * 3;
-                ob[0] = (uint8_t)o[0]; ob[1] = (uint8_t)o[1]; ob[2] = (uint8_t)o[2];
+                if (OUTX) {
+                    reinterpret_cast<uint32_t*>(s_out)[y * US_TW + x] = (uint32_t)o[0] | ((uint32_t)o[1] << 8) | ((uint32_t)o[2] << 16) | 0x01000000u;
+                } else {
+                    uint8_t* ob = s_out + y * (US_TW * 3) + x * 3;
+                    ob[0] = (uint8_t)o[0]; ob[1] = (uint8_t)o[1]; ob[2] = (uint8_t)o[2];
+                }
                 if (a.sums && x < vw && y < vh) {
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch) { acc6[ch] += o[ch]; acc6[3 + ch] += o[ch] * o[ch]; }
@@ -551,7 +561,7 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const __grid_constant__ Upsha
     // ---- P6: staged tile -> HBM: one TMA bulk store per row (16-byte aligned frames), else bytes ----
     if (a.dst && a.use_tm_dst) {
         // one box store; the part of an edge tile outside the frame is clipped by the TMA unit
-        if (tid == 0) { tma_store_2d(&a.tm_dst, x0 * 3, y0, s_out); bulk_commit(); bulk_wait_read0(); }
+        if (tid == 0) { tma_store_2d(&a.tm_dst, OUTX ? x0 : x0 * 3, y0, s_out); bulk_commit(); bulk_wait_read0(); }
     } else if (a.dst) {
         const int rb = vw * 3;                               // valid bytes per tile row
         const bool al = aligned16(a.dst, a.dpitch);          // x0*3 = 192*blockIdx.x is a multiple of 16

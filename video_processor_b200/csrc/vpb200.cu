@@ -165,6 +165,8 @@ struct vp_ctx {
     // chain buffers
     size_t pre_pitch = 0;
     size_t frame_pitch = 0;                                 // pitch of dst-sized intermediates / states
+    size_t sharp4_pitch = 0;                                // pitch of a lane's d_sharp when it holds 32-bit (B, G, R, 1) pixels
+    bool lane_bgrx = false;                                 // plain chain on a driver with tensor maps: k_upsharp -> POST goes as words
     uint8_t* d_state[4] = {nullptr, nullptr, nullptr, nullptr};
     int nring = 0, head = 0, nvalid = 0;                    // temporal ring
     BilCand* d_cand_pre = nullptr; BilCand* d_cand_post = nullptr; BilCand* d_cand_tmp = nullptr;
@@ -405,13 +407,14 @@ EncodeTiledFn encode_tiled_fn() {
     }();
     return fn;
 }
-// rows of `w_elems` elements (1 or 2 bytes each), `h` rows `pitch` bytes apart (a multiple of 16, base 16-byte aligned)
+// rows of `w_elems` elements (1, 2 or 4 bytes each), `h` rows `pitch` bytes apart (a multiple of 16, base 16-byte aligned)
 bool make_tmap_2d(CUtensorMap* tm, int elem_bytes, const void* base, uint64_t w_elems, uint64_t h, uint64_t pitch, uint32_t box_w, uint32_t box_h) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn || ((uintptr_t)base & 15) || (pitch & 15) || box_w > 256 || box_h > 256) return false;
     const cuuint64_t gdim[2] = {w_elems, h}, gstride[1] = {pitch};
     const cuuint32_t box[2] = {box_w, box_h}, estr[2] = {1, 1};
-    return fn(tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride,
+    const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    return fn(tm, dt, 2, const_cast<void*>(base), gdim, gstride,
               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -441,10 +444,16 @@ int launch_bilateral(vp_ctx* c, BilArgs& a, const int radius[3], cudaStream_t st
     a.use_tm = 1;                                   // one box per candidate radius
     for (int i = 0; i < 3 && a.use_tm; ++i) {
         if (i > 0 && radius[i] == radius[i - 1]) { a.tm[i] = a.tm[i - 1]; continue; }
-        a.use_tm = make_tmap_2d(&a.tm[i], 1, a.src, (uint64_t)a.w * 3, a.h, a.spitch, (uint32_t)bil_raw_pitch(radius[i]) - 16,
-                                (uint32_t)(BIL_TH * a.ns + 2 * radius[i]));
+        if (a.src_bgrx)                             // 32-bit pixels: the box is the tile itself
+            a.use_tm = make_tmap_2d(&a.tm[i], 4, a.src, (uint64_t)a.w, a.h, a.spitch, (uint32_t)bil_tile_pitch_x(radius[i]),
+                                    (uint32_t)(BIL_TH * a.ns + 2 * radius[i]));
+        else
+            a.use_tm = make_tmap_2d(&a.tm[i], 1, a.src, (uint64_t)a.w * 3, a.h, a.spitch, (uint32_t)bil_raw_pitch(radius[i]) - 16,
+                                    (uint32_t)(BIL_TH * a.ns + 2 * radius[i]));
     }
-    k_bilateral<<<grid, BIL_NT, smem, st>>>(a);
+    if (a.src_bgrx && !a.use_tm) return fail(c, VP_ERR_STATE, "internal: 32-bit lane buffer without tensor maps");
+    if (a.src_bgrx) k_bilateral<true><<<grid, BIL_NT, smem, st>>>(a);
+    else k_bilateral<false><<<grid, BIL_NT, smem, st>>>(a);
     VP_CUDA(c, cudaGetLastError());
     c->launches++;
     return VP_OK;
@@ -970,9 +979,19 @@ int launch_upsharp(vp_ctx* c, UpsharpArgs& a, bool do_resize, bool do_sharpen, c
     if (L.total > 200 * 1024) return fail(c, VP_ERR_UNSUPPORTED, "resize ratio needs more shared memory than a CTA has");
     const dim3 grid((a.dw + US_TW - 1) / US_TW, (a.dh + US_TH - 1) / US_TH);
     a.use_tm_src = make_tmap_2d(&a.tm_src, 1, a.src, (uint64_t)a.sw * 3, a.sh, a.spitch, (uint32_t)L.raw_pitch - 16, (uint32_t)a.max_src_rows);
-    a.use_tm_dst = a.dst && make_tmap_2d(&a.tm_dst, 1, a.dst, (uint64_t)a.dw * 3, a.dh, a.dpitch, US_TW * 3, US_TH);
+    if (a.out_bgrx) {
+        a.use_tm_dst = make_tmap_2d(&a.tm_dst, 4, a.dst, (uint64_t)a.dw, a.dh, a.dpitch, US_TW, US_TH);
+        if (!a.use_tm_dst) return fail(c, VP_ERR_STATE, "internal: 32-bit lane buffer without tensor maps");
+    } else
+        a.use_tm_dst = a.dst && make_tmap_2d(&a.tm_dst, 1, a.dst, (uint64_t)a.dw * 3, a.dh, a.dpitch, US_TW * 3, US_TH);
     ProfScope ps(c, K_UPSHARP, st);
-    if (!do_sharpen) k_upsharp<true, false, 5><<<grid, US_NT, L.total, st>>>(a);
+    if (a.out_bgrx && !do_resize) return fail(c, VP_ERR_STATE, "internal: 32-bit lane output is built for the resizing forms only");
+    if (a.out_bgrx) {
+        if (!do_sharpen) k_upsharp<true, false, 5, true><<<grid, US_NT, L.total, st>>>(a);
+        else if (a.gk == 3) k_upsharp<true, true, 3, true><<<grid, US_NT, L.total, st>>>(a);
+        else if (a.gk == 5) k_upsharp<true, true, 5, true><<<grid, US_NT, L.total, st>>>(a);
+        else k_upsharp<true, true, 7, true><<<grid, US_NT, L.total, st>>>(a);
+    } else if (!do_sharpen) k_upsharp<true, false, 5><<<grid, US_NT, L.total, st>>>(a);
     else if (do_resize) {
         if (a.gk == 3) k_upsharp<true, true, 3><<<grid, US_NT, L.total, st>>>(a);
         else if (a.gk == 5) k_upsharp<true, true, 5><<<grid, US_NT, L.total, st>>>(a);
@@ -1170,13 +1189,18 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
         size_t bil_max = 0;                         // every (candidate radius, strips per thread) pair launch_bilateral can pick
         for (int rmax = 1; rmax <= BIL_RMAX; ++rmax)
             for (int r = 1; r <= rmax; ++r) bil_max = std::max(bil_max, bil_smem_bytes(r, rmax <= 2 ? 4 : (rmax <= 3 ? 2 : 1)));
-        VP_CUDA(c, cudaFuncSetAttribute(k_bilateral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bil_max));
+        VP_CUDA(c, cudaFuncSetAttribute(k_bilateral<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bil_max));
+        VP_CUDA(c, cudaFuncSetAttribute(k_bilateral<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bil_max));
     }
     VP_CUDA(c, cudaFuncSetAttribute(k_bicubic<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_bicubic<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_bicubic<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_bicubic_int<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BicubicIntGeom<2>::TOTAL));
     VP_CUDA(c, cudaFuncSetAttribute(k_bicubic_int<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BicubicIntGeom<4>::TOTAL));
+    VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, false, 5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, true, 5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, true, 7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_upsharp<true, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1220,7 +1244,11 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
         if (bil_has_modes(g.post) || (g.temporal.mode == VP_TEMPORAL_BLEND_FRAMES && g.temporal.use_flow))
             VP_CUDA(c, cudaMalloc(&c->lanes[0].d_post, c->frame_pitch * g.dst_h));
     }
-    VP_CUDA(c, cudaMalloc(&c->lanes[0].d_sharp, c->frame_pitch * g.dst_h));
+    c->sharp4_pitch = align_up((size_t)g.dst_w * 4, 256);
+    // 32-bit pixels between k_upsharp and the plain POST bilateral (the POST halo tile then needs no expansion pass)
+    c->lane_bgrx = encode_tiled_fn() != nullptr && g.use_post && !bil_has_modes(g.post) && !g.bicubic_enhance &&
+                   g.dst_w > 2 * BIL_RMAX && g.dst_h > 2 * BIL_RMAX && !std::getenv("VPB200_NO_BGRX");
+    VP_CUDA(c, cudaMalloc(&c->lanes[0].d_sharp, std::max(c->frame_pitch, c->sharp4_pitch) * g.dst_h));
     c->nring = g.temporal.mode == VP_TEMPORAL_MAIN_BLEND ? 2
              : g.temporal.mode == VP_TEMPORAL_BLEND_FRAMES ? std::max(1, g.temporal.buffer_size) + 1 : 0;
     const bool flow_tc = g.temporal.mode == VP_TEMPORAL_BLEND_FRAMES && g.temporal.use_flow;
@@ -1434,6 +1462,7 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
         VP_CUDA(c, cudaMemsetAsync(L.d_sums, 0, 12 * sizeof(unsigned long long), st));
 
     const uint8_t* cur = d_src; size_t cur_pitch = src_pitch;
+    bool cur_bgrx = false;                    // `cur` holds 32-bit (B, G, R, 1) pixels (k_upsharp's out_bgrx form)
     // 1. SelectiveBilateral PRE (src resolution)
     if (pre_modes) {
         rc = run_bilateral_modes(c, L.ms_pre, g.pre, c->d_cand_pre, c->cand_pre_rad, c->d_cand_ms_pre, c->ms_pre_rad,
@@ -1480,6 +1509,7 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
         a.src = cur; a.spitch = cur_pitch; a.sw = g.src_w; a.sh = g.src_h;
         a.dst = last_is_upsharp ? d_dst : L.d_sharp; a.dpitch = last_is_upsharp ? dst_pitch : c->frame_pitch;
         a.dw = g.dst_w; a.dh = g.dst_h;
+        if (!last_is_upsharp && plain_post && c->lane_bgrx && do_resize) { a.out_bgrx = 1; a.dpitch = c->sharp4_pitch; cur_bgrx = true; }
         const int k = g.use_sharpen ? 1 : 0, halo = g.use_sharpen ? US_HALO : 0;
         if (do_resize) {
             a.rt = ResizeTables{c->rc_chain.xofs, c->rc_chain.xcoef, c->rc_chain.yofs, c->rc_chain.ycoef};
@@ -1512,6 +1542,7 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
         if (plain_post) {
             BilArgs a{};
             a.src = cur; a.spitch = cur_pitch; a.dst = L.d_post; a.dpitch = c->frame_pitch; a.w = g.dst_w; a.h = g.dst_h;
+            a.src_bgrx = cur_bgrx ? 1 : 0;
             a.cand = c->d_cand_post; a.sel = need_post_stats ? L.d_sel + 1 : nullptr;
             rc = launch_bilateral(c, a, c->cand_post_rad, st, K_BIL_POST); if (rc) return rc;
             cur = L.d_post; cur_pitch = c->frame_pitch;
@@ -1541,6 +1572,7 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
         if (plain_post) {
             BilArgs a{};
             a.src = cur; a.spitch = cur_pitch; a.dst = nullptr; a.dpitch = 0; a.w = g.dst_w; a.h = g.dst_h;
+            a.src_bgrx = cur_bgrx ? 1 : 0;
             a.cand = c->d_cand_post; a.sel = need_post_stats ? L.d_sel + 1 : nullptr;
             a.blend = bl;                         // state store + previous frame for the gray difference
             a.scene = c->d_scene_acc;
@@ -1574,6 +1606,7 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
     if (plain_post) {
         BilArgs a{};
         a.src = cur; a.spitch = cur_pitch; a.dst = d_dst; a.dpitch = dst_pitch; a.w = g.dst_w; a.h = g.dst_h;
+        a.src_bgrx = cur_bgrx ? 1 : 0;
         a.cand = c->d_cand_post; a.sel = need_post_stats ? L.d_sel + 1 : nullptr;
         a.blend = bl;
         rc = launch_bilateral(c, a, c->cand_post_rad, st, K_BIL_POST); if (rc) return rc;
@@ -1614,7 +1647,7 @@ static int ensure_lane(vp_ctx* c, int ln) {
     const vp_chain_config& g = c->cfg;
     VP_CUDA(c, cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
     if (g.use_pre && !g.bicubic_enhance) VP_CUDA(c, cudaMalloc(&L.d_pre, c->pre_pitch * g.src_h));
-    VP_CUDA(c, cudaMalloc(&L.d_sharp, c->frame_pitch * g.dst_h));
+    VP_CUDA(c, cudaMalloc(&L.d_sharp, std::max(c->frame_pitch, c->sharp4_pitch) * g.dst_h));
     if (g.use_post && !g.bicubic_enhance && (bil_has_modes(g.post) || (g.temporal.mode == VP_TEMPORAL_BLEND_FRAMES && g.temporal.use_flow)))
         VP_CUDA(c, cudaMalloc(&L.d_post, c->frame_pitch * g.dst_h));
     VP_CUDA(c, cudaMalloc(&L.d_sums, 18 * sizeof(unsigned long long)));
