@@ -62,6 +62,8 @@ with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.csv"), "w") as f:
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         b = float(r[h.index("dram__bytes_read.sum")]) * scale.get(ur, 1) + float(r[h.index("dram__bytes_write.sum")]) * scale.get(uw, 1)
         base = name.split("(")[0]
+        if "k_bilateral" in base:          # k_bilateral<0> (3-byte source) and k_bilateral<1> (32-bit source) are one kernel family
+            base = "k_bilateral"
         traffic.setdefault(base + f"@grid{grid}#{seen[base]}", []).append(int(b))
         kind = {"k_stats": "stats", "k_bilateral": "bilateral_pre" if seen[base] == 0 else "bilateral_post"}.get(base)
         if kind is None and "k_upsharp" in base:

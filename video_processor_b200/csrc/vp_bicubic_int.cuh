@@ -130,7 +130,7 @@ template <int S> struct BiWindow {
 };
 
 template <int S>
-__global__ void __launch_bounds__(BI_NT) k_bicubic_int(const __grid_constant__ BicubicIntArgs a, int ntx, int ntiles) {
+__global__ void __launch_bounds__(BI_NT, 5) k_bicubic_int(const __grid_constant__ BicubicIntArgs a, int ntx, int ntiles) {
     using G = BicubicIntGeom<S>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_raw = smem + G::RAW;
@@ -176,7 +176,24 @@ __global__ void __launch_bounds__(BI_NT) k_bicubic_int(const __grid_constant__ B
         else stage_rows_wait(s_raw, G::RP, a.src, a.spitch, 3 * a.sw, w.sy0, w.sy1 + 1, w.bx0, w.bx1, false, bar);
 
         // ---- P1: raw bytes -> float4 (B, G, R, 0) per window pixel, replicate border materialised ------------------
-        {
+        const bool interior = w.ux0 >= 0 && w.ux0 + G::WC <= a.sw && w.uy0 >= 0 && w.uy0 + G::WR <= a.sh && (RPW & 3) == 0;
+        if (interior) {
+            // no clamping in this tile: a pixel's three bytes come out of two aligned words by one funnel shift (consecutive
+            // lanes write consecutive float4s: conflict-free, unlike four pixels per lane)
+            const unsigned long long bias = pack2(0xCB000000u, 0xCB000000u);       // (-2^23, -2^23)
+            const int c0 = 3 * w.ux0 - w.bx0;              // byte offset of window column 0 inside a raw row, 0..15
+            const uint32_t K = 0x4B000000u;
+            for (int i = tid; i < G::WC * G::WR; i += BI_NT) {
+                const int rr = i / G::WC, cc = i - rr * G::WC;
+                const int bo = c0 + 3 * cc;
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(s_raw + (w.uy0 + rr - w.sy0) * RPW + (bo & ~3));
+                const uint32_t v = __funnelshift_r(q[0], q[1], 8 * (bo & 3));
+                float b, g;
+                unpack2(fadd2(pack2(__byte_perm(v, K, 0x7440), __byte_perm(v, K, 0x7441)), bias), b, g);
+                const float r = __uint_as_float(__byte_perm(v, K, 0x7442)) - 8388608.0f;
+                s_f4[i] = make_float4(b, g, r, 0.0f);
+            }
+        } else {
             const unsigned long long bias = pack2(0xCB000000u, 0xCB000000u);       // (-2^23, -2^23)
             for (int i = tid; i < G::WC * G::WR; i += BI_NT) {
                 const int rr = i / G::WC, cc = i - rr * G::WC;
