@@ -21,7 +21,16 @@
 
 namespace vp {
 
-constexpr int BI_TW = 128, BI_TH = 32, BI_NT = 128;
+constexpr int BI_TW = 128, BI_NT = 128;
+#ifndef VP_BI_TH4
+#define VP_BI_TH4 64
+#endif
+// tile height: at x4 a band of RB output rows costs 4 + RB/4 horizontally filtered source rows, so taller tiles halve the
+// band overlap (RB 8 -> 16); at x2 the overlap is small already
+#ifndef VP_BI_TH2
+#define VP_BI_TH2 32
+#endif
+__host__ __device__ constexpr int bi_th(int S) { return S == 4 ? VP_BI_TH4 : VP_BI_TH2; }
 
 struct BicubicIntArgs {
     const uint8_t* src; size_t spitch; int sw, sh;
@@ -43,16 +52,17 @@ constexpr int BI_K = VP_BI_K;      // consecutive tiles (along x, then y) one CT
 template <int S> struct BicubicIntGeom {
     static constexpr int NCG = BI_TW / S;          // column groups per tile
     static constexpr int NB = BI_NT / NCG;         // row bands per tile
-    static constexpr int RB = BI_TH / NB;          // output rows per band
+    static constexpr int TH = bi_th(S);
+    static constexpr int RB = TH / NB;             // output rows per band
     static constexpr int WC = BI_TW / S + 4;       // source window of a tile: columns x0/S - 2 .. x0/S + TW/S + 1
-    static constexpr int WR = BI_TH / S + 4;
+    static constexpr int WR = TH / S + 4;
     static constexpr int WB = (WC * 3 + 15 + 15) & ~15;            // bytes of a window row from its 16-byte aligned start: the TMA box width
     static constexpr int RP = WB + 16;                             // raw row pitch of the row-copy path (16 bytes of slack)
     // raw window | staged output tile | float4 window | mbarrier: the raw bytes are free again once P1 has converted
     // them (the next tile's load is issued right behind that barrier), the output tile drains by TMA during the next P1
     static constexpr int RAW = 0;
     static constexpr int OUT = (RP * WR + 127) & ~127;
-    static constexpr int F4 = OUT + BI_TH * BI_TW * 3;
+    static constexpr int F4 = OUT + TH * BI_TW * 3;
     static_assert(WB <= 256 && BI_TW * 3 / 2 <= 256, "TMA box dimensions");
     static constexpr int BAR = F4 + WC * WR * 16;
     static constexpr int TOTAL = BAR + 16;
@@ -147,7 +157,7 @@ __global__ void __launch_bounds__(BI_NT, 5) k_bicubic_int(const __grid_constant_
     auto issue = [&](int t) {
         if (!fast_stage || tid >= 32) return;
         const int ty = t / ntx, tx = t - ty * ntx;
-        const BiWindow<S> w(a, tx * BI_TW, ty * BI_TH);
+        const BiWindow<S> w(a, tx * BI_TW, ty * G::TH);
         if (tm) {          // rows below the image are zero-filled (and counted): always the whole box
             if (tid == 0) {
                 mbar_arrive_expect_tx(bar, (uint32_t)(G::WB * G::WR));
@@ -170,7 +180,7 @@ __global__ void __launch_bounds__(BI_NT, 5) k_bicubic_int(const __grid_constant_
 
     for (int t = t0; t < t1; ++t) {
         const int ty = t / ntx, tx = t - ty * ntx;
-        const int x0 = tx * BI_TW, y0 = ty * BI_TH;
+        const int x0 = tx * BI_TW, y0 = ty * G::TH;
         const BiWindow<S> w(a, x0, y0);
         if (fast_stage) mbar_wait(bar, (uint32_t)(t - t0) & 1u);    // long since complete for every tile but the first
         else stage_rows_wait(s_raw, G::RP, a.src, a.spitch, 3 * a.sw, w.sy0, w.sy1 + 1, w.bx0, w.bx1, false, bar);
@@ -245,7 +255,7 @@ __global__ void __launch_bounds__(BI_NT, 5) k_bicubic_int(const __grid_constant_
             stores_pending = tid == 0;
             continue;
         }
-        const int vw = min(BI_TW, a.dw - x0), vh = min(BI_TH, a.dh - y0);
+        const int vw = min(BI_TW, a.dw - x0), vh = min(G::TH, a.dh - y0);
         const int rb = vw * 3;
         const int nb16 = aligned16(a.dst, a.dpitch) ? (rb & ~15) : 0;
         stores_pending = false;

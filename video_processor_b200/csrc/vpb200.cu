@@ -1016,11 +1016,11 @@ int launch_bicubic(vp_ctx* c, const uint8_t* src, size_t spitch, int sw, int sh,
             for (int t = 0; t < 4; ++t) { b.xk[p][t] = make_float2(rcache.xk[p][t], rcache.xk[p][t]); b.yk[p][t] = make_float2(rcache.yk[p][t], rcache.yk[p][t]); }
         if (rcache.int_ratio == 2)
             b.use_tm = make_tmap_2d(&b.tm_src, 1, src, (uint64_t)sw * 3, sh, spitch, BicubicIntGeom<2>::WB, BicubicIntGeom<2>::WR) &&
-                       make_tmap_2d(&b.tm_dst, 2, dst, (uint64_t)dw * 3 / 2, dh, dpitch, BI_TW * 3 / 2, BI_TH);
+                       make_tmap_2d(&b.tm_dst, 2, dst, (uint64_t)dw * 3 / 2, dh, dpitch, BI_TW * 3 / 2, bi_th(2));
         else
             b.use_tm = make_tmap_2d(&b.tm_src, 1, src, (uint64_t)sw * 3, sh, spitch, BicubicIntGeom<4>::WB, BicubicIntGeom<4>::WR) &&
-                       make_tmap_2d(&b.tm_dst, 2, dst, (uint64_t)dw * 3 / 2, dh, dpitch, BI_TW * 3 / 2, BI_TH);
-        const int ntx = (dw + BI_TW - 1) / BI_TW, ntiles = ntx * ((dh + BI_TH - 1) / BI_TH);
+                       make_tmap_2d(&b.tm_dst, 2, dst, (uint64_t)dw * 3 / 2, dh, dpitch, BI_TW * 3 / 2, bi_th(4));
+        const int ntx = (dw + BI_TW - 1) / BI_TW, ntiles = ntx * ((dh + bi_th(rcache.int_ratio) - 1) / bi_th(rcache.int_ratio));
         const int grid = (ntiles + BI_K - 1) / BI_K;
         ProfScope ps(c, K_UPSHARP, st);
         if (rcache.int_ratio == 2) k_bicubic_int<2><<<grid, BI_NT, BicubicIntGeom<2>::TOTAL, st>>>(b, ntx, ntiles);
