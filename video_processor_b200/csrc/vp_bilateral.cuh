@@ -106,6 +106,9 @@ __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsign
 __device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b) {
     unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
 }
+__device__ __forceinline__ unsigned long long fadd2_rm(unsigned long long a, unsigned long long b) {     // rounded toward -inf
+    unsigned long long d; asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
 __device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
     unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
 }

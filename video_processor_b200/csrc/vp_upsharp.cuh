@@ -35,6 +35,9 @@
 namespace vp {
 
 constexpr int US_TW = 64, US_TH = 32, US_NT = 256, US_HALO = 3;
+#ifndef VP_US_P5_FLOAT
+#define VP_US_P5_FLOAT 1
+#endif
 
 struct ResizeTables {            // device memory, built on the host exactly as cv::resize does
     const int* xofs;             // [dst_w]  first tap column (s-1), unclamped
@@ -478,17 +481,33 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const __grid_constant__ Upsha
             const int x = tid & 63, g = tid >> 6;
             const int yb = g * 8;
             float fw[5];
+#if VP_US_P5_FLOAT
+            unsigned long long bgf[GK], qf2[GK];
+            float rf[GK], qf[GK];
+#pragma unroll
+            for (int k = 0; k < GK; ++k) { qf[k] = (float)a.gq[k]; qf2[k] = pack2(__float_as_uint(qf[k]), __float_as_uint(qf[k])); }
+#else
             uint32_t bgw[GK], rw[GK];
             int q[GK];
 #pragma unroll
             for (int k = 0; k < GK; ++k) q[k] = a.gq[k];
+#endif
             const float gf0 = a.gf[0], gf1 = a.gf[1], gf2 = a.gf[2], gf3 = a.gf[3], gf4 = a.gf[4];
             if (own_mask) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) fw[k] = s_rowf[(yb + k) * US_TW + x];
             }
 #pragma unroll
-            for (int k = 0; k < GK - 1; ++k) { bgw[k] = s_rowbg[(yb + k) * US_TW + x]; rw[k] = s_rowr[(yb + k) * US_TW + x]; }
+            for (int k = 0; k < GK - 1; ++k) {
+#if VP_US_P5_FLOAT
+                const uint32_t nbg = s_rowbg[(yb + k) * US_TW + x];
+                const uint32_t nr = s_rowr[(yb + k) * US_TW + x];
+                bgf[k] = fadd2(pack2(__byte_perm(nbg, 0x4B000000u, 0x7410), __byte_perm(nbg, 0x4B000000u, 0x7432)), pack2(0xCB000000u, 0xCB000000u));
+                rf[k] = __uint_as_float(__byte_perm(nr, 0x4B000000u, 0x7410)) - 8388608.0f;
+#else
+                bgw[k] = s_rowbg[(yb + k) * US_TW + x]; rw[k] = s_rowr[(yb + k) * US_TW + x];
+#endif
+            }
             const float es = a.edge_strength, ssm = a.smooth_strength, stg = a.strength;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -507,6 +526,48 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const __grid_constant__ Upsha
                 }
                 if (MASKIO && a.mask_out && x < vw && y < vh)
                     *reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a.mask_out) + (size_t)(y0 + y) * a.mask_out_pitch + (size_t)(x0 + x) * 4) = e;
+#if VP_US_P5_FLOAT
+                // Q8.16 column pass, unsharp mask and blend in float32: the row sums (<= 65,280), their products with the
+                // Q0.8 taps and the column sums (< 2^24) are integers a float holds exactly, so the packed FMA chains below
+                // equal the integer arithmetic bit for bit; (v + 2^15) >> 16 is floor(v * 2^-16 + 0.5), taken by an add
+                // rounded toward -inf onto 2^23, and `up` enters as 2^23 + u straight out of a PRMT, so u - blur needs no
+                // unbiasing at all.
+                {
+                    const uint32_t nbg = s_rowbg[(y + GK - 1) * US_TW + x];
+                    const uint32_t nr = s_rowr[(y + GK - 1) * US_TW + x];
+                    bgf[(i + GK - 1) % GK] = fadd2(pack2(__byte_perm(nbg, 0x4B000000u, 0x7410), __byte_perm(nbg, 0x4B000000u, 0x7432)),
+                                                   pack2(0xCB000000u, 0xCB000000u));
+                    rf[(i + GK - 1) % GK] = __uint_as_float(__byte_perm(nr, 0x4B000000u, 0x7410)) - 8388608.0f;
+                }
+                unsigned long long cbg = fmul2(bgf[i % GK], qf2[0]);
+                float crf = __fmul_rn(rf[i % GK], qf[0]);
+#pragma unroll
+                for (int k = 1; k < GK; ++k) {
+                    cbg = ffma2(bgf[(i + k) % GK], qf2[k], cbg);
+                    crf = __fmaf_rn(rf[(i + k) % GK], qf[k], crf);
+                }
+                const uint32_t px = s_up[(y + US_HALO) * EW + x + US_HALO];
+                const int u[3] = {(int)(px & 0xff), (int)((px >> 8) & 0xff), (int)((px >> 16) & 0xff)};
+                const float t1 = __fmul_rn(e, es);
+                const float t2 = __fmul_rn(__fsub_rn(1.0f, e), ssm);
+                const float st = __fmul_rn(stg, __fadd_rn(t1, t2));
+                const unsigned long long c16 = pack2(0x37800000u, 0x37800000u), half2 = pack2(0x3F000000u, 0x3F000000u);   // 2^-16, 0.5
+                const unsigned long long big = pack2(0x4B000000u, 0x4B000000u), nbig = pack2(0xCB000000u, 0xCB000000u);     // +-2^23
+                const unsigned long long blb = fadd2_rm(ffma2(cbg, c16, half2), big);                     // 2^23 + blur (B, G)
+                const float blr = __fadd_rd(__fmaf_rn(crf, 1.52587890625e-05f, 0.5f), 8388608.0f);         // 2^23 + blur R
+                const unsigned long long ubg = pack2(__byte_perm(px, 0x4B000000u, 0x7440), __byte_perm(px, 0x4B000000u, 0x7441));   // 2^23 + u
+                const float ubr = __uint_as_float(__byte_perm(px, 0x4B000000u, 0x7442));
+                float umb, umg;
+                unpack2(ffma2(blb, pack2(0xBF800000u, 0xBF800000u), ubg), umb, umg);                      // u - blur, exact
+                const float umr = fmaxf(__fsub_rn(ubr, blr), 0.0f);
+                const unsigned long long um2 = pack2(__float_as_uint(fmaxf(umb, 0.0f)), __float_as_uint(fmaxf(umg, 0.0f)));
+                const uint32_t stb = __float_as_uint(st);
+                float ob, og;
+                unpack2(fadd2(fadd2(ubg, nbig), fmul2(pack2(stb, stb), um2)), ob, og);                    // u + st * um: separate mul, add
+                int o[3];
+                o[0] = (int)f2u8(ob); o[1] = (int)f2u8(og);
+                o[2] = (int)f2u8(__fadd_rn(__fsub_rn(ubr, 8388608.0f), __fmul_rn(st, umr)));
+#else
                 bgw[(i + GK - 1) % GK] = s_rowbg[(y + GK - 1) * US_TW + x];
                 rw[(i + GK - 1) % GK] = s_rowr[(y + GK - 1) * US_TW + x];
                 uint32_t cb_ = 1u << 15, cg_ = 1u << 15, cr_ = 1u << 15;
@@ -530,6 +591,7 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const __grid_constant__ Upsha
                     // I2F here on purpose: the conversion pipe is idle in this kernel, the issue slots are not
                     o[ch] = (int)f2u8(__fadd_rn((float)u[ch], __fmul_rn(st, (float)um)));
                 }
+#endif
                 if (a.preserve_tone) {
                     const int yi = (4899 * u[2] + 9617 * u[1] + 1868 * u[0] + (1 << 13)) >> 14;
                     const int cr = sat_u8(((u[2] - yi) * 11682 + (128 << 14) + (1 << 13)) >> 14) - 128;

@@ -438,6 +438,10 @@ int launch_bilateral(vp_ctx* c, BilArgs& a, const int radius[3], cudaStream_t st
     int rmax = 0;
     for (int i = 0; i < 3; ++i) { a.radius[i] = radius[i]; rmax = std::max(rmax, radius[i]); }
     a.ns = rmax <= 2 ? 4 : (rmax <= 3 ? 2 : 1);     // small windows: taller tiles amortise the per-CTA table/halo cost
+    if (const char* e = std::getenv("VPB200_BIL_NS")) {      // development: "a,b,c" = strips per thread for r <= 2, r == 3, r >= 4
+        int v[3] = {4, 2, 1};
+        if (std::sscanf(e, "%d,%d,%d", &v[0], &v[1], &v[2]) == 3) a.ns = std::min(8, std::max(1, rmax <= 2 ? v[0] : (rmax <= 3 ? v[1] : v[2])));
+    }
     const dim3 grid((a.w + BIL_TW - 1) / BIL_TW, (a.h + BIL_TH * a.ns - 1) / (BIL_TH * a.ns));
     size_t smem = 0;                                // the device picks one of the candidates: size for the largest layout
     for (int i = 0; i < 3; ++i) smem = std::max(smem, bil_smem_bytes(radius[i], a.ns));
@@ -1188,7 +1192,7 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
     {
         size_t bil_max = 0;                         // every (candidate radius, strips per thread) pair launch_bilateral can pick
         for (int rmax = 1; rmax <= BIL_RMAX; ++rmax)
-            for (int r = 1; r <= rmax; ++r) bil_max = std::max(bil_max, bil_smem_bytes(r, rmax <= 2 ? 4 : (rmax <= 3 ? 2 : 1)));
+            for (int r = 1; r <= rmax; ++r) bil_max = std::max(bil_max, bil_smem_bytes(r, std::getenv("VPB200_BIL_NS") ? 8 : (rmax <= 2 ? 4 : (rmax <= 3 ? 2 : 1))));
         VP_CUDA(c, cudaFuncSetAttribute(k_bilateral<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bil_max));
         VP_CUDA(c, cudaFuncSetAttribute(k_bilateral<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bil_max));
     }
