@@ -207,6 +207,24 @@ def test_batch_graph_replay_is_bit_identical(vp, temporal):
         assert vp.lib.vp_batch_graph_replays(ctx.handle) == 5
 
 
+@pytest.mark.parametrize("size", [(160, 96), (131, 67), (320, 200)])
+@pytest.mark.parametrize("kind", ["scene", "noise"])
+def test_lane_buffer_format_is_transparent(vp, monkeypatch, size, kind):
+    """The plain chain hands k_upsharp's output to the POST bilateral as 32-bit (B, G, R, 1) pixels whose halo tile arrives by
+    one TMA box (interior tiles untouched, border tiles mirrored in place).  With VPB200_NO_BGRX the same chain uses the packed
+    3-byte lane buffer and the expansion pass; both must produce the same bytes - odd sizes put every kind of border tile
+    (left / right / top / bottom, partial last tile) on the 32-bit path."""
+    sw, sh = size
+    ocfg = RC.ChainConfig(dst_w=2 * sw, dst_h=2 * sh, temporal=RC.TEMPORAL_BLEND_FRAMES)
+    frames = synth.clip(kind, sw, sh, 5)
+    monkeypatch.delenv("VPB200_NO_BGRX", raising=False)
+    words, _ = run_chain_device(vp, ocfg, frames, sw, sh)
+    monkeypatch.setenv("VPB200_NO_BGRX", "1")
+    packed, _ = run_chain_device(vp, ocfg, frames, sw, sh)
+    for i, (a, b) in enumerate(zip(words, packed)):
+        assert np.array_equal(a, b), (i, G.diff_stats(a, b))
+
+
 @pytest.mark.parametrize("kind", ["scene", "noise", "flat"])
 @pytest.mark.parametrize("size,scale", [((160, 96), 2), ((131, 67), 2), ((96, 54), 4)])
 def test_bicubic_wrapper_chain(vp, kind, size, scale):
