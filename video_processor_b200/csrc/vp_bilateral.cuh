@@ -79,6 +79,7 @@ struct BilArgs {
     // TMA directly as the tile words (box TP x TROWS of 32-bit units at (x0 - r, y0 - r), zero-filled outside the image);
     // only tiles on the image border run a pass that mirrors the outside positions.  Requires use_tm.
     int src_bgrx;
+    int dst_bgrx;                  // `dst` takes 32-bit (B, G, R, 1) pixels; no blend / state / scene / edge map (k_bilateral<., DSTX>)
     alignas(64) CUtensorMap tm[3];
 };
 
@@ -378,7 +379,9 @@ __host__ inline size_t bil_smem_bytes(int r, int ns) {
 
 // BGRX: the source holds 32-bit (B, G, R, 1) pixels (BilArgs::src_bgrx) - compiled as its own kernel so neither form carries
 // the other's registers
-template <bool BGRX>
+// DSTX: the output goes out as one 32-bit word (B, G, R, 1) per pixel and nothing else happens in the epilogue
+// (BilArgs::dst_bgrx: the PRE stage feeding k_upsharp's 32-bit source window)
+template <bool BGRX, bool DSTX = false>
 __global__ void __launch_bounds__(BIL_NT, VP_BIL_MINB) k_bilateral(const __grid_constant__ BilArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ BilHead s_cand;
@@ -520,6 +523,13 @@ __global__ void __launch_bounds__(BIL_NT, VP_BIL_MINB) k_bilateral(const __grid_
             case 5: bil_strip<5, BGRX ? bil_xo(5) : 0>(s_tile, s_cand, s_cls, lx, ly, out); break;
             case 6: bil_strip<6, BGRX ? bil_xo(6) : 0>(s_tile, s_cand, s_cls, lx, ly, out); break;
             default: bil_strip<7, BGRX ? bil_xo(7) : 0>(s_tile, s_cand, s_cls, lx, ly, out); break;
+        }
+        if (DSTX) {      // 4 words per strip: one 128-bit store (gx is a multiple of 4, base and pitch 16-byte aligned)
+            uint32_t* dp = reinterpret_cast<uint32_t*>(a.dst + (size_t)gy * a.dpitch) + gx;
+            if (npx == 4) *reinterpret_cast<uint4*>(dp) = make_uint4(out[0] | 0x01000000u, out[1] | 0x01000000u, out[2] | 0x01000000u, out[3] | 0x01000000u);
+            else
+                for (int j = 0; j < npx; ++j) dp[j] = out[j] | 0x01000000u;
+            continue;
         }
         if (!BGRX && a.emap) {
             // 2x2 dilate (anchor (1,1)): pixel x is an edge if map[y-1..y][x-1..x] holds a 2.  The strip's four

@@ -70,6 +70,10 @@ struct UpsharpArgs {
     // bilateral, whose halo tile then arrives by TMA already in the form its tap loop reads (no expansion pass there);
     // tm_dst is then a tensor of 32-bit units and use_tm_dst is set
     int out_bgrx;
+    // src_bgrx: `src` holds 32-bit (B, G, R, 1) pixels (k_bilateral<., DSTX>): the source window arrives by TMA as the
+    // BGR0-word tile the horizontal pass reads (box src_pitch_x x max_src_rows of 32-bit units, origin rounded down to 4
+    // pixels); only tiles on the image border run a pass that replicates the zero-filled outside positions.  RESIZE only.
+    int src_bgrx, src_pitch_x;
     alignas(64) CUtensorMap tm_src;
     alignas(64) CUtensorMap tm_dst;
 };
@@ -231,12 +235,15 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const __grid_constant__ Upsha
     const bool tm_src = a.use_tm_src != 0;                    // implies fast_stage
     const int RP = L.raw_pitch - (tm_src ? 16 : 0);           // a TMA box is dense
     const bool fast_stage = aligned16(a.src, a.spitch);
-    if (tm_src) stage_box_issue(s_raw, &a.tm_src, bx0, sy0, (uint32_t)(RP * a.max_src_rows), bar);
+    const bool srcx = RESIZE && a.src_bgrx != 0;
+    const int ux0a = srcx ? ux0 - (((ux0 % 4) + 4) % 4) : ux0;   // 32-bit source: the box starts on a multiple of 4 pixels
+    if (srcx) stage_box_issue(smem + L.raw, &a.tm_src, ux0a, uy0, (uint32_t)(a.src_pitch_x * a.max_src_rows * 4), bar);
+    else if (tm_src) stage_box_issue(s_raw, &a.tm_src, bx0, sy0, (uint32_t)(RP * a.max_src_rows), bar);
     else stage_rows_issue(s_raw, RP, a.src, a.spitch, sy0, sy1 + 1, bx0, bx1, fast_stage, bar);
     if (RESIZE) {
         for (int i = tid; i < EW; i += US_NT) {
             const int dx = clampi(reflect101(x0 - HALO + i, a.dw), dxa, dxb);   // clamp: unused columns of edge tiles
-            s_xo[i] = a.rt.xofs[dx] - ux0; s_xc[i] = a.rt.xcoef[dx];
+            s_xo[i] = a.rt.xofs[dx] - ux0a; s_xc[i] = a.rt.xcoef[dx];
         }
         for (int i = tid; i < EH; i += US_NT) {
             const int dy = clampi(reflect101(y0 - HALO + i, a.dh), dya, dyb);
@@ -247,11 +254,24 @@ __global__ void __launch_bounds__(US_NT) k_upsharp(const __grid_constant__ Upsha
     stage_rows_wait(s_raw, RP, a.src, a.spitch, 3 * a.sw, sy0, sy1 + 1, bx0, bx1, fast_stage, bar);
 
     if (RESIZE) {
-        const int SP = L.src_pitch;
+        const int SP = srcx ? a.src_pitch_x : L.src_pitch;
+        if (srcx) s_src = reinterpret_cast<uint32_t*>(smem + L.raw);      // the TMA box IS the word tile
         const int ncols = ux1 - ux0 + 1, nrows = uy1 - uy0 + 1;
         // raw bytes -> BGR0 words, replicate border materialised; warp per row, lanes along x
         const int lane = tid & 31, wrp = tid >> 5;
-        if (ux0 >= 0 && ux1 < a.sw && aligned16(a.src, a.spitch)) {
+        if (srcx) {
+            // positions outside the image (zero-filled by the TMA unit) take their replicate-border source, which lies inside
+            // the image and inside this window
+            if (ux0a < 0 || uy0 < 0 || ux0a + SP > a.sw || uy0 + a.max_src_rows > a.sh) {
+                for (int i = tid; i < a.max_src_rows * SP; i += US_NT) {
+                    const int rr = i / SP, cc = i - rr * SP;
+                    const int ux = ux0a + cc, uy = uy0 + rr;
+                    if ((unsigned)ux < (unsigned)a.sw && (unsigned)uy < (unsigned)a.sh) continue;
+                    const int qx = clampi(ux, 0, a.sw - 1) - ux0a, qy = clampi(uy, 0, a.sh - 1) - uy0;
+                    if ((unsigned)qx < (unsigned)SP && (unsigned)qy < (unsigned)a.max_src_rows) s_src[i] = s_src[qy * SP + qx];
+                }
+            }
+        } else if (ux0 >= 0 && ux1 < a.sw && aligned16(a.src, a.spitch)) {
             // no horizontal clamping in this tile: a lane turns 12 raw bytes (4 pixels, any byte phase) into four
             // BGR0 words with funnel shifts and byte permutes and stores them as one 128-bit word
             const int c0 = 3 * ux0 - bx0;               // byte offset of window column 0 inside a raw row, 0..15

@@ -166,7 +166,8 @@ struct vp_ctx {
     size_t pre_pitch = 0;
     size_t frame_pitch = 0;                                 // pitch of dst-sized intermediates / states
     size_t sharp4_pitch = 0;                                // pitch of a lane's d_sharp when it holds 32-bit (B, G, R, 1) pixels
-    bool lane_bgrx = false;                                 // plain chain on a driver with tensor maps: k_upsharp -> POST goes as words
+    size_t pre4_pitch = 0;                                  // the same for a lane's d_pre (PRE -> k_upsharp)
+    bool lane_bgrx = false, pre_bgrx = false;                                 // plain chain on a driver with tensor maps: k_upsharp -> POST goes as words
     uint8_t* d_state[4] = {nullptr, nullptr, nullptr, nullptr};
     int nring = 0, head = 0, nvalid = 0;                    // temporal ring
     BilCand* d_cand_pre = nullptr; BilCand* d_cand_post = nullptr; BilCand* d_cand_tmp = nullptr;
@@ -456,7 +457,11 @@ int launch_bilateral(vp_ctx* c, BilArgs& a, const int radius[3], cudaStream_t st
                                     (uint32_t)(BIL_TH * a.ns + 2 * radius[i]));
     }
     if (a.src_bgrx && !a.use_tm) return fail(c, VP_ERR_STATE, "internal: 32-bit lane buffer without tensor maps");
-    if (a.src_bgrx) k_bilateral<true><<<grid, BIL_NT, smem, st>>>(a);
+    if (a.dst_bgrx) {
+        if (a.src_bgrx || a.blend.mode != 0 || a.blend.state || a.scene || a.emap || !a.dst || (a.dpitch & 15) || ((uintptr_t)a.dst & 15))
+            return fail(c, VP_ERR_STATE, "internal: 32-bit bilateral output is the bare PRE stage only");
+        k_bilateral<false, true><<<grid, BIL_NT, smem, st>>>(a);
+    } else if (a.src_bgrx) k_bilateral<true><<<grid, BIL_NT, smem, st>>>(a);
     else k_bilateral<false><<<grid, BIL_NT, smem, st>>>(a);
     VP_CUDA(c, cudaGetLastError());
     c->launches++;
@@ -982,7 +987,14 @@ int launch_upsharp(vp_ctx* c, UpsharpArgs& a, bool do_resize, bool do_sharpen, c
     const UpsharpSmem L = upsharp_layout(do_resize, do_sharpen, a.max_src_rows, a.max_src_cols);
     if (L.total > 200 * 1024) return fail(c, VP_ERR_UNSUPPORTED, "resize ratio needs more shared memory than a CTA has");
     const dim3 grid((a.dw + US_TW - 1) / US_TW, (a.dh + US_TH - 1) / US_TH);
-    a.use_tm_src = make_tmap_2d(&a.tm_src, 1, a.src, (uint64_t)a.sw * 3, a.sh, a.spitch, (uint32_t)L.raw_pitch - 16, (uint32_t)a.max_src_rows);
+    if (a.src_bgrx) {
+        a.src_pitch_x = (a.max_src_cols + 3 + 3) & ~3;          // up to 3 columns left of the window (box origin on 4 pixels)
+        if (!do_resize || a.src_pitch_x * a.max_src_rows * 4 > L.raw_pitch * a.max_src_rows + L.src_pitch * a.max_src_rows * 4 ||
+            !make_tmap_2d(&a.tm_src, 4, a.src, (uint64_t)a.sw, a.sh, a.spitch, (uint32_t)a.src_pitch_x, (uint32_t)a.max_src_rows))
+            return fail(c, VP_ERR_STATE, "internal: 32-bit source window without tensor maps");
+        a.use_tm_src = 1;
+    } else
+        a.use_tm_src = make_tmap_2d(&a.tm_src, 1, a.src, (uint64_t)a.sw * 3, a.sh, a.spitch, (uint32_t)L.raw_pitch - 16, (uint32_t)a.max_src_rows);
     if (a.out_bgrx) {
         a.use_tm_dst = make_tmap_2d(&a.tm_dst, 4, a.dst, (uint64_t)a.dw, a.dh, a.dpitch, US_TW, US_TH);
         if (!a.use_tm_dst) return fail(c, VP_ERR_STATE, "internal: 32-bit lane buffer without tensor maps");
@@ -1105,7 +1117,7 @@ bool host_ptr_is_pinned(const void* p) {
 int alloc_enhance_buffers(vp_ctx* c, Lane& L) {
     const vp_chain_config& g = c->cfg;
     if (!g.bicubic_enhance || L.d_map) return VP_OK;
-    if (!L.d_pre) VP_CUDA(c, cudaMalloc(&L.d_pre, c->pre_pitch * g.src_h));
+    if (!L.d_pre) VP_CUDA(c, cudaMalloc(&L.d_pre, std::max(c->pre_pitch, c->pre4_pitch) * g.src_h));
     VP_CUDA(c, cudaMalloc(&L.d_map, c->map_pitch * g.dst_h));
     VP_CUDA(c, cudaMalloc(&L.d_dirty, c->dirty_bytes));
     return VP_OK;
@@ -1195,6 +1207,7 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
             for (int r = 1; r <= rmax; ++r) bil_max = std::max(bil_max, bil_smem_bytes(r, std::getenv("VPB200_BIL_NS") ? 8 : (rmax <= 2 ? 4 : (rmax <= 3 ? 2 : 1))));
         VP_CUDA(c, cudaFuncSetAttribute(k_bilateral<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bil_max));
         VP_CUDA(c, cudaFuncSetAttribute(k_bilateral<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bil_max));
+        VP_CUDA(c, cudaFuncSetAttribute(k_bilateral<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bil_max));
     }
     VP_CUDA(c, cudaFuncSetAttribute(k_bicubic<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VP_CUDA(c, cudaFuncSetAttribute(k_bicubic<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1232,9 +1245,10 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
     if (g.temporal.mode == VP_TEMPORAL_BLEND_FRAMES && (g.temporal.buffer_size < 1 || g.temporal.buffer_size > 3))
         return fail(c, VP_ERR_UNSUPPORTED, "vp_create: temporal.buffer_size must be 1..3");
     c->pre_pitch = align_up((size_t)g.src_w * 3, 256);
+    c->pre4_pitch = align_up((size_t)g.src_w * 4, 256);
     c->frame_pitch = align_up((size_t)g.dst_w * 3, 256);
     if (g.use_pre && !g.bicubic_enhance) {
-        VP_CUDA(c, cudaMalloc(&c->lanes[0].d_pre, c->pre_pitch * g.src_h));
+        VP_CUDA(c, cudaMalloc(&c->lanes[0].d_pre, std::max(c->pre_pitch, c->pre4_pitch) * g.src_h));
         VP_CUDA(c, cudaMalloc(&c->d_cand_pre, 3 * sizeof(BilCand)));
         int rc = build_selective_cands(c, g.pre, c->d_cand_pre, c->cand_pre_rad, c->s_compute);
         if (rc) return rc;
@@ -1252,6 +1266,8 @@ static int create_impl(vp_ctx* c, const vp_chain_config* cfg) {
     // 32-bit pixels between k_upsharp and the plain POST bilateral (the POST halo tile then needs no expansion pass)
     c->lane_bgrx = encode_tiled_fn() != nullptr && g.use_post && !bil_has_modes(g.post) && !g.bicubic_enhance &&
                    g.dst_w > 2 * BIL_RMAX && g.dst_h > 2 * BIL_RMAX && !std::getenv("VPB200_NO_BGRX");
+    c->pre_bgrx = encode_tiled_fn() != nullptr && g.use_pre && !bil_has_modes(g.pre) && !g.bicubic_enhance &&
+                  g.src_w > 2 * BIL_RMAX && g.src_h > 2 * BIL_RMAX && !std::getenv("VPB200_NO_BGRX") && !std::getenv("VPB200_NO_PRE_BGRX");
     VP_CUDA(c, cudaMalloc(&c->lanes[0].d_sharp, std::max(c->frame_pitch, c->sharp4_pitch) * g.dst_h));
     c->nring = g.temporal.mode == VP_TEMPORAL_MAIN_BLEND ? 2
              : g.temporal.mode == VP_TEMPORAL_BLEND_FRAMES ? std::max(1, g.temporal.buffer_size) + 1 : 0;
@@ -1467,6 +1483,7 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
 
     const uint8_t* cur = d_src; size_t cur_pitch = src_pitch;
     bool cur_bgrx = false;                    // `cur` holds 32-bit (B, G, R, 1) pixels (k_upsharp's out_bgrx form)
+    bool pre_is_bgrx = false;                 // the PRE stage wrote 32-bit pixels for k_upsharp
     // 1. SelectiveBilateral PRE (src resolution)
     if (pre_modes) {
         rc = run_bilateral_modes(c, L.ms_pre, g.pre, c->d_cand_pre, c->cand_pre_rad, c->d_cand_ms_pre, c->ms_pre_rad,
@@ -1481,8 +1498,12 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
         BilArgs a{};
         a.src = cur; a.spitch = cur_pitch; a.dst = L.d_pre; a.dpitch = c->pre_pitch; a.w = g.src_w; a.h = g.src_h;
         a.cand = c->d_cand_pre; a.sel = need_pre_stats ? L.d_sel : nullptr;
+        // the next stage is k_upsharp with a resize: hand it 32-bit pixels (its source window then needs no expansion pass)
+        const bool next_is_upsharp = (g.dst_w != g.src_w || g.dst_h != g.src_h) && !(g.use_sharpen && g.sharpen.adaptive_sigma) &&
+                                     (g.use_sharpen || need_post_stats);
+        if (next_is_upsharp && c->pre_bgrx) { a.dst_bgrx = 1; a.dpitch = c->pre4_pitch; pre_is_bgrx = true; }
         rc = launch_bilateral(c, a, c->cand_pre_rad, st, K_BIL_PRE); if (rc) return rc;
-        cur = L.d_pre; cur_pitch = c->pre_pitch;
+        cur = L.d_pre; cur_pitch = a.dpitch;
     }
     // 2+3. bicubic resize + AdaptiveSharpening (dst resolution)
     const bool do_resize = (g.dst_w != g.src_w || g.dst_h != g.src_h);
@@ -1511,6 +1532,7 @@ static int process_frame(vp_ctx* c, int ln, cudaStream_t st, cudaEvent_t tempora
     } else if (do_resize || g.use_sharpen) {
         UpsharpArgs a{};
         a.src = cur; a.spitch = cur_pitch; a.sw = g.src_w; a.sh = g.src_h;
+        a.src_bgrx = pre_is_bgrx ? 1 : 0;
         a.dst = last_is_upsharp ? d_dst : L.d_sharp; a.dpitch = last_is_upsharp ? dst_pitch : c->frame_pitch;
         a.dw = g.dst_w; a.dh = g.dst_h;
         if (!last_is_upsharp && plain_post && c->lane_bgrx && do_resize) { a.out_bgrx = 1; a.dpitch = c->sharp4_pitch; cur_bgrx = true; }
@@ -1650,7 +1672,7 @@ static int ensure_lane(vp_ctx* c, int ln) {
     if (L.st) return VP_OK;
     const vp_chain_config& g = c->cfg;
     VP_CUDA(c, cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
-    if (g.use_pre && !g.bicubic_enhance) VP_CUDA(c, cudaMalloc(&L.d_pre, c->pre_pitch * g.src_h));
+    if (g.use_pre && !g.bicubic_enhance) VP_CUDA(c, cudaMalloc(&L.d_pre, std::max(c->pre_pitch, c->pre4_pitch) * g.src_h));
     VP_CUDA(c, cudaMalloc(&L.d_sharp, std::max(c->frame_pitch, c->sharp4_pitch) * g.dst_h));
     if (g.use_post && !g.bicubic_enhance && (bil_has_modes(g.post) || (g.temporal.mode == VP_TEMPORAL_BLEND_FRAMES && g.temporal.use_flow)))
         VP_CUDA(c, cudaMalloc(&L.d_post, c->frame_pitch * g.dst_h));
