@@ -200,11 +200,19 @@ def test_batch_graph_replay_is_bit_identical(vp, temporal):
         ctx.call("vp_set_batch_graphs", 0)
         run_and_check(refs[1])
         assert vp.lib.vp_batch_graph_replays(ctx.handle) == 4
+        # another lane count is another batch: eager once, captured on the next sighting, same bytes
+        ctx.call("vp_set_batch_graphs", 1)
+        ctx.call("vp_set_batch_lanes", 2)
+        run_and_check(refs[1])
+        run_and_check(refs[1])
+        assert vp.lib.vp_batch_graph_replays(ctx.handle) == 5
+        ctx.call("vp_set_batch_lanes", 4)
+        ctx.call("vp_set_batch_graphs", 0)
         # switched on again: the cache was dropped, so one eager pass, then a fresh capture
         ctx.call("vp_set_batch_graphs", 1)
         run_and_check(refs[1])
         run_and_check(refs[1])
-        assert vp.lib.vp_batch_graph_replays(ctx.handle) == 5
+        assert vp.lib.vp_batch_graph_replays(ctx.handle) == 6
 
 
 @pytest.mark.parametrize("size", [(160, 96), (131, 67), (320, 200)])

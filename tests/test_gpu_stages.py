@@ -190,3 +190,24 @@ def test_error_codes(vp, ctx):
     assert vp.lib.vp_bilateral(ctx.handle, src.data_ptr(), 24, src.data_ptr(), 24, 8, 8, 17, 10.0, 10.0, None) == vp.VP_ERR_UNSUPPORTED
     assert b"radius" in vp.lib.vp_last_error(ctx.handle)
     assert vp.lib.vp_process_device(ctx.handle, src.data_ptr(), 24, src.data_ptr(), 24, None) == vp.VP_ERR_STATE
+
+
+def test_stage_calls_on_two_streams_share_tables_safely(vp, ctx):
+    """The stage-wise entry points share per-context tables (here vp_bilateral's candidate table, re-uploaded whenever the
+    parameters change).  Calls alternating between two streams with alternating parameters, with no host synchronisation in
+    between, must each see their own table: the context orders a call behind the previous call's kernels on the device."""
+    w, h = 512, 288
+    img = synth.frame("scene", w, h, 3)
+    want = {p: G.run_bilateral(vp, ctx, img, *p) for p in [(5, 30.0, 30.0), (9, 12.0, 20.0)]}
+    src = G.to_dev(img)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for i in range(8):
+        p = (5, 30.0, 30.0) if i % 2 == 0 else (9, 12.0, 20.0)
+        st = s1 if i % 2 == 0 else s2
+        dst = G.dev_empty(h, w)
+        ctx.call("vp_bilateral", src.data_ptr(), G.pitch(src), dst.data_ptr(), G.pitch(dst), w, h, p[0], p[1], p[2], st.cuda_stream)
+        outs.append((p, dst))
+    G.sync()
+    for p, dst in outs:
+        assert np.array_equal(dst.cpu().numpy(), want[p]), p
