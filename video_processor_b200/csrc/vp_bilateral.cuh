@@ -505,16 +505,15 @@ __global__ void __launch_bounds__(BIL_NT, VP_BIL_MINB) k_bilateral(const __grid_
         if (gy >= a.h) break;
         // previous frames of the temporal blend: issue the loads before the tap loop hides their latency
         uint32_t p0[3] = {0, 0, 0}, p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0};
-#if VP_BIL_PREFETCH
-        if (doblend || scene_prev) {
+        // (two of them in the 32-bit-source kernel; the general kernel has no registers to spare for them - measured: it
+        // spills with any prefetch and is 1-2 % faster without - and fetches all three behind the tap loop)
+        constexpr int PREF = BGRX ? VP_BIL_PREFETCH : 0;
+        if (PREF > 0 && (doblend || scene_prev)) {
             load12(b.prev[0] + (size_t)gy * b.ppitch + boff, p0, npx);
-            if (VP_BIL_PREFETCH > 1 && doblend && b.nprev > 1) load12(b.prev[1] + (size_t)gy * b.ppitch + boff, p1, npx);
+            if (PREF > 1 && doblend && b.nprev > 1) load12(b.prev[1] + (size_t)gy * b.ppitch + boff, p1, npx);
         }
-#endif
         uint32_t out[BIL_PX];
-#if VP_BIL_PREFETCH < 2
-        const bool late_p1 = doblend && b.nprev > 1;
-#endif
+        const bool late_p1 = PREF < 2 && doblend && b.nprev > 1;
         switch (R) {
             case 1: bil_strip<1, BGRX ? bil_xo(1) : 0>(s_tile, s_cand, s_cls, lx, ly, out); break;
             case 2: bil_strip<2, BGRX ? bil_xo(2) : 0>(s_tile, s_cand, s_cls, lx, ly, out); break;
@@ -568,12 +567,8 @@ __global__ void __launch_bounds__(BIL_NT, VP_BIL_MINB) k_bilateral(const __grid_
                 }
             }
         }
-#if VP_BIL_PREFETCH < 1
-        if (doblend || scene_prev) load12(b.prev[0] + (size_t)gy * b.ppitch + boff, p0, npx);
-#endif
-#if VP_BIL_PREFETCH < 2
+        if (PREF < 1 && (doblend || scene_prev)) load12(b.prev[0] + (size_t)gy * b.ppitch + boff, p0, npx);
         if (late_p1) load12(b.prev[1] + (size_t)gy * b.ppitch + boff, p1, npx);
-#endif
         // epilogue: optional temporal blend, state store, output store (12 contiguous bytes per strip)
         uint32_t cur[3];   // 12 packed bytes B G R B | G R B G | R B G R
         cur[0] = (out[0] & 0xffffffu) | (out[1] << 24);
