@@ -369,6 +369,9 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-c5-latency", action="store_true", help="skip the C5 single-frame latency sample of the default line")
+    ap.add_argument("--zero-copy-out", action="store_true",
+                    help="experiment (DESIGN.md 5): the last kernel writes its frames straight into mapped pinned host memory "
+                         "instead of device memory + a D2H copy; reported as `zero_copy_out`, never as value / e2e")
     ap.add_argument("--scene-detect", action="store_true", help="enable TemporalConsistency::detectSceneChange (blend becomes its own kernel)")
     ap.add_argument("--lanes", type=int, default=0, help="stream lanes of the batch API (0 = library default)")
     ap.add_argument("--per-frame", action="store_true", help="one vp_process_device call per frame on one stream (no batch API)")
@@ -555,6 +558,30 @@ def main():
                                  "achieved": per_frame * per_gpu_fps, "peak": ipeak, "peak_def": f"{sms} SMs x 4 schedulers x {mhz:.0f} MHz",
                                  "frac": round(per_frame * per_gpu_fps / ipeak, 4)}
 
+    # ---- experiment: output frames written by the POST kernel itself into mapped pinned host memory ----
+    zero_copy = None
+    if args.zero_copy_out and not args.per_frame:
+        hz = [torch.empty((dh, dw, 3), dtype=torch.uint8).pin_memory() for _ in range(NOUT)]     # UVA: device-visible at the same address
+        zdst = (C.c_void_p * (warm + F))(*([None] * warm + [hz[i % NOUT].data_ptr() for i in range(F)]))
+
+        def zstep():
+            capi.lib.vp_reset_temporal(h)
+            capi.check(batch(h, warm + F, src_ptrs, sw * 3, zdst, dw * 3, stream), h)
+
+        for _ in range(2):
+            zstep()
+        barrier()
+        z0, z1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        z0.record()
+        for _ in range(max(1, min(args.steps, 3))):
+            zstep()
+        z1.record()
+        torch.cuda.synchronize()
+        zms = z0.elapsed_time(z1) / max(1, min(args.steps, 3))
+        same = bool(torch.equal(hz[(F - 1) % NOUT], outs[(F - 1) % NOUT].cpu())) if rank == 0 else None
+        zero_copy = {"frames_per_s_per_gpu": F / (zms / 1e3), "ms_per_step": zms, "equals_device_output": same,
+                     "what": "device-resident inputs, output frames stored by the last kernel into mapped pinned host memory (no D2H copy)"}
+
     # ---- e2e: pinned host frames through vp_submit_host / vp_wait -----------------------------------
     e2e = None
     if not args.no_e2e:
@@ -673,7 +700,7 @@ def main():
                        "l2": f"inputs ({F}x{inb >> 20} MiB) and output ring ({NOUT}x{outb >> 20} MiB) exceed the 126 MB L2",
                        "roofline_pass": "per-kernel CUDA events in a separate pass of one step, one stream, one frame at a time",
                        "api": "vp_process_device per frame" if args.per_frame else "vp_process_batch_device (four stream lanes)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(tl.item()), "batch_graph_replays": int(capi.lib.vp_batch_graph_replays(h)), "roofline": roof, "cpu_baseline": cpu, "latency": latency, "latency_c5": latency_c5,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(tl.item()), "batch_graph_replays": int(capi.lib.vp_batch_graph_replays(h)), "zero_copy_out": zero_copy, "roofline": roof, "cpu_baseline": cpu, "latency": latency, "latency_c5": latency_c5,
             "parity_check": ("ok" if parity and all(v["result"] == "ok" for v in parity.values()) else ("FAILED" if parity else None)),
             "parity_detail": parity or None,
         }
